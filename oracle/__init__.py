@@ -1,0 +1,22 @@
+"""CPU oracle for the Sebulba hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+This package is a CPU restatement (numpy for integer/byte work, PyTorch-CPU fp32/fp64 for the
+floating-point network and autograd) of the algorithm behind the two hot paths of
+vwxyzjn/cleanba (`cleanba/cleanba_ppo.py`, `cleanba/cleanba_impala.py`).  Every function cites the
+reference `file:line` it follows.  Only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import it.  Nothing under
+`cleanba_b200/` imports it: the product path is CUDA-only and fails loudly without its extension.
+
+PARITY PINNING STATUS
+---------------------
+* `oracle.threefry` (JAX 0.4.8 threefry2x32 PRNG: PRNGKey/split/random_bits/uniform/permutation) is
+  PINNED: it reproduces the three Random123 threefry2x32-20 known-answer vectors and the public JAX
+  documentation constants for `split(PRNGKey(0))` and `uniform(PRNGKey(0))` (tests/test_oracle_prng.py).
+* Everything else is "PARITY UNPINNED": the reference ships no tests, golden vectors or fixtures
+  (SURVEY.md section 4), and its third-party arithmetic (jax 0.4.8, flax 0.6.8, optax 0.1.4, rlax 0.1.5 --
+  poetry.lock) is neither vendored under /root/reference nor installable in this image, so the
+  reference cannot be run to generate fixtures.  Those parts restate the published semantics of the
+  pinned upstream versions and are anchored by closed-form identities and autograd checks
+  (tests/test_oracle_*.py).  The golden vectors in tests/golden/ are produced BY THIS ORACLE
+  (tests/golden/make_golden.py) and pin it against regressions, not against JAX.
+"""
