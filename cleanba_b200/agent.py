@@ -1,0 +1,216 @@
+"""Host-side mirror of the reference's jitted hot-path callables, backed by libcleanba_b200 (CUDA, sm_100a).
+
+  Actor.get_action_and_value  <-> cleanba/cleanba_ppo.py:245-261      Actor.get_action <-> cleanba/cleanba_impala.py:287-301
+  Learner.compute_gae         <-> cleanba/cleanba_ppo.py:543-560 (+ :592-595 normalisation)
+  Learner.ppo_update          <-> single_device_update, cleanba/cleanba_ppo.py:579-654
+  Learner.impala_update       <-> single_device_update, cleanba/cleanba_impala.py:599-639
+  publish_params              <-> cleanba/cleanba_ppo.py:721-725
+
+PyTorch is plumbing only (device memory, streams, torch.distributed); all arithmetic runs in the C-ABI library.
+"""
+import ctypes
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .lib import CB_ALGO_IMPALA, CB_ALGO_PPO, CB_CONV_SIMT, CB_CONV_TCGEN05, CleanbaError, cb_config, check
+
+NUM_ACTIONS = 18
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, device, name):
+    if t.dtype != dtype or t.device != device or not t.is_contiguous():
+        raise CleanbaError(f"{name}: expected contiguous {dtype} on {device}, got {t.dtype} on {t.device} "
+                           f"(contiguous={t.is_contiguous()})")
+    return t
+
+
+class Context:
+    """One model replica on one GPU (an actor copy or a learner replica)."""
+
+    def __init__(self, device, max_batch: int, algo: int = CB_ALGO_PPO, train: bool = False,
+                 num_actions: int = NUM_ACTIONS, conv_backend: int = CB_CONV_TCGEN05):
+        if not torch.cuda.is_available():
+            raise CleanbaError("cleanba_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise CleanbaError("cleanba_b200 contexts live on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_actions = num_actions
+        self.algo = algo
+        self.train = train
+        self.max_batch = max_batch
+        cfg = cb_config(self.device.index, algo, max_batch, int(train), num_actions, conv_backend)
+        h = ctypes.c_void_p()
+        check(self.lib.cb_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self.h = h
+        self.num_params = int(self.lib.cb_num_params(num_actions))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters
+    def set_params(self, flat):
+        if isinstance(flat, np.ndarray):
+            flat = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float32))
+        flat = flat.to(torch.float32).contiguous()
+        if flat.numel() != self.num_params:
+            raise CleanbaError(f"expected {self.num_params} parameters, got {flat.numel()}")
+        with torch.cuda.device(self.device):
+            check(self.lib.cb_set_params(self.h, _ptr(flat), _stream(self.device)))
+            if not flat.is_cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+
+    def get_params(self) -> torch.Tensor:
+        out = torch.empty(self.num_params, dtype=torch.float32, device=self.device)
+        check(self.lib.cb_get_params(self.h, _ptr(out), _stream(self.device)))
+        return out
+
+    def params_view(self) -> torch.Tensor:
+        """Zero-copy view of the master parameter vector (for NCCL broadcast); call refresh_weights() after writing."""
+        ptr = self.lib.cb_params_ptr(self.h)
+        iface = {"shape": (self.num_params,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        holder = type("_CudaView", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.device)
+
+    def refresh_weights(self):
+        check(self.lib.cb_refresh_weights(self.h, _stream(self.device)))
+
+    def publish_to(self, dst: "Context"):
+        """learner -> actor parameter publish (cleanba_ppo.py:721-725), enqueued on dst's current stream."""
+        check(self.lib.cb_publish_params(dst.h, self.h, _stream(dst.device)))
+
+    def get_opt_state(self):
+        m = torch.empty(self.num_params, dtype=torch.float32, device=self.device)
+        v = torch.empty(self.num_params, dtype=torch.float32, device=self.device)
+        cnt = ctypes.c_longlong()
+        check(self.lib.cb_get_opt_state(self.h, _ptr(m), _ptr(v), ctypes.byref(cnt), _stream(self.device)))
+        return m, v, cnt.value
+
+    def profile(self, enable: bool):
+        check(self.lib.cb_profile(self.h, int(enable)))
+
+    def profile_report(self):
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(self.lib.cb_profile_report(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
+    def debug_tensor(self, name: str, shape) -> np.ndarray:
+        out = np.empty(int(np.prod(shape)), np.float32)
+        n = self.lib.cb_debug_tensor(self.h, name.encode(), out.ctypes.data_as(ctypes.c_void_p), out.size)
+        if n < 0:
+            raise CleanbaError(self.lib.cb_last_error().decode())
+        return out[:n].reshape(shape)
+
+    # ---- actor side
+    def actor_step(self, obs: torch.Tensor, key: torch.Tensor, want_logprob_value=True, want_logits=False, out=None):
+        """obs uint8 [n,4,84,84] (device); key uint32-as-int32 [2] (device, advanced in place).
+        -> action int32[n], logprob f32[n]|None, value f32[n]|None, logits f32[n,A]|None
+        `out` = (action, logprob, value, logits) pre-allocated contiguous device tensors (e.g. rows of the rollout
+        storage) to write into instead of allocating."""
+        d = self.device
+        _req(obs, torch.uint8, d, "obs")
+        n = obs.shape[0]
+        if out is not None:
+            action, logprob, value, logits = out
+        else:
+            action = torch.empty(n, dtype=torch.int32, device=d)
+            logprob = torch.empty(n, dtype=torch.float32, device=d) if want_logprob_value else None
+            value = torch.empty(n, dtype=torch.float32, device=d) if want_logprob_value else None
+            logits = torch.empty(n, self.num_actions, dtype=torch.float32, device=d) if want_logits else None
+        check(self.lib.cb_actor_step(self.h, _ptr(obs), n, _ptr(key), _ptr(action), _ptr(logprob), _ptr(value),
+                                     _ptr(logits), _stream(d)))
+        return action, logprob, value, logits
+
+    def policy_value(self, obs: torch.Tensor, idx: Optional[torch.Tensor] = None, n: Optional[int] = None):
+        d = self.device
+        _req(obs, torch.uint8, d, "obs")
+        n = int(idx.numel()) if idx is not None else (obs.shape[0] if n is None else n)
+        logits = torch.empty(n, self.num_actions, dtype=torch.float32, device=d)
+        value = torch.empty(n, dtype=torch.float32, device=d)
+        check(self.lib.cb_policy_value(self.h, _ptr(obs), _ptr(idx), n, _ptr(logits), _ptr(value), _stream(d)))
+        return logits, value
+
+    # ---- learner pieces
+    def gae(self, rewards, values, dones, next_value, next_done, gamma, gae_lambda, num_groups):
+        d = self.device
+        T, B = rewards.shape
+        adv = torch.empty(T, B, dtype=torch.float32, device=d)
+        ret = torch.empty(T, B, dtype=torch.float32, device=d)
+        check(self.lib.cb_gae(self.h, _ptr(_req(rewards, torch.float32, d, "rewards")),
+                              _ptr(_req(values, torch.float32, d, "values")), _ptr(_as_u8(dones, d, "dones")),
+                              _ptr(_req(next_value, torch.float32, d, "next_value")),
+                              _ptr(_as_u8(next_done, d, "next_done")), T, B, gamma, gae_lambda, num_groups,
+                              _ptr(adv), _ptr(ret), _stream(d)))
+        return adv, ret
+
+    def split_key(self, key: torch.Tensor) -> torch.Tensor:
+        sub = torch.empty(2, dtype=torch.int32, device=self.device)
+        check(self.lib.cb_split_key(self.h, _ptr(key), _ptr(sub), _stream(self.device)))
+        return sub
+
+    def permutation(self, key: torch.Tensor, n: int) -> torch.Tensor:
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        check(self.lib.cb_permutation(self.h, _ptr(key), n, _ptr(out), _stream(self.device)))
+        return out
+
+    def ppo_grad(self, obs, idx, mb, actions, logprobs, advantages, returns, clip_coef, ent_coef, vf_coef,
+                 grads: torch.Tensor, stats: torch.Tensor):
+        d = self.device
+        check(self.lib.cb_ppo_grad(self.h, _ptr(_req(obs, torch.uint8, d, "obs")), _ptr(idx), mb,
+                                   _ptr(_req(actions, torch.int32, d, "actions")),
+                                   _ptr(_req(logprobs, torch.float32, d, "logprobs")),
+                                   _ptr(_req(advantages, torch.float32, d, "advantages")),
+                                   _ptr(_req(returns, torch.float32, d, "returns")), clip_coef, ent_coef, vf_coef,
+                                   _ptr(grads), _ptr(stats), _stream(d)))
+
+    def impala_grad(self, obs, idx, T1, B, actions, behaviour_logits, rewards, dones, firststeps, gamma, vf_coef,
+                    ent_coef, grads, stats):
+        d = self.device
+        check(self.lib.cb_impala_grad(self.h, _ptr(_req(obs, torch.uint8, d, "obs")), _ptr(idx), T1, B,
+                                      _ptr(_req(actions, torch.int32, d, "actions")),
+                                      _ptr(_req(behaviour_logits, torch.float32, d, "behaviour_logits")),
+                                      _ptr(_req(rewards, torch.float32, d, "rewards")), _ptr(_as_u8(dones, d, "dones")),
+                                      _ptr(_as_u8(firststeps, d, "firststeps")), gamma, vf_coef, ent_coef,
+                                      _ptr(grads), _ptr(stats), _stream(d)))
+
+    def optimizer_step(self, grads, grad_scale, lr, max_norm, norm_out=None):
+        check(self.lib.cb_optimizer_step(self.h, _ptr(grads), float(grad_scale), float(lr), float(max_norm),
+                                         _ptr(norm_out), _stream(self.device)))
+
+
+def _as_u8(t: torch.Tensor, device, name):
+    if t.dtype == torch.bool:
+        t = t.view(torch.uint8)
+    return _req(t, torch.uint8, device, name)
+
+
+def key_tensor(key, device) -> torch.Tensor:
+    """uint32[2] PRNG key as an int32 device tensor (bit pattern preserved)."""
+    k = np.asarray(key, dtype=np.uint32).view(np.int32)
+    return torch.from_numpy(k.copy()).to(device)
+
+
+def key_numpy(key: torch.Tensor) -> np.ndarray:
+    return key.detach().cpu().numpy().view(np.uint32).copy()

@@ -1,0 +1,178 @@
+// Shared definitions for libcleanba_b200 (sm_100a only).
+//
+// Activation layout used by every trunk kernel ("chunk planes"):
+//   A tensor with C channels (C % 8 == 0) over a batch of n images of H x W pixels is stored on a zero
+//   padded grid Hp = H + 2, Wp = W + 2 (the SAME-padding ring of the 3x3 convs, cleanba_ppo.py:156,167),
+//   flattened over (image, y', x') into NP = n * Hp * Wp "flat pixels", and split into C/8 planes of
+//   8 channels:   plane[c / 8][flat pixel][c % 8].
+//   * "planes"  = two bf16 arrays (hi, lo) with x ~= hi + lo (16 significant bits); each plane has
+//     GUARD zero pixels before and after so a 3x3 tap window of a 128-pixel tile is one contiguous,
+//     in-bounds byte range (a 1-D bulk TMA copy) and the tile itself is an UMMA operand.
+//   * "stream"  = one fp32 array [C/8][NP][8] (residual stream / pre-pool conv output / gradients).
+//   Border pixels of every tensor are kept at exactly zero by the producing kernel.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cb {
+
+constexpr int GUARD = 256;          // zero pixels before / after every bf16 plane
+constexpr int NUM_TAPS = 9;
+constexpr int HIDDEN = 256;
+constexpr int MAX_ACTIONS = 32;
+
+typedef __nv_bfloat16 bf16;
+
+struct Planes {           // bf16 hi/lo chunk planes; pointers address flat pixel 0 (guard lies before it)
+    bf16* hi;
+    bf16* lo;             // may be null (exact-in-bf16 data, e.g. the unpacked uint8 frames)
+    long long plane_px;   // pixels per plane INCLUDING both guards (plane stride = plane_px * 8 elements)
+};
+
+struct ConvGeom {
+    int n, H, W;          // images, unpadded height / width
+    int Hp, Wp, P;        // padded dims, P = Hp * Wp
+    long long NP;         // n * P flat pixels
+};
+
+__host__ __device__ inline ConvGeom make_geom(int n, int H, int W) {
+    ConvGeom g;
+    g.n = n; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2; g.P = g.Hp * g.Wp; g.NP = (long long)n * g.P;
+    return g;
+}
+
+// Epilogue shared by the SIMT and the tcgen05 conv kernels (forward conv and dgrad):
+//   v = acc * acc_scale + bias;  v *= (mask_hi > 0);  v += res;  border -> 0
+//   out_s <- v ;  out planes <- split_bf16(relu ? max(v, 0) : v)
+struct ConvEpilogue {
+    const float* bias;        // [Cout] or null
+    float acc_scale;          // 1/255 for the first conv (cleanba_ppo.py:181), else 1
+    const bf16* mask_hi;      // planes (hi) of the forward activation whose sign gates the gradient, or null
+    long long mask_plane_px;
+    const float* res;         // fp32 stream added after the mask, or null
+    float* out_s;             // fp32 stream out, or null
+    Planes out;               // bf16 planes out (hi may be null)
+    int relu;
+};
+
+struct ConvArgs {
+    ConvGeom g;
+    Planes in;                // input planes
+    int cin_chunks;           // input channel chunks (8 channels each)
+    int cin_real;             // real input channels (4 for the frame stack, else cin_chunks * 8)
+    int cout;                 // output channels (16 / 32)
+    const float* w;           // fp32 master kernel, HWIO [3][3][Cin_f][Cout_f] (SIMT path)
+    int w_cin, w_cout;        // Cin_f, Cout_f of the master kernel
+    int transpose;            // 0: forward conv; 1: dgrad (flipped taps, in/out channels swapped)
+    const bf16* wp_hi;        // packed bf16 UMMA weight image (hi), see pack.cu
+    const bf16* wp_lo;
+    ConvEpilogue ep;
+};
+
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__device__ __forceinline__ float bf16lo_to_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_to_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// 8 bf16 (one uint4) -> 8 floats
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+    f[0] = bf16lo_to_f(v.x); f[1] = bf16hi_to_f(v.x);
+    f[2] = bf16lo_to_f(v.y); f[3] = bf16hi_to_f(v.y);
+    f[4] = bf16lo_to_f(v.z); f[5] = bf16hi_to_f(v.z);
+    f[6] = bf16lo_to_f(v.w); f[7] = bf16hi_to_f(v.w);
+}
+
+// Is flat pixel q (q < NP) an interior (non-border) pixel of its image?
+__device__ __forceinline__ bool interior(const ConvGeom& g, long long q) {
+    int r = (int)(q % g.P);
+    int y = r / g.Wp, x = r - y * g.Wp;
+    return (y >= 1) & (y <= g.H) & (x >= 1) & (x <= g.W);
+}
+
+// Apply the epilogue to the 8 accumulators of (flat pixel q, output chunk oc) and store.
+__device__ __forceinline__ void conv_epilogue_store(const ConvEpilogue& ep, const ConvGeom& g, long long q, int oc,
+                                                    float* acc) {
+    const bool tail = q >= g.NP;   // pixels past the last image (rest of the last 128-tile): planes get zeros
+    const bool in = !tail && interior(g, q);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (in) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float b = ep.bias ? ep.bias[oc * 8 + e] : 0.f;
+            v[e] = acc[e] * ep.acc_scale + b;
+        }
+        if (ep.mask_hi) {
+            uint4 m = *reinterpret_cast<const uint4*>(ep.mask_hi + ((long long)oc * ep.mask_plane_px + q) * 8);
+            float mf[8];
+            unpack8(m, mf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = mf[e] > 0.f ? v[e] : 0.f;
+        }
+        if (ep.res) {
+            const float4* r = reinterpret_cast<const float4*>(ep.res + ((long long)oc * g.NP + q) * 8);
+            float4 r0 = r[0], r1 = r[1];
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+    }
+    if (ep.out_s && !tail) {
+        float4* o = reinterpret_cast<float4*>(ep.out_s + ((long long)oc * g.NP + q) * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (ep.out.hi) {
+        bf16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = ep.relu ? fmaxf(v[e], 0.f) : v[e];
+            split_bf16(x, h[e], l[e]);
+        }
+        long long off = ((long long)oc * ep.out.plane_px + q) * 8;
+        *reinterpret_cast<uint4*>(ep.out.hi + off) =
+            make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+        if (ep.out.lo)
+            *reinterpret_cast<uint4*>(ep.out.lo + off) =
+                make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing (host)
+void set_error(const char* fmt, ...);
+}  // namespace cb
+#include <atomic>
+namespace cb {
+extern std::atomic<long long> g_launches;
+#define CB_CUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            (void)cudaGetLastError(); /* clear the non-sticky error state */                           \
+            cb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+            return -1;                                                                                 \
+        }                                                                                              \
+    } while (0)
+#define CB_CHECK(cond, ...)                                                                            \
+    do {                                                                                               \
+        if (!(cond)) {                                                                                 \
+            cb::set_error(__VA_ARGS__);                                                                \
+            return -1;                                                                                 \
+        }                                                                                              \
+    } while (0)
+#define CB_LAUNCH_CHECK()                 \
+    do {                                  \
+        cb::g_launches.fetch_add(1);      \
+        CB_CUDA(cudaGetLastError());      \
+    } while (0)
+
+}  // namespace cb

@@ -1,0 +1,809 @@
+// Context, buffer management, forward / backward orchestration and the C ABI (include/cleanba_b200.h).
+// Model: IMPALA-ResNet channels (16,32,32), hidden 256, linear actor/critic  (cleanba/cleanba_ppo.py:149-203).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <math.h>
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cleanba_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cb {
+
+std::atomic<long long> g_launches{0};   // every kernel launch of this library (CB_LAUNCH_CHECK increments it)
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------ model tables
+static const int kStageCin[3] = {4, 16, 32};
+static const int kStageC[3] = {16, 32, 32};
+static const int kStageHin[3] = {84, 42, 21};
+static const int kStageHout[3] = {42, 21, 11};
+static const int kStagePadLo[3] = {0, 0, 1};
+constexpr int kFlat = 11 * 11 * 32;
+
+struct Leaf {
+    std::string name;
+    long long offset;
+    int ndim;
+    int shape[4];
+    long long size() const {
+        long long s = 1;
+        for (int i = 0; i < ndim; ++i) s *= shape[i];
+        return s;
+    }
+};
+
+static std::vector<Leaf> build_leaves(int A) {
+    std::vector<Leaf> L;
+    long long off = 0;
+    auto add = [&](const std::string& n, std::initializer_list<int> shp) {
+        Leaf l;
+        l.name = n; l.offset = off; l.ndim = (int)shp.size();
+        int i = 0;
+        for (int s : shp) l.shape[i++] = s;
+        for (; i < 4; ++i) l.shape[i] = 1;
+        off += l.size();
+        L.push_back(l);
+    };
+    for (int s = 0; s < 3; ++s) {
+        std::string p = "network_params/params/ConvSequence_" + std::to_string(s);
+        add(p + "/Conv_0/bias", {kStageC[s]});
+        add(p + "/Conv_0/kernel", {3, 3, kStageCin[s], kStageC[s]});
+        for (int r = 0; r < 2; ++r)
+            for (int k = 0; k < 2; ++k) {
+                std::string q = p + "/ResidualBlock_" + std::to_string(r) + "/Conv_" + std::to_string(k);
+                add(q + "/bias", {kStageC[s]});
+                add(q + "/kernel", {3, 3, kStageC[s], kStageC[s]});
+            }
+    }
+    add("network_params/params/Dense_0/bias", {HIDDEN});
+    add("network_params/params/Dense_0/kernel", {kFlat, HIDDEN});
+    add("actor_params/params/Dense_0/bias", {A});
+    add("actor_params/params/Dense_0/kernel", {HIDDEN, A});
+    add("critic_params/params/Dense_0/bias", {1});
+    add("critic_params/params/Dense_0/kernel", {HIDDEN, 1});
+    return L;
+}
+
+struct ConvLayer {
+    int cin, cout;          // real channels
+    long long off_b, off_w; // offsets in the flat parameter vector
+    bf16 *fwd_hi, *fwd_lo, *dg_hi, *dg_lo;
+};
+
+struct Act {                // one activation / gradient tensor
+    Planes pl = {nullptr, nullptr, 0};
+    float* s = nullptr;
+    int C = 0, H = 0;
+};
+
+struct Stage {
+    Act x;                  // input planes of the sequence conv (stage 0: frames, hi only; else previous stage output)
+    Act y;                  // conv output (fp32 stream, pre-pool)
+    Act p;                  // pooled: stream + relu planes
+    Act a0, b0, a1, out;    // residual blocks (see trunk_forward)
+    Act gA, gB, gC, gBin;   // gradients (learner contexts)
+};
+
+}  // namespace cb
+
+using namespace cb;
+
+struct ProfAgg { long long launches = 0; double ms = 0, flops = 0, bytes = 0; };
+struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; int launches; };
+
+struct cb_ctx {
+    cb_config cfg;
+    bool prof_on = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    int num_sms = 148;
+    int A = 18;
+    std::vector<Leaf> leaves;
+    long long nparam = 0;
+    std::vector<void*> allocs;
+    float *params = nullptr, *m = nullptr, *v = nullptr;
+    long long opt_count = 0;
+    ConvLayer conv[15];
+    PackLayer* pack_dev = nullptr;
+    long long off_dense_b, off_dense_w, off_actor_b, off_actor_w, off_critic_b, off_critic_w;
+    Stage st[3];
+    float *hidden = nullptr, *dense_part = nullptr, *dpre = nullptr, *dlogits = nullptr, *terms = nullptr;
+    float *logits_scratch = nullptr, *cell_scratch = nullptr, *wg_partial = nullptr, *opt_partials = nullptr;
+    uint32_t* subkey = nullptr;
+    uint32_t* key_tmp = nullptr;
+    int* perm_tmp = nullptr;
+    uint32_t* sort_keys = nullptr;
+    int perm_cap = 0;
+    int last_n = 0;
+};
+
+namespace cb {
+
+static int dev_alloc(cb_ctx* c, void** p, size_t bytes, bool zero = true) {
+    CB_CUDA(cudaMalloc(p, bytes));
+    c->allocs.push_back(*p);
+    if (zero) CB_CUDA(cudaMemset(*p, 0, bytes));
+    return 0;
+}
+
+static long long plane_px_for(int max_batch, int H) {
+    long long np = (long long)max_batch * (H + 2) * (H + 2);
+    np = (np + 127) / 128 * 128;
+    return GUARD + np + GUARD;
+}
+
+static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool planes, bool lo, bool stream) {
+    a.C = C; a.H = H;
+    const int chunks = (C + 7) / 8;
+    if (planes) {
+        a.pl.plane_px = plane_px_for(c->cfg.max_batch, H);
+        size_t bytes = (size_t)chunks * a.pl.plane_px * 8 * sizeof(bf16);
+        void* p;
+        if (dev_alloc(c, &p, bytes)) return -1;
+        a.pl.hi = (bf16*)p + (long long)GUARD * 8;
+        if (lo) {
+            if (dev_alloc(c, &p, bytes)) return -1;
+            a.pl.lo = (bf16*)p + (long long)GUARD * 8;
+        }
+    }
+    if (stream) {
+        size_t bytes = (size_t)chunks * c->cfg.max_batch * (H + 2) * (H + 2) * 8 * sizeof(float);
+        void* p;
+        if (dev_alloc(c, &p, bytes)) return -1;
+        a.s = (float*)p;
+    }
+    return 0;
+}
+
+// CUDA-event bracket around one launcher call (only when profiling is enabled): per-kernel device time measured on the
+// launching stream, with the kernel's algorithmic flops / bytes, for bench.py's roofline.
+struct ProfScope {
+    cb_ctx* c; cudaStream_t st; ProfRec r; bool on; long long l0;
+    ProfScope(cb_ctx* c_, const std::string& name, double flops, double bytes, cudaStream_t st_) : c(c_), st(st_), on(c_->prof_on) {
+        if (!on) return;
+        auto get = [&]() { cudaEvent_t e; if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        r.name = name; r.flops = flops; r.bytes = bytes; r.a = get(); r.b = get();
+        l0 = g_launches.load();
+        cudaEventRecord(r.a, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.b, st);
+        r.launches = (int)(g_launches.load() - l0);
+        c->prof_recs.push_back(r);
+    }
+};
+static double planes_bytes(const ConvGeom& g, int chunks, bool lo) { return (double)g.NP * chunks * 8 * (lo ? 4 : 2); }
+static double stream_bytes(const ConvGeom& g, int chunks) { return (double)g.NP * chunks * 8 * 4; }
+
+static int refresh_weights(cb_ctx* c, cudaStream_t st) {
+    ProfScope ps(c, "pack_weights", 0, 1089232.0 * (4 + 8), st);
+    return launch_pack_conv(c->pack_dev, 15, st);
+}
+
+static ConvArgs conv_args(cb_ctx* c, int layer, const ConvGeom& g, const Act& in, bool transpose) {
+    const ConvLayer& L = c->conv[layer];
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g;
+    a.in = in.pl;
+    a.w = c->params + L.off_w;
+    a.w_cin = L.cin; a.w_cout = L.cout;
+    a.transpose = transpose ? 1 : 0;
+    if (!transpose) {
+        a.cin_real = L.cin; a.cin_chunks = (L.cin + 7) / 8; a.cout = L.cout;
+        a.wp_hi = L.fwd_hi; a.wp_lo = L.fwd_lo;
+    } else {
+        a.cin_real = L.cout; a.cin_chunks = L.cout / 8; a.cout = L.cin;
+        a.wp_hi = L.dg_hi; a.wp_lo = L.dg_lo;
+    }
+    a.ep.acc_scale = 1.f;
+    return a;
+}
+
+static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
+    char name[96];
+    snprintf(name, sizeof(name), "%s<cin%d,cout%d>@%dx%d", a.transpose ? "conv_dgrad" : "conv_fwd", a.cin_real, a.cout, a.g.H, a.g.W);
+    const double flops = 2.0 * a.g.n * a.g.H * a.g.W * 9.0 * a.cin_real * a.cout;
+    double bytes = planes_bytes(a.g, a.cin_chunks, a.in.lo != nullptr);
+    if (a.ep.out_s) bytes += stream_bytes(a.g, a.cout / 8);
+    if (a.ep.out.hi) bytes += planes_bytes(a.g, a.cout / 8, true);
+    if (a.ep.res) bytes += stream_bytes(a.g, a.cout / 8);
+    if (a.ep.mask_hi) bytes += planes_bytes(a.g, a.cout / 8, false);
+    ProfScope ps(c, name, flops, bytes, st);
+    if (c->cfg.conv_backend == CB_CONV_SIMT) return launch_conv_simt(a, st);
+    return launch_conv_umma(a, c->num_sms, st);
+}
+
+static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, const Act& gy, float* grads, cudaStream_t st) {
+    const ConvLayer& L = c->conv[layer];
+    WgradArgs w;
+    w.g = g; w.x = x.pl; w.cin_chunks = (L.cin + 7) / 8; w.cin_real = L.cin; w.gy = gy.pl; w.cout = L.cout;
+    w.dw = grads + L.off_w; w.db = grads + L.off_b;
+    w.scale = (layer == 0) ? (1.0f / 255.0f) : 1.0f;
+    char name[96];
+    snprintf(name, sizeof(name), "conv_wgrad<cin%d,cout%d>@%dx%d", L.cin, L.cout, g.H, g.W);
+    ProfScope ps(c, name, 2.0 * g.n * g.H * g.W * 9.0 * L.cin * L.cout,
+                 planes_bytes(g, w.cin_chunks, x.pl.lo != nullptr) + planes_bytes(g, L.cout / 8, true), st);
+    if (c->cfg.conv_backend == CB_CONV_SIMT) return launch_wgrad_simt(w, c->wg_partial, 296, st);
+    return launch_wgrad_umma(w, c->wg_partial, c->num_sms, st);
+}
+
+// Network.__call__ (cleanba_ppo.py:178-189) on n frames -> c->hidden [n,256]
+static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStream_t st) {
+    CB_CHECK(n > 0 && n <= c->cfg.max_batch, "batch %d outside (0, max_batch=%d]", n, c->cfg.max_batch);
+    c->last_n = n;
+    {
+        ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 86.0 * 86 * 16), st);
+        if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st)) return -1;
+    }
+    for (int s = 0; s < 3; ++s) {
+        Stage& S = c->st[s];
+        const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
+        const ConvGeom go = make_geom(n, kStageHout[s], kStageHout[s]);
+        const int base = s * 5;
+        {   // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
+            ConvArgs a = conv_args(c, base + 0, gi, S.x, false);
+            a.ep.bias = c->params + c->conv[base].off_b;
+            a.ep.acc_scale = (s == 0) ? (1.0f / 255.0f) : 1.0f;   // x / 255.0 (cleanba_ppo.py:181) folded into the epilogue
+            a.ep.out_s = S.y.s;
+            if (run_conv(c, a, st)) return -1;
+        }
+        // x = nn.max_pool(x, (3,3), strides=(2,2), padding="SAME")              (cleanba_ppo.py:168)
+        {
+            ProfScope ps(c, "pool_fwd@" + std::to_string(kStageHin[s]), 0,
+                         stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(go, kStageC[s] / 8, true), st);
+            if (launch_pool_fwd(S.y.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.p.s, S.p.pl, st)) return -1;
+        }
+        {   // ResidualBlock 0: x + Conv(relu(Conv(relu(x))))                    (cleanba_ppo.py:153-159)
+            ConvArgs a = conv_args(c, base + 1, go, S.p, false);
+            a.ep.bias = c->params + c->conv[base + 1].off_b;
+            a.ep.out = S.a0.pl; a.ep.relu = 1;
+            if (run_conv(c, a, st)) return -1;
+            ConvArgs b = conv_args(c, base + 2, go, S.a0, false);
+            b.ep.bias = c->params + c->conv[base + 2].off_b;
+            b.ep.res = S.p.s; b.ep.out_s = S.b0.s; b.ep.out = S.b0.pl; b.ep.relu = 1;
+            if (run_conv(c, b, st)) return -1;
+        }
+        {   // ResidualBlock 1; its output feeds the next ConvSequence un-rectified, or the final nn.relu (cleanba_ppo.py:184)
+            ConvArgs a = conv_args(c, base + 3, go, S.b0, false);
+            a.ep.bias = c->params + c->conv[base + 3].off_b;
+            a.ep.out = S.a1.pl; a.ep.relu = 1;
+            if (run_conv(c, a, st)) return -1;
+            ConvArgs b = conv_args(c, base + 4, go, S.a1, false);
+            b.ep.bias = c->params + c->conv[base + 4].off_b;
+            b.ep.res = S.b0.s; b.ep.out = S.out.pl; b.ep.relu = (s == 2) ? 1 : 0;
+            if (run_conv(c, b, st)) return -1;
+        }
+    }
+    DenseArgs d;
+    d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
+    ProfScope ps(c, "dense_fwd", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 4 + (double)kFlat * HIDDEN * 4, st);
+    return launch_dense_fwd(d, c->dense_part, st);
+}
+
+// Backward of the trunk given c->dpre (gradient w.r.t. the pre-relu dense output); writes all trunk gradients.
+static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
+    DenseArgs d;
+    d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
+    {
+        ProfScope ps(c, "dense_bwd_w", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 4 + (double)kFlat * HIDDEN * 4, st);
+        if (launch_dense_bwd_w(d, c->dpre, grads + c->off_dense_w, grads + c->off_dense_b, st)) return -1;
+    }
+    {
+        ProfScope ps(c, "dense_bwd_x", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 12 + (double)kFlat * HIDDEN * 4, st);
+        if (launch_dense_bwd_x(d, c->dpre, c->st[2].gA.s, c->st[2].gA.pl, st)) return -1;
+    }
+    for (int s = 2; s >= 0; --s) {
+        Stage& S = c->st[s];
+        const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
+        const ConvGeom go = make_geom(n, kStageHout[s], kStageHout[s]);
+        const int base = s * 5;
+        // ---- ResidualBlock 1: out = b0 + conv4(relu(conv3(relu(b0))))
+        if (run_wgrad(c, base + 4, go, S.a1, S.gA, grads, st)) return -1;
+        {
+            ConvArgs a = conv_args(c, base + 4, go, S.gA, true);
+            a.ep.mask_hi = S.a1.pl.hi; a.ep.mask_plane_px = S.a1.pl.plane_px; a.ep.out = S.gB.pl;
+            if (run_conv(c, a, st)) return -1;
+        }
+        if (run_wgrad(c, base + 3, go, S.b0, S.gB, grads, st)) return -1;
+        {
+            ConvArgs a = conv_args(c, base + 3, go, S.gB, true);
+            a.ep.mask_hi = S.b0.pl.hi; a.ep.mask_plane_px = S.b0.pl.plane_px; a.ep.res = S.gA.s;
+            a.ep.out_s = S.gC.s; a.ep.out = S.gC.pl;
+            if (run_conv(c, a, st)) return -1;
+        }
+        // ---- ResidualBlock 0: b0 = p + conv2(relu(conv1(relu(p))))
+        if (run_wgrad(c, base + 2, go, S.a0, S.gC, grads, st)) return -1;
+        {
+            ConvArgs a = conv_args(c, base + 2, go, S.gC, true);
+            a.ep.mask_hi = S.a0.pl.hi; a.ep.mask_plane_px = S.a0.pl.plane_px; a.ep.out = S.gB.pl;
+            if (run_conv(c, a, st)) return -1;
+        }
+        if (run_wgrad(c, base + 1, go, S.p, S.gB, grads, st)) return -1;
+        {
+            ConvArgs a = conv_args(c, base + 1, go, S.gB, true);
+            a.ep.mask_hi = S.p.pl.hi; a.ep.mask_plane_px = S.p.pl.plane_px; a.ep.res = S.gC.s;
+            a.ep.out_s = S.gA.s;   // gradient w.r.t. the pooled tensor (gA.s is free again)
+            if (run_conv(c, a, st)) return -1;
+        }
+        // ---- max-pool backward, then the sequence conv
+        {
+            ProfScope ps(c, "pool_bwd@" + std::to_string(kStageHin[s]), 0,
+                         stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(gi, kStageC[s] / 8, true), st);
+            if (launch_pool_bwd(S.y.s, S.gA.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.gBin.pl, st)) return -1;
+        }
+        if (run_wgrad(c, base + 0, gi, S.x, S.gBin, grads, st)) return -1;
+        if (s > 0) {
+            ConvArgs a = conv_args(c, base + 0, gi, S.gBin, true);
+            a.ep.out_s = c->st[s - 1].gA.s; a.ep.out = c->st[s - 1].gA.pl;
+            if (run_conv(c, a, st)) return -1;
+        }
+    }
+    return 0;
+}
+
+static int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    CB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+    return 0;
+}
+
+}  // namespace cb
+
+// ================================================================================================ C ABI
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* cb_last_error(void) { return g_err; }
+int cb_version(void) { return 1; }
+
+long long cb_num_params(int num_actions) {
+    auto L = build_leaves(num_actions);
+    return L.back().offset + L.back().size();
+}
+int cb_num_leaves(void) { return 36; }
+int cb_leaf_info(int index, int num_actions, char* name, int name_cap, long long* offset, int* ndim, int* shape) {
+    auto L = build_leaves(num_actions);
+    CB_CHECK(index >= 0 && index < (int)L.size(), "leaf index %d out of range", index);
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", L[index].name.c_str());
+    if (offset) *offset = L[index].offset;
+    if (ndim) *ndim = L[index].ndim;
+    if (shape) for (int i = 0; i < 4; ++i) shape[i] = L[index].shape[i];
+    return 0;
+}
+
+void cb_destroy(cb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    for (void* p : c->allocs) cudaFree(p);
+    delete c;
+}
+
+int cb_create(const cb_config* cfg, cb_ctx** out) {
+    CB_CHECK(cfg && out, "null argument");
+    CB_CHECK(cfg->max_batch > 0, "max_batch must be positive");
+    CB_CHECK(cfg->num_actions > 0 && cfg->num_actions <= MAX_ACTIONS, "num_actions must be in [1,%d]", MAX_ACTIONS);
+    int ndev = 0;
+    CB_CUDA(cudaGetDeviceCount(&ndev));
+    CB_CHECK(cfg->device >= 0 && cfg->device < ndev, "device %d not available (%d CUDA devices)", cfg->device, ndev);
+    CB_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    CB_CHECK(prop.major == 10, "libcleanba_b200 needs an sm_100a (Blackwell B200) device, found sm_%d%d", prop.major, prop.minor);
+    cb_ctx* c = new cb_ctx();
+    c->cfg = *cfg;
+    c->num_sms = prop.multiProcessorCount;
+    c->A = cfg->num_actions;
+    c->leaves = build_leaves(c->A);
+    c->nparam = c->leaves.back().offset + c->leaves.back().size();
+    bool ok = false;
+    do {
+        void* p;
+        if (dev_alloc(c, &p, c->nparam * sizeof(float))) break;
+        c->params = (float*)p;
+        if (cfg->train) {
+            if (dev_alloc(c, &p, c->nparam * sizeof(float))) break;
+            c->m = (float*)p;
+            if (dev_alloc(c, &p, c->nparam * sizeof(float))) break;
+            c->v = (float*)p;
+            if (dev_alloc(c, &p, OPT_BLOCKS * sizeof(float))) break;
+            c->opt_partials = (float*)p;
+        }
+        // conv layer table + packed weights
+        std::vector<PackLayer> pl(15);
+        bool fail = false;
+        for (int s = 0; s < 3 && !fail; ++s)
+            for (int k = 0; k < 5 && !fail; ++k) {
+                int li = s * 5 + k;
+                ConvLayer& L = c->conv[li];
+                L.cin = (k == 0) ? kStageCin[s] : kStageC[s];
+                L.cout = kStageC[s];
+                L.off_b = c->leaves[s * 10 + k * 2].offset;
+                L.off_w = c->leaves[s * 10 + k * 2 + 1].offset;
+                long long ef = packed_conv_elems((L.cin + 7) / 8, L.cout);
+                if (dev_alloc(c, &p, ef * sizeof(bf16))) { fail = true; break; }
+                L.fwd_hi = (bf16*)p;
+                if (dev_alloc(c, &p, ef * sizeof(bf16))) { fail = true; break; }
+                L.fwd_lo = (bf16*)p;
+                L.dg_hi = L.dg_lo = nullptr;
+                if (li != 0) {
+                    long long ed = packed_conv_elems(L.cout / 8, L.cin);
+                    if (dev_alloc(c, &p, ed * sizeof(bf16))) { fail = true; break; }
+                    L.dg_hi = (bf16*)p;
+                    if (dev_alloc(c, &p, ed * sizeof(bf16))) { fail = true; break; }
+                    L.dg_lo = (bf16*)p;
+                }
+                pl[li].w = c->params + L.off_w; pl[li].cin = L.cin; pl[li].cout = L.cout;
+                pl[li].fwd_hi = L.fwd_hi; pl[li].fwd_lo = L.fwd_lo; pl[li].dg_hi = L.dg_hi; pl[li].dg_lo = L.dg_lo;
+            }
+        if (fail) break;
+        if (dev_alloc(c, &p, 15 * sizeof(PackLayer))) break;
+        c->pack_dev = (PackLayer*)p;
+        if (cudaMemcpy(c->pack_dev, pl.data(), 15 * sizeof(PackLayer), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("cudaMemcpy(pack table) failed");
+            break;
+        }
+        c->off_dense_b = c->leaves[30].offset; c->off_dense_w = c->leaves[31].offset;
+        c->off_actor_b = c->leaves[32].offset; c->off_actor_w = c->leaves[33].offset;
+        c->off_critic_b = c->leaves[34].offset; c->off_critic_w = c->leaves[35].offset;
+        // activations
+        for (int s = 0; s < 3 && !fail; ++s) {
+            Stage& S = c->st[s];
+            const int C = kStageC[s], Hin = kStageHin[s], Ho = kStageHout[s];
+            if (s == 0) fail |= alloc_act(c, S.x, 8, Hin, true, false, false) != 0;
+            fail |= alloc_act(c, S.y, C, Hin, false, false, true) != 0;
+            fail |= alloc_act(c, S.p, C, Ho, true, true, true) != 0;
+            fail |= alloc_act(c, S.a0, C, Ho, true, true, false) != 0;
+            fail |= alloc_act(c, S.b0, C, Ho, true, true, true) != 0;
+            fail |= alloc_act(c, S.a1, C, Ho, true, true, false) != 0;
+            fail |= alloc_act(c, S.out, C, Ho, true, true, false) != 0;
+            if (s < 2 && !fail) c->st[s + 1].x = S.out;
+            if (cfg->train) {
+                fail |= alloc_act(c, S.gA, C, Ho, true, true, true) != 0;
+                fail |= alloc_act(c, S.gB, C, Ho, true, true, false) != 0;
+                fail |= alloc_act(c, S.gC, C, Ho, true, true, true) != 0;
+                fail |= alloc_act(c, S.gBin, C, Hin, true, true, false) != 0;
+            }
+        }
+        if (fail) break;
+        const size_t mb = (size_t)cfg->max_batch;
+        if (dev_alloc(c, &p, mb * HIDDEN * sizeof(float))) break;
+        c->hidden = (float*)p;
+        size_t part = mb * HIDDEN;
+        if (part < (size_t)11 * 256 * HIDDEN) part = (size_t)11 * 256 * HIDDEN;
+        if (part < (size_t)4 * 1024 * HIDDEN) part = (size_t)4 * 1024 * HIDDEN;
+        if (dev_alloc(c, &p, part * sizeof(float))) break;
+        c->dense_part = (float*)p;
+        if (dev_alloc(c, &p, 2 * sizeof(uint32_t))) break;
+        c->subkey = (uint32_t*)p;
+        if (dev_alloc(c, &p, 2 * sizeof(uint32_t))) break;
+        c->key_tmp = (uint32_t*)p;
+        if (cfg->train) {
+            if (dev_alloc(c, &p, mb * HIDDEN * sizeof(float))) break;
+            c->dpre = (float*)p;
+            if (dev_alloc(c, &p, mb * (MAX_ACTIONS + 1) * sizeof(float))) break;
+            c->dlogits = (float*)p;
+            if (dev_alloc(c, &p, mb * 8 * sizeof(float))) break;
+            c->terms = (float*)p;
+            if (dev_alloc(c, &p, mb * (MAX_ACTIONS + 1) * sizeof(float))) break;
+            c->logits_scratch = (float*)p;
+            if (dev_alloc(c, &p, mb * 8 * sizeof(float))) break;
+            c->cell_scratch = (float*)p;
+            if (dev_alloc(c, &p, (size_t)4 * 1024 * 1024 * sizeof(float))) break;
+            c->wg_partial = (float*)p;
+        }
+        ok = true;
+    } while (0);
+    if (!ok) {
+        cb_destroy(c);
+        return -1;
+    }
+    *out = c;
+    return 0;
+}
+
+int cb_set_params(cb_ctx* c, const float* src, cb_stream stream) {
+    CB_CHECK(c && src, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    if (copy_any(c->params, src, c->nparam * sizeof(float), (cudaStream_t)stream)) return -1;
+    return refresh_weights(c, (cudaStream_t)stream);
+}
+int cb_get_params(cb_ctx* c, float* dst, cb_stream stream) {
+    CB_CHECK(c && dst, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    return copy_any(dst, c->params, c->nparam * sizeof(float), (cudaStream_t)stream);
+}
+float* cb_params_ptr(cb_ctx* c) { return c ? c->params : nullptr; }
+int cb_refresh_weights(cb_ctx* c, cb_stream stream) {
+    CB_CHECK(c, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    return refresh_weights(c, (cudaStream_t)stream);
+}
+int cb_publish_params(cb_ctx* dst, cb_ctx* src, cb_stream stream) {
+    CB_CHECK(dst && src, "null argument");
+    CB_CHECK(dst->nparam == src->nparam, "parameter count mismatch");
+    CB_CUDA(cudaSetDevice(dst->cfg.device));
+    if (dst->cfg.device == src->cfg.device) {
+        if (copy_any(dst->params, src->params, dst->nparam * sizeof(float), (cudaStream_t)stream)) return -1;
+    } else {
+        CB_CUDA(cudaMemcpyPeerAsync(dst->params, dst->cfg.device, src->params, src->cfg.device, dst->nparam * sizeof(float),
+                                    (cudaStream_t)stream));
+    }
+    return refresh_weights(dst, (cudaStream_t)stream);
+}
+int cb_get_opt_state(cb_ctx* c, float* m, float* v, long long* count, cb_stream stream) {
+    CB_CHECK(c && c->cfg.train, "not a learner context");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    if (m && copy_any(m, c->m, c->nparam * sizeof(float), (cudaStream_t)stream)) return -1;
+    if (v && copy_any(v, c->v, c->nparam * sizeof(float), (cudaStream_t)stream)) return -1;
+    if (count) *count = c->opt_count;
+    return 0;
+}
+int cb_set_opt_state(cb_ctx* c, const float* m, const float* v, long long count, cb_stream stream) {
+    CB_CHECK(c && c->cfg.train, "not a learner context");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    if (m && copy_any(c->m, m, c->nparam * sizeof(float), (cudaStream_t)stream)) return -1;
+    if (v && copy_any(c->v, v, c->nparam * sizeof(float), (cudaStream_t)stream)) return -1;
+    c->opt_count = count;
+    return 0;
+}
+
+int cb_actor_step(cb_ctx* c, const uint8_t* obs, int n, uint32_t* key, int32_t* action, float* logprob, float* value,
+                  float* logits, cb_stream stream) {
+    CB_CHECK(c && obs && key && action, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (trunk_forward(c, obs, nullptr, n, st)) return -1;
+    if (launch_split_key(key, c->subkey, st)) return -1;   // key, subkey = jax.random.split(key)
+    ProfScope ps(c, "actor_head", 2.0 * n * HIDDEN * (c->A + 1), (double)n * (HIDDEN * 4 + 12), st);
+    return launch_actor_head(c->hidden, n, c->A, c->params + c->off_actor_w, c->params + c->off_actor_b,
+                             c->params + c->off_critic_w, c->params + c->off_critic_b, c->subkey, logits, value, action,
+                             logprob, st);
+}
+
+// forward-only heads (no sampling): reuse the actor head kernel with a scratch action buffer
+int cb_policy_value(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int n, float* logits, float* value, cb_stream stream) {
+    CB_CHECK(c && obs, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (trunk_forward(c, obs, idx, n, st)) return -1;
+    // scratch for the (unused) sampled actions: the dense partial buffer is free after the forward
+    int* scratch_act = reinterpret_cast<int*>(c->dense_part);
+    return launch_actor_head(c->hidden, n, c->A, c->params + c->off_actor_w, c->params + c->off_actor_b,
+                             c->params + c->off_critic_w, c->params + c->off_critic_b, c->subkey, logits, value,
+                             scratch_act, nullptr, st);
+}
+
+int cb_gae(cb_ctx* c, const float* rewards, const float* values, const uint8_t* dones, const float* next_value,
+           const uint8_t* next_done, int T, int B, float gamma, float gae_lambda, int num_groups, float* adv, float* ret,
+           cb_stream stream) {
+    CB_CHECK(c && rewards && values && dones && next_value && next_done && adv && ret, "null argument");
+    CB_CHECK(T > 0 && B > 0, "empty rollout T=%d B=%d", T, B);
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    ProfScope ps(c, "gae_advnorm_scan", 0, 17.0 * T * B, (cudaStream_t)stream);
+    return launch_gae(rewards, values, dones, next_value, next_done, T, B, gamma, gae_lambda, num_groups, adv, ret,
+                      (cudaStream_t)stream);
+}
+
+int cb_split_key(cb_ctx* c, uint32_t* key, uint32_t* subkey, cb_stream stream) {
+    CB_CHECK(c && key && subkey, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    return launch_split_key(key, subkey, (cudaStream_t)stream);
+}
+
+int cb_permutation(cb_ctx* c, const uint32_t* key, int n, int32_t* out, cb_stream stream) {
+    CB_CHECK(c && key && out, "null argument");
+    CB_CHECK(n >= 0, "negative n");
+    if (n == 0) return 0;
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > c->perm_cap) {
+        void* p;
+        if (dev_alloc(c, &p, (size_t)n * sizeof(int))) return -1;
+        c->perm_tmp = (int*)p;
+        if (dev_alloc(c, &p, (size_t)n * sizeof(uint32_t))) return -1;
+        c->sort_keys = (uint32_t*)p;
+        c->perm_cap = n;
+    }
+    // num_rounds = ceil(3 ln n / ln(2^32 - 1))  (jax._src.random._shuffle)
+    int rounds = (int)ceil(3.0 * log((double)(n > 1 ? n : 1)) / log(4294967295.0));
+    if (copy_any(c->key_tmp, key, 2 * sizeof(uint32_t), st)) return -1;
+    ProfScope ps(c, "permutation", 0, 12.0 * n, st);
+    return launch_permutation(c->key_tmp, n, rounds, out, c->perm_tmp, c->sort_keys, c->subkey, st);
+}
+
+int cb_ppo_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int mb, const int32_t* actions, const float* logprobs,
+                const float* advantages, const float* returns, float clip_coef, float ent_coef, float vf_coef, float* grads,
+                float* stats, cb_stream stream) {
+    CB_CHECK(c && obs && actions && logprobs && advantages && returns && grads && stats, "null argument");
+    CB_CHECK(c->cfg.train, "cb_ppo_grad needs a learner context (train=1)");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (trunk_forward(c, obs, idx, mb, st)) return -1;
+    PpoHeadArgs h;
+    h.n = mb; h.num_actions = c->A; h.hidden = c->hidden;
+    h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
+    h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
+    h.idx = idx; h.actions = actions; h.old_logprobs = logprobs; h.advantages = advantages; h.returns = returns;
+    h.clip_coef = clip_coef; h.ent_coef = ent_coef; h.vf_coef = vf_coef;
+    h.dpre = c->dpre; h.dlogits = c->dlogits; h.terms = c->terms; h.stats = stats;
+    h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
+    {
+        ProfScope ps(c, "ppo_loss_head", 6.0 * mb * HIDDEN * (c->A + 1), (double)mb * (2 * HIDDEN * 4 + 92 + 76), st);
+        if (launch_ppo_head(h, st)) return -1;
+    }
+    return trunk_backward(c, mb, grads, st);
+}
+
+int cb_impala_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int T1, int B, const int32_t* actions,
+                   const float* behaviour_logits, const float* rewards, const uint8_t* dones, const uint8_t* firststeps,
+                   float gamma, float vf_coef, float ent_coef, float* grads, float* stats, cb_stream stream) {
+    CB_CHECK(c && obs && actions && behaviour_logits && rewards && dones && firststeps && grads && stats, "null argument");
+    CB_CHECK(c->cfg.train, "cb_impala_grad needs a learner context (train=1)");
+    CB_CHECK(T1 >= 2 && B >= 1, "need T+1 >= 2 rows and B >= 1 columns");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = T1 * B;
+    if (trunk_forward(c, obs, idx, n, st)) return -1;
+    ImpalaHeadArgs h;
+    h.T1 = T1; h.B = B; h.num_actions = c->A; h.hidden = c->hidden;
+    h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
+    h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
+    h.idx = idx; h.actions = actions; h.behaviour_logits = behaviour_logits; h.rewards = rewards; h.dones = dones;
+    h.firststeps = firststeps; h.gamma = gamma; h.vf_coef = vf_coef; h.ent_coef = ent_coef;
+    h.logits_scratch = c->logits_scratch; h.cell_scratch = c->cell_scratch; h.dpre = c->dpre; h.dlogits = c->dlogits;
+    h.stats = stats;
+    h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
+    {
+        ProfScope ps(c, "vtrace_loss_head", 6.0 * n * HIDDEN * (c->A + 1), (double)n * (2 * HIDDEN * 4 + 157 + 76), st);
+        if (launch_impala_head(h, st)) return -1;
+    }
+    return trunk_backward(c, n, grads, st);
+}
+
+int cb_optimizer_step(cb_ctx* c, const float* grads, float grad_scale, float lr, float max_norm, float* norm_out,
+                      cb_stream stream) {
+    CB_CHECK(c && grads, "null argument");
+    CB_CHECK(c->cfg.train, "cb_optimizer_step needs a learner context (train=1)");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    OptArgs o;
+    o.n = c->nparam; o.p = c->params; o.g = grads; o.m = c->m; o.v = c->v;
+    o.grad_scale = grad_scale; o.max_norm = max_norm; o.lr = lr;
+    o.partials = c->opt_partials; o.norm_out = norm_out;
+    c->opt_count += 1;
+    if (c->cfg.algo == CB_ALGO_PPO) {
+        o.kind = 0; o.b1 = 0.9f; o.b2 = 0.999f; o.eps = 1e-5f;
+        o.bc1 = 1.0f - powf(0.9f, (float)c->opt_count);
+        o.bc2 = 1.0f - powf(0.999f, (float)c->opt_count);
+    } else {
+        o.kind = 1; o.b1 = 0.f; o.b2 = 0.99f; o.eps = 0.01f; o.bc1 = o.bc2 = 1.f;
+    }
+    {
+        ProfScope ps(c, c->cfg.algo == CB_ALGO_PPO ? "clip_adam" : "clip_rmsprop", 0,
+                     (double)c->nparam * (c->cfg.algo == CB_ALGO_PPO ? 28 : 20), st);
+        if (launch_optimizer(o, st)) return -1;
+    }
+    return refresh_weights(c, st);
+}
+
+long long cb_launch_count(void) { return g_launches.load(); }
+
+int cb_profile(cb_ctx* c, int enable) {
+    CB_CHECK(c, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    for (auto& r : c->prof_recs) { c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b); }
+    c->prof_recs.clear();
+    c->prof_on = enable != 0;
+    return 0;
+}
+
+int cb_profile_report(cb_ctx* c, char* buf, int cap) {
+    CB_CHECK(c && buf && cap > 2, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    CB_CUDA(cudaDeviceSynchronize());
+    std::map<std::string, ProfAgg> agg;
+    for (auto& r : c->prof_recs) {
+        float ms = 0.f;
+        CB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ProfAgg& a = agg[r.name];
+        a.launches += r.launches; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    }
+    std::string out = "[";
+    bool first = true;
+    for (auto& kv : agg) {
+        char line[384];
+        snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"calls\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                 first ? "" : ", ", kv.first.c_str(), kv.second.launches, kv.second.ms, kv.second.flops, kv.second.bytes);
+        out += line;
+        first = false;
+    }
+    out += "]";
+    CB_CHECK((int)out.size() + 1 <= cap, "profile report needs %d bytes", (int)out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+long long cb_debug_tensor(cb_ctx* c, const char* name, float* host_out, long long cap) {
+    CB_CHECK(c && name && host_out, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    CB_CUDA(cudaDeviceSynchronize());
+    const int n = c->last_n;
+    if (!strcmp(name, "hidden") || !strcmp(name, "dpre")) {
+        const float* src = !strcmp(name, "hidden") ? c->hidden : c->dpre;
+        CB_CHECK(src, "tensor %s not allocated", name);
+        long long cnt = (long long)n * HIDDEN;
+        CB_CHECK(cnt <= cap, "buffer too small");
+        CB_CUDA(cudaMemcpy(host_out, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+        return cnt;
+    }
+    CB_CHECK(strlen(name) >= 4 && (name[0] == 's' || name[0] == 'g') && name[2] == '.', "bad tensor name %s", name);
+    int s = name[1] - '0';
+    CB_CHECK(s >= 0 && s < 3, "bad stage in %s", name);
+    Stage& S = c->st[s];
+    const char* f = name + 3;
+    const Act* a = nullptr;
+    bool want_stream = false;
+    if (name[0] == 's') {
+        if (!strcmp(f, "x")) a = &S.x;
+        else if (!strcmp(f, "y")) { a = &S.y; want_stream = true; }
+        else if (!strcmp(f, "p")) { a = &S.p; want_stream = true; }
+        else if (!strcmp(f, "pr")) a = &S.p;
+        else if (!strcmp(f, "a0")) a = &S.a0;
+        else if (!strcmp(f, "b0")) { a = &S.b0; want_stream = true; }
+        else if (!strcmp(f, "b0r")) a = &S.b0;
+        else if (!strcmp(f, "a1")) a = &S.a1;
+        else if (!strcmp(f, "out")) a = &S.out;
+    } else {
+        if (!strcmp(f, "A")) a = &S.gA;
+        else if (!strcmp(f, "As")) { a = &S.gA; want_stream = true; }
+        else if (!strcmp(f, "B")) a = &S.gB;
+        else if (!strcmp(f, "C")) a = &S.gC;
+        else if (!strcmp(f, "Bin")) a = &S.gBin;
+    }
+    CB_CHECK(a && (want_stream ? a->s != nullptr : a->pl.hi != nullptr), "tensor %s not available", name);
+    const int H = a->H, C = a->C, Hp = H + 2, P = Hp * Hp, chunks = (C + 7) / 8;
+    const long long NP = (long long)n * P;
+    const long long cnt = (long long)n * H * H * C;
+    CB_CHECK(cnt <= cap, "buffer too small (%lld > %lld)", cnt, cap);
+    std::vector<float> tmp((size_t)chunks * NP * 8);
+    if (want_stream) {
+        CB_CUDA(cudaMemcpy(tmp.data(), a->s, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<uint16_t> h((size_t)NP * 8), l((size_t)NP * 8);
+        for (int j = 0; j < chunks; ++j) {
+            CB_CUDA(cudaMemcpy(h.data(), a->pl.hi + (long long)j * a->pl.plane_px * 8, h.size() * 2, cudaMemcpyDeviceToHost));
+            if (a->pl.lo) CB_CUDA(cudaMemcpy(l.data(), a->pl.lo + (long long)j * a->pl.plane_px * 8, l.size() * 2, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < h.size(); ++i) {
+                uint32_t uh = (uint32_t)h[i] << 16, ul = a->pl.lo ? (uint32_t)l[i] << 16 : 0u;
+                float fh, fl;
+                memcpy(&fh, &uh, 4); memcpy(&fl, &ul, 4);
+                tmp[(size_t)j * NP * 8 + i] = fh + fl;
+            }
+        }
+    }
+    for (int b = 0; b < n; ++b)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < H; ++x)
+                for (int ch = 0; ch < C; ++ch) {
+                    long long q = (long long)b * P + (long long)(y + 1) * Hp + (x + 1);
+                    host_out[(((long long)b * H + y) * H + x) * C + ch] = tmp[((size_t)(ch / 8) * NP + q) * 8 + ch % 8];
+                }
+    return cnt;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

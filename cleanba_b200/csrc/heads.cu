@@ -1,0 +1,365 @@
+// Actor / critic heads, threefry Gumbel-max sampling and the fused loss heads (forward + backward).
+//   actor   : get_action_and_value  cleanba/cleanba_ppo.py:245-261, get_action cleanba/cleanba_impala.py:287-301
+//   PPO     : get_logprob_entropy_value + ppo_loss + its gradient  cleanba/cleanba_ppo.py:516-530,562-577,590
+//   IMPALA  : impala_loss (V-trace, rlax 0.1.5 semantics) + its gradient  cleanba/cleanba_impala.py:557-597
+#include "common.cuh"
+#include "kernels.h"
+#include "prng.cuh"
+
+namespace cb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Shared-memory copy of the two head matrices: [256][A] actor kernel, [256] critic kernel, biases.
+struct HeadSmem {
+    float* wa;   // [256 * A]
+    float* wc;   // [256]
+    float* ba;   // [A]
+    float bc;
+};
+
+__device__ __forceinline__ HeadSmem load_head_smem(float* sm, const float* wa, const float* ba, const float* wc,
+                                                   const float* bc, int A) {
+    HeadSmem h;
+    h.wa = sm; h.wc = sm + HIDDEN * A; h.ba = h.wc + HIDDEN;
+    for (int t = threadIdx.x; t < HIDDEN * A; t += blockDim.x) h.wa[t] = wa[t];
+    for (int t = threadIdx.x; t < HIDDEN; t += blockDim.x) h.wc[t] = wc[t];
+    for (int t = threadIdx.x; t < A; t += blockDim.x) h.ba[t] = ba[t];
+    h.bc = bc[0];
+    __syncthreads();
+    return h;
+}
+static inline size_t head_smem_bytes(int A) { return (size_t)(HIDDEN * A + HIDDEN + A) * sizeof(float); }
+
+// One warp computes the A logits and the value of one sample.  Lane a (< A) returns logit a; every lane returns value.
+// The summation order is fixed, so the actor and the learner see bit-identical logits for identical hidden rows.
+__device__ __forceinline__ void head_forward(const HeadSmem& h, const float* hid /*[256]*/, int A, int lane,
+                                             float hreg[8], float& mylogit, float& value) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hreg[i] = hid[lane + 32 * i];
+    mylogit = -INFINITY;
+    for (int a = 0; a < A; ++a) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(hreg[i], h.wa[(lane + 32 * i) * A + a], s);
+        s = warp_sum(s);
+        if (lane == a) mylogit = s + h.ba[a];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(hreg[i], h.wc[lane + 32 * i], s);
+    value = warp_sum(s) + h.bc;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_split_key(uint32_t* key, uint32_t* subkey) {
+    if (threadIdx.x == 0) {
+        uint32_t k0 = key[0], k1 = key[1], nk0, nk1, sk0, sk1;
+        jax_split2(k0, k1, nk0, nk1, sk0, sk1);
+        key[0] = nk0; key[1] = nk1; subkey[0] = sk0; subkey[1] = sk1;
+    }
+}
+int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st) {
+    k_split_key<<<1, 32, 0, st>>>(key_inout, subkey_out);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Sampling head: u = uniform(subkey, (n, A)); action = argmax(logits - log(-log u)) (first index on ties);
+// logprob = log_softmax(logits)[action]; value.  One warp per sample.
+__global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hidden, int n, int A, const float* wa,
+                                                    const float* ba, const float* wc, const float* bc,
+                                                    const uint32_t* __restrict__ subkey, float* logits_out,
+                                                    float* value_out, int* action_out, float* logprob_out) {
+    extern __shared__ float sm[];
+    HeadSmem h = load_head_smem(sm, wa, ba, wc, bc, A);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const uint32_t k0 = subkey[0], k1 = subkey[1];
+    const uint32_t total = (uint32_t)n * (uint32_t)A;
+    for (int b = blockIdx.x * nwarp + warp; b < n; b += gridDim.x * nwarp) {
+        float hreg[8], logit, value;
+        head_forward(h, hidden + (long long)b * HIDDEN, A, lane, hreg, logit, value);
+        float pert = -INFINITY;
+        if (lane < A) {
+            uint32_t bits = jax_random_bits_elem(k0, k1, (uint32_t)b * A + lane, total);
+            float u = jax_bits_to_uniform(bits);
+            pert = logit - logf(-logf(u));
+        }
+        // argmax with first-index tie break (a NaN-free input is assumed, as in the reference)
+        float best = pert;
+        int besti = lane < A ? lane : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        float m = warp_max(lane < A ? logit : -INFINITY);
+        float se = warp_sum(lane < A ? expf(logit - m) : 0.f);
+        float logp = logit - m - logf(se);
+        float lp_a = __shfl_sync(0xffffffffu, logp, besti);
+        if (logits_out && lane < A) logits_out[(long long)b * A + lane] = logit;
+        if (lane == 0) {
+            action_out[b] = besti;
+            if (logprob_out) logprob_out[b] = lp_a;
+            if (value_out) value_out[b] = value;
+        }
+    }
+}
+
+int launch_actor_head(const float* hidden, int n, int A, const float* wa, const float* ba, const float* wc,
+                      const float* bc, const uint32_t* subkey, float* logits_out, float* value_out, int* action_out,
+                      float* logprob_out, cudaStream_t st) {
+    int blocks = (n + 7) / 8;
+    if (blocks > 296) blocks = 296;
+    k_actor_head<<<blocks, 256, head_smem_bytes(A), st>>>(hidden, n, A, wa, ba, wc, bc, subkey, logits_out, value_out,
+                                                         action_out, logprob_out);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dpre[k] = (sum_a dl[a] Wa[k][a] + dv Wc[k]) * (hidden[k] > 0)   for the 8 k's of this lane
+__device__ __forceinline__ void head_backward_hidden(const HeadSmem& h, int A, int lane, const float hreg[8], float dl,
+                                                     float dv, float* dpre_row) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = dv * h.wc[lane + 32 * i];
+    for (int a = 0; a < A; ++a) {
+        float d = __shfl_sync(0xffffffffu, dl, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(d, h.wa[(lane + 32 * i) * A + a], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dpre_row[lane + 32 * i] = hreg[i] > 0.f ? acc[i] : 0.f;
+}
+
+// PPO loss head, forward + backward, one warp per minibatch sample.
+__global__ void __launch_bounds__(256) k_ppo_head(PpoHeadArgs a) {
+    extern __shared__ float sm[];
+    const int A = a.num_actions;
+    HeadSmem h = load_head_smem(sm, a.wa, a.ba, a.wc, a.bc, A);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float inv_n = 1.f / (float)a.n;
+    for (int b = blockIdx.x * nwarp + warp; b < a.n; b += gridDim.x * nwarp) {
+        float hreg[8], logit, value;
+        head_forward(h, a.hidden + (long long)b * HIDDEN, A, lane, hreg, logit, value);
+        const int src = a.idx ? a.idx[b] : b;
+        const int act = a.actions[src];
+        const float oldlp = a.old_logprobs[src], adv = a.advantages[src], ret = a.returns[src];
+        float m = warp_max(lane < A ? logit : -INFINITY);
+        float ex = lane < A ? expf(logit - m) : 0.f;
+        float se = warp_sum(ex);
+        float logp = lane < A ? (logit - m - logf(se)) : 0.f;
+        float p = ex / se;
+        float ent = -warp_sum(lane < A ? p * logp : 0.f);
+        float newlp = __shfl_sync(0xffffffffu, logp, act);
+        float logratio = newlp - oldlp;
+        float ratio = expf(logratio);
+        float lo = 1.f - a.clip_coef, hi = 1.f + a.clip_coef;
+        float clipped = fminf(fmaxf(ratio, lo), hi);
+        float pg1 = -adv * ratio, pg2 = -adv * clipped;
+        float pg = fmaxf(pg1, pg2);
+        // d pg / d newlogprob  (jnp.maximum / jnp.clip sub-gradients; ties inside the clip range sum to -adv*ratio)
+        float dpg;
+        if (ratio >= lo && ratio <= hi) dpg = -adv * ratio;
+        else dpg = (pg1 > pg2) ? -adv * ratio : 0.f;
+        float verr = value - ret;
+        float c_lp = dpg * inv_n;
+        float dl = 0.f;
+        if (lane < A) dl = c_lp * ((lane == act ? 1.f : 0.f) - p) + a.ent_coef * inv_n * p * (logp + ent);
+        float dv = a.vf_coef * verr * inv_n;
+        head_backward_hidden(h, A, lane, hreg, dl, dv, a.dpre + (long long)b * HIDDEN);
+        if (lane < A) a.dlogits[(long long)b * (A + 1) + lane] = dl;
+        if (lane == 0) {
+            a.dlogits[(long long)b * (A + 1) + A] = dv;
+            float* t = a.terms + (long long)b * 5;
+            t[0] = pg; t[1] = 0.5f * verr * verr; t[2] = ent; t[3] = (ratio - 1.f) - logratio; t[4] = 0.f;
+        }
+    }
+}
+
+// stats = mean over samples of the per-sample terms (fixed summation order)
+__global__ void __launch_bounds__(256) k_ppo_stats(const float* __restrict__ terms, int n, float ent_coef, float vf_coef,
+                                                   float* __restrict__ stats) {
+    __shared__ float red[4][256];
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int b = threadIdx.x; b < n; b += 256)
+        for (int j = 0; j < 4; ++j) s[j] += terms[(long long)b * 5 + j];
+    for (int j = 0; j < 4; ++j) red[j][threadIdx.x] = s[j];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int j = 0; j < 4; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float inv = 1.f / (float)n;
+        float pg = red[0][0] * inv, vl = red[1][0] * inv, en = red[2][0] * inv, kl = red[3][0] * inv;
+        stats[0] = pg - ent_coef * en + vl * vf_coef;
+        stats[1] = pg; stats[2] = vl; stats[3] = en; stats[4] = kl;
+    }
+}
+
+// Head weight gradients: dWa[k][a] = sum_b hidden[b][k] dl[b][a]; column A of dl is dvalue (critic); k == 256 is the bias.
+__global__ void __launch_bounds__(128) k_head_wgrad(const float* __restrict__ hidden, const float* __restrict__ dl, int n,
+                                                    int A, float* dwa, float* dba, float* dwc, float* dbc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int K1 = HIDDEN + 1;
+    if (t >= K1 * (A + 1)) return;
+    int a = t / K1, k = t % K1;
+    float s = 0.f;
+    if (k < HIDDEN) {
+        for (int b = 0; b < n; ++b) s = fmaf(hidden[(long long)b * HIDDEN + k], dl[(long long)b * (A + 1) + a], s);
+        if (a < A) dwa[k * A + a] = s; else dwc[k] = s;
+    } else {
+        for (int b = 0; b < n; ++b) s += dl[(long long)b * (A + 1) + a];
+        if (a < A) dba[a] = s; else dbc[0] = s;
+    }
+}
+
+int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
+    int blocks = (a.n + 7) / 8;
+    if (blocks > 592) blocks = 592;
+    k_ppo_head<<<blocks, 256, head_smem_bytes(a.num_actions), st>>>(a);
+    CB_LAUNCH_CHECK();
+    k_ppo_stats<<<1, 256, 0, st>>>(a.terms, a.n, a.ent_coef, a.vf_coef, a.stats);
+    CB_LAUNCH_CHECK();
+    int total = (HIDDEN + 1) * (a.num_actions + 1);
+    k_head_wgrad<<<(total + 127) / 128, 128, 0, st>>>(a.hidden, a.dlogits, a.n, a.num_actions, a.dwa, a.dba, a.dwc, a.dbc);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IMPALA / V-trace loss head (one block; a minibatch is [T1 = T+1, B] frames ordered f = t*B + b).
+__global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a) {
+    extern __shared__ float sm[];
+    const int A = a.num_actions, T1 = a.T1, B = a.B, T = T1 - 1;
+    HeadSmem h = load_head_smem(sm, a.wa, a.ba, a.wc, a.bc, A);
+    float* red = h.ba + A + 1;   // [3][1024]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int nf = T1 * B, nc = T * B;
+    // phase 0: logits + value of every frame
+    for (int f = warp; f < nf; f += nwarp) {
+        float hreg[8], logit, value;
+        head_forward(h, a.hidden + (long long)f * HIDDEN, A, lane, hreg, logit, value);
+        if (lane < A) a.logits_scratch[(long long)f * (A + 1) + lane] = logit;
+        if (lane == 0) a.logits_scratch[(long long)f * (A + 1) + A] = value;
+    }
+    __syncthreads();
+    // phase 1: per cell log pi(a), rho, entropy
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        const int src = a.idx ? a.idx[c] : c;
+        const int act = a.actions[src];
+        const float* z = a.logits_scratch + (long long)c * (A + 1);
+        const float* mu = a.behaviour_logits + (long long)src * A;
+        float m = -INFINITY, mm = -INFINITY;
+        for (int j = 0; j < A; ++j) { m = fmaxf(m, z[j]); mm = fmaxf(mm, mu[j]); }
+        float se = 0.f, sm_ = 0.f;
+        for (int j = 0; j < A; ++j) { se += expf(z[j] - m); sm_ += expf(mu[j] - mm); }
+        float lse = m + logf(se), lsm = mm + logf(sm_);
+        float ent = 0.f;
+        for (int j = 0; j < A; ++j) {
+            float lp = z[j] - lse, p = expf(z[j] - m) / se;
+            if (p > 0.f) ent -= p * lp;
+        }
+        float lpa = z[act] - lse, lma = mu[act] - lsm;
+        float* cs = a.cell_scratch + (long long)c * 8;
+        cs[0] = lpa; cs[1] = expf(lpa - lma); cs[2] = ent; cs[3] = lse;
+    }
+    __syncthreads();
+    // phase 2: V-trace backward scan per column (rlax.vtrace + vtrace_td_error_and_advantage, lambda = 1, clips = 1)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float err = 0.f;
+        float target_next = 0.f;
+        for (int t = T - 1; t >= 0; --t) {
+            int c = t * B + b;
+            const int src = a.idx ? a.idx[c] : c;
+            float r = a.rewards[src];
+            float disc = (1.f - (float)a.dones[src]) * a.gamma;
+            float v_tm1 = a.logits_scratch[(long long)c * (A + 1) + A];
+            float v_t = a.logits_scratch[(long long)(c + B) * (A + 1) + A];
+            float* cs = a.cell_scratch + (long long)c * 8;
+            float cr = fminf(1.f, cs[1]);
+            float td = cr * (r + disc * v_t - v_tm1);
+            err = td + disc * cr * err;
+            float q_boot = (t == T - 1) ? v_t : target_next;
+            float q = r + disc * q_boot;
+            cs[4] = err;                   // errors (value gradient flows through -v_tm1 only)
+            cs[5] = cr * (q - v_tm1);      // pg_advantage
+            target_next = err + v_tm1;
+        }
+    }
+    __syncthreads();
+    // phase 3: per cell loss terms and d/dlogits, d/dvalue
+    float s_pg = 0.f, s_bl = 0.f, s_en = 0.f;
+    for (int c = threadIdx.x; c < nf; c += blockDim.x) {
+        float* dl = a.dlogits + (long long)c * (A + 1);
+        if (c >= nc) {
+            for (int j = 0; j <= A; ++j) dl[j] = 0.f;
+            continue;
+        }
+        const int src = a.idx ? a.idx[c] : c;
+        const int act = a.actions[src];
+        const float mask = 1.f - (float)a.firststeps[src];
+        const float* z = a.logits_scratch + (long long)c * (A + 1);
+        const float* cs = a.cell_scratch + (long long)c * 8;
+        float lpa = cs[0], ent = cs[2], lse = cs[3], err = cs[4], adv = cs[5];
+        s_pg += -lpa * adv * mask;
+        s_bl += 0.5f * err * err * mask;
+        s_en += -ent * mask;
+        for (int j = 0; j < A; ++j) {
+            float lp = z[j] - lse, p = expf(lp);
+            float g = -adv * ((j == act ? 1.f : 0.f) - p) + a.ent_coef * p * (lp + ent);
+            dl[j] = mask * g;
+        }
+        dl[A] = -a.vf_coef * err * mask;
+    }
+    red[threadIdx.x] = s_pg; red[1024 + threadIdx.x] = s_bl; red[2048 + threadIdx.x] = s_en;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            red[threadIdx.x] += red[threadIdx.x + o];
+            red[1024 + threadIdx.x] += red[1024 + threadIdx.x + o];
+            red[2048 + threadIdx.x] += red[2048 + threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float pg = red[0], bl = red[1024], en = red[2048];
+        a.stats[0] = pg + a.vf_coef * bl + a.ent_coef * en;
+        a.stats[1] = pg; a.stats[2] = bl; a.stats[3] = en;
+    }
+    // phase 4: gradient w.r.t. the pre-relu dense output
+    for (int f = warp; f < nf; f += nwarp) {
+        float hreg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hreg[i] = a.hidden[(long long)f * HIDDEN + lane + 32 * i];
+        float dl = lane < A ? a.dlogits[(long long)f * (A + 1) + lane] : 0.f;
+        float dv = a.dlogits[(long long)f * (A + 1) + A];
+        head_backward_hidden(h, A, lane, hreg, dl, dv, a.dpre + (long long)f * HIDDEN);
+    }
+}
+
+int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st) {
+    size_t smem = head_smem_bytes(a.num_actions) + (1 + 3 * 1024) * sizeof(float);
+    k_impala_head<<<1, 1024, smem, st>>>(a);
+    CB_LAUNCH_CHECK();
+    int total = (HIDDEN + 1) * (a.num_actions + 1);
+    k_head_wgrad<<<(total + 127) / 128, 128, 0, st>>>(a.hidden, a.dlogits, a.T1 * a.B, a.num_actions, a.dwa, a.dba,
+                                                       a.dwc, a.dbc);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace cb

@@ -1,0 +1,120 @@
+// Internal launcher declarations (host side) for libcleanba_b200.
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+struct WgradArgs {
+    ConvGeom g;
+    Planes x;            // forward input planes of the conv
+    int cin_chunks, cin_real;
+    Planes gy;           // gradient planes w.r.t. the conv output
+    int cout;
+    float* dw;           // [3][3][cin_real][cout] fp32 (HWIO, flax order)
+    float* db;           // [cout]
+    float scale;         // applied to dW only (1/255 for the first conv, whose forward folds x/255 into the epilogue)
+};
+
+// trunk_simt.cu
+int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st);
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
+                    cudaStream_t st);
+int launch_pool_bwd(const float* y, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
+                    cudaStream_t st);
+int launch_wgrad_simt(const WgradArgs& a, float* partial, int max_blocks, cudaStream_t st);
+
+// conv_umma.cu (tcgen05 + TMA bulk copies)
+int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st);
+int launch_wgrad_umma(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st);
+int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp);
+
+// dense.cu
+struct DenseArgs {
+    int n;                       // samples
+    Planes x;                    // final feature planes (relu'd), 4 chunks on the 13x13 padded grid
+    const float* w;              // [3872][256] fp32 master (k = (h*11+w)*32 + c)
+    const float* b;              // [256]
+    float* hidden;               // [n][256]  relu(x W + b)
+};
+int dense_fwd_splits(int n);
+int launch_dense_fwd(const DenseArgs& a, float* part, cudaStream_t st);
+// dpre: [n][256] gradient w.r.t. the pre-relu dense output.
+int launch_dense_bwd_w(const DenseArgs& a, const float* dpre, float* dw, float* db, cudaStream_t st);
+// dX -> gradient w.r.t. the (pre-relu) trunk output, masked by the forward relu, as fp32 stream + planes
+int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, float* out_s, Planes out, cudaStream_t st);
+
+// heads.cu
+int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st);
+int launch_actor_head(const float* hidden, int n, int num_actions, const float* wa, const float* ba, const float* wc,
+                      const float* bc, const uint32_t* subkey, float* logits_out, float* value_out, int* action_out,
+                      float* logprob_out, cudaStream_t st);
+struct PpoHeadArgs {
+    int n, num_actions;
+    const float* hidden;         // [n][256]
+    const float *wa, *ba, *wc, *bc;
+    const int* idx;              // minibatch sample indices into the flat [T*B] fields (null = identity)
+    const int* actions;          // flat fields of the whole update
+    const float* old_logprobs;
+    const float* advantages;
+    const float* returns;
+    float clip_coef, ent_coef, vf_coef;
+    float* dpre;                 // [n][256] gradient w.r.t. pre-relu dense output
+    float* dlogits;              // [n][num_actions + 1] (last column = dvalue) scratch for the head weight grads
+    float* terms;                // [n][5] per-sample loss terms scratch
+    float* stats;                // [5] loss, pg_loss, v_loss, entropy, approx_kl
+    float *dwa, *dba, *dwc, *dbc;
+};
+int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st);
+struct ImpalaHeadArgs {
+    int T1, B, num_actions;      // T1 = T + 1 rows; frames are ordered f = t * B + b
+    const float* hidden;
+    const float *wa, *ba, *wc, *bc;
+    const int* idx;              // [T1*B] indices into the flat [T1*Bl] fields (null = identity)
+    const int* actions;
+    const float* behaviour_logits;   // flat [T1*Bl][A]
+    const float* rewards;
+    const uint8_t* dones;
+    const uint8_t* firststeps;
+    float gamma, vf_coef, ent_coef;
+    float* logits_scratch;       // [T1*B][A + 1] logits and value
+    float* cell_scratch;         // [T1*B][8]
+    float* dpre;
+    float* dlogits;
+    float* stats;                // [4] total, pg, baseline, entropy
+    float *dwa, *dba, *dwc, *dbc;
+};
+int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st);
+
+// learner_misc.cu
+int launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* next_value,
+               const uint8_t* next_done, int T, int B, float gamma, float lambda, int num_groups, float* adv, float* ret,
+               cudaStream_t st);
+int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tmp, uint32_t* sort_keys,
+                       uint32_t* subkey, cudaStream_t st);
+struct OptArgs {
+    int kind;                    // 0 = Adam, 1 = RMSProp (PyTorch style)
+    long long n;
+    float* p;
+    const float* g;
+    float* m;                    // Adam first moment (unused for RMSProp)
+    float* v;                    // Adam second moment / RMSProp nu
+    float grad_scale;            // 1 / L for the pmean over learner devices
+    float max_norm, lr, b1, b2, eps, bc1, bc2;
+    float* partials;             // [OPT_BLOCKS]
+    float* norm_out;             // [1] global norm (after grad_scale), optional
+};
+constexpr int OPT_BLOCKS = 296;
+int launch_optimizer(const OptArgs& a, cudaStream_t st);
+
+// pack.cu
+struct PackLayer {
+    const float* w;              // HWIO master
+    int cin, cout;               // real channel counts
+    bf16 *fwd_hi, *fwd_lo;       // packed forward image
+    bf16 *dg_hi, *dg_lo;         // packed dgrad image (null for the first conv)
+};
+int launch_pack_conv(const PackLayer* layers_dev, int nlayers, cudaStream_t st);
+long long packed_conv_elems(int cin_chunks, int cout);
+
+}  // namespace cb

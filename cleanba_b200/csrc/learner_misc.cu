@@ -1,0 +1,239 @@
+// Learner-side scalar kernels: GAE scan + advantage normalisation, the minibatch permutation and the fused
+// global-norm-clip + Adam / RMSProp step.
+//   GAE        : compute_gae / compute_gae_once   cleanba/cleanba_ppo.py:532-560
+//   adv norm   : cleanba/cleanba_ppo.py:592-595
+//   shuffle    : jax.random.permutation in update_epoch  cleanba/cleanba_ppo.py:599-615
+//   optimizers : optax chain cleanba/cleanba_ppo.py:492-500, rmsprop_pytorch_style cleanba/cleanba_impala.py:152-188
+#include "common.cuh"
+#include "kernels.h"
+#include "prng.cuh"
+
+namespace cb {
+
+// ------------------------------------------------------------------------------------------------
+// GAE: one warp per env column.  The 32 lanes load 4 consecutive time steps each (all loads in flight at once),
+// then the recurrence  A[t] = delta[t] + (gamma*lambda*nonterminal[t+1]) * A[t+1]  is carried lane to lane with warp
+// shuffles, in exactly the sequential order (and with the un-fused fp32 mul/add) of the reference scan, so the
+// raw advantages are bit-identical to the CPU restatement.  One block per advantage-normalisation column group.
+__global__ void __launch_bounds__(1024) k_gae(const float* __restrict__ rewards, const float* __restrict__ values,
+                                              const uint8_t* __restrict__ dones, const float* __restrict__ next_value,
+                                              const uint8_t* __restrict__ next_done, int T, int B, float gamma,
+                                              float gamma_lambda, int num_groups, int normalize, float* __restrict__ adv,
+                                              float* __restrict__ ret) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int Bg = B / num_groups;
+    const int col0 = blockIdx.x * Bg;
+    for (int cb_ = warp; cb_ < Bg; cb_ += nwarp) {
+        const int b = col0 + cb_;
+        float carry = 0.f;  // A[T] = 0
+        for (int end = T; end > 0; end -= 128) {
+            const int base = end - 128;  // may be negative: those slots are invalid
+            float delta[4], coef[4], val[4];
+            bool ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int t = base + lane * 4 + i;
+                ok[i] = (t >= 0);
+                delta[i] = 0.f; coef[i] = 0.f; val[i] = 0.f;
+                if (ok[i]) {
+                    float r = rewards[(long long)t * B + b];
+                    float v = values[(long long)t * B + b];
+                    float vn = (t + 1 < T) ? values[(long long)(t + 1) * B + b] : next_value[b];
+                    float dn = (t + 1 < T) ? (float)dones[(long long)(t + 1) * B + b] : (float)next_done[b];
+                    float nn = __fsub_rn(1.0f, dn);
+                    // delta = reward + gamma * nextvalues * nextnonterminal - curvalues
+                    delta[i] = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, vn), nn)), v);
+                    coef[i] = __fmul_rn(gamma_lambda, nn);
+                    val[i] = v;
+                }
+            }
+            float a_out[4] = {0.f, 0.f, 0.f, 0.f};
+            float a_next = carry;
+            for (int L = 31; L >= 0; --L) {
+                float a_run = a_next;
+                if (lane == L) {
+#pragma unroll
+                    for (int i = 3; i >= 0; --i)
+                        if (ok[i]) {
+                            a_run = __fadd_rn(delta[i], __fmul_rn(coef[i], a_run));
+                            a_out[i] = a_run;
+                        }
+                }
+                a_next = __shfl_sync(0xffffffffu, a_run, L);
+            }
+            carry = a_next;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int t = base + lane * 4 + i;
+                if (ok[i]) {
+                    adv[(long long)t * B + b] = a_out[i];
+                    ret[(long long)t * B + b] = __fadd_rn(a_out[i], val[i]);
+                }
+            }
+        }
+    }
+    if (!normalize) return;
+    // per-group mean / population std over (T x Bg) elements, fixed summation order
+    __shared__ float red[1024];
+    __shared__ float s_mean, s_std;
+    __syncthreads();
+    const int cnt = T * Bg;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) s += adv[(long long)(i / Bg) * B + col0 + (i % Bg)];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_mean = red[0] / (float)cnt;
+    __syncthreads();
+    const float mean = s_mean;
+    s = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        float d = adv[(long long)(i / Bg) * B + col0 + (i % Bg)] - mean;
+        s += d * d;
+    }
+    __syncthreads();
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_std = sqrtf(red[0] / (float)cnt);
+    __syncthreads();
+    const float denom = s_std + 1e-8f;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        long long o = (long long)(i / Bg) * B + col0 + (i % Bg);
+        adv[o] = (adv[o] - mean) / denom;
+    }
+}
+
+int launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* next_value,
+               const uint8_t* next_done, int T, int B, float gamma, float lambda, int num_groups, float* adv, float* ret,
+               cudaStream_t st) {
+    int normalize = num_groups > 0;
+    int groups = normalize ? num_groups : 1;
+    CB_CHECK(B % groups == 0, "gae: B=%d not divisible by num_groups=%d", B, groups);
+    float gl = (float)((double)gamma * (double)lambda);  // python-float product, then cast (cleanba_ppo.py:538)
+    k_gae<<<groups, 1024, 0, st>>>(rewards, values, dones, next_value, next_done, T, B, gamma, gl, groups, normalize, adv, ret);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// jax.random.permutation(key, n): `rounds` rounds of { key, sub = split(key); keys = random_bits(sub, n);
+// x = stable_sort_by_key(keys, x) }.  The stable sort is a rank-by-counting pass (n <= 65536 here, n^2 compares are
+// microseconds on 148 SMs) which is deterministic and needs no scratch beyond the key array.
+__global__ void k_iota(int* x, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = i;
+}
+__global__ void k_random_bits(const uint32_t* __restrict__ subkey, int n, uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = jax_random_bits_elem(subkey[0], subkey[1], (uint32_t)i, (uint32_t)n);
+}
+__global__ void __launch_bounds__(256) k_rank_scatter(const uint32_t* __restrict__ keys, const int* __restrict__ xin,
+                                                      int* __restrict__ xout, int n) {
+    __shared__ uint32_t tile[2048];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ki = i < n ? keys[i] : 0u;
+    int rank = 0;
+    for (int j0 = 0; j0 < n; j0 += 2048) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 2048; t += 256) tile[t] = (j0 + t < n) ? keys[j0 + t] : 0xffffffffu;
+        __syncthreads();
+        int lim = min(2048, n - j0);
+        for (int t = 0; t < lim; ++t) {
+            uint32_t kj = tile[t];
+            rank += (kj < ki) || (kj == ki && (j0 + t) < i);
+        }
+    }
+    if (i < n) xout[rank] = xin[i];
+}
+
+int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tmp, uint32_t* sort_keys, uint32_t* subkey,
+                       cudaStream_t st) {
+    int blocks = (n + 255) / 256;
+    int* cur = (rounds % 2 == 0) ? out : tmp;   // after `rounds` swaps the result lands in `out`
+    int* nxt = (rounds % 2 == 0) ? tmp : out;
+    k_iota<<<blocks, 256, 0, st>>>(cur, n);
+    CB_LAUNCH_CHECK();
+    for (int r = 0; r < rounds; ++r) {
+        if (launch_split_key(key_inout, subkey, st)) return -1;
+        k_random_bits<<<blocks, 256, 0, st>>>(subkey, n, sort_keys);
+        CB_LAUNCH_CHECK();
+        k_rank_scatter<<<blocks, 256, 0, st>>>(sort_keys, cur, nxt, n);
+        CB_LAUNCH_CHECK();
+        int* t = cur; cur = nxt; nxt = t;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer: pass 1 writes OPT_BLOCKS partial sums of (g * grad_scale)^2; pass 2 re-reduces them in a fixed order,
+// applies clip_by_global_norm and the Adam / RMSProp update on the flat parameter vector.
+__global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, long long n, float scale, float* __restrict__ partials) {
+    __shared__ float red[256];
+    long long per = (n + gridDim.x - 1) / gridDim.x;
+    long long lo = (long long)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+    float s = 0.f;
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+        float x = g[i] * scale;
+        s = fmaf(x, x, s);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) k_opt_apply(OptArgs a) {
+    __shared__ float red[512];
+    __shared__ float s_norm;
+    for (int t = threadIdx.x; t < 512; t += 256) red[t] = t < OPT_BLOCKS ? a.partials[t] : 0.f;
+    __syncthreads();
+    for (int o = 256; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        s_norm = sqrtf(red[0]);
+        if (blockIdx.x == 0 && a.norm_out) a.norm_out[0] = s_norm;
+    }
+    __syncthreads();
+    const float norm = s_norm;
+    const bool clip = !(norm < a.max_norm);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (long long)gridDim.x * 256) {
+        float g = a.g[i] * a.grad_scale;
+        if (clip) g = (g / norm) * a.max_norm;      // optax.clip_by_global_norm: (g / norm) * max_norm
+        float p = a.p[i];
+        if (a.kind == 0) {
+            float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
+            float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
+            a.m[i] = m; a.v[i] = v;
+            float mhat = m / a.bc1, vhat = v / a.bc2;
+            float u = mhat / (sqrtf(vhat) + a.eps);
+            a.p[i] = p - a.lr * u;
+        } else {
+            float nu = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
+            a.v[i] = nu;
+            float u = g / (sqrtf(nu) + a.eps);
+            a.p[i] = p - a.lr * u;
+        }
+    }
+}
+
+int launch_optimizer(const OptArgs& a, cudaStream_t st) {
+    k_sumsq<<<OPT_BLOCKS, 256, 0, st>>>(a.g, a.n, a.grad_scale, a.partials);
+    CB_LAUNCH_CHECK();
+    k_opt_apply<<<OPT_BLOCKS, 256, 0, st>>>(a);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace cb

@@ -1,0 +1,339 @@
+// CUDA-core (fp32 FFMA) kernels of the IMPALA-ResNet trunk: frame unpack, max-pool forward/backward and
+// the reference implementation of the 3x3 convolutions (forward, dgrad, wgrad).  The conv kernels here
+// are the in-library cross-check for the tcgen05 kernels (conv_umma.cu) and run on the same layouts.
+// Reference semantics: cleanba/cleanba_ppo.py:149-189 (Network / ConvSequence / ResidualBlock).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cb {
+
+// ------------------------------------------------------------------------------------------------
+// uint8 NCHW frame stack -> bf16 chunk plane (8 channels: 4 real + 4 zero), borders zero.
+// cleanba_ppo.py:180-181 (transpose + /255; the 1/255 is folded into the conv epilogue, 0..255 are exact in bf16).
+// One block per (image, padded row): the 4 channel rows are staged through shared memory with coalesced
+// 4-byte reads, then every thread emits one 16-byte pixel.
+__global__ void k_unpack_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, int n, bf16* __restrict__ out_hi) {
+    const int H = 84, W = 84, Wp = 86, Hp = 86;
+    int img = blockIdx.x / Hp;
+    int yp = blockIdx.x % Hp;
+    __shared__ uint32_t srow[4][W / 4];
+    bool row_in = (yp >= 1 && yp <= H);
+    if (row_in) {
+        long long src = idx ? (long long)idx[img] : (long long)img;
+        const uint8_t* base = obs + src * (4LL * H * W) + (long long)(yp - 1) * W;
+        for (int t = threadIdx.x; t < 4 * (W / 4); t += blockDim.x) {
+            int c = t / (W / 4), w4 = t % (W / 4);
+            srow[c][w4] = *reinterpret_cast<const uint32_t*>(base + (long long)c * H * W + w4 * 4);
+        }
+    }
+    __syncthreads();
+    for (int xp = threadIdx.x; xp < Wp; xp += blockDim.x) {
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (row_in && xp >= 1 && xp <= W) {
+            int x = xp - 1;
+            const uint8_t* s = reinterpret_cast<const uint8_t*>(&srow[0][0]);
+            float c0 = s[0 * W + x], c1 = s[1 * W + x], c2 = s[2 * W + x], c3 = s[3 * W + x];
+            o.x = pack_bf16x2(__float2bfloat16_rn(c0), __float2bfloat16_rn(c1));
+            o.y = pack_bf16x2(__float2bfloat16_rn(c2), __float2bfloat16_rn(c3));
+        }
+        long long q = (long long)img * (Hp * Wp) + (long long)yp * Wp + xp;
+        *reinterpret_cast<uint4*>(out_hi + q * 8) = o;
+    }
+}
+
+int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st) {
+    k_unpack_frames<<<n * 86, 96, 0, st>>>(obs, idx, n, out_hi);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference 3x3 conv (forward or dgrad): one thread per (flat pixel, output chunk of 8 channels).
+__global__ void __launch_bounds__(128) k_conv_simt(ConvArgs a) {
+    extern __shared__ float sw[];  // [9][cin_real][8] weights of this output chunk
+    const int oc = blockIdx.y;
+    const int cin = a.cin_real;
+    for (int t = threadIdx.x; t < 9 * cin * 8; t += blockDim.x) {
+        int e = t % 8, ci = (t / 8) % cin, tap = t / (8 * cin);
+        int co = oc * 8 + e;
+        float w;
+        if (!a.transpose) w = a.w[((long long)tap * a.w_cin + ci) * a.w_cout + co];
+        else w = a.w[((long long)(8 - tap) * a.w_cin + co) * a.w_cout + ci];  // dX[ci'] = sum G[co'] W[flip][ci'][co']
+        sw[t] = w;
+    }
+    __syncthreads();
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (q < a.g.NP && interior(a.g, q)) {
+        for (int tap = 0; tap < 9; ++tap) {
+            int d = (tap / 3 - 1) * a.g.Wp + (tap % 3 - 1);
+            for (int jc = 0; jc < a.cin_chunks; ++jc) {
+                long long off = ((long long)jc * a.in.plane_px + q + d) * 8;
+                float x[8], xl[8];
+                unpack8(*reinterpret_cast<const uint4*>(a.in.hi + off), x);
+                if (a.in.lo) {
+                    unpack8(*reinterpret_cast<const uint4*>(a.in.lo + off), xl);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] += xl[e];
+                }
+                int nci = min(8, cin - jc * 8);
+                for (int c = 0; c < nci; ++c) {
+                    const float* wr = sw + ((tap * cin) + jc * 8 + c) * 8;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(x[c], wr[e], acc[e]);
+                }
+            }
+        }
+    }
+    conv_epilogue_store(a.ep, a.g, q, oc, acc);
+}
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
+    dim3 grid((unsigned)((a.g.NP + 127) / 128), a.cout / 8);
+    size_t smem = (size_t)9 * a.cin_real * 8 * sizeof(float);
+    k_conv_simt<<<grid, 128, smem, st>>>(a);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// max_pool 3x3 stride 2 SAME, -inf padding, pad_lo = 0 (84->42, 42->21) or 1 (21->11)  (cleanba_ppo.py:168)
+// in : fp32 stream [C/8][n*Pin][8] (conv output)      out: fp32 stream + relu'd bf16 planes on the pooled grid
+__global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks,
+                           float* __restrict__ out_s, Planes out_relu) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= go.NP * chunks) return;
+    int jc = (int)(t / go.NP);
+    long long q = t % go.NP;
+    int img = (int)(q / go.P);
+    int r = (int)(q % go.P);
+    int yp = r / go.Wp, xp = r % go.Wp;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (yp >= 1 && yp <= go.H && xp >= 1 && xp <= go.W) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = -INFINITY;
+        int i = yp - 1, j = xp - 1;
+        for (int dy = 0; dy < 3; ++dy) {
+            int y = 2 * i - pad_lo + dy;
+            if (y < 0 || y >= gi.H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                int x = 2 * j - pad_lo + dx;
+                if (x < 0 || x >= gi.W) continue;
+                long long qi = (long long)img * gi.P + (long long)(y + 1) * gi.Wp + (x + 1);
+                const float4* p = reinterpret_cast<const float4*>(in + ((long long)jc * gi.NP + qi) * 8);
+                float4 a = p[0], b = p[1];
+                v[0] = fmaxf(v[0], a.x); v[1] = fmaxf(v[1], a.y); v[2] = fmaxf(v[2], a.z); v[3] = fmaxf(v[3], a.w);
+                v[4] = fmaxf(v[4], b.x); v[5] = fmaxf(v[5], b.y); v[6] = fmaxf(v[6], b.z); v[7] = fmaxf(v[7], b.w);
+            }
+        }
+    }
+    float4* o = reinterpret_cast<float4*>(out_s + ((long long)jc * go.NP + q) * 8);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    bf16 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(fmaxf(v[e], 0.f), h[e], l[e]);
+    long long off = ((long long)jc * out_relu.plane_px + q) * 8;
+    *reinterpret_cast<uint4*>(out_relu.hi + off) =
+        make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(out_relu.lo + off) =
+        make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+
+int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
+                    cudaStream_t st) {
+    long long total = go.NP * chunks;
+    k_pool_fwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, gi, go, pad_lo, chunks, out_s, out_relu);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Backward of the pool in gather form (deterministic): every input pixel sums the gradients of the (<= 4)
+// windows whose arg-max it is; ties go to the first element in row-major window order (XLA select_and_scatter
+// with a `ge` select).   y: forward conv output stream;  dpool: gradient stream on the pooled grid;
+// out: gradient planes (hi/lo) on the input grid.
+__global__ void k_pool_bwd(const float* __restrict__ y, const float* __restrict__ dpool, ConvGeom gi, ConvGeom go,
+                           int pad_lo, int chunks, Planes out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long NPr = (gi.NP + 127) / 128 * 128;   // planes are zero-filled up to the 128-pixel tile boundary
+    if (t >= NPr * chunks) return;
+    int jc = (int)(t / NPr);
+    long long q = t % NPr;
+    int img = (int)(q / gi.P);
+    int rr = (int)(q % gi.P);
+    int yp = rr / gi.Wp, xp = rr % gi.Wp;
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = 0.f;
+    if (q < gi.NP && yp >= 1 && yp <= gi.H && xp >= 1 && xp <= gi.W) {
+        int r = yp - 1, c = xp - 1;
+        const float* ybase = y + (long long)jc * gi.NP * 8;
+        float self[8];
+        {
+            const float4* p = reinterpret_cast<const float4*>(ybase + q * 8);
+            float4 a = p[0], b = p[1];
+            self[0] = a.x; self[1] = a.y; self[2] = a.z; self[3] = a.w; self[4] = b.x; self[5] = b.y; self[6] = b.z; self[7] = b.w;
+        }
+        int i_lo = max(0, (r + pad_lo - 1) / 2), i_hi = min(go.H - 1, (r + pad_lo) / 2);   // ceil((r+pad-2)/2)
+        int j_lo = max(0, (c + pad_lo - 1) / 2), j_hi = min(go.W - 1, (c + pad_lo) / 2);
+        for (int i = i_lo; i <= i_hi; ++i)
+            for (int j = j_lo; j <= j_hi; ++j) {
+                // is (r,c) the first maximum of window (i,j)?  earlier elements must be strictly smaller,
+                // later elements must be smaller or equal.
+                bool win[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) win[e] = true;
+                for (int dy = 0; dy < 3; ++dy) {
+                    int yy = 2 * i - pad_lo + dy;
+                    if (yy < 0 || yy >= gi.H) continue;
+                    for (int dx = 0; dx < 3; ++dx) {
+                        int xx = 2 * j - pad_lo + dx;
+                        if (xx < 0 || xx >= gi.W) continue;
+                        if (yy == r && xx == c) continue;
+                        bool earlier = (yy < r) || (yy == r && xx < c);
+                        long long qi = (long long)img * gi.P + (long long)(yy + 1) * gi.Wp + (xx + 1);
+                        const float4* p = reinterpret_cast<const float4*>(ybase + qi * 8);
+                        float4 a = p[0], b = p[1];
+                        float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) win[e] = win[e] && (earlier ? (o[e] < self[e]) : (o[e] <= self[e]));
+                    }
+                }
+                long long qo = (long long)img * go.P + (long long)(i + 1) * go.Wp + (j + 1);
+                const float4* p = reinterpret_cast<const float4*>(dpool + ((long long)jc * go.NP + qo) * 8);
+                float4 a = p[0], b = p[1];
+                float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] += win[e] ? d[e] : 0.f;
+            }
+    }
+    bf16 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(g[e], h[e], l[e]);
+    long long off = ((long long)jc * out.plane_px + q) * 8;
+    *reinterpret_cast<uint4*>(out.hi + off) =
+        make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(out.lo + off) =
+        make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+
+int launch_pool_bwd(const float* y, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
+                    cudaStream_t st) {
+    long long total = (gi.NP + 127) / 128 * 128 * chunks;
+    k_pool_bwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, dpool, gi, go, pad_lo, chunks, out);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference wgrad: dW[tap][ci][co] = sum_q X[q + d_tap][ci] * G[q][co],  db[co] = sum_q G[q][co].
+// Each block reduces a slab of TP-pixel tiles into registers, then writes one partial; a second kernel sums
+// the partials in a fixed order (deterministic).
+constexpr int WG_TP = 64;
+constexpr int WG_MAXP = 36;   // (tap, ci) pairs per thread: 288 pairs / 8 groups
+
+__global__ void __launch_bounds__(256) k_wgrad_simt(WgradArgs a, float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    const int cin = a.cin_real, cout = a.cout;
+    const int Wp = a.g.Wp;
+    const int win = WG_TP + 2 * Wp + 2;
+    float* sx = sm;                 // [win][cin]
+    float* sg = sm + win * cin;     // [WG_TP][cout]
+    const int co = threadIdx.x % cout;
+    const int grp = threadIdx.x / cout;
+    const int ngrp = 256 / cout;
+    const int npairs = 9 * cin;
+    float acc[WG_MAXP];
+#pragma unroll
+    for (int k = 0; k < WG_MAXP; ++k) acc[k] = 0.f;
+    float accb = 0.f;
+    const long long ntiles = (a.g.NP + WG_TP - 1) / WG_TP;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        long long q0 = tile * WG_TP;
+        __syncthreads();
+        for (int t = threadIdx.x; t < win * a.cin_chunks; t += 256) {
+            int jc = t / win, p = t % win;
+            long long q = q0 - Wp - 1 + p;  // guard zones make this in-bounds
+            long long off = ((long long)jc * a.x.plane_px + q) * 8;
+            float x[8], xl[8];
+            unpack8(*reinterpret_cast<const uint4*>(a.x.hi + off), x);
+            if (a.x.lo) {
+                unpack8(*reinterpret_cast<const uint4*>(a.x.lo + off), xl);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] += xl[e];
+            }
+            for (int e = 0; e < 8; ++e) {
+                int c = jc * 8 + e;
+                if (c < cin) sx[p * cin + c] = x[e];
+            }
+        }
+        for (int t = threadIdx.x; t < WG_TP * (cout / 8); t += 256) {
+            int jc = t / WG_TP, p = t % WG_TP;
+            long long q = q0 + p;
+            float gg[8], gl[8];
+            if (q < a.g.NP) {
+                long long off = ((long long)jc * a.gy.plane_px + q) * 8;
+                unpack8(*reinterpret_cast<const uint4*>(a.gy.hi + off), gg);
+                unpack8(*reinterpret_cast<const uint4*>(a.gy.lo + off), gl);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gg[e] += gl[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gg[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sg[p * cout + jc * 8 + e] = gg[e];
+        }
+        __syncthreads();
+        for (int p = 0; p < WG_TP; ++p) {
+            float gv = sg[p * cout + co];
+            if (grp == 0) accb += gv;
+#pragma unroll
+            for (int k = 0; k < WG_MAXP; ++k) {
+                int pair = grp + k * ngrp;
+                if (pair < npairs) {
+                    int tap = pair / cin, ci = pair - tap * cin;
+                    int pp = p + (tap / 3) * Wp + (tap % 3);
+                    acc[k] = fmaf(sx[pp * cin + ci], gv, acc[k]);
+                }
+            }
+        }
+    }
+    float* out = partial + (long long)blockIdx.x * (npairs * cout + cout);
+#pragma unroll
+    for (int k = 0; k < WG_MAXP; ++k) {
+        int pair = grp + k * ngrp;
+        if (pair < npairs) out[pair * cout + co] = acc[k];
+    }
+    if (grp == 0) out[npairs * cout + co] = accb;
+}
+
+// out[i] = sum_b partial[b][i]  (fixed order);  first nw entries -> dW (HWIO), last cout entries -> db
+__global__ void k_wgrad_reduce(const float* __restrict__ partial, int nblocks, int nw, int cout, float scale,
+                               float* __restrict__ dw, float* __restrict__ db) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nw + cout) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * (nw + cout) + i];
+    if (i < nw) dw[i] = s * scale;
+    else db[i - nw] = s;
+}
+
+int launch_wgrad_simt(const WgradArgs& a, float* partial, int max_blocks, cudaStream_t st) {
+    long long ntiles = (a.g.NP + WG_TP - 1) / WG_TP;
+    int nb = (int)(ntiles < max_blocks ? ntiles : max_blocks);
+    int win = WG_TP + 2 * a.g.Wp + 2;
+    size_t smem = ((size_t)win * a.cin_real + (size_t)WG_TP * a.cout) * sizeof(float);
+    k_wgrad_simt<<<nb, 256, smem, st>>>(a, partial);
+    CB_LAUNCH_CHECK();
+    int nw = 9 * a.cin_real * a.cout;
+    k_wgrad_reduce<<<(nw + a.cout + 255) / 256, 256, 0, st>>>(partial, nb, nw, a.cout, a.scale, a.dw, a.db);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace cb

@@ -1,0 +1,140 @@
+"""Learner-side host logic: one learner replica = one GPU = one `Context`; the per-update loop of the reference's
+`single_device_update` is driven from Python over the C ABI, with the data-parallel gradient mean
+(`jax.lax.pmean(grads, "local_devices")`, cleanba/cleanba_ppo.py:628, cleanba/cleanba_impala.py:619) as ONE allreduce
+on the flat gradient buffer between the gradient call and the optimizer call.
+
+PPO    : cleanba/cleanba_ppo.py:579-654      IMPALA : cleanba/cleanba_impala.py:599-639
+"""
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from .agent import Context, CB_ALGO_IMPALA, CB_ALGO_PPO, CB_CONV_TCGEN05, CleanbaError
+
+# allreduce hook: f(flat_grad_tensor) -> None, sums in place over all learner devices of all processes
+AllReduce = Optional[Callable[[torch.Tensor], None]]
+
+
+def linear_schedule(count: int, base_lr: float, steps_per_update: int, num_updates: int, anneal: bool) -> float:
+    """cleanba_ppo.py:475-479 / cleanba_impala.py:515-519, evaluated at the pre-increment optimizer count, in fp32."""
+    if not anneal:
+        return float(np.float32(base_lr))
+    frac = 1.0 - (count // steps_per_update) / num_updates
+    return float(np.float32(base_lr * frac))
+
+
+@dataclass
+class PPOHyper:
+    """Algorithm-specific arguments of cleanba_ppo.py:60-91 (defaults identical)."""
+    learning_rate: float = 2.5e-4
+    anneal_lr: bool = True
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    num_minibatches: int = 4
+    update_epochs: int = 4
+    norm_adv: bool = True
+    clip_coef: float = 0.1
+    ent_coef: float = 0.01
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    num_updates: int = 3255
+
+
+class PPOLearner:
+    def __init__(self, device, hyper: PPOHyper, T: int, Bl: int, world_learners: int = 1, allreduce: AllReduce = None,
+                 conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18):
+        if (T * Bl) % hyper.num_minibatches:
+            raise CleanbaError("T*Bl must be divisible by num_minibatches")
+        if Bl % hyper.num_minibatches and hyper.norm_adv:
+            raise CleanbaError("Bl must be divisible by num_minibatches (cleanba_ppo.py:416-418)")
+        self.h, self.T, self.Bl = hyper, T, Bl
+        self.mb = T * Bl // hyper.num_minibatches
+        self.world_learners = world_learners
+        self.allreduce = allreduce
+        self.ctx = Context(device, max_batch=max(self.mb, Bl), algo=CB_ALGO_PPO, train=True,
+                           num_actions=num_actions, conv_backend=conv_backend)
+        d = self.ctx.device
+        self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
+        self.stats = torch.zeros(hyper.update_epochs * hyper.num_minibatches, 5, dtype=torch.float32, device=d)
+        self.opt_count = 0
+
+    def update(self, obs, dones, actions, logprobs, values, rewards, next_obs, next_done, key) -> torch.Tensor:
+        """single_device_update (cleanba_ppo.py:579-654).  Fields are [T,Bl,...] device tensors (the hstack of the actor
+        payloads); `key` is the uint32[2] learner key (device, advanced in place).  Returns the 5 averaged scalars
+        (loss, pg_loss, v_loss, entropy, approx_kl) as a device tensor (no host sync)."""
+        h, c = self.h, self.ctx
+        T, Bl = self.T, self.Bl
+        _, next_value = c.policy_value(next_obs)                      # bootstrap value (cleanba_ppo.py:550-552)
+        adv, ret = c.gae(rewards, values, dones, next_value, next_done, h.gamma, h.gae_lambda,
+                         h.num_minibatches if h.norm_adv else 0)      # compute_gae + norm (cleanba_ppo.py:591-595)
+        obs_f = obs.reshape(T * Bl, 4, 84, 84)
+        act_f, lp_f, adv_f, ret_f = actions.reshape(-1), logprobs.reshape(-1), adv.reshape(-1), ret.reshape(-1)
+        k = 0
+        for _ in range(h.update_epochs):
+            sub = c.split_key(key)                                    # key, subkey = split(key) (cleanba_ppo.py:599)
+            perm = c.permutation(sub, T * Bl)                         # jax.random.permutation(subkey, .) (:606)
+            for j in range(h.num_minibatches):
+                idx = perm[j * self.mb:(j + 1) * self.mb]
+                c.ppo_grad(obs_f, idx, self.mb, act_f, lp_f, adv_f, ret_f, h.clip_coef, h.ent_coef, h.vf_coef,
+                           self.grads, self.stats[k])
+                if self.allreduce is not None and self.world_learners > 1:
+                    self.allreduce(self.grads)                        # lax.pmean(grads) (cleanba_ppo.py:628)
+                lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches * h.update_epochs,
+                                     h.num_updates, h.anneal_lr)
+                c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
+                self.opt_count += 1
+                k += 1
+        return self.stats.mean(0)
+
+
+@dataclass
+class ImpalaHyper:
+    """Algorithm-specific arguments of cleanba_impala.py:60-87 (defaults identical)."""
+    learning_rate: float = 6e-4
+    anneal_lr: bool = True
+    gamma: float = 0.99
+    num_minibatches: int = 4
+    ent_coef: float = 0.01
+    vf_coef: float = 0.5
+    max_grad_norm: float = 40.0
+    num_updates: int = 20833
+
+
+class ImpalaLearner:
+    def __init__(self, device, hyper: ImpalaHyper, T1: int, Bl: int, world_learners: int = 1, allreduce: AllReduce = None,
+                 conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18):
+        if Bl % hyper.num_minibatches:
+            raise CleanbaError("Bl must be divisible by num_minibatches (cleanba_impala.py:456-458)")
+        self.h, self.T1, self.Bl = hyper, T1, Bl
+        self.B = Bl // hyper.num_minibatches
+        self.world_learners = world_learners
+        self.allreduce = allreduce
+        self.ctx = Context(device, max_batch=T1 * self.B, algo=CB_ALGO_IMPALA, train=True, num_actions=num_actions,
+                           conv_backend=conv_backend)
+        d = self.ctx.device
+        self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
+        self.stats = torch.zeros(hyper.num_minibatches, 4, dtype=torch.float32, device=d)
+        # contiguous env-column blocks, never shuffled (cleanba_impala.py:626-633): idx[j][t*B+b] = t*Bl + j*B + b
+        t = torch.arange(T1, device=d, dtype=torch.int32)[:, None] * Bl
+        self.idx = [(t + (j * self.B + torch.arange(self.B, device=d, dtype=torch.int32))[None, :]).reshape(-1).contiguous()
+                    for j in range(hyper.num_minibatches)]
+        self.opt_count = 0
+
+    def update(self, obs, dones, actions, logitss, rewards, firststeps) -> torch.Tensor:
+        """single_device_update (cleanba_impala.py:599-639).  Fields are [T+1,Bl,...] device tensors.  Returns the 4
+        averaged scalars (loss, pg_loss, v_loss, entropy_loss)."""
+        h, c = self.h, self.ctx
+        T1, Bl = self.T1, self.Bl
+        obs_f = obs.reshape(T1 * Bl, 4, 84, 84)
+        A = c.num_actions
+        for j in range(h.num_minibatches):
+            c.impala_grad(obs_f, self.idx[j], T1, self.B, actions.reshape(-1), logitss.reshape(-1, A), rewards.reshape(-1),
+                          dones.reshape(-1), firststeps.reshape(-1), h.gamma, h.vf_coef, h.ent_coef, self.grads, self.stats[j])
+            if self.allreduce is not None and self.world_learners > 1:
+                self.allreduce(self.grads)                            # lax.pmean(grads) (cleanba_impala.py:619)
+            lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches, h.num_updates, h.anneal_lr)
+            c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
+            self.opt_count += 1
+        return self.stats.mean(0)

@@ -125,24 +125,33 @@ def _max_pool_same(x):
     return F.max_pool2d(x, kernel_size=3, stride=2)
 
 
-def trunk_forward(p: Dict[str, torch.Tensor], obs_u8: torch.Tensor, channels=CHANNELS) -> torch.Tensor:
+def trunk_forward(p: Dict[str, torch.Tensor], obs_u8: torch.Tensor, channels=CHANNELS, record: dict = None) -> torch.Tensor:
     """Network.__call__ (cleanba_ppo.py:178-189).  obs_u8: [b,4,84,84] uint8 (NCHW) -> hidden [b,256].
 
     The reference transposes to NHWC; torch computes in NCHW, which is the same arithmetic.  Only the
     flatten order (h,w,c) (cleanba_ppo.py:185) needs an explicit permute."""
     dt = p["network_params/params/Dense_0/kernel"].dtype
+
+    def rec(name, t):
+        # test hook: keep intermediates (NCHW) and, when differentiating, their gradients
+        if record is not None:
+            if t.requires_grad:
+                t.retain_grad()
+            record[name] = t
+        return t
+
     x = obs_u8.to(dt) / 255.0
     for s in range(len(channels)):
         pre = f"network_params/params/ConvSequence_{s}"
-        x = _conv(x, p[f"{pre}/Conv_0/kernel"], p[f"{pre}/Conv_0/bias"])
-        x = _max_pool_same(x)
+        x = rec(f"s{s}.y", _conv(x, p[f"{pre}/Conv_0/kernel"], p[f"{pre}/Conv_0/bias"]))
+        x = rec(f"s{s}.p", _max_pool_same(x))
         for r in range(2):
             inputs = x
             x = torch.relu(x)
-            x = _conv(x, p[f"{pre}/ResidualBlock_{r}/Conv_0/kernel"], p[f"{pre}/ResidualBlock_{r}/Conv_0/bias"])
+            x = rec(f"s{s}.a{r}pre", _conv(x, p[f"{pre}/ResidualBlock_{r}/Conv_0/kernel"], p[f"{pre}/ResidualBlock_{r}/Conv_0/bias"]))
             x = torch.relu(x)
             x = _conv(x, p[f"{pre}/ResidualBlock_{r}/Conv_1/kernel"], p[f"{pre}/ResidualBlock_{r}/Conv_1/bias"])
-            x = x + inputs
+            x = rec(f"s{s}.b{r}", x + inputs)
     x = torch.relu(x)
     x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # NHWC flatten
     x = x @ p["network_params/params/Dense_0/kernel"] + p["network_params/params/Dense_0/bias"]

@@ -59,7 +59,7 @@ def compute_gae(rewards, values, dones, next_value, next_done, gamma=0.99, gae_l
     r = rewards.astype(F32)
     v = np.concatenate([values.astype(F32), next_value.astype(F32)[None]], 0)
     d = np.concatenate([dones.astype(F32), next_done.astype(F32)[None]], 0)
-    g, gl = F32(gamma), F32(gamma) * F32(gae_lambda)
+    g, gl = F32(gamma), F32(gamma * gae_lambda)  # python-float product, then cast (cleanba_ppo.py:538)
     adv = np.zeros(B, F32)
     out = np.zeros((T, B), F32)
     for t in range(T - 1, -1, -1):
