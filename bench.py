@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the Sebulba hot path (BASELINE.json: env-steps/sec, Breakout-v5-shaped synthetic 84x84x4 frames).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, libcleanba_b200)
+  python bench.py --impl reference --gpus N --steps K ...  the reference path's CPU restatement (oracle/) on host cores
+
+One STEP = one full pass of the hot path over one batch = one PPO update cycle of config[1]
+(`cleanba_ppo.py a0-l0-d1 --local-num-envs 60`): 128 rollout steps x 2 actor threads x 60 envs through the actor's
+get_action_and_value, then single_device_update (GAE + 4 epochs x 4 shuffled minibatches of 3840: forward, loss,
+backward, [allreduce], clip + Adam) and the parameter publish back to the actor = 15,360 env steps.
+With N > 1 every rank runs that cycle on its own GPU (a0-l0 per process, `--distributed` d=N, weak scaling) and the
+gradients are averaged with one NCCL allreduce on the flat gradient buffer per minibatch.
+
+`value`  : frames already resident in HBM (a device pool larger than L2, cycled).
+`e2e`    : same cycle through the public API with HOST frames: every actor step copies its [60,4,84,84] uint8 batch
+           from pinned host memory and reads the int32 actions back (the reference's per-step sync, cleanba_ppo.py:313-317),
+           every update reads the loss scalars back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ENVS, N_THREADS, T_STEPS, N_MB, N_EPOCHS = 60, 2, 128, 4, 4
+FLOP_PER_ENV_STEP = 1.4108e9            # actor fwd + 4 epochs x 3 x fwd
+WORKLOAD = "cleanba_ppo a0-l0-d1 Breakout-v5-shaped synthetic frames, local_num_envs=60, 2 actor threads, num_steps=128"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d.get("bf16_tflops_sustained", d["bf16_tflops"]), tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+                for nme, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_sample(T_s, threads=N_THREADS, n_envs=N_ENVS, seed=1):
+    """One bounded sample of the workload on the CPU oracle: a T_s-step rollout of `threads` x `n_envs` envs through
+    get_action_and_value, then a full single_device_update on it.  Returns env steps processed."""
+    from oracle import network as net, ppo as oppo, threefry as tf
+    st = cpu_sample.state
+    if st is None:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        st = cpu_sample.state = dict(params=net.init_params(seed), rng=rng, key=tf.split(tf.PRNGKey(seed), 4)[0])
+    rng, params = st["rng"], st["params"]
+    Bl = threads * n_envs
+    obs = np.zeros((T_s, Bl, 4, 84, 84), np.uint8)
+    act = np.zeros((T_s, Bl), np.int32); lp = np.zeros((T_s, Bl), np.float32); val = np.zeros((T_s, Bl), np.float32)
+    keys = [st["key"].copy() for _ in range(threads)]
+    for t in range(T_s):
+        for th in range(threads):
+            c = slice(th * n_envs, (th + 1) * n_envs)
+            o = rng.integers(0, 256, (n_envs, 4, 84, 84), dtype=np.uint8)
+            _, a, l, v, keys[th], _ = oppo.get_action_and_value(params, o, keys[th])
+            obs[t, c], act[t, c], lp[t, c], val[t, c] = o, a, l, v
+    shard = oppo.Shard(obs=obs, dones=rng.random((T_s, Bl)) < 0.002, actions=act, logprobs=lp, values=val,
+                       rewards=rng.choice(np.array([-1, 0, 1], np.float32), size=(T_s, Bl), p=[.05, .9, .05]),
+                       next_obs=rng.integers(0, 256, (Bl, 4, 84, 84), dtype=np.uint8), next_done=np.zeros(Bl, bool))
+    learner = oppo.PPOLearner(params, oppo.PPOConfig(num_minibatches=N_MB, update_epochs=N_EPOCHS))
+    learner.update([shard], st["key"])
+    st["params"] = learner.params
+    return T_s * Bl
+
+
+cpu_sample.state = None
+
+
+def run_cpu_arm(steps, warmup, budget_s=150.0):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t0 = time.time(); cpu_sample(1); t1 = time.time() - t0          # calibration (also warms torch)
+    per_T = max(t1, 1e-3)
+    T_s = int(max(1, min(T_STEPS, budget_s / max(1, steps + warmup) / per_T)))
+    for _ in range(warmup):
+        cpu_sample(T_s)
+    t0 = time.time(); n = 0
+    for _ in range(steps):
+        n += cpu_sample(T_s)
+    dt = time.time() - t0
+    return dict(value=n / dt, cores=cores, T_s=T_s, ms_per_step=1e3 * dt / steps,
+                sample=f"{T_s}-step rollout x {N_THREADS} actor threads x {N_ENVS} envs + one PPO update "
+                       f"({N_EPOCHS} epochs x {N_MB} minibatches) = {T_s * N_THREADS * N_ENVS} env steps per bench step")
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class Cycle:
+    """One actor (2 logical threads) + one learner replica on one GPU; PPO a0-l0 topology."""
+
+    def __init__(self, device, world, allreduce, seed=1):
+        import torch
+        from cleanba_b200 import agent as ag
+        from cleanba_b200.learner import PPOHyper, PPOLearner
+        from cleanba_b200.params import init_params
+        self.torch, self.ag = torch, ag
+        self.dev = torch.device(device)
+        Bl = N_ENVS * N_THREADS
+        self.Bl = Bl
+        self.learner = PPOLearner(self.dev, PPOHyper(), T=T_STEPS, Bl=Bl, world_learners=world, allreduce=allreduce)
+        self.actor = ag.Context(self.dev, max_batch=N_ENVS, train=False)
+        params = init_params(seed)
+        self.learner.ctx.set_params(params)
+        self.learner.ctx.publish_to(self.actor)
+        d = self.dev
+        self.obs = torch.zeros(T_STEPS, Bl, 4, 84, 84, dtype=torch.uint8, device=d)
+        self.actions = torch.zeros(T_STEPS, Bl, dtype=torch.int32, device=d)
+        self.logprobs = torch.zeros(T_STEPS, Bl, dtype=torch.float32, device=d)
+        self.values = torch.zeros(T_STEPS, Bl, dtype=torch.float32, device=d)
+        g = torch.Generator(device="cpu"); g.manual_seed(seed)
+        self.rew_pool = (torch.multinomial(torch.tensor([.05, .9, .05]), 8 * T_STEPS * Bl, True, generator=g).float() - 1).reshape(8, T_STEPS, Bl).to(d)
+        self.done_pool = (torch.rand(8, T_STEPS, Bl, generator=g) < 1 / 500).to(d)
+        self.next_done = torch.zeros(Bl, dtype=torch.bool, device=d)
+        from cleanba_b200.prng import first_key
+        self.keys = [ag.key_tensor(first_key(seed), d) for _ in range(N_THREADS)]
+        self.lkey = ag.key_tensor(first_key(seed), d)
+        # frame pools: 256 distinct [60,4,84,84] batches = 433 MB (> 126 MB L2); host copy pinned for the e2e path
+        rng = np.random.Generator(np.random.PCG64(seed))
+        host = torch.empty(256, N_ENVS, 4, 84, 84, dtype=torch.uint8).pin_memory()
+        host.numpy()[...] = rng.integers(0, 256, size=tuple(host.shape), dtype=np.uint8)
+        self.host_pool = host
+        self.dev_pool = host.to(d)
+        self.cursor = 0
+        self.h2d = self.d2h = 0
+
+    def step(self, e2e: bool):
+        torch = self.torch
+        pool = self.host_pool if e2e else self.dev_pool
+        for t in range(T_STEPS):
+            for th in range(N_THREADS):
+                c = slice(th * N_ENVS, (th + 1) * N_ENVS)
+                slot = self.obs[t, c]
+                slot.copy_(pool[self.cursor % 256], non_blocking=True)     # env frame -> rollout storage (H2D when e2e)
+                self.cursor += 1
+                self.actor.actor_step(slot, self.keys[th], out=(self.actions[t, c], self.logprobs[t, c], self.values[t, c], None))
+                if e2e:
+                    _ = self.actions[t, c].cpu()                           # np.array(action): the per-step sync (cleanba_ppo.py:317)
+                    self.h2d += slot.numel(); self.d2h += N_ENVS * 4
+        k = (self.cursor // 256) % 8
+        stats = self.learner.update(self.obs, self.done_pool[k], self.actions, self.logprobs, self.values, self.rew_pool[k],
+                                    self.obs[0], self.next_done, self.lkey)
+        self.learner.ctx.publish_to(self.actor)                            # params_queue.put(device_params) (cleanba_ppo.py:721-725)
+        if e2e:
+            _ = stats.cpu(); self.d2h += 20
+        return stats
+
+
+def run_our_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    from cleanba_b200 import lib
+    cyc = Cycle(f"cuda:{local_rank}", world, allreduce)
+    if world > 1:   # identical initial parameters on every learner (the reference relies on equal seeds, cleanba_ppo.py:468)
+        pv = cyc.learner.ctx.params_view(); dist.broadcast(pv, 0); cyc.learner.ctx.refresh_weights(); cyc.learner.ctx.publish_to(cyc.actor)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, steps, profile=False):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if profile:
+            cyc.learner.ctx.profile(True); cyc.actor.profile(True)
+        l0 = lib.load().cb_launch_count()
+        ev0.record()
+        for _ in range(steps):
+            cyc.step(e2e)
+        ev1.record()
+        barrier()
+        launches = lib.load().cb_launch_count() - l0
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+        return ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        cyc.step(False)
+    cyc.step(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(False, args.steps, profile=True)
+    rep = cyc.learner.ctx.profile_report() + cyc.actor.profile_report()
+    cyc.learner.ctx.profile(False); cyc.actor.profile(False)
+    cyc.h2d = cyc.d2h = 0
+    ms_e2e, _ = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    env_steps = T_STEPS * N_THREADS * N_ENVS * world
+    value = env_steps * args.steps / (ms * 1e-3)
+    e2e_value = env_steps * args.steps / (ms_e2e * 1e-3)
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    agg = {}
+    for r in rep:
+        a = agg.setdefault(r["name"], dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+        a["ms"] += r["ms"]; a["calls"] += r["calls"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    name, a = top
+    ai = a["flops"] / max(a["bytes"], 1.0)
+    balance = peaks["tf"] * 1e12 / (peaks["hbm"] * 1e9)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(name)
+    if a["flops"] > 0 and ai >= balance:
+        roof = dict(bound="tensor", achieved=a["flops"] / (a["ms"] * 1e-3) / 1e12, peak=peaks["tf"], unit="TFLOP/s")
+    else:
+        roof = dict(bound="hbm", achieved=a["bytes"] / (a["ms"] * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=name, kernel_share_of_step=a["ms"] / ms,
+                peak_source=peaks["src"], launches=a["calls"],
+                algorithmic_tflops=a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["flops"] else 0.0,
+                kernels={k: round(v["ms"] / args.steps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]})
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_arm(1, 0, budget_s=25.0)
+        cpu = dict(value=r["value"], unit="env-steps/s", cores=r["cores"], kind="port", sample=r["sample"] +
+                   " (CPU restatement of the reference path in PyTorch-CPU fp32, not JAX: jax/flax/optax are not installable here)")
+    out = {
+        "metric": "env-steps/sec (Breakout-v5 84x84x4, synthetic frames)", "value": value, "unit": "env-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32-compensated bf16 tensor-core products, fp32 accumulate/state)",
+        "data": "synthetic", "impl": "ours",
+        "config": {"workload": WORKLOAD, "env_steps_per_bench_step": env_steps, "topology": f"a0-l0-d{world}",
+                   "cache": "inputs larger than L2: 433 MB device frame pool cycled, 433 MB rollout storage per update",
+                   "tensor_roof_frac_end_to_end": value * FLOP_PER_ENV_STEP / (peaks["tf"] * 1e12 * world)},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": cyc.h2d // args.steps,
+                "d2h_bytes_per_step": cyc.d2h // args.steps, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        r = run_cpu_arm(args.steps, args.warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": "env-steps/sec (Breakout-v5 84x84x4, synthetic frames)", "value": r["value"],
+            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"] + " (PyTorch-CPU restatement of the reference path; the JAX reference cannot be installed here)"},
+            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    run_our_arm(args)
+
+
+if __name__ == "__main__":
+    main()
