@@ -5,9 +5,10 @@
 //   padded grid Hp = H + 2, Wp = W + 2 (the SAME-padding ring of the 3x3 convs, cleanba_ppo.py:156,167),
 //   flattened over (image, y', x') into NP = n * Hp * Wp "flat pixels", and split into C/8 planes of
 //   8 channels:   plane[c / 8][flat pixel][c % 8].
-//   * "planes"  = two bf16 arrays (hi, lo) with x ~= hi + lo (16 significant bits); each plane has
-//     GUARD zero pixels before and after so a 3x3 tap window of a 128-pixel tile is one contiguous,
-//     in-bounds byte range (a 1-D bulk TMA copy) and the tile itself is an UMMA operand.
+//   * "planes"  = three bf16 arrays (hi, mid, lo) with x == hi + mid + lo to 24 significant bits (an exact
+//     3-way split of the fp32 value); each plane has GUARD zero pixels before and after so a 3x3 tap window
+//     of a 128-pixel tile is one contiguous, in-bounds byte range (a 1-D bulk TMA copy) and the tile itself
+//     is an UMMA operand.
 //   * "stream"  = one fp32 array [C/8][NP][8] (residual stream / pre-pool conv output / gradients).
 //   Border pixels of every tensor are kept at exactly zero by the producing kernel.
 #pragma once
@@ -24,9 +25,10 @@ constexpr int MAX_ACTIONS = 32;
 
 typedef __nv_bfloat16 bf16;
 
-struct Planes {           // bf16 hi/lo chunk planes; pointers address flat pixel 0 (guard lies before it)
+struct Planes {           // bf16 hi/mid/lo chunk planes; pointers address flat pixel 0 (guard lies before it)
     bf16* hi;
-    bf16* lo;             // may be null (exact-in-bf16 data, e.g. the unpacked uint8 frames)
+    bf16* mid;            // mid / lo may be null (exact-in-bf16 data, e.g. the unpacked uint8 frames)
+    bf16* lo;
     long long plane_px;   // pixels per plane INCLUDING both guards (plane stride = plane_px * 8 elements)
 };
 
@@ -44,7 +46,7 @@ __host__ __device__ inline ConvGeom make_geom(int n, int H, int W) {
 
 // Epilogue shared by the SIMT and the tcgen05 conv kernels (forward conv and dgrad):
 //   v = acc * acc_scale + bias;  v *= (mask_hi > 0);  v += res;  border -> 0
-//   out_s <- v ;  out planes <- split_bf16(relu ? max(v, 0) : v)
+//   out_s <- v ;  out planes <- split_bf16x3(relu ? max(v, 0) : v)
 struct ConvEpilogue {
     const float* bias;        // [Cout] or null
     float acc_scale;          // 1/255 for the first conv (cleanba_ppo.py:181), else 1
@@ -65,14 +67,16 @@ struct ConvArgs {
     const float* w;           // fp32 master kernel, HWIO [3][3][Cin_f][Cout_f] (SIMT path)
     int w_cin, w_cout;        // Cin_f, Cout_f of the master kernel
     int transpose;            // 0: forward conv; 1: dgrad (flipped taps, in/out channels swapped)
-    const bf16* wp_hi;        // packed bf16 UMMA weight image (hi), see pack.cu
-    const bf16* wp_lo;
+    const bf16* wp;           // packed bf16 UMMA weight image ([hi|mid|lo] stacked along N), see pack.cu
     ConvEpilogue ep;
 };
 
-__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+// exact 3-way split: x == hi + mid + lo up to 24 significant bits (each residual is exact in fp32)
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& mid, bf16& lo) {
     hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    float r1 = x - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
@@ -88,6 +92,33 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
     f[2] = bf16lo_to_f(v.y); f[3] = bf16hi_to_f(v.y);
     f[4] = bf16lo_to_f(v.z); f[5] = bf16hi_to_f(v.z);
     f[6] = bf16lo_to_f(v.w); f[7] = bf16hi_to_f(v.w);
+}
+
+// 8 consecutive channels of one pixel-chunk (element offset `off`) <- -> fp32
+__device__ __forceinline__ void load_planes8(const Planes& p, long long off, float* f) {
+    unpack8(*reinterpret_cast<const uint4*>(p.hi + off), f);
+    if (p.mid) {
+        float t[8];
+        unpack8(*reinterpret_cast<const uint4*>(p.mid + off), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += t[e];
+        unpack8(*reinterpret_cast<const uint4*>(p.lo + off), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += t[e];
+    }
+}
+__device__ __forceinline__ void store_planes8(const Planes& p, long long off, const float* v) {
+    bf16 h[8], m[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], m[e], l[e]);
+    *reinterpret_cast<uint4*>(p.hi + off) =
+        make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    if (p.mid) {
+        *reinterpret_cast<uint4*>(p.mid + off) =
+            make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+        *reinterpret_cast<uint4*>(p.lo + off) =
+            make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    }
 }
 
 // Is flat pixel q (q < NP) an interior (non-border) pixel of its image?
@@ -131,18 +162,10 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvEpilogue& ep, cons
         o[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
     if (ep.out.hi) {
-        bf16 h[8], l[8];
+        float x[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float x = ep.relu ? fmaxf(v[e], 0.f) : v[e];
-            split_bf16(x, h[e], l[e]);
-        }
-        long long off = ((long long)oc * ep.out.plane_px + q) * 8;
-        *reinterpret_cast<uint4*>(ep.out.hi + off) =
-            make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-        if (ep.out.lo)
-            *reinterpret_cast<uint4*>(ep.out.lo + off) =
-                make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+        for (int e = 0; e < 8; ++e) x[e] = ep.relu ? fmaxf(v[e], 0.f) : v[e];
+        store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, x);
     }
 }
 

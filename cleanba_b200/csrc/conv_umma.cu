@@ -10,8 +10,15 @@
 //   * that window is ONE contiguous byte range per channel plane -> one 1-D bulk TMA copy per plane per tile,
 //   * a plane [pixel][8 ch] of bf16 is exactly a column of SWIZZLE_NONE 8x16-byte core matrices, both K-major
 //     (conv / dgrad: K = channels) and MN-major (wgrad: K = pixels), so no data is ever re-laid out.
-// Precision: x ~= x_hi + x_lo, w ~= w_hi + w_lo in bf16; every K step issues hi*hi + hi*lo + lo*hi with fp32
-// accumulation in TMEM (error ~2^-17 relative, needed for the 1e-4 parity bar against the fp32 reference).
+//
+// Precision (parity bar: 1e-4 against an fp32 reference, with discontinuous relu / max-pool gates downstream):
+// every fp32 value is carried as an exact 3-way bf16 split x = hi + mid + lo (24 significant bits).  The six
+// significant cross products are obtained with THREE tcgen05.mma per K step by stacking the weight planes along N:
+//     D[:, 0:3C] += A_hi  * [W_hi | W_mid | W_lo]        (N = 3C)
+//     D[:, 0:2C] += A_mid * [W_hi | W_mid]               (N = 2C)
+//     D[:, 0:C ] += A_lo  * [W_hi]                       (N = C)
+// and the epilogue adds the three C-column blocks.  The MMAs are bound by the A-operand shared-memory fetch (ncu:
+// sm__pipe_tc_cycles_active ~80%), which does not depend on N, so the extra precision costs no tensor-pipe time.
 //
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quadrant = warp id), warp 4 TMA producer, warp 5 MMA issuer.
 #include "common.cuh"
@@ -26,7 +33,8 @@ constexpr int CONV_STAGES = 3;
 constexpr int CONV_THREADS = 192;
 
 __host__ __device__ constexpr int conv_steps(int cin_chunks) { return cin_chunks == 1 ? 5 : 9 * (cin_chunks / 2); }
-__host__ __device__ constexpr int conv_wbytes(int cin_chunks, int cout) { return conv_steps(cin_chunks) * 2 * cout * 16; }
+// bytes of the packed weight image: per step [kc(2)][3*cout][8] bf16
+__host__ __device__ constexpr int conv_wbytes(int cin_chunks, int cout) { return conv_steps(cin_chunks) * 2 * 3 * cout * 16; }
 
 long long packed_conv_elems(int cin_chunks, int cout) { return (long long)conv_wbytes(cin_chunks, cout) / 2; }
 
@@ -38,9 +46,9 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int c
     // frames path: the zero-weight half of the last K step reads one pixel past the 3x3 window -> load it too
     L.win = TILE_M + 2 * Wp + 2 + (cin_chunks == 1 ? 1 : 0);
     L.plane_bytes = L.win * 16;
-    L.nplanes = cin_chunks == 1 ? 1 : 2 * cin_chunks;        // hi planes then lo planes (frames: hi only)
+    L.nplanes = cin_chunks == 1 ? 1 : 3 * cin_chunks;        // hi planes, mid planes, lo planes (frames: hi only, exact)
     L.stage_bytes = L.nplanes * L.plane_bytes;
-    L.w_bytes = conv_wbytes(cin_chunks, cout) * 2;           // hi image then lo image
+    L.w_bytes = conv_wbytes(cin_chunks, cout);
     L.total = 1024 + L.w_bytes + CONV_STAGES * L.stage_bytes;
     return L;
 }
@@ -50,7 +58,7 @@ template <int CIN_CHUNKS, int COUT>
 __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
-    // [0,1024): barriers + tmem pointer; then weights (hi, lo); then stages
+    // [0,1024): barriers + tmem pointer; then the weight image; then the activation stages
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [CONV_STAGES]
     uint64_t* empty = full + CONV_STAGES;                        // [CONV_STAGES]
     uint64_t* tfull = empty + CONV_STAGES;                       // [2]
@@ -62,8 +70,9 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(CIN_CHUNKS);
-    constexpr int WB = conv_wbytes(CIN_CHUNKS, COUT);            // bytes of one (hi or lo) weight image
-    constexpr uint32_t TMEM_COLS = 64;                           // 2 accumulators x 32 columns
+    constexpr int ACC_COLS = 3 * COUT;                           // three C-column blocks per accumulator
+    constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 128) ? 128 : 256;
+    constexpr int NPLANES = CIN_CHUNKS == 1 ? 1 : 3 * CIN_CHUNKS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CONV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -78,44 +87,43 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (lanes share the bulk copies of a stage) =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(wbar, (uint32_t)L.w_bytes);
-            bulk_g2s(wsm, a.wp_hi, WB, wbar);
-            bulk_g2s(wsm + WB, a.wp_lo, WB, wbar);
-            int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], (uint32_t)L.stage_bytes);
-                const long long q_lo = (long long)tile * TILE_M - a.g.Wp - 1;   // inside the front guard for tile 0
-                uint8_t* dst = stages + s * L.stage_bytes;
-#pragma unroll
-                for (int j = 0; j < CIN_CHUNKS; ++j)
-                    bulk_g2s(dst + j * L.plane_bytes, a.in.hi + ((long long)j * a.in.plane_px + q_lo) * 8, L.plane_bytes, &full[s]);
-                if (CIN_CHUNKS > 1) {
-#pragma unroll
-                    for (int j = 0; j < CIN_CHUNKS; ++j)
-                        bulk_g2s(dst + (CIN_CHUNKS + j) * L.plane_bytes, a.in.lo + ((long long)j * a.in.plane_px + q_lo) * 8,
-                                 L.plane_bytes, &full[s]);
-                }
-                if (++s == CONV_STAGES) { s = 0; ph ^= 1; }
+            bulk_g2s(wsm, a.wp, L.w_bytes, wbar);
+        }
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)L.stage_bytes);
+            const long long q_lo = (long long)tile * TILE_M - a.g.Wp - 1;   // inside the front guard for tile 0
+            uint8_t* dst = stages + s * L.stage_bytes;
+            if (lane < NPLANES) {
+                const int pl = lane / CIN_CHUNKS, j = lane % CIN_CHUNKS;      // pl: 0 hi, 1 mid, 2 lo
+                const bf16* src = pl == 0 ? a.in.hi : (pl == 1 ? a.in.mid : a.in.lo);
+                bulk_g2s(dst + lane * L.plane_bytes, src + ((long long)j * a.in.plane_px + q_lo) * 8, L.plane_bytes, &full[s]);
             }
+            __syncwarp();
+            if (++s == CONV_STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t IDESC = make_idesc_bf16(TILE_M, COUT, 0, 0);
+        constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * COUT, 0, 0);
+        constexpr uint32_t IDESC2 = make_idesc_bf16(TILE_M, 2 * COUT, 0, 0);
+        constexpr uint32_t IDESC1 = make_idesc_bf16(TILE_M, COUT, 0, 0);
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         int acc = 0; uint32_t aph = 0;
-        const uint32_t w_hi = smem_u32(wsm), w_lo = w_hi + WB;
+        const uint32_t w_base = smem_u32(wsm);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(&tempty[acc], aph ^ 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t d_tmem = tmem_base + acc * 32;
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 const uint32_t st_hi = smem_u32(stages + s * L.stage_bytes);
-                const uint32_t st_lo = st_hi + CIN_CHUNKS * L.plane_bytes;
+                const uint32_t st_mid = st_hi + CIN_CHUNKS * L.plane_bytes;
+                const uint32_t st_lo = st_mid + CIN_CHUNKS * L.plane_bytes;
                 uint32_t accum = 0;
 #pragma unroll 1
                 for (int step = 0; step < STEPS; ++step) {
@@ -131,16 +139,12 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
                         a_off = (pair * 2) * L.plane_bytes + ((tap / 3) * a.g.Wp + (tap % 3)) * 16;
                         a_lbo = L.plane_bytes;
                     }
-                    const uint32_t b_off = step * (2 * COUT * 16);
-                    const uint64_t da_hi = make_desc(st_hi + a_off, a_lbo, 128);
-                    const uint64_t db_hi = make_desc(w_hi + b_off, COUT * 16, 128);
-                    const uint64_t db_lo = make_desc(w_lo + b_off, COUT * 16, 128);
-                    mma_bf16(d_tmem, da_hi, db_hi, IDESC, accum);
+                    const uint64_t db = make_desc(w_base + step * (2 * 3 * COUT * 16), 3 * COUT * 16, 128);
+                    mma_bf16(d_tmem, make_desc(st_hi + a_off, a_lbo, 128), db, IDESC3, accum);
                     accum = 1;
-                    mma_bf16(d_tmem, da_hi, db_lo, IDESC, 1);
                     if (CIN_CHUNKS > 1) {
-                        const uint64_t da_lo = make_desc(st_lo + a_off, a_lbo, 128);
-                        mma_bf16(d_tmem, da_lo, db_hi, IDESC, 1);
+                        mma_bf16(d_tmem, make_desc(st_mid + a_off, a_lbo, 128), db, IDESC2, 1);
+                        mma_bf16(d_tmem, make_desc(st_lo + a_off, a_lbo, 128), db, IDESC1, 1);
                     }
                 }
                 mma_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
@@ -156,10 +160,21 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
             float v[COUT];
-            tmem_ld16(taddr, v);
-            if (COUT == 32) tmem_ld16(taddr + 16, v + 16);
+            {   // sum the three column blocks, smallest contributions first
+                float t[16];
+#pragma unroll
+                for (int h = 0; h < COUT / 16; ++h) {
+                    tmem_ld16(taddr + 2 * COUT + h * 16, v + h * 16);
+                    tmem_ld16(taddr + COUT + h * 16, t);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                    tmem_ld16(taddr + h * 16, t);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -177,6 +192,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
 template <int CIN_CHUNKS, int COUT>
 static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
     ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
+    CB_CHECK(L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
     CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int ntiles = (int)((a.g.NP + TILE_M - 1) / TILE_M);
     int ctas_per_sm = L.total <= 110 * 1024 ? 2 : 1;
@@ -187,7 +203,7 @@ static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
 }
 
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
-    CB_CHECK(a.g.Wp + 1 <= GUARD && TILE_M + a.g.Wp + 1 <= GUARD, "conv_umma: guard too small for Wp=%d", a.g.Wp);
+    CB_CHECK(a.g.Wp + 1 <= GUARD && TILE_M + a.g.Wp + 2 <= GUARD, "conv_umma: guard too small for Wp=%d", a.g.Wp);
     if (a.cin_chunks == 1 && a.cout == 16) return launch_conv_umma_t<1, 16>(a, num_sms, st);
     if (a.cin_chunks == 2 && a.cout == 16) return launch_conv_umma_t<2, 16>(a, num_sms, st);
     if (a.cin_chunks == 2 && a.cout == 32) return launch_conv_umma_t<2, 32>(a, num_sms, st);
@@ -198,67 +214,70 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
 
 // =================================================================================================
 // wgrad on tcgen05:  dW[(ky,kx), ci, co] = sum_q X[q + d(ky,kx)][ci] * G[q][co],  db[co] = sum_q G[q][co].
-// GEMM view per 128-pixel block:  D_kx[m, co] += A_kx[m, q] * B[q, co]  with the reduction over pixels (K), where
+// GEMM view per 64-pixel block:  D_kx[m, co] += A_kx[m, q] * B[q, co]  with the reduction over pixels (K), where
 //   m = ky * C + ci  stacks the three filter ROWS (three bulk copies of the same planes shifted by one image row) and
 //   kx is a 16-byte shift of the start address.  A is MN-major (M = channels contiguous), B (= G) is MN-major too,
 //   so both operands are again the untouched chunk planes.  One extra M group of bf16 ones yields the bias gradient.
-// Three accumulators (kx) x Cout columns stay in TMEM across ALL pixel blocks of a CTA; one partial per CTA is
+// Precision: same 3-way split as above, the three G planes are stacked along N (they are adjacent in shared memory):
+//   D += X_hi * [G_hi|G_mid|G_lo],  D[:, :2C] += X_mid * [G_hi|G_mid],  D[:, :C] += X_lo * [G_hi].
+// Three accumulators (kx) x 3*Cout columns stay in TMEM across ALL pixel blocks of a CTA; one partial per CTA is
 // written at the end and reduced in a fixed order by k_wgrad_umma_reduce (deterministic).
-constexpr int WG_WINX = TILE_M + 2;       // pixels per shifted copy
+constexpr int WG_BLOCK = 64;              // pixels per pipeline stage (K block)
+constexpr int WG_STAGES = 3;
+constexpr int WG_WINX = WG_BLOCK + 2;     // pixels per shifted copy
 constexpr int WG_PLANE = WG_WINX * 16;    // bytes
 constexpr int WG_THREADS = 192;
 constexpr int WG_MROWS = 128;
 
 struct WgSmemLayout {
-    int stages;        // pipeline depth (2 for the widest shapes so the CTA fits in 227 KB)
     int groups;        // real M groups = 3 * cin_chunks
-    int a_bytes;       // one (hi or lo) A region: (groups + 1) planes (last = ones / zeros)
-    int b_bytes;       // one (hi or lo) B region
+    int xplanes;       // 3 (hi, mid, lo) or 1 (frames)
+    int a_bytes;       // one A region (one split plane): (groups + 1) copies (last = ones / zeros)
+    int b_chunk;       // bytes of one (plane, chunk) of G
+    int b_bytes;       // all of B: 3 planes x cout/8 chunks
     int stage_bytes, total;
-    bool x_lo;
 };
-__host__ __device__ inline WgSmemLayout wg_smem_layout(int cin_chunks, int cout, bool x_lo) {
+__host__ __device__ inline WgSmemLayout wg_smem_layout(int cin_chunks, int cout) {
     WgSmemLayout L;
     L.groups = 3 * cin_chunks;
+    L.xplanes = cin_chunks == 1 ? 1 : 3;
     L.a_bytes = (L.groups + 1) * WG_PLANE;
-    L.b_bytes = (cout / 8) * TILE_M * 16;
-    L.x_lo = x_lo;
-    L.stage_bytes = (x_lo ? 2 : 1) * L.a_bytes + 2 * L.b_bytes;
-    L.stages = L.stage_bytes > 60 * 1024 ? 2 : 3;
+    L.b_chunk = WG_BLOCK * 16;
+    L.b_bytes = 3 * (cout / 8) * L.b_chunk;
+    L.stage_bytes = L.xplanes * L.a_bytes + L.b_bytes;
     // the M = 128 instruction reads 16 groups from the A base: pad so the unused groups stay inside the allocation
-    L.total = 1024 + L.stages * L.stage_bytes + 16 * WG_PLANE;
+    L.total = 1024 + WG_STAGES * L.stage_bytes + 16 * WG_PLANE;
     return L;
 }
 
 template <int CIN_CHUNKS, int COUT>
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblocks, float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr bool X_LO = CIN_CHUNKS > 1;
-    const WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, X_LO);
-    const int WG_STAGES = L.stages;
+    constexpr int XPL = CIN_CHUNKS > 1 ? 3 : 1;
+    const WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + 3;
-    uint64_t* done = empty + 3;
+    uint64_t* empty = full + WG_STAGES;
+    uint64_t* done = empty + WG_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     uint8_t* stages = smem + 1024;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t TMEM_COLS = (3 * COUT <= 64) ? 64 : 128;
+    constexpr int ACC_COLS = 3 * COUT;
+    constexpr uint32_t TMEM_COLS = (3 * ACC_COLS <= 256) ? 256 : 512;
     constexpr int GROUPS = 3 * CIN_CHUNKS;
+    constexpr int NCOPY_A = XPL * GROUPS, NCOPY_B = 3 * (COUT / 8);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(done, 1);
         fence_barrier_init();
     }
-    // constant "ones" group (hi region) and "zeros" group (lo region) of every stage
-    for (int s = 0; s < WG_STAGES; ++s) {
-        uint32_t* one = reinterpret_cast<uint32_t*>(stages + s * L.stage_bytes + GROUPS * WG_PLANE);
-        for (int t = threadIdx.x; t < WG_PLANE / 4; t += WG_THREADS) one[t] = 0x3F803F80u;   // bf16 1.0 x2
-        if (X_LO) {
-            uint32_t* zero = reinterpret_cast<uint32_t*>(stages + s * L.stage_bytes + L.a_bytes + GROUPS * WG_PLANE);
-            for (int t = threadIdx.x; t < WG_PLANE / 4; t += WG_THREADS) zero[t] = 0u;
+    // constant "ones" group (hi region) and "zeros" groups (mid / lo regions) of every stage
+    for (int s = 0; s < WG_STAGES; ++s)
+        for (int pl = 0; pl < XPL; ++pl) {
+            uint32_t* g = reinterpret_cast<uint32_t*>(stages + s * L.stage_bytes + pl * L.a_bytes + GROUPS * WG_PLANE);
+            const uint32_t val = pl == 0 ? 0x3F803F80u : 0u;   // bf16 1.0 x2
+            for (int t = threadIdx.x; t < WG_PLANE / 4; t += WG_THREADS) g[t] = val;
         }
-    }
     fence_proxy_async();
     if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -268,32 +287,32 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     const int Wp = a.g.Wp;
 
     if (warp == 4) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)((X_LO ? 2 : 1) * GROUPS * WG_PLANE + 2 * L.b_bytes);
-            for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], tx);
-                uint8_t* dst = stages + s * L.stage_bytes;
-                const long long q0 = (long long)blk * TILE_M;
-                for (int ky = 0; ky < 3; ++ky)
-                    for (int j = 0; j < CIN_CHUNKS; ++j) {
-                        const long long q = q0 + (ky - 1) * Wp - 1;
-                        bulk_g2s(dst + (ky * CIN_CHUNKS + j) * WG_PLANE, a.x.hi + ((long long)j * a.x.plane_px + q) * 8, WG_PLANE, &full[s]);
-                        if (X_LO)
-                            bulk_g2s(dst + L.a_bytes + (ky * CIN_CHUNKS + j) * WG_PLANE,
-                                     a.x.lo + ((long long)j * a.x.plane_px + q) * 8, WG_PLANE, &full[s]);
-                    }
-                uint8_t* bdst = dst + (X_LO ? 2 : 1) * L.a_bytes;
-                for (int j = 0; j < COUT / 8; ++j) {
-                    bulk_g2s(bdst + j * TILE_M * 16, a.gy.hi + ((long long)j * a.gy.plane_px + q0) * 8, TILE_M * 16, &full[s]);
-                    bulk_g2s(bdst + L.b_bytes + j * TILE_M * 16, a.gy.lo + ((long long)j * a.gy.plane_px + q0) * 8, TILE_M * 16, &full[s]);
+        int s = 0; uint32_t ph = 0;
+        const uint32_t tx = (uint32_t)(NCOPY_A * WG_PLANE + NCOPY_B * L.b_chunk);
+        for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], tx);
+            uint8_t* dst = stages + s * L.stage_bytes;
+            const long long q0 = (long long)blk * WG_BLOCK;
+            for (int i = lane; i < NCOPY_A + NCOPY_B; i += 32) {
+                if (i < NCOPY_A) {
+                    const int pl = i / GROUPS, g = i % GROUPS, ky = g / CIN_CHUNKS, j = g % CIN_CHUNKS;
+                    const bf16* src = pl == 0 ? a.x.hi : (pl == 1 ? a.x.mid : a.x.lo);
+                    const long long q = q0 + (ky - 1) * Wp - 1;
+                    bulk_g2s(dst + pl * L.a_bytes + g * WG_PLANE, src + ((long long)j * a.x.plane_px + q) * 8, WG_PLANE, &full[s]);
+                } else {
+                    const int k = i - NCOPY_A, pl = k / (COUT / 8), j = k % (COUT / 8);
+                    const bf16* src = pl == 0 ? a.gy.hi : (pl == 1 ? a.gy.mid : a.gy.lo);
+                    bulk_g2s(dst + XPL * L.a_bytes + k * L.b_chunk, src + ((long long)j * a.gy.plane_px + q0) * 8, L.b_chunk, &full[s]);
                 }
-                if (++s == WG_STAGES) { s = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++s == WG_STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 5) {
-        constexpr uint32_t IDESC = make_idesc_bf16(WG_MROWS, COUT, 1, 1);
+        constexpr uint32_t IDESC3 = make_idesc_bf16(WG_MROWS, 3 * COUT, 1, 1);
+        constexpr uint32_t IDESC2 = make_idesc_bf16(WG_MROWS, 2 * COUT, 1, 1);
+        constexpr uint32_t IDESC1 = make_idesc_bf16(WG_MROWS, COUT, 1, 1);
         int s = 0; uint32_t ph = 0;
         uint32_t accum = 0;
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
@@ -301,23 +320,19 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_hi = smem_u32(stages + s * L.stage_bytes);
-                const uint32_t a_lo = a_hi + L.a_bytes;
-                const uint32_t b_hi = a_hi + (X_LO ? 2 : 1) * L.a_bytes;
-                const uint32_t b_lo = b_hi + L.b_bytes;
+                const uint32_t b_base = a_hi + XPL * L.a_bytes;
 #pragma unroll 1
-                for (int ks = 0; ks < TILE_M / 16; ++ks) {
-                    // K step = 16 pixels = 2 core-matrix groups of 8 pixels (128 bytes each)
-                    const uint64_t dbh = make_desc(b_hi + ks * 256, 128, TILE_M * 16);
-                    const uint64_t dbl = make_desc(b_lo + ks * 256, 128, TILE_M * 16);
+                for (int ks = 0; ks < WG_BLOCK / 16; ++ks) {
+                    // K step = 16 pixels = 2 core-matrix groups of 8 pixels (128 bytes each); N groups 1024 bytes apart
+                    const uint64_t db = make_desc(b_base + ks * 256, 128, L.b_chunk);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        const uint32_t d_tmem = tmem_base + kx * COUT;
-                        const uint64_t dah = make_desc(a_hi + ks * 256 + kx * 16, 128, WG_PLANE);
-                        mma_bf16(d_tmem, dah, dbh, IDESC, accum);
-                        mma_bf16(d_tmem, dah, dbl, IDESC, 1);
-                        if (X_LO) {
-                            const uint64_t dal = make_desc(a_lo + ks * 256 + kx * 16, 128, WG_PLANE);
-                            mma_bf16(d_tmem, dal, dbh, IDESC, 1);
+                        const uint32_t d_tmem = tmem_base + kx * ACC_COLS;
+                        const uint32_t ao = a_hi + ks * 256 + kx * 16;
+                        mma_bf16(d_tmem, make_desc(ao, 128, WG_PLANE), db, IDESC3, accum);
+                        if (XPL > 1) {
+                            mma_bf16(d_tmem, make_desc(ao + L.a_bytes, 128, WG_PLANE), db, IDESC2, 1);
+                            mma_bf16(d_tmem, make_desc(ao + 2 * L.a_bytes, 128, WG_PLANE), db, IDESC1, 1);
                         }
                     }
                     accum = 1;
@@ -338,9 +353,18 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
         float* out = partial + (long long)blockIdx.x * (3 * MROWS_USED * COUT);
         for (int kx = 0; kx < 3; ++kx) {
             float v[COUT];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + kx * COUT;
-            tmem_ld16(taddr, v);
-            if (COUT == 32) tmem_ld16(taddr + 16, v + 16);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + kx * ACC_COLS;
+            float t[16];
+#pragma unroll
+            for (int h = 0; h < COUT / 16; ++h) {
+                tmem_ld16(taddr + 2 * COUT + h * 16, v + h * 16);
+                tmem_ld16(taddr + COUT + h * 16, t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                tmem_ld16(taddr + h * 16, t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+            }
             if (m < MROWS_USED) {
 #pragma unroll
                 for (int c = 0; c < COUT; c += 4)
@@ -354,7 +378,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// dW[(ky*3+kx)][ci][co] = sum_cta partial[cta][kx][ky*Cpad + ci][co];  db[co] = sum_cta partial[cta][1][3*Cpad][co]
+// dW[(ky*3+kx)][ci][co] = scale * sum_cta partial[cta][kx][ky*Cpad + ci][co];  db[co] = sum_cta partial[cta][1][3*Cpad][co]
 __global__ void k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas, int cpad, int cin_real, int cout,
                                     float scale, float* __restrict__ dw, float* __restrict__ db) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -376,9 +400,10 @@ __global__ void k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas
 
 template <int CIN_CHUNKS, int COUT>
 static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st) {
-    WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, CIN_CHUNKS > 1);
+    WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT);
+    CB_CHECK(L.total <= 227 * 1024, "wgrad_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
     CB_CUDA(cudaFuncSetAttribute(k_wgrad_umma<CIN_CHUNKS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int nblocks = (int)((a.g.NP + TILE_M - 1) / TILE_M);
+    int nblocks = (int)((a.g.NP + WG_BLOCK - 1) / WG_BLOCK);
     int grid = nblocks < num_sms ? nblocks : num_sms;
     k_wgrad_umma<CIN_CHUNKS, COUT><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);
     CB_LAUNCH_CHECK();

@@ -80,11 +80,11 @@ static std::vector<Leaf> build_leaves(int A) {
 struct ConvLayer {
     int cin, cout;          // real channels
     long long off_b, off_w; // offsets in the flat parameter vector
-    bf16 *fwd_hi, *fwd_lo, *dg_hi, *dg_lo;
+    bf16 *fwd, *dg;         // packed [hi|mid|lo] weight images (forward / dgrad)
 };
 
 struct Act {                // one activation / gradient tensor
-    Planes pl = {nullptr, nullptr, 0};
+    Planes pl = {nullptr, nullptr, nullptr, 0};
     float* s = nullptr;
     int C = 0, H = 0;
 };
@@ -93,6 +93,7 @@ struct Stage {
     Act x;                  // input planes of the sequence conv (stage 0: frames, hi only; else previous stage output)
     Act y;                  // conv output (fp32 stream, pre-pool)
     Act p;                  // pooled: stream + relu planes
+    uint8_t* amax = nullptr; // arg-max slots of the pool (learner contexts)
     Act a0, b0, a1, out;    // residual blocks (see trunk_forward)
     Act gA, gB, gC, gBin;   // gradients (learner contexts)
 };
@@ -156,6 +157,8 @@ static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool planes, bool lo, bool
         a.pl.hi = (bf16*)p + (long long)GUARD * 8;
         if (lo) {
             if (dev_alloc(c, &p, bytes)) return -1;
+            a.pl.mid = (bf16*)p + (long long)GUARD * 8;
+            if (dev_alloc(c, &p, bytes)) return -1;
             a.pl.lo = (bf16*)p + (long long)GUARD * 8;
         }
     }
@@ -186,11 +189,11 @@ struct ProfScope {
         c->prof_recs.push_back(r);
     }
 };
-static double planes_bytes(const ConvGeom& g, int chunks, bool lo) { return (double)g.NP * chunks * 8 * (lo ? 4 : 2); }
+static double planes_bytes(const ConvGeom& g, int chunks, bool lo) { return (double)g.NP * chunks * 8 * (lo ? 6 : 2); }
 static double stream_bytes(const ConvGeom& g, int chunks) { return (double)g.NP * chunks * 8 * 4; }
 
 static int refresh_weights(cb_ctx* c, cudaStream_t st) {
-    ProfScope ps(c, "pack_weights", 0, 1089232.0 * (4 + 8), st);
+    ProfScope ps(c, "pack_weights", 0, 1089232.0 * (4 + 12), st);
     return launch_pack_conv(c->pack_dev, 15, st);
 }
 
@@ -205,10 +208,10 @@ static ConvArgs conv_args(cb_ctx* c, int layer, const ConvGeom& g, const Act& in
     a.transpose = transpose ? 1 : 0;
     if (!transpose) {
         a.cin_real = L.cin; a.cin_chunks = (L.cin + 7) / 8; a.cout = L.cout;
-        a.wp_hi = L.fwd_hi; a.wp_lo = L.fwd_lo;
+        a.wp = L.fwd;
     } else {
         a.cin_real = L.cout; a.cin_chunks = L.cout / 8; a.cout = L.cin;
-        a.wp_hi = L.dg_hi; a.wp_lo = L.dg_lo;
+        a.wp = L.dg;
     }
     a.ep.acc_scale = 1.f;
     return a;
@@ -266,7 +269,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
         {
             ProfScope ps(c, "pool_fwd@" + std::to_string(kStageHin[s]), 0,
                          stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(go, kStageC[s] / 8, true), st);
-            if (launch_pool_fwd(S.y.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.p.s, S.p.pl, st)) return -1;
+            if (launch_pool_fwd(S.y.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.p.s, S.p.pl, S.amax, st)) return -1;
         }
         {   // ResidualBlock 0: x + Conv(relu(Conv(relu(x))))                    (cleanba_ppo.py:153-159)
             ConvArgs a = conv_args(c, base + 1, go, S.p, false);
@@ -343,8 +346,8 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         // ---- max-pool backward, then the sequence conv
         {
             ProfScope ps(c, "pool_bwd@" + std::to_string(kStageHin[s]), 0,
-                         stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(gi, kStageC[s] / 8, true), st);
-            if (launch_pool_bwd(S.y.s, S.gA.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.gBin.pl, st)) return -1;
+                         (double)go.NP * kStageC[s] * 5 + planes_bytes(gi, kStageC[s] / 8, true), st);
+            if (launch_pool_bwd(S.amax, S.gA.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.gBin.pl, st)) return -1;
         }
         if (run_wgrad(c, base + 0, gi, S.x, S.gBin, grads, st)) return -1;
         if (s > 0) {
@@ -435,19 +438,15 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
                 L.off_w = c->leaves[s * 10 + k * 2 + 1].offset;
                 long long ef = packed_conv_elems((L.cin + 7) / 8, L.cout);
                 if (dev_alloc(c, &p, ef * sizeof(bf16))) { fail = true; break; }
-                L.fwd_hi = (bf16*)p;
-                if (dev_alloc(c, &p, ef * sizeof(bf16))) { fail = true; break; }
-                L.fwd_lo = (bf16*)p;
-                L.dg_hi = L.dg_lo = nullptr;
+                L.fwd = (bf16*)p;
+                L.dg = nullptr;
                 if (li != 0) {
                     long long ed = packed_conv_elems(L.cout / 8, L.cin);
                     if (dev_alloc(c, &p, ed * sizeof(bf16))) { fail = true; break; }
-                    L.dg_hi = (bf16*)p;
-                    if (dev_alloc(c, &p, ed * sizeof(bf16))) { fail = true; break; }
-                    L.dg_lo = (bf16*)p;
+                    L.dg = (bf16*)p;
                 }
                 pl[li].w = c->params + L.off_w; pl[li].cin = L.cin; pl[li].cout = L.cout;
-                pl[li].fwd_hi = L.fwd_hi; pl[li].fwd_lo = L.fwd_lo; pl[li].dg_hi = L.dg_hi; pl[li].dg_lo = L.dg_lo;
+                pl[li].fwd = L.fwd; pl[li].dg = L.dg;
             }
         if (fail) break;
         if (dev_alloc(c, &p, 15 * sizeof(PackLayer))) break;
@@ -472,6 +471,9 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             fail |= alloc_act(c, S.out, C, Ho, true, true, false) != 0;
             if (s < 2 && !fail) c->st[s + 1].x = S.out;
             if (cfg->train) {
+                void* ap;
+                if (dev_alloc(c, &ap, (size_t)cfg->max_batch * (Ho + 2) * (Ho + 2) * C)) { fail = true; break; }
+                S.amax = (uint8_t*)ap;
                 fail |= alloc_act(c, S.gA, C, Ho, true, true, true) != 0;
                 fail |= alloc_act(c, S.gB, C, Ho, true, true, false) != 0;
                 fail |= alloc_act(c, S.gC, C, Ho, true, true, true) != 0;
@@ -783,15 +785,19 @@ long long cb_debug_tensor(cb_ctx* c, const char* name, float* host_out, long lon
     if (want_stream) {
         CB_CUDA(cudaMemcpy(tmp.data(), a->s, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
-        std::vector<uint16_t> h((size_t)NP * 8), l((size_t)NP * 8);
+        std::vector<uint16_t> h((size_t)NP * 8);
         for (int j = 0; j < chunks; ++j) {
-            CB_CUDA(cudaMemcpy(h.data(), a->pl.hi + (long long)j * a->pl.plane_px * 8, h.size() * 2, cudaMemcpyDeviceToHost));
-            if (a->pl.lo) CB_CUDA(cudaMemcpy(l.data(), a->pl.lo + (long long)j * a->pl.plane_px * 8, l.size() * 2, cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < h.size(); ++i) {
-                uint32_t uh = (uint32_t)h[i] << 16, ul = a->pl.lo ? (uint32_t)l[i] << 16 : 0u;
-                float fh, fl;
-                memcpy(&fh, &uh, 4); memcpy(&fl, &ul, 4);
-                tmp[(size_t)j * NP * 8 + i] = fh + fl;
+            const bf16* planes[3] = {a->pl.hi, a->pl.mid, a->pl.lo};
+            for (size_t i = 0; i < h.size(); ++i) tmp[(size_t)j * NP * 8 + i] = 0.f;
+            for (int pi = 0; pi < 3; ++pi) {
+                if (!planes[pi]) continue;
+                CB_CUDA(cudaMemcpy(h.data(), planes[pi] + (long long)j * a->pl.plane_px * 8, h.size() * 2, cudaMemcpyDeviceToHost));
+                for (size_t i = 0; i < h.size(); ++i) {
+                    uint32_t u = (uint32_t)h[i] << 16;
+                    float f;
+                    memcpy(&f, &u, 4);
+                    tmp[(size_t)j * NP * 8 + i] += f;
+                }
             }
         }
     }

@@ -30,12 +30,7 @@ __device__ __forceinline__ void tile_fma(const float (*As)[LDS_], const float (*
 
 // load 8 channels (one chunk) of sample b, feature pixel `pix` as fp32 (hi + lo)
 __device__ __forceinline__ void load_feat8(const Planes& x, int b, int pix, int chunk, float* f) {
-    long long off = ((long long)chunk * x.plane_px + feat_pixel(b, pix)) * 8;
-    float l[8];
-    unpack8(*reinterpret_cast<const uint4*>(x.hi + off), f);
-    unpack8(*reinterpret_cast<const uint4*>(x.lo + off), l);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] += l[e];
+    load_planes8(x, ((long long)chunk * x.plane_px + feat_pixel(b, pix)) * 8, f);
 }
 
 // ---------------- forward: part[z][b][j] = sum_{k in split z} x[b][k] W[k][j]
@@ -191,15 +186,16 @@ __global__ void __launch_bounds__(256) k_dense_bwd_x(DenseArgs a, const float* _
         uint2 m = *reinterpret_cast<const uint2*>(a.x.hi + poff);
         float mf[4] = {bf16lo_to_f(m.x), bf16hi_to_f(m.x), bf16lo_to_f(m.y), bf16hi_to_f(m.y)};
         float v[4];
-        bf16 h[4], l[4];
+        bf16 h[4], md[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             v[j] = mf[j] > 0.f ? acc[i][j] : 0.f;
-            split_bf16(v[j], h[j], l[j]);
+            split_bf16(v[j], h[j], md[j], l[j]);
         }
         *reinterpret_cast<float4*>(out_s + ((long long)chunk * NP + q) * 8 + e0) = make_float4(v[0], v[1], v[2], v[3]);
         long long ooff = ((long long)chunk * out.plane_px + q) * 8 + e0;
         *reinterpret_cast<uint2*>(out.hi + ooff) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        *reinterpret_cast<uint2*>(out.mid + ooff) = make_uint2(pack_bf16x2(md[0], md[1]), pack_bf16x2(md[2], md[3]));
         *reinterpret_cast<uint2*>(out.lo + ooff) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
     }
 }
@@ -211,6 +207,7 @@ int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, float* out_s, Plan
     for (int c = 0; c < FC / 8; ++c) {
         size_t npr = (size_t)((NP + 127) / 128 * 128);   // zero up to the 128-pixel tile boundary (wgrad reads it)
         CB_CUDA(cudaMemsetAsync(out.hi + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
+        CB_CUDA(cudaMemsetAsync(out.mid + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
         CB_CUDA(cudaMemsetAsync(out.lo + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
     }
     dim3 grid((a.n + TM - 1) / TM, (DK + TN - 1) / TN);

@@ -19,8 +19,8 @@ struct WgradArgs {
 int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
-                    cudaStream_t st);
-int launch_pool_bwd(const float* y, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
+                    uint8_t* amax, cudaStream_t st);
+int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
                     cudaStream_t st);
 int launch_wgrad_simt(const WgradArgs& a, float* partial, int max_blocks, cudaStream_t st);
 
@@ -111,8 +111,8 @@ int launch_optimizer(const OptArgs& a, cudaStream_t st);
 struct PackLayer {
     const float* w;              // HWIO master
     int cin, cout;               // real channel counts
-    bf16 *fwd_hi, *fwd_lo;       // packed forward image
-    bf16 *dg_hi, *dg_lo;         // packed dgrad image (null for the first conv)
+    bf16* fwd;                   // packed forward image ([hi|mid|lo] stacked along N)
+    bf16* dg;                    // packed dgrad image (null for the first conv)
 };
 int launch_pack_conv(const PackLayer* layers_dev, int nlayers, cudaStream_t st);
 long long packed_conv_elems(int cin_chunks, int cout);

@@ -70,14 +70,8 @@ __global__ void __launch_bounds__(128) k_conv_simt(ConvArgs a) {
         for (int tap = 0; tap < 9; ++tap) {
             int d = (tap / 3 - 1) * a.g.Wp + (tap % 3 - 1);
             for (int jc = 0; jc < a.cin_chunks; ++jc) {
-                long long off = ((long long)jc * a.in.plane_px + q + d) * 8;
-                float x[8], xl[8];
-                unpack8(*reinterpret_cast<const uint4*>(a.in.hi + off), x);
-                if (a.in.lo) {
-                    unpack8(*reinterpret_cast<const uint4*>(a.in.lo + off), xl);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] += xl[e];
-                }
+                float x[8];
+                load_planes8(a.in, ((long long)jc * a.in.plane_px + q + d) * 8, x);
                 int nci = min(8, cin - jc * 8);
                 for (int c = 0; c < nci; ++c) {
                     const float* wr = sw + ((tap * cin) + jc * 8 + c) * 8;
@@ -100,9 +94,11 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------
 // max_pool 3x3 stride 2 SAME, -inf padding, pad_lo = 0 (84->42, 42->21) or 1 (21->11)  (cleanba_ppo.py:168)
-// in : fp32 stream [C/8][n*Pin][8] (conv output)      out: fp32 stream + relu'd bf16 planes on the pooled grid
+// in : fp32 stream [C/8][n*Pin][8] (conv output)      out: fp32 stream + relu'd bf16 planes on the pooled grid, and
+// (training) the arg-max window slot 0..8 of every pooled element as one byte, first maximum in row-major window
+// order (XLA select_and_scatter with a `ge` select), which is all the backward pass needs.
 __global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks,
-                           float* __restrict__ out_s, Planes out_relu) {
+                           float* __restrict__ out_s, Planes out_relu, uint8_t* __restrict__ amax) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= go.NP * chunks) return;
     int jc = (int)(t / go.NP);
@@ -111,8 +107,9 @@ __global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom g
     int r = (int)(q % go.P);
     int yp = r / go.Wp, xp = r % go.Wp;
     float v[8];
+    int am[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    for (int e = 0; e < 8; ++e) { v[e] = 0.f; am[e] = 15; }
     if (yp >= 1 && yp <= go.H && xp >= 1 && xp <= go.W) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = -INFINITY;
@@ -126,37 +123,40 @@ __global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom g
                 long long qi = (long long)img * gi.P + (long long)(y + 1) * gi.Wp + (x + 1);
                 const float4* p = reinterpret_cast<const float4*>(in + ((long long)jc * gi.NP + qi) * 8);
                 float4 a = p[0], b = p[1];
-                v[0] = fmaxf(v[0], a.x); v[1] = fmaxf(v[1], a.y); v[2] = fmaxf(v[2], a.z); v[3] = fmaxf(v[3], a.w);
-                v[4] = fmaxf(v[4], b.x); v[5] = fmaxf(v[5], b.y); v[6] = fmaxf(v[6], b.z); v[7] = fmaxf(v[7], b.w);
+                float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (o[e] > v[e]) { v[e] = o[e]; am[e] = dy * 3 + dx; }
             }
         }
     }
     float4* o = reinterpret_cast<float4*>(out_s + ((long long)jc * go.NP + q) * 8);
     o[0] = make_float4(v[0], v[1], v[2], v[3]);
     o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    bf16 h[8], l[8];
+    float rl[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split_bf16(fmaxf(v[e], 0.f), h[e], l[e]);
-    long long off = ((long long)jc * out_relu.plane_px + q) * 8;
-    *reinterpret_cast<uint4*>(out_relu.hi + off) =
-        make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    *reinterpret_cast<uint4*>(out_relu.lo + off) =
-        make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
+    store_planes8(out_relu, ((long long)jc * out_relu.plane_px + q) * 8, rl);
+    if (amax) {
+        uint2 pk;
+        pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+        pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+        *reinterpret_cast<uint2*>(amax + ((long long)jc * go.NP + q) * 8) = pk;
+    }
 }
 
 int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
-                    cudaStream_t st) {
+                    uint8_t* amax, cudaStream_t st) {
     long long total = go.NP * chunks;
-    k_pool_fwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, gi, go, pad_lo, chunks, out_s, out_relu);
+    k_pool_fwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, gi, go, pad_lo, chunks, out_s, out_relu, amax);
     CB_LAUNCH_CHECK();
     return 0;
 }
 
-// Backward of the pool in gather form (deterministic): every input pixel sums the gradients of the (<= 4)
-// windows whose arg-max it is; ties go to the first element in row-major window order (XLA select_and_scatter
-// with a `ge` select).   y: forward conv output stream;  dpool: gradient stream on the pooled grid;
-// out: gradient planes (hi/lo) on the input grid.
-__global__ void k_pool_bwd(const float* __restrict__ y, const float* __restrict__ dpool, ConvGeom gi, ConvGeom go,
+// Backward of the pool in gather form (deterministic, no atomics): every input pixel visits the (<= 4) windows that
+// contain it and takes the window's gradient iff the stored arg-max slot is its own position in that window.
+//   amax: bytes from the forward pass;  dpool: gradient stream on the pooled grid;  out: gradient planes on the input grid
+__global__ void k_pool_bwd(const uint8_t* __restrict__ amax, const float* __restrict__ dpool, ConvGeom gi, ConvGeom go,
                            int pad_lo, int chunks, Planes out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long NPr = (gi.NP + 127) / 128 * 128;   // planes are zero-filled up to the 128-pixel tile boundary
@@ -171,60 +171,30 @@ __global__ void k_pool_bwd(const float* __restrict__ y, const float* __restrict_
     for (int e = 0; e < 8; ++e) g[e] = 0.f;
     if (q < gi.NP && yp >= 1 && yp <= gi.H && xp >= 1 && xp <= gi.W) {
         int r = yp - 1, c = xp - 1;
-        const float* ybase = y + (long long)jc * gi.NP * 8;
-        float self[8];
-        {
-            const float4* p = reinterpret_cast<const float4*>(ybase + q * 8);
-            float4 a = p[0], b = p[1];
-            self[0] = a.x; self[1] = a.y; self[2] = a.z; self[3] = a.w; self[4] = b.x; self[5] = b.y; self[6] = b.z; self[7] = b.w;
-        }
-        int i_lo = max(0, (r + pad_lo - 1) / 2), i_hi = min(go.H - 1, (r + pad_lo) / 2);   // ceil((r+pad-2)/2)
+        int i_lo = max(0, (r + pad_lo - 1) / 2), i_hi = min(go.H - 1, (r + pad_lo) / 2);
         int j_lo = max(0, (c + pad_lo - 1) / 2), j_hi = min(go.W - 1, (c + pad_lo) / 2);
         for (int i = i_lo; i <= i_hi; ++i)
             for (int j = j_lo; j <= j_hi; ++j) {
-                // is (r,c) the first maximum of window (i,j)?  earlier elements must be strictly smaller,
-                // later elements must be smaller or equal.
-                bool win[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) win[e] = true;
-                for (int dy = 0; dy < 3; ++dy) {
-                    int yy = 2 * i - pad_lo + dy;
-                    if (yy < 0 || yy >= gi.H) continue;
-                    for (int dx = 0; dx < 3; ++dx) {
-                        int xx = 2 * j - pad_lo + dx;
-                        if (xx < 0 || xx >= gi.W) continue;
-                        if (yy == r && xx == c) continue;
-                        bool earlier = (yy < r) || (yy == r && xx < c);
-                        long long qi = (long long)img * gi.P + (long long)(yy + 1) * gi.Wp + (xx + 1);
-                        const float4* p = reinterpret_cast<const float4*>(ybase + qi * 8);
-                        float4 a = p[0], b = p[1];
-                        float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) win[e] = win[e] && (earlier ? (o[e] < self[e]) : (o[e] <= self[e]));
-                    }
-                }
+                const int slot = (r - (2 * i - pad_lo)) * 3 + (c - (2 * j - pad_lo));   // my position inside window (i,j)
                 long long qo = (long long)img * go.P + (long long)(i + 1) * go.Wp + (j + 1);
+                uint2 pk = *reinterpret_cast<const uint2*>(amax + ((long long)jc * go.NP + qo) * 8);
                 const float4* p = reinterpret_cast<const float4*>(dpool + ((long long)jc * go.NP + qo) * 8);
                 float4 a = p[0], b = p[1];
                 float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] += win[e] ? d[e] : 0.f;
+                for (int e = 0; e < 8; ++e) {
+                    int am = ((e < 4 ? pk.x : pk.y) >> (8 * (e & 3))) & 0xff;
+                    g[e] += (am == slot) ? d[e] : 0.f;
+                }
             }
     }
-    bf16 h[8], l[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) split_bf16(g[e], h[e], l[e]);
-    long long off = ((long long)jc * out.plane_px + q) * 8;
-    *reinterpret_cast<uint4*>(out.hi + off) =
-        make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    *reinterpret_cast<uint4*>(out.lo + off) =
-        make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    store_planes8(out, ((long long)jc * out.plane_px + q) * 8, g);
 }
 
-int launch_pool_bwd(const float* y, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
+int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
                     cudaStream_t st) {
     long long total = (gi.NP + 127) / 128 * 128 * chunks;
-    k_pool_bwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, dpool, gi, go, pad_lo, chunks, out);
+    k_pool_bwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(amax, dpool, gi, go, pad_lo, chunks, out);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -258,14 +228,8 @@ __global__ void __launch_bounds__(256) k_wgrad_simt(WgradArgs a, float* __restri
         for (int t = threadIdx.x; t < win * a.cin_chunks; t += 256) {
             int jc = t / win, p = t % win;
             long long q = q0 - Wp - 1 + p;  // guard zones make this in-bounds
-            long long off = ((long long)jc * a.x.plane_px + q) * 8;
-            float x[8], xl[8];
-            unpack8(*reinterpret_cast<const uint4*>(a.x.hi + off), x);
-            if (a.x.lo) {
-                unpack8(*reinterpret_cast<const uint4*>(a.x.lo + off), xl);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] += xl[e];
-            }
+            float x[8];
+            load_planes8(a.x, ((long long)jc * a.x.plane_px + q) * 8, x);
             for (int e = 0; e < 8; ++e) {
                 int c = jc * 8 + e;
                 if (c < cin) sx[p * cin + c] = x[e];
@@ -274,13 +238,9 @@ __global__ void __launch_bounds__(256) k_wgrad_simt(WgradArgs a, float* __restri
         for (int t = threadIdx.x; t < WG_TP * (cout / 8); t += 256) {
             int jc = t / WG_TP, p = t % WG_TP;
             long long q = q0 + p;
-            float gg[8], gl[8];
+            float gg[8];
             if (q < a.g.NP) {
-                long long off = ((long long)jc * a.gy.plane_px + q) * 8;
-                unpack8(*reinterpret_cast<const uint4*>(a.gy.hi + off), gg);
-                unpack8(*reinterpret_cast<const uint4*>(a.gy.lo + off), gl);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) gg[e] += gl[e];
+                load_planes8(a.gy, ((long long)jc * a.gy.plane_px + q) * 8, gg);
             } else {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) gg[e] = 0.f;

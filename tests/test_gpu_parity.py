@@ -142,8 +142,8 @@ def test_forward_intermediates(agent, params, backend):
     errs["logits"] = _relerr(logits.cpu().numpy(), ol.numpy())
     errs["value"] = _relerr(value.cpu().numpy(), ov.numpy())
     _diag(f"forward_backend{backend}", **errs)
-    bad = {k: v for k, v in errs.items() if not v < 1e-4}
-    assert not bad, f"forward mismatch (rel-to-max error, bar 1e-4): {bad}"
+    bad = {k: v for k, v in errs.items() if not v < 2e-5}
+    assert not bad, f"forward mismatch (rel-to-max error, bar 2e-5): {bad}"
     ctx.close()
 
 
@@ -248,12 +248,13 @@ def test_ppo_grad_matches_autograd(agent, params, backend, mb):
           worst_leaf=max(lw, key=lw.get), worst=max(lw.values()))
     assert max(serr) < 1e-4, (st, ostats)                     # losses: 1e-4 relative
     assert abs(st[4] - ostats[4]) < 1e-5
-    # Gradient bar.  The forward matches the fp32 oracle to ~1e-5 (activations are kept as bf16 hi+lo pairs, 16-17
-    # significant bits).  max-pool arg-max and relu gates are discontinuous: a 1e-5 forward difference flips a few of
-    # them, which moves the gradient by ~2e-3 in norm (reproduced on the CPU oracle alone by perturbing the pool
-    # inputs by 1e-5, see DESIGN.md "precision").  Losses/values (the stated 1e-4 bar) are unaffected.
-    assert tot < 5e-3, f"gradient relative error {tot}; per-leaf {lw}"
-    assert max(lw.values()) < 2e-2, lw
+    # Gradient bar.  relu / max-pool gates are discontinuous, so gradient parity needs the forward to agree to ~1e-6:
+    # activations are carried as exact 3-way bf16 splits (24 significant bits) for this reason (DESIGN.md "precision").
+    # Typical agreement with the fp64 autograd oracle is 2e-6 .. 1.5e-5 (see gpurun_out/parity_diag.json); a single gate
+    # whose pre-activation sits within 1e-6 of zero flips once in a while -- it does so between the fp32 and the fp64
+    # CPU oracle too -- and moves the gradient by a few 1e-4, hence the looser assertion.
+    assert tot < 1e-3, f"gradient relative error {tot}; per-leaf {lw}"
+    assert max(lw.values()) < 1e-2, lw
     # determinism: a second identical call gives bit-identical gradients
     g2 = torch.zeros_like(grads)
     ctx.ppo_grad(tt(obs), tt(idx), mb, tt(actions), tt(oldlp), tt(adv), tt(ret), 0.1, 0.01, 0.5, g2, stats)
@@ -292,7 +293,7 @@ def test_impala_grad_matches_autograd(agent, params, backend):
     serr = [abs(st[i] - ostats[i]) / max(abs(ostats[i]), 1e-6) for i in range(4)]
     _diag(f"impala_grad_backend{backend}", total=tot, stats_relerr=serr, worst_leaf=max(lw, key=lw.get), worst=max(lw.values()))
     assert max(serr) < 1e-4, (st, ostats)
-    assert tot < 5e-3, f"gradient relative error {tot}; per-leaf {lw}"   # see test_ppo_grad_matches_autograd
+    assert tot < 1e-3, f"gradient relative error {tot}; per-leaf {lw}"   # see test_ppo_grad_matches_autograd
     ctx.close()
 
 
@@ -348,8 +349,9 @@ def test_ppo_update_end_to_end(agent, params, backend):
     serr = [abs(float(stats[i]) - ostats[i]) / max(abs(ostats[i]), 1e-6) for i in range(4)]
     perr = _relerr(L.ctx.get_params().cpu().numpy(), ol.params)
     _diag(f"ppo_update_backend{backend}", stats_relerr=serr, params_relerr=perr, kl=[float(stats[4]), float(ostats[4])])
-    # Multi-step bar.  Adam's normalised update g/(sqrt(v)+eps) turns the ~1e-3 gradient differences caused by relu /
-    # max-pool gate flips (see test_ppo_grad_matches_autograd) into O(lr) parameter differences, so the scalars averaged
-    # over the 8 optimizer steps agree to ~1e-2, not 1e-4, until the forward is carried at full fp32 precision.
-    assert max(serr) < 5e-2, (stats, ostats)
+    # Eight chained optimizer steps on 16-sample minibatches are chaotic at the 1e-3 level: the CPU oracle run twice
+    # (multi-threaded reductions) differs from itself by 2e-4 in these scalars, and perturbing its gradients by 1e-5
+    # relative moves them by 7e-4 .. 1.5e-3 (a relu / max-pool gate flips in a later minibatch).  Single-step parity at
+    # 1e-4 / 1e-5 is asserted by the gradient and optimizer tests above; here the bar is the oracle's own sensitivity.
+    assert max(serr) < 1e-2, (stats, ostats)
     assert perr < 1e-2
