@@ -1,0 +1,238 @@
+"""Product backend of the Sebulba plumbing (cleanba_b200.sebulba): every hot-path call goes through the C ABI of
+libcleanba_b200 on CUDA devices.  There is no CPU path here; constructing it without a GPU raises.
+
+  actor -> learner payload (prepare_data + device_put_sharded, cleanba_ppo.py:276-278,357-363): each step's observation is
+  copied from pinned host memory straight into row t of a pre-allocated [T,N,...] device buffer (no list / stack), the
+  env axis is split into L contiguous slices and each slice is copied to its learner GPU on the actor's side stream
+  (cudaMemcpyAsync / peer copy); an event travels with the payload.
+"""
+import threading
+import time
+from typing import List
+
+import numpy as np
+import torch
+
+from . import agent as ag
+from .learner import ImpalaHyper, ImpalaLearner, PPOHyper, PPOLearner
+from .params import init_params
+from .prng import first_key as _first_key
+
+
+class _Storage:
+    def __init__(self, actor, rows):
+        d, N, A = actor.dev, actor.N, actor.ctx.num_actions
+        self.rows = rows
+        self.obs = torch.empty(rows, N, 4, 84, 84, dtype=torch.uint8, device=d)
+        self.actions = torch.empty(rows, N, dtype=torch.int32, device=d)
+        if actor.impala:
+            self.logitss = torch.empty(rows, N, A, dtype=torch.float32, device=d)
+        else:
+            self.logprobs = torch.empty(rows, N, dtype=torch.float32, device=d)
+            self.values = torch.empty(rows, N, dtype=torch.float32, device=d)
+        self.host = {k: np.zeros((rows, N), dt) for k, dt in (("dones", bool), ("rewards", np.float32), ("firststeps", bool),
+                                                              ("truncations", bool), ("terminations", np.int32), ("env_ids", np.int32))}
+        self.impala = actor.impala
+
+    def put_host(self, t, **fields):
+        for k, v in fields.items():
+            self.host[k][t] = v
+
+    def take_carry(self):
+        last = self.rows - 1
+        c = {"obs": self.obs[last], "actions": self.actions[last], "logitss": self.logitss[last]}
+        c["host"] = {k: v[last].copy() for k, v in self.host.items()}
+        return c
+
+    def put_carry(self, c):
+        self.obs[0].copy_(c["obs"]); self.actions[0].copy_(c["actions"]); self.logitss[0].copy_(c["logitss"])
+        for k, v in c["host"].items():
+            self.host[k][0] = v
+
+
+class CudaActor:
+    def __init__(self, device_id, N, args, key):
+        self.dev = torch.device("cuda", device_id)
+        self.N = N
+        self.impala = args.algo == "impala"
+        self.ctx = ag.Context(self.dev, max_batch=N, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO)
+        self.stream = torch.cuda.Stream(self.dev)
+        self.key = ag.key_tensor(key, self.dev)
+        self.act_host = torch.empty(N, dtype=torch.int32).pin_memory()
+        self.staging = torch.empty(N, 4, 84, 84, dtype=torch.uint8).pin_memory()
+
+    def new_storage(self, rows):
+        with torch.cuda.device(self.dev):
+            return _Storage(self, rows)
+
+    def set_params(self, handle):
+        snapshot, event = handle
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            self.stream.wait_event(event)
+            self.ctx.set_params(snapshot if snapshot.device == self.dev else snapshot.to(self.dev, non_blocking=True))
+            self.stream.synchronize()      # the reference blocks on the new params too (cleanba_ppo.py:294-300)
+
+    def step(self, storage, t, obs_host):
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            if isinstance(obs_host, np.ndarray):
+                self.staging.numpy()[...] = obs_host
+                obs_host = self.staging
+            slot = storage.obs[t]
+            slot.copy_(obs_host, non_blocking=True)
+            if self.impala:
+                self.ctx.actor_step(slot, self.key, out=(storage.actions[t], None, None, storage.logitss[t]))
+            else:
+                self.ctx.actor_step(slot, self.key, out=(storage.actions[t], storage.logprobs[t], storage.values[t], None))
+            t0 = time.time()
+            self.act_host.copy_(storage.actions[t], non_blocking=True)
+            self.stream.synchronize()
+            return self.act_host.numpy().copy(), time.time() - t0
+
+    def shard_to_learners(self, storage, next_obs, next_done, L, learner_devices=None):
+        N = self.N
+        shards = []
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            for l in range(L):
+                c = slice(l * N // L, (l + 1) * N // L)
+                ld = self.learner_devices[l]
+                sh = {"obs": storage.obs[:, c].to(ld, non_blocking=True) if (L > 1 or ld != self.dev) else storage.obs,
+                      "actions": storage.actions[:, c].to(ld, non_blocking=True)}
+                if self.impala:
+                    sh["logitss"] = storage.logitss[:, c].to(ld, non_blocking=True)
+                else:
+                    sh["logprobs"] = storage.logprobs[:, c].to(ld, non_blocking=True)
+                    sh["values"] = storage.values[:, c].to(ld, non_blocking=True)
+                for k in ("dones", "rewards", "firststeps"):
+                    sh[k] = torch.from_numpy(np.ascontiguousarray(storage.host[k][:, c])).to(ld, non_blocking=True)
+                if next_obs is not None:
+                    no = next_obs if torch.is_tensor(next_obs) else torch.from_numpy(next_obs)
+                    sh["next_obs"] = no[c].to(ld, non_blocking=True)
+                    sh["next_done"] = torch.from_numpy(np.ascontiguousarray(next_done[c])).to(ld, non_blocking=True)
+                shards.append(sh)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        for sh in shards:
+            sh["event"] = ev
+        return shards
+
+
+class CudaLearner:
+    """multi_device_update over the local learner devices (cleanba_ppo.py:656-660) + parameter publish (:721-725)."""
+
+    def __init__(self, args, key, allreduce):
+        self.args = args
+        self.impala = args.algo == "impala"
+        self.devices = [torch.device("cuda", i) for i in args.learner_device_ids]
+        L = len(self.devices)
+        Bl = args.local_num_envs // L * args.num_actor_threads * len(args.actor_device_ids)
+        world_learners = L * max(args.world_size, 1)
+        self.cross = allreduce
+        hooks = [self._make_hook(l) for l in range(L)]
+        if self.impala:
+            h = ImpalaHyper(learning_rate=args.learning_rate, anneal_lr=args.anneal_lr, gamma=args.gamma,
+                            num_minibatches=args.num_minibatches, ent_coef=args.ent_coef, vf_coef=args.vf_coef,
+                            max_grad_norm=args.max_grad_norm, num_updates=max(args.num_updates, 1))
+            self.learners = [ImpalaLearner(d, h, args.num_steps + 1, Bl, world_learners, hooks[l]) for l, d in enumerate(self.devices)]
+        else:
+            h = PPOHyper(learning_rate=args.learning_rate, anneal_lr=args.anneal_lr, gamma=args.gamma, gae_lambda=args.gae_lambda,
+                         num_minibatches=args.num_minibatches, update_epochs=args.update_epochs, norm_adv=args.norm_adv,
+                         clip_coef=args.clip_coef, ent_coef=args.ent_coef, vf_coef=args.vf_coef, max_grad_norm=args.max_grad_norm,
+                         num_updates=max(args.num_updates, 1))
+            self.learners = [PPOLearner(d, h, args.num_steps, Bl, world_learners, hooks[l]) for l, d in enumerate(self.devices)]
+        params = init_params(args.seed)
+        for lr in self.learners:
+            lr.ctx.set_params(params)
+        self.keys = [ag.key_tensor(key, d) for d in self.devices]    # learner_keys = device_put_replicated(key) (cleanba_ppo.py:470)
+        self.barrier = threading.Barrier(L) if L > 1 else None
+        self.hyper = h
+
+    def _make_hook(self, l):
+        """Gradient sum over all learner devices: local devices rendezvous on device 0, device 0 joins the cross-process
+        allreduce (one NCCL allreduce on the flat buffer), the result is copied back."""
+        def hook(g):
+            L = len(self.devices)
+            if L == 1:
+                if self.cross is not None:
+                    self.cross(g)
+                return
+            torch.cuda.current_stream(g.device).synchronize()
+            self.barrier.wait()
+            if l == 0:
+                g0 = self.learners[0].grads
+                for k in range(1, L):
+                    g0.add_(self.learners[k].grads.to(g0.device))
+                if self.cross is not None:
+                    self.cross(g0)
+                torch.cuda.current_stream(g0.device).synchronize()
+            self.barrier.wait()
+            if l != 0:
+                g.copy_(self.learners[0].grads)
+                torch.cuda.current_stream(g.device).synchronize()
+            self.barrier.wait()
+        return hook
+
+    def _update_one(self, l, payloads, out):
+        lr, d = self.learners[l], self.devices[l]
+        with torch.cuda.device(d):
+            st = torch.cuda.current_stream(d)
+            shards = [p[l] for p in payloads]
+            for s in shards:
+                st.wait_event(s["event"])
+            cat = (lambda k: shards[0][k]) if len(shards) == 1 else (lambda k: torch.cat([s[k] for s in shards], dim=1).contiguous())
+            if self.impala:
+                out[l] = lr.update(cat("obs"), cat("dones"), cat("actions"), cat("logitss"), cat("rewards"), cat("firststeps"))
+            else:
+                nobs = shards[0]["next_obs"] if len(shards) == 1 else torch.cat([s["next_obs"] for s in shards]).contiguous()
+                ndone = shards[0]["next_done"] if len(shards) == 1 else torch.cat([s["next_done"] for s in shards]).contiguous()
+                out[l] = lr.update(cat("obs"), cat("dones"), cat("actions"), cat("logprobs"), cat("values"), cat("rewards"),
+                                   nobs, ndone, self.keys[l])
+
+    def update(self, payloads):
+        L = len(self.devices)
+        out = [None] * L
+        if L == 1:
+            self._update_one(0, payloads, out)
+        else:
+            ths = [threading.Thread(target=self._update_one, args=(l, payloads, out)) for l in range(L)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+        return out[-1]     # the reference logs the scalars of the last learner device (cleanba_ppo.py:745-749)
+
+    def params_for_actor(self, actor_device_id):
+        lr = self.learners[0]
+        with torch.cuda.device(lr.ctx.device):
+            snap = lr.ctx.get_params()
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(lr.ctx.device))
+        return snap, ev
+
+    def stats_to_host(self, stats):
+        s = stats.detach().cpu().numpy()
+        names = ("loss", "pg_loss", "v_loss", "entropy_loss") + (() if self.impala else ("approx_kl",))
+        return {k: float(v) for k, v in zip(names, s)}
+
+    def current_lr(self):
+        from .learner import linear_schedule
+        lr = self.learners[0]
+        spu = self.hyper.num_minibatches * (1 if self.impala else self.hyper.update_epochs)
+        return linear_schedule(lr.opt_count, self.hyper.learning_rate, spu, self.hyper.num_updates, self.hyper.anneal_lr)
+
+
+class CudaBackend:
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise ag.CleanbaError("CudaBackend needs CUDA devices (sm_100a); there is no CPU fallback")
+        self._learner_devices = None
+
+    def first_key(self, seed):
+        return _first_key(seed)
+
+    def make_learner(self, args, key, allreduce):
+        learner = CudaLearner(args, key, allreduce)
+        self._learner_devices = learner.devices
+        return learner
+
+    def make_actor(self, device_id, N, args, key):
+        a = CudaActor(device_id, N, args, key)
+        a.learner_devices = self._learner_devices
+        return a

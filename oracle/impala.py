@@ -150,6 +150,8 @@ class ImpalaLearner:
                 grads.append(g)
                 stats.append(st)
             g = np.mean(np.stack(grads), axis=0, dtype=F32)  # lax.pmean of summed-loss grads (quirk D.7)
+            if getattr(self, "cross_allreduce", None) is not None:
+                g = self.cross_allreduce(g)
             lr = optim.linear_schedule(self.opt.count, cfg.learning_rate, cfg.num_minibatches, cfg.num_updates, cfg.anneal_lr)
             g = optim.clip_by_global_norm(g, cfg.max_grad_norm)
             self.params = self.opt.step(self.params, g, lr)

@@ -196,6 +196,8 @@ class PPOLearner:
                     grads.append(g)
                     stats.append(st)
                 g = np.mean(np.stack(grads), axis=0, dtype=F32)  # lax.pmean (cleanba_ppo.py:628)
+                if getattr(self, "cross_allreduce", None) is not None:   # pmean also spans processes when --distributed
+                    g = self.cross_allreduce(g)
                 lr = optim.linear_schedule(self.opt.count, cfg.learning_rate, cfg.num_minibatches * cfg.update_epochs,
                                            cfg.num_updates, cfg.anneal_lr)
                 g = optim.clip_by_global_norm(g, cfg.max_grad_norm)

@@ -1,0 +1,160 @@
+"""CPU tests of the host side: C-ABI symbol table, Args size derivation, Sebulba plumbing (queues, policy-version lag,
+payload sharding) driven by the oracle backend, and the world_size-2 data-parallel path over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from cleanba_b200 import build, lib
+    build.build()
+    header = open(os.path.join(ROOT, "include", "cleanba_b200.h")).read()
+    declared = set(re.findall(r"\b(cb_[a-z_0-9]+)\s*\(", header))
+    declared -= {"cb_ctx", "cb_config", "cb_stream"}
+    assert declared, "no declarations found"
+    dll = ctypes.CDLL(lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(dll, s)]
+    assert not missing, f"symbols declared in include/cleanba_b200.h but not exported: {missing}"
+    assert declared == set(lib.SIGNATURES), (declared ^ set(lib.SIGNATURES))
+    # metadata calls work without a GPU
+    assert lib.load().cb_num_params(18) == 1_094_115 and len(lib.leaves()) == 36
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from cleanba_b200 import agent
+    with pytest.raises(agent.CleanbaError):
+        agent.Context("cuda:0", max_batch=4)
+    from cleanba_b200.cuda_backend import CudaBackend
+    with pytest.raises(agent.CleanbaError):
+        CudaBackend()
+
+
+def test_product_params_and_keys_match_oracle():
+    from cleanba_b200 import params, prng
+    from oracle import network as net, threefry as tf
+    assert np.array_equal(params.init_params(3), net.init_params(3))
+    assert [(n, s) for n, _, s in params.leaves()] == net.param_spec()
+    assert prng.first_key(1).tolist() == tf.split(tf.PRNGKey(1), 4)[0].tolist()
+    assert prng.split(prng.first_key(5), 3).tolist() == tf.split(tf.split(tf.PRNGKey(5), 4)[0], 3).tolist()
+
+
+def test_size_derivation_matches_reference_configs():
+    from cleanba_b200.sebulba import Args, derive_sizes, impala_defaults
+    a = derive_sizes(Args(local_num_envs=60), 1)              # config 2: a0-l0-d1
+    assert (a.local_batch_size, a.local_minibatch_size, a.num_updates, a.batch_size) == (15360, 3840, 3255, 15360)
+    a = derive_sizes(Args(local_num_envs=60, learner_device_ids=[1, 2, 3]), 2)   # config 5: a0-l1,2,3-d2
+    assert (a.batch_size, a.num_envs, a.num_updates) == (30720, 240, 1627)
+    a = derive_sizes(Args(local_num_envs=8), 1)               # config 1
+    assert (a.local_batch_size, a.local_minibatch_size) == (2048, 512)
+    a = derive_sizes(impala_defaults(Args(local_num_envs=60)), 1)   # config 3
+    assert (a.local_batch_size, a.num_updates, a.concurrency, a.num_steps) == (2400, 20833, True, 20)
+    with pytest.raises(AssertionError):
+        derive_sizes(Args(local_num_envs=60, learner_device_ids=[0, 1, 2, 3, 4, 5, 6]), 1)   # 60 % 7
+    with pytest.raises(AssertionError):
+        derive_sizes(Args(local_num_envs=6, num_actor_threads=1, learner_device_ids=[0, 1]), 1)   # 3 % 4
+
+
+def _tiny_args(algo="ppo", **kw):
+    from cleanba_b200.sebulba import Args, derive_sizes, impala_defaults
+    a = Args(local_num_envs=4, num_actor_threads=2, num_steps=3, num_minibatches=2, update_epochs=1, total_timesteps=10 ** 6,
+             log_frequency=1000, max_updates=3, **kw)
+    if algo == "impala":
+        a = impala_defaults(a)
+        a.num_steps = 3
+    return derive_sizes(a, 1)
+
+
+def _make_env(env_id, seed, num_envs):
+    def thunk():
+        from cleanba_b200.envs import SyntheticAtari
+        return SyntheticAtari(num_envs, seed=seed, pool_batches=8, pin=False)
+    return thunk
+
+
+@pytest.mark.parametrize("algo,concurrency", [("ppo", False), ("ppo", True), ("impala", True)])
+def test_plumbing_runs_and_keeps_policy_lag(algo, concurrency):
+    """README pseudocode of the reference: with --concurrency the actor's policy is exactly one version behind from the
+    second rollout on (`update != 2` rule, cleanba_ppo.py:287-304); without it the versions are equal."""
+    from cleanba_b200.sebulba import train
+    from oracle.backend import OracleBackend
+    args = _tiny_args(algo)
+    args.concurrency = concurrency
+    res = train(args, OracleBackend(), _make_env)
+    assert res.updates == 3 and np.isfinite(np.asarray(res.stats, dtype=np.float64)).all()
+    for actor_version, actor_update, learner_version in res.versions:
+        assert actor_update == learner_version
+        assert actor_version == (learner_version if not concurrency or learner_version == 1 else learner_version - 1)
+    assert res.global_step == 3 * args.local_num_envs * args.num_actor_threads * args.num_steps * (1 if algo == "ppo" else 1) \
+        + (args.local_num_envs * args.num_actor_threads if algo == "impala" else 0)
+
+
+def test_plumbing_is_deterministic():
+    from cleanba_b200.sebulba import train
+    from oracle.backend import OracleBackend
+    r1 = train(_tiny_args(), OracleBackend(), _make_env)
+    r2 = train(_tiny_args(), OracleBackend(), _make_env)
+    assert np.array_equal(r1.learner.learner.params, r2.learner.learner.params)
+    np.testing.assert_array_equal(np.asarray(r1.stats), np.asarray(r2.stats))
+
+
+def test_two_learner_devices_shard_the_env_axis():
+    """a0-l0,1: payloads are split along the env axis and each learner sees [T, N/L * threads] (cleanba_ppo.py:278,587)."""
+    from cleanba_b200.sebulba import train
+    from oracle.backend import OracleBackend
+    seen = []
+    args = _tiny_args(learner_device_ids=[0, 1])
+    backend = OracleBackend()
+    res = train(args, backend, _make_env, on_update=lambda v, gs, st: seen.append(v))
+    assert seen == [1, 2, 3]
+    assert res.learner.L == 2
+
+
+WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from cleanba_b200.sebulba import Args, derive_sizes, train
+from cleanba_b200.envs import SyntheticAtari
+from oracle.backend import OracleBackend
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+def allreduce(g):   # jax.lax.pmean over the learner devices of all processes
+    t = torch.from_numpy(np.ascontiguousarray(g)); dist.all_reduce(t); return (t / world).numpy()
+a = Args(local_num_envs=4, num_actor_threads=1, num_steps=2, num_minibatches=2, update_epochs=1, total_timesteps=10**6,
+         log_frequency=1000, max_updates=2, distributed=True)
+derive_sizes(a, world, rank)
+def make_env(env_id, seed, n):
+    return lambda: SyntheticAtari(n, seed=seed, pool_batches=8, pin=False)
+res = train(a, OracleBackend(), make_env, allreduce=allreduce)
+p = torch.from_numpy(res.learner.learner.params.copy())
+gathered = [torch.zeros_like(p) for _ in range(world)]
+dist.all_gather(gathered, p)
+if rank == 0:
+    assert all(torch.equal(gathered[0], g) for g in gathered), "replicas diverged"
+    np.save({out!r}, gathered[0].numpy())
+    print("OK", a.num_updates, a.batch_size, a.num_envs)
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo_replicas_stay_identical(tmp_path):
+    """Two processes (one learner each) with an allreduce-mean on the flat gradient: parameters stay bit-identical
+    across replicas, and the global sizes follow cleanba_ppo.py:425-430."""
+    script = tmp_path / "worker.py"
+    out = str(tmp_path / "params.npy")
+    script.write_text(WORKER.format(root=ROOT, out=out))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK 62500 16 8" in r.stdout, r.stdout[-500:]
+    assert np.isfinite(np.load(out)).all()
