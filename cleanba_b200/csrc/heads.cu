@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_ppo_head(PpoHeadArgs a) {
         float hreg[8], logit, value;
         head_forward(h, a.hidden + (long long)b * HIDDEN, A, lane, hreg, logit, value);
         const int src = a.idx ? a.idx[b] : b;
-        const int act = a.actions[src];
+        const int act = min(max(a.actions[src], 0), A - 1);   // defensive: never index with a corrupt action
         const float oldlp = a.old_logprobs[src], adv = a.advantages[src], ret = a.returns[src];
         float m = warp_max(lane < A ? logit : -INFINITY);
         float ex = lane < A ? expf(logit - m) : 0.f;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a) {
     // phase 1: per cell log pi(a), rho, entropy
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
         const int src = a.idx ? a.idx[c] : c;
-        const int act = a.actions[src];
+        const int act = min(max(a.actions[src], 0), A - 1);
         const float* z = a.logits_scratch + (long long)c * (A + 1);
         const float* mu = a.behaviour_logits + (long long)src * A;
         float m = -INFINITY, mm = -INFINITY;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a) {
             continue;
         }
         const int src = a.idx ? a.idx[c] : c;
-        const int act = a.actions[src];
+        const int act = min(max(a.actions[src], 0), A - 1);
         const float mask = 1.f - (float)a.firststeps[src];
         const float* z = a.logits_scratch + (long long)c * (A + 1);
         const float* cs = a.cell_scratch + (long long)c * 8;

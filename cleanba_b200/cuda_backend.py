@@ -178,6 +178,9 @@ class CudaLearner:
             shards = [p[l] for p in payloads]
             for s in shards:
                 st.wait_event(s["event"])
+                for v in s.values():      # payload memory was allocated on the actor's stream: tell the caching allocator
+                    if torch.is_tensor(v) and v.is_cuda:   # that this stream uses it too, so it is not recycled early
+                        v.record_stream(st)
             cat = (lambda k: shards[0][k]) if len(shards) == 1 else (lambda k: torch.cat([s[k] for s in shards], dim=1).contiguous())
             if self.impala:
                 out[l] = lr.update(cat("obs"), cat("dones"), cat("actions"), cat("logitss"), cat("rewards"), cat("firststeps"))

@@ -132,8 +132,18 @@ class _NullWriter:
         pass
 
 
-def rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue, params_queue: queue.Queue, writer,
-            device_thread_id: int, actor_device_id: int, stop: threading.Event, key):
+def rollout(args, backend, make_env, rollout_queue, params_queue, writer, device_thread_id, actor_device_id, stop, key, errors):
+    """Thread target: runs `_rollout` and hands any exception to the learner loop (in the reference a dead actor thread
+    deadlocks the learner on Queue.get(), cleanba_ppo.py:708; here it is re-raised in the main thread)."""
+    try:
+        _rollout(args, backend, make_env, rollout_queue, params_queue, writer, device_thread_id, actor_device_id, stop, key)
+    except BaseException as e:  # noqa: BLE001
+        errors.append(e)
+        stop.set()
+
+
+def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue, params_queue: queue.Queue, writer,
+             device_thread_id: int, actor_device_id: int, stop: threading.Event, key):
     """Actor thread (cleanba_ppo.py:226-406 / cleanba_impala.py:268-447)."""
     impala = args.algo == "impala"
     envs = make_env(args.env_id, args.seed + args.local_rank + device_thread_id, args.local_num_envs)()
@@ -167,8 +177,14 @@ def rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue,
         # exactly one version behind the learner's (cleanba_ppo.py:287-304)
         t0 = time.time()
         if not args.concurrency or update != 2:
-            params = params_queue.get()
-            if params is None:                    # shutdown sentinel from train()
+            params = None
+            while not stop.is_set():
+                try:
+                    params = params_queue.get(timeout=0.5)
+                    break
+                except queue.Empty:
+                    continue
+            if params is None:                    # shutdown (sentinel from train() or stop flag)
                 break
             actor.set_params(params)              # includes the block_until_ready of the reference
             actor_policy_version += 1
@@ -256,7 +272,17 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
     learner = backend.make_learner(args, key, allreduce)
     params_queues, rollout_queues, threads = [], [], []
     stop = threading.Event()
+    errors: list = []
     dummy_writer = _NullWriter()
+
+    def get_payload(q):
+        while True:
+            try:
+                return q.get(timeout=0.5)
+            except queue.Empty:
+                if errors:
+                    raise RuntimeError("an actor thread failed") from errors[0]
+
     for d_idx, d_id in enumerate(args.actor_device_ids):
         device_params = learner.params_for_actor(d_id)
         for thread_id in range(args.num_actor_threads):
@@ -266,7 +292,7 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
             th = threading.Thread(target=rollout, daemon=True, args=(
                 args, backend, make_env, rollout_queues[-1], params_queues[-1],
                 writer if d_idx == 0 and thread_id == 0 else dummy_writer,
-                d_idx * args.num_actor_threads + thread_id, d_id, stop, key))
+                d_idx * args.num_actor_threads + thread_id, d_id, stop, key, errors))
             th.start()
             threads.append(th)
 
@@ -282,7 +308,7 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
             for d_idx, d_id in enumerate(args.actor_device_ids):
                 for thread_id in range(args.num_actor_threads):
                     (global_step, actor_policy_version, update, sharded, avg_params_queue_get_time,
-                     device_thread_id) = rollout_queues[d_idx * args.num_actor_threads + thread_id].get()
+                     device_thread_id) = get_payload(rollout_queues[d_idx * args.num_actor_threads + thread_id])
                     payloads.append(sharded)
             rollout_queue_get_time.append(time.time() - t0)
             training_time_start = time.time()
@@ -320,6 +346,10 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
                 q.put_nowait(None)
             except queue.Full:
                 pass
+        for th in threads:        # actor threads leave on `stop`; never let daemon threads die inside CUDA calls at exit
+            th.join(timeout=10)
+        if errors:
+            raise RuntimeError("an actor thread failed") from errors[0]
     result.sps = global_step / max(time.time() - start, 1e-9)
     result.global_step = global_step
     return result

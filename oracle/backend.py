@@ -102,9 +102,10 @@ class OracleLearner:
                                          values=cat("values"), rewards=cat("rewards"),
                                          next_obs=np.concatenate([s["next_obs"] for s in parts]),
                                          next_done=np.concatenate([s["next_done"] for s in parts])))
+        self.last_record = []
         if self.impala:
-            return self.learner.update(shards)
-        stats, self.key = self.learner.update(shards, self.key)
+            return self.learner.update(shards, record=self.last_record)
+        stats, self.key = self.learner.update(shards, self.key, record=self.last_record)
         return stats
 
     def params_for_actor(self, actor_device_id):
