@@ -355,3 +355,65 @@ def test_ppo_update_end_to_end(agent, params, backend):
     # 1e-4 / 1e-5 is asserted by the gradient and optimizer tests above; here the bar is the oracle's own sensitivity.
     assert max(serr) < 1e-2, (stats, ostats)
     assert perr < 1e-2
+
+
+# --------------------------------------------------------------------------------------------- golden fixtures
+def test_cuda_against_committed_golden_fixtures(agent):
+    """tests/golden/oracle_golden.npz (made by tests/golden/make_golden.py from the oracle) against the CUDA path."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden.npz"))
+    ctx = agent.Context("cuda:0", max_batch=8, train=True)
+    ctx.set_params(net.init_params(1))
+    dev = ctx.device
+    tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    kt = agent.key_tensor(G["key"], dev)
+    action, logprob, value, logits = ctx.actor_step(tt(G["obs"]), kt, True, True)
+    assert np.array_equal(action.cpu().numpy(), G["action"]) and agent.key_numpy(kt).tolist() == G["key_after"].tolist()
+    assert _relerr(logits.cpu().numpy(), G["logits"]) < 1e-4 and _relerr(value.cpu().numpy(), G["value"]) < 1e-4
+    assert np.array_equal(ctx.permutation(agent.key_tensor(G["key"], dev), 2048).cpu().numpy()[:64], G["perm_2048_head"])
+    adv, ret = ctx.gae(tt(G["gae_r"]), tt(G["gae_v"]), tt(G["gae_d"]), tt(G["gae_nv"]), tt(G["gae_nd"]), 0.99, 0.95, 0)
+    assert np.array_equal(adv.cpu().numpy(), G["gae_adv"]) and np.array_equal(ret.cpu().numpy(), G["gae_ret"])
+    grads = torch.zeros(ctx.num_params, device=dev)
+    stats = torch.zeros(5, device=dev)
+    ctx.ppo_grad(tt(G["obs"]), None, 4, tt(G["ppo_actions"]), tt(G["logprob"]), tt(G["ppo_adv"]), tt(G["ppo_ret"]), 0.1, 0.01, 0.5, grads, stats)
+    st = stats.cpu().numpy()
+    assert max(abs(st[i] - G["ppo_stats"][i]) / max(abs(G["ppo_stats"][i]), 1e-6) for i in range(4)) < 1e-4
+    assert abs(float(grads.norm()) - float(G["ppo_grad_norm"])) / float(G["ppo_grad_norm"]) < 1e-3
+    ctx.close()
+
+
+# --------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_minibatch_properties(agent, params):
+    """BASELINE config 2 sizes (minibatch 3840 of a 15360-sample update): size-independent properties instead of the
+    (minutes-long) CPU oracle: determinism, agreement of the tcgen05 path with the fp32 CUDA-core path, invariance of
+    the minibatch loss under a re-ordering of the minibatch, idx-gather == explicit gather."""
+    rng = np.random.default_rng(31)
+    N, mb = 4096, 3840
+    obs = torch.from_numpy(rng.integers(0, 256, (N, 4, 84, 84), dtype=np.uint8)).cuda()
+    actions = torch.from_numpy(rng.integers(0, 18, N).astype(np.int32)).cuda()
+    oldlp = torch.from_numpy((np.log(1 / 18) + rng.standard_normal(N) * 0.02).astype(np.float32)).cuda()
+    adv = torch.randn(N, device="cuda"); ret = torch.randn(N, device="cuda")
+    idx = torch.from_numpy(rng.permutation(N)[:mb].astype(np.int32)).cuda()
+    out = {}
+    for backend in (0, 1):
+        ctx = agent.Context("cuda:0", max_batch=mb, train=True, conv_backend=backend)
+        ctx.set_params(params)
+        g = torch.zeros(ctx.num_params, device="cuda"); s = torch.zeros(5, device="cuda")
+        ctx.ppo_grad(obs, idx, mb, actions, oldlp, adv, ret, 0.1, 0.01, 0.5, g, s)
+        out[backend] = (g.clone(), s.clone())
+        if backend == 0:
+            g2 = torch.zeros_like(g); s2 = torch.zeros_like(s)
+            ctx.ppo_grad(obs, idx, mb, actions, oldlp, adv, ret, 0.1, 0.01, 0.5, g2, s2)
+            assert torch.equal(g, g2) and torch.equal(s, s2), "not deterministic at full size"
+            perm = torch.randperm(mb, device="cuda")
+            ctx.ppo_grad(obs, idx[perm].contiguous(), mb, actions, oldlp, adv, ret, 0.1, 0.01, 0.5, g2, s2)
+            assert _relerr(s2.cpu().numpy()[:4], s.cpu().numpy()[:4]) < 1e-5
+            assert float((g2 - g).norm() / g.norm()) < 1e-4
+            ii = idx.long()
+            ctx.ppo_grad(obs[ii].contiguous(), None, mb, actions[ii].contiguous(), oldlp[ii].contiguous(), adv[ii].contiguous(),
+                         ret[ii].contiguous(), 0.1, 0.01, 0.5, g2, s2)
+            assert torch.equal(g, g2) and torch.equal(s, s2), "idx gather differs from an explicit gather"
+        ctx.close()
+    serr = _relerr(out[0][1].cpu().numpy()[:4], out[1][1].cpu().numpy()[:4])
+    gerr = float((out[0][0] - out[1][0]).norm() / out[1][0].norm())
+    _diag("full_size_mb3840", stats_tcgen05_vs_simt=serr, grad_tcgen05_vs_simt=gerr)
+    assert serr < 1e-5 and gerr < 1e-3
