@@ -27,8 +27,8 @@ typedef __nv_bfloat16 bf16;
 
 struct Planes {           // bf16 hi/mid/lo chunk planes; pointers address flat pixel 0 (guard lies before it)
     bf16* hi;
-    bf16* mid;            // mid / lo may be null (exact-in-bf16 data, e.g. the unpacked uint8 frames)
-    bf16* lo;
+    bf16* mid;            // 1 plane (hi only: exact-in-bf16 data, the unpacked uint8 frames), 2 planes (hi, mid: 16
+    bf16* lo;             // significant bits, gradient tensors) or 3 planes (hi, mid, lo: 24 bits, forward activations)
     long long plane_px;   // pixels per plane INCLUDING both guards (plane stride = plane_px * 8 elements)
 };
 
@@ -102,9 +102,11 @@ __device__ __forceinline__ void load_planes8(const Planes& p, long long off, flo
         unpack8(*reinterpret_cast<const uint4*>(p.mid + off), t);
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] += t[e];
-        unpack8(*reinterpret_cast<const uint4*>(p.lo + off), t);
+        if (p.lo) {
+            unpack8(*reinterpret_cast<const uint4*>(p.lo + off), t);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] += t[e];
+            for (int e = 0; e < 8; ++e) f[e] += t[e];
+        }
     }
 }
 __device__ __forceinline__ void store_planes8(const Planes& p, long long off, const float* v) {
@@ -113,12 +115,12 @@ __device__ __forceinline__ void store_planes8(const Planes& p, long long off, co
     for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], m[e], l[e]);
     *reinterpret_cast<uint4*>(p.hi + off) =
         make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    if (p.mid) {
+    if (p.mid)
         *reinterpret_cast<uint4*>(p.mid + off) =
             make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+    if (p.lo)
         *reinterpret_cast<uint4*>(p.lo + off) =
             make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
-    }
 }
 
 // Is flat pixel q (q < NP) an interior (non-border) pixel of its image?
@@ -166,6 +168,71 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvEpilogue& ep, cons
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = ep.relu ? fmaxf(v[e], 0.f) : v[e];
         store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, x);
+    }
+}
+
+// Split epilogue for the tcgen05 kernels: the residual / gate operands of a tile are fetched into registers BEFORE the
+// accumulator is waited for, so their global-memory latency overlaps the MMAs instead of following them.
+template <int COUT>
+struct EpiPrefetch {
+    float res[COUT];
+    uint4 mask[COUT / 8];
+    bool in, tail;
+};
+
+template <int COUT>
+__device__ __forceinline__ void epi_prefetch(const ConvEpilogue& ep, const ConvGeom& g, long long q, EpiPrefetch<COUT>& p) {
+    p.tail = q >= g.NP;
+    p.in = !p.tail && interior(g, q);
+    if (!p.in) return;
+#pragma unroll
+    for (int oc = 0; oc < COUT / 8; ++oc) {
+        if (ep.mask_hi) p.mask[oc] = *reinterpret_cast<const uint4*>(ep.mask_hi + ((long long)oc * ep.mask_plane_px + q) * 8);
+        if (ep.res) {
+            const float4* r = reinterpret_cast<const float4*>(ep.res + ((long long)oc * g.NP + q) * 8);
+            float4 r0 = r[0], r1 = r[1];
+            p.res[oc * 8 + 0] = r0.x; p.res[oc * 8 + 1] = r0.y; p.res[oc * 8 + 2] = r0.z; p.res[oc * 8 + 3] = r0.w;
+            p.res[oc * 8 + 4] = r1.x; p.res[oc * 8 + 5] = r1.y; p.res[oc * 8 + 6] = r1.z; p.res[oc * 8 + 7] = r1.w;
+        }
+    }
+}
+
+template <int COUT>
+__device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeom& g, long long q, const float* acc,
+                                           const EpiPrefetch<COUT>& p) {
+#pragma unroll
+    for (int oc = 0; oc < COUT / 8; ++oc) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (p.in) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float b = ep.bias ? ep.bias[oc * 8 + e] : 0.f;
+                v[e] = acc[oc * 8 + e] * ep.acc_scale + b;
+            }
+            if (ep.mask_hi) {
+                float mf[8];
+                unpack8(p.mask[oc], mf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = mf[e] > 0.f ? v[e] : 0.f;
+            }
+            if (ep.res) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += p.res[oc * 8 + e];
+            }
+        }
+        if (ep.out_s && !p.tail) {
+            float4* o = reinterpret_cast<float4*>(ep.out_s + ((long long)oc * g.NP + q) * 8);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (ep.out.hi) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = ep.relu ? fmaxf(v[e], 0.f) : v[e];
+            store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, x);
+        }
     }
 }
 

@@ -20,7 +20,9 @@
 // and the epilogue adds the three C-column blocks.  The MMAs are bound by the A-operand shared-memory fetch (ncu:
 // sm__pipe_tc_cycles_active ~80%), which does not depend on N, so the extra precision costs no tensor-pipe time.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quadrant = warp id), warp 4 TMA producer, warp 5 MMA issuer.
+// Warp roles (320 threads): warps 0-3 / 4-7 two epilogue groups, one per TMEM accumulator (TMEM lane quadrant = warp % 4),
+// which prefetch the residual / gate operands of their next tile before waiting for its accumulator; warp 8 TMA producer;
+// warp 9 MMA issuer.
 #include "common.cuh"
 #include "kernels.h"
 #include "umma.cuh"
@@ -30,7 +32,7 @@ using namespace umma;
 
 constexpr int TILE_M = 128;
 constexpr int CONV_STAGES = 3;
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_THREADS = 320;   // warps 0-7: two epilogue groups (one per TMEM accumulator), warp 8: TMA, warp 9: MMA
 
 __host__ __device__ constexpr int conv_steps(int cin_chunks) { return cin_chunks == 1 ? 5 : 9 * (cin_chunks / 2); }
 // bytes of the packed weight image: per step [kc(2)][3*cout][8] bf16
@@ -41,23 +43,25 @@ long long packed_conv_elems(int cin_chunks, int cout) { return (long long)conv_w
 struct ConvSmemLayout {
     int win, plane_bytes, nplanes, stage_bytes, w_bytes, total;
 };
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int cout, int Wp) {
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int cout, int Wp, int apl = 3) {
     ConvSmemLayout L;
     // frames path: the zero-weight half of the last K step reads one pixel past the 3x3 window -> load it too
     L.win = TILE_M + 2 * Wp + 2 + (cin_chunks == 1 ? 1 : 0);
     L.plane_bytes = L.win * 16;
-    L.nplanes = cin_chunks == 1 ? 1 : 3 * cin_chunks;        // hi planes, mid planes, lo planes (frames: hi only, exact)
+    L.nplanes = cin_chunks == 1 ? 1 : apl * cin_chunks;      // hi planes, mid planes[, lo planes] (frames: hi only, exact)
     L.stage_bytes = L.nplanes * L.plane_bytes;
     L.w_bytes = conv_wbytes(cin_chunks, cout);
     L.total = 1024 + L.w_bytes + CONV_STAGES * L.stage_bytes;
     return L;
 }
-int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_layout(cin_chunks, cout, Wp).total; }
+int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_layout(cin_chunks, cout, Wp, 3).total; }
 
-template <int CIN_CHUNKS, int COUT>
+// APL = bf16 planes of the A operand: 1 (frames, exact), 2 (gradient tensors, 16 bits: A_hi*[W_hi|W_mid] + A_mid*[W_hi])
+// or 3 (forward activations, 24 bits, the three MMAs above).
+template <int CIN_CHUNKS, int COUT, int APL>
 __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
+    const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, APL);
     // [0,1024): barriers + tmem pointer; then the weight image; then the activation stages
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [CONV_STAGES]
     uint64_t* empty = full + CONV_STAGES;                        // [CONV_STAGES]
@@ -70,9 +74,10 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(CIN_CHUNKS);
-    constexpr int ACC_COLS = 3 * COUT;                           // three C-column blocks per accumulator
-    constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 128) ? 128 : 256;
-    constexpr int NPLANES = CIN_CHUNKS == 1 ? 1 : 3 * CIN_CHUNKS;
+    constexpr int NBLK = APL == 2 ? 2 : 3;                       // C-column blocks per accumulator
+    constexpr int ACC_COLS = NBLK * COUT;
+    constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : ((2 * ACC_COLS <= 128) ? 128 : 256);
+    constexpr int NPLANES = CIN_CHUNKS == 1 ? 1 : APL * CIN_CHUNKS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CONV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -80,13 +85,13 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== TMA producer (lanes share the bulk copies of a stage) =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(wbar, (uint32_t)L.w_bytes);
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
             __syncwarp();
             if (++s == CONV_STAGES) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================== MMA issuer =====================
         constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * COUT, 0, 0);
         constexpr uint32_t IDESC2 = make_idesc_bf16(TILE_M, 2 * COUT, 0, 0);
@@ -114,37 +119,46 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         int acc = 0; uint32_t aph = 0;
-        const uint32_t w_base = smem_u32(wsm);
+        // Per-step descriptor low words relative to the stage base, in 16-byte units (hoisted out of the tile loop; the
+        // issue loop below is fully unrolled and costs one integer add per operand per MMA).
+        const uint32_t win16 = (uint32_t)L.win;                  // plane stride in 16-byte units
+        const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
+        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 3 * COUT * 16);
+        uint32_t a_rel[STEPS];
+#pragma unroll
+        for (int step = 0; step < STEPS; ++step) {
+            if (CIN_CHUNKS == 1) {
+                // frame stack: 8-channel pixels, two taps per K=16 step (see pack.cu for the matching weights)
+                if (step < 3) a_rel[step] = (uint32_t)(step * a.g.Wp) | (1u << 16);                 // LBO = 16 bytes
+                else if (step == 3) a_rel[step] = 2u | ((uint32_t)a.g.Wp << 16);                    // LBO = one image row
+                else a_rel[step] = (uint32_t)(2 * a.g.Wp + 2) | (1u << 16);
+            } else {
+                constexpr int HALF = CIN_CHUNKS > 1 ? CIN_CHUNKS / 2 : 1;
+                const int tap = step / HALF, pair = step % HALF;
+                a_rel[step] = ((uint32_t)(pair * 2) * win16 + (uint32_t)((tap / 3) * a.g.Wp + (tap % 3))) | (win16 << 16);
+            }
+        }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(&tempty[acc], aph ^ 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-                const uint32_t st_hi = smem_u32(stages + s * L.stage_bytes);
-                const uint32_t st_mid = st_hi + CIN_CHUNKS * L.plane_bytes;
-                const uint32_t st_lo = st_mid + CIN_CHUNKS * L.plane_bytes;
-                uint32_t accum = 0;
-#pragma unroll 1
+                const uint32_t st16 = (smem_u32(stages + s * L.stage_bytes) >> 4);   // stage base (hi planes), 16-byte units
+                const uint32_t mid16 = CIN_CHUNKS * win16, lo16 = 2 * CIN_CHUNKS * win16;
+#pragma unroll
                 for (int step = 0; step < STEPS; ++step) {
-                    uint32_t a_off, a_lbo;
-                    if (CIN_CHUNKS == 1) {
-                        // frame stack: 8-channel pixels, two taps per K=16 step (see pack.cu for the matching weights)
-                        if (step < 3) { a_off = (step * a.g.Wp) * 16; a_lbo = 16; }
-                        else if (step == 3) { a_off = 2 * 16; a_lbo = a.g.Wp * 16; }
-                        else { a_off = (2 * a.g.Wp + 2) * 16; a_lbo = 16; }
+                    const uint32_t a_lo = st16 + a_rel[step];
+                    const uint32_t b_lo = b_lo0 + step * (2 * 3 * COUT);
+                    if (APL == 2) {
+                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0);
+                        mma_bf16_parts(d_tmem, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1);
                     } else {
-                        constexpr int HALF = CIN_CHUNKS > 1 ? CIN_CHUNKS / 2 : 1;
-                        const int tap = step / HALF, pair = step % HALF;
-                        a_off = (pair * 2) * L.plane_bytes + ((tap / 3) * a.g.Wp + (tap % 3)) * 16;
-                        a_lbo = L.plane_bytes;
-                    }
-                    const uint64_t db = make_desc(w_base + step * (2 * 3 * COUT * 16), 3 * COUT * 16, 128);
-                    mma_bf16(d_tmem, make_desc(st_hi + a_off, a_lbo, 128), db, IDESC3, accum);
-                    accum = 1;
-                    if (CIN_CHUNKS > 1) {
-                        mma_bf16(d_tmem, make_desc(st_mid + a_off, a_lbo, 128), db, IDESC2, 1);
-                        mma_bf16(d_tmem, make_desc(st_lo + a_off, a_lbo, 128), db, IDESC1, 1);
+                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC3, step > 0);
+                        if (APL == 3) {
+                            mma_bf16_parts(d_tmem, a_lo + mid16, a_hi, b_lo, b_hi, IDESC2, 1);
+                            mma_bf16_parts(d_tmem, a_lo + lo16, a_hi, b_lo, b_hi, IDESC1, 1);
+                        }
                     }
                 }
                 mma_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
@@ -155,63 +169,69 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
             if (++acc == 2) { acc = 0; aph ^= 1; }
         }
     } else {
-        // ===================== epilogue warps 0..3 =====================
-        int acc = 0; uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            mbar_wait(&tfull[acc], aph);
+        // ===================== epilogue: group g = warp / 4 owns accumulator g (every second tile of this CTA) ==========
+        const int grp = warp >> 2, quad = warp & 3;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
+            const long long q = (long long)tile * TILE_M + quad * 32 + lane;
+            EpiPrefetch<COUT> pre;
+            epi_prefetch<COUT>(a.ep, a.g, q, pre);          // global loads in flight while the MMAs of this tile run
+            mbar_wait(&tfull[grp], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * ACC_COLS;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * ACC_COLS;
             float v[COUT];
-            {   // sum the three column blocks, smallest contributions first
+            {   // sum the column blocks, smallest contributions first
                 float t[16];
 #pragma unroll
                 for (int h = 0; h < COUT / 16; ++h) {
-                    tmem_ld16(taddr + 2 * COUT + h * 16, v + h * 16);
-                    tmem_ld16(taddr + COUT + h * 16, t);
+                    tmem_ld16(taddr + (NBLK - 1) * COUT + h * 16, v + h * 16);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
-                    tmem_ld16(taddr + h * 16, t);
+                    for (int blk = NBLK - 2; blk >= 0; --blk) {
+                        tmem_ld16(taddr + blk * COUT + h * 16, t);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                        for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            const long long q = (long long)tile * TILE_M + warp * 32 + lane;
-#pragma unroll
-            for (int oc = 0; oc < COUT / 8; ++oc) conv_epilogue_store(a.ep, a.g, q, oc, v + oc * 8);
-            if (++acc == 2) { acc = 0; aph ^= 1; }
+            if (lane == 0) mbar_arrive(&tempty[grp]);
+            epi_finish<COUT>(a.ep, a.g, q, v, pre);
+            aph ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int CIN_CHUNKS, int COUT>
+template <int CIN_CHUNKS, int COUT, int APL>
 static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
-    ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
+    ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, APL);
     CB_CHECK(L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
     // always the device maximum: the attribute is per function and contexts on other host threads launch the same
     // instantiation with other window sizes concurrently
-    CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int ntiles = (int)((a.g.NP + TILE_M - 1) / TILE_M);
     int ctas_per_sm = L.total <= 110 * 1024 ? 2 : 1;
     int grid = ntiles < num_sms * ctas_per_sm ? ntiles : num_sms * ctas_per_sm;
-    k_conv_umma<CIN_CHUNKS, COUT><<<grid, CONV_THREADS, L.total, st>>>(a, ntiles);
+    k_conv_umma<CIN_CHUNKS, COUT, APL><<<grid, CONV_THREADS, L.total, st>>>(a, ntiles);
     CB_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
     CB_CHECK(a.g.Wp + 1 <= GUARD && TILE_M + a.g.Wp + 2 <= GUARD, "conv_umma: guard too small for Wp=%d", a.g.Wp);
-    if (a.cin_chunks == 1 && a.cout == 16) return launch_conv_umma_t<1, 16>(a, num_sms, st);
-    if (a.cin_chunks == 2 && a.cout == 16) return launch_conv_umma_t<2, 16>(a, num_sms, st);
-    if (a.cin_chunks == 2 && a.cout == 32) return launch_conv_umma_t<2, 32>(a, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 16) return launch_conv_umma_t<4, 16>(a, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 32) return launch_conv_umma_t<4, 32>(a, num_sms, st);
-    CB_CHECK(false, "conv_umma: unsupported shape cin_chunks=%d cout=%d", a.cin_chunks, a.cout);
+    const int apl = a.in.lo ? 3 : (a.in.mid ? 2 : 1);
+    if (a.cin_chunks == 1 && a.cout == 16 && apl == 1) return launch_conv_umma_t<1, 16, 1>(a, num_sms, st);
+    if (a.cin_chunks == 2 && a.cout == 16 && apl == 3) return launch_conv_umma_t<2, 16, 3>(a, num_sms, st);
+    if (a.cin_chunks == 2 && a.cout == 16 && apl == 2) return launch_conv_umma_t<2, 16, 2>(a, num_sms, st);
+    if (a.cin_chunks == 2 && a.cout == 32 && apl == 3) return launch_conv_umma_t<2, 32, 3>(a, num_sms, st);
+    if (a.cin_chunks == 4 && a.cout == 16 && apl == 2) return launch_conv_umma_t<4, 16, 2>(a, num_sms, st);
+    if (a.cin_chunks == 4 && a.cout == 16 && apl == 3) return launch_conv_umma_t<4, 16, 3>(a, num_sms, st);
+    if (a.cin_chunks == 4 && a.cout == 32 && apl == 3) return launch_conv_umma_t<4, 32, 3>(a, num_sms, st);
+    if (a.cin_chunks == 4 && a.cout == 32 && apl == 2) return launch_conv_umma_t<4, 32, 2>(a, num_sms, st);
+    CB_CHECK(false, "conv_umma: unsupported shape cin_chunks=%d cout=%d planes=%d", a.cin_chunks, a.cout, apl);
 }
 
 // =================================================================================================
@@ -233,40 +253,42 @@ constexpr int WG_MROWS = 128;
 
 struct WgSmemLayout {
     int groups;        // real M groups = 3 * cin_chunks
-    int xplanes;       // 3 (hi, mid, lo) or 1 (frames)
+    int xplanes;       // X planes used: 1 (frames) .. 3
+    int gplanes;       // G planes (2 or 3), stacked along N
     int a_bytes;       // one A region (one split plane): (groups + 1) copies (last = ones / zeros)
     int b_chunk;       // bytes of one (plane, chunk) of G
     int b_bytes;       // all of B: 3 planes x cout/8 chunks
     int stage_bytes, total;
 };
-__host__ __device__ inline WgSmemLayout wg_smem_layout(int cin_chunks, int cout) {
+__host__ __device__ inline WgSmemLayout wg_smem_layout(int cin_chunks, int cout, int xpl, int gpl) {
     WgSmemLayout L;
     L.groups = 3 * cin_chunks;
-    L.xplanes = cin_chunks == 1 ? 1 : 3;
+    L.xplanes = xpl;
+    L.gplanes = gpl;
     L.a_bytes = (L.groups + 1) * WG_PLANE;
     L.b_chunk = WG_BLOCK * 16;
-    L.b_bytes = 3 * (cout / 8) * L.b_chunk;
+    L.b_bytes = gpl * (cout / 8) * L.b_chunk;
     L.stage_bytes = L.xplanes * L.a_bytes + L.b_bytes;
     // the M = 128 instruction reads 16 groups from the A base: pad so the unused groups stay inside the allocation
     L.total = 1024 + WG_STAGES * L.stage_bytes + 16 * WG_PLANE;
     return L;
 }
 
-template <int CIN_CHUNKS, int COUT>
+// XPL = planes of X used (1 frames, 2 or 3), GPL = planes of G (2 or 3); plane p of X multiplies the first GPL - p planes of G.
+template <int CIN_CHUNKS, int COUT, int XPL, int GPL>
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblocks, float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int XPL = CIN_CHUNKS > 1 ? 3 : 1;
-    const WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT);
+    const WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, XPL, GPL);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + WG_STAGES;
     uint64_t* done = empty + WG_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     uint8_t* stages = smem + 1024;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int ACC_COLS = 3 * COUT;
-    constexpr uint32_t TMEM_COLS = (3 * ACC_COLS <= 256) ? 256 : 512;
+    constexpr int ACC_COLS = GPL * COUT;
+    constexpr uint32_t TMEM_COLS = (3 * ACC_COLS <= 128) ? 128 : ((3 * ACC_COLS <= 256) ? 256 : 512);
     constexpr int GROUPS = 3 * CIN_CHUNKS;
-    constexpr int NCOPY_A = XPL * GROUPS, NCOPY_B = 3 * (COUT / 8);
+    constexpr int NCOPY_A = XPL * GROUPS, NCOPY_B = GPL * (COUT / 8);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -312,33 +334,34 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
             if (++s == WG_STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 5) {
-        constexpr uint32_t IDESC3 = make_idesc_bf16(WG_MROWS, 3 * COUT, 1, 1);
-        constexpr uint32_t IDESC2 = make_idesc_bf16(WG_MROWS, 2 * COUT, 1, 1);
-        constexpr uint32_t IDESC1 = make_idesc_bf16(WG_MROWS, COUT, 1, 1);
+        constexpr uint32_t IDESC_A = make_idesc_bf16(WG_MROWS, GPL * COUT, 1, 1);                         // X plane 0
+        constexpr uint32_t IDESC_B = make_idesc_bf16(WG_MROWS, (GPL > 1 ? GPL - 1 : 1) * COUT, 1, 1);     // X plane 1
+        constexpr uint32_t IDESC_C = make_idesc_bf16(WG_MROWS, (GPL > 2 ? GPL - 2 : 1) * COUT, 1, 1);     // X plane 2
         int s = 0; uint32_t ph = 0;
         uint32_t accum = 0;
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_hi = smem_u32(stages + s * L.stage_bytes);
-                const uint32_t b_base = a_hi + XPL * L.a_bytes;
-#pragma unroll 1
+                const uint32_t a_base = smem_u32(stages + s * L.stage_bytes);
+                // K step = 16 pixels = 2 core-matrix groups of 8 pixels (128 bytes each, LBO); M groups WG_PLANE apart,
+                // N groups (8 channels of one G plane chunk) b_chunk apart (SBO)
+                const uint32_t a_lo0 = desc_lo(a_base, 128), a_hi_w = desc_hi(WG_PLANE);
+                const uint32_t b_lo0 = desc_lo(a_base + XPL * L.a_bytes, 128), b_hi_w = desc_hi(L.b_chunk);
+                const uint32_t apl16 = (uint32_t)L.a_bytes >> 4;
+#pragma unroll
                 for (int ks = 0; ks < WG_BLOCK / 16; ++ks) {
-                    // K step = 16 pixels = 2 core-matrix groups of 8 pixels (128 bytes each); N groups 1024 bytes apart
-                    const uint64_t db = make_desc(b_base + ks * 256, 128, L.b_chunk);
+                    const uint32_t b_lo = b_lo0 + ks * 16;
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
                         const uint32_t d_tmem = tmem_base + kx * ACC_COLS;
-                        const uint32_t ao = a_hi + ks * 256 + kx * 16;
-                        mma_bf16(d_tmem, make_desc(ao, 128, WG_PLANE), db, IDESC3, accum);
-                        if (XPL > 1) {
-                            mma_bf16(d_tmem, make_desc(ao + L.a_bytes, 128, WG_PLANE), db, IDESC2, 1);
-                            mma_bf16(d_tmem, make_desc(ao + 2 * L.a_bytes, 128, WG_PLANE), db, IDESC1, 1);
-                        }
+                        const uint32_t a_lo = a_lo0 + ks * 16 + kx;
+                        mma_bf16_parts(d_tmem, a_lo, a_hi_w, b_lo, b_hi_w, IDESC_A, ks == 0 ? accum : 1u);
+                        if (XPL > 1 && GPL > 1) mma_bf16_parts(d_tmem, a_lo + apl16, a_hi_w, b_lo, b_hi_w, IDESC_B, 1);
+                        if (XPL > 2 && GPL > 2) mma_bf16_parts(d_tmem, a_lo + 2 * apl16, a_hi_w, b_lo, b_hi_w, IDESC_C, 1);
                     }
-                    accum = 1;
                 }
+                accum = 1;
                 mma_commit(&empty[s]);
             }
             __syncwarp();
@@ -359,13 +382,13 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
             float t[16];
 #pragma unroll
             for (int h = 0; h < COUT / 16; ++h) {
-                tmem_ld16(taddr + 2 * COUT + h * 16, v + h * 16);
-                tmem_ld16(taddr + COUT + h * 16, t);
+                tmem_ld16(taddr + (GPL - 1) * COUT + h * 16, v + h * 16);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
-                tmem_ld16(taddr + h * 16, t);
+                for (int blk = GPL - 2; blk >= 0; --blk) {
+                    tmem_ld16(taddr + blk * COUT + h * 16, t);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                    for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                }
             }
             if (m < MROWS_USED) {
 #pragma unroll
@@ -400,14 +423,14 @@ __global__ void k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas
     if (i < nw) dw[i] = s * scale; else db[i - nw] = s;
 }
 
-template <int CIN_CHUNKS, int COUT>
+template <int CIN_CHUNKS, int COUT, int XPL, int GPL>
 static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st) {
-    WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT);
+    WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, XPL, GPL);
     CB_CHECK(L.total <= 227 * 1024, "wgrad_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
-    CB_CUDA(cudaFuncSetAttribute(k_wgrad_umma<CIN_CHUNKS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CUDA(cudaFuncSetAttribute(k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int nblocks = (int)((a.g.NP + WG_BLOCK - 1) / WG_BLOCK);
     int grid = nblocks < num_sms ? nblocks : num_sms;
-    k_wgrad_umma<CIN_CHUNKS, COUT><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);
+    k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);
     CB_LAUNCH_CHECK();
     int nw = 9 * a.cin_real * a.cout;
     k_wgrad_umma_reduce<<<(nw + a.cout + 255) / 256, 256, 0, st>>>(partial, grid, CIN_CHUNKS * 8, a.cin_real, a.cout, a.scale, a.dw, a.db);
@@ -417,10 +440,20 @@ static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, 
 
 int launch_wgrad_umma(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st) {
     CB_CHECK(TILE_M + a.g.Wp + 2 <= GUARD, "wgrad_umma: guard too small for Wp=%d", a.g.Wp);
-    if (a.cin_chunks == 1 && a.cout == 16) return launch_wgrad_umma_t<1, 16>(a, partial, num_sms, st);
-    if (a.cin_chunks == 2 && a.cout == 16) return launch_wgrad_umma_t<2, 16>(a, partial, num_sms, st);
-    if (a.cin_chunks == 2 && a.cout == 32) return launch_wgrad_umma_t<2, 32>(a, partial, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 32) return launch_wgrad_umma_t<4, 32>(a, partial, num_sms, st);
+    // gradients are carried with 2 planes (16 bits): X_hi*[G_hi|G_mid] + X_mid*[G_hi]; with 3-plane G the full 6 products
+    const int gpl = a.gy.lo ? 3 : 2;
+    const int xpl = a.x.mid ? (gpl == 3 && a.x.lo ? 3 : 2) : 1;
+    if (gpl == 2) {
+        if (a.cin_chunks == 1 && a.cout == 16) return launch_wgrad_umma_t<1, 16, 1, 2>(a, partial, num_sms, st);
+        if (a.cin_chunks == 2 && a.cout == 16 && xpl == 2) return launch_wgrad_umma_t<2, 16, 2, 2>(a, partial, num_sms, st);
+        if (a.cin_chunks == 2 && a.cout == 32 && xpl == 2) return launch_wgrad_umma_t<2, 32, 2, 2>(a, partial, num_sms, st);
+        if (a.cin_chunks == 4 && a.cout == 32 && xpl == 2) return launch_wgrad_umma_t<4, 32, 2, 2>(a, partial, num_sms, st);
+    } else {
+        if (a.cin_chunks == 1 && a.cout == 16) return launch_wgrad_umma_t<1, 16, 1, 3>(a, partial, num_sms, st);
+        if (a.cin_chunks == 2 && a.cout == 16 && xpl == 3) return launch_wgrad_umma_t<2, 16, 3, 3>(a, partial, num_sms, st);
+        if (a.cin_chunks == 2 && a.cout == 32 && xpl == 3) return launch_wgrad_umma_t<2, 32, 3, 3>(a, partial, num_sms, st);
+        if (a.cin_chunks == 4 && a.cout == 32 && xpl == 3) return launch_wgrad_umma_t<4, 32, 3, 3>(a, partial, num_sms, st);
+    }
     CB_CHECK(false, "wgrad_umma: unsupported shape cin_chunks=%d cout=%d", a.cin_chunks, a.cout);
 }
 

@@ -2,6 +2,7 @@
 // Model: IMPALA-ResNet channels (16,32,32), hidden 256, linear actor/critic  (cleanba/cleanba_ppo.py:149-203).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <math.h>
@@ -129,6 +130,7 @@ struct cb_ctx {
     uint32_t* sort_keys = nullptr;
     int perm_cap = 0;
     int last_n = 0;
+    int grad_planes = 2;    // bf16 planes of gradient tensors (2 = 16 bits; CLEANBA_GRAD_PLANES=3 for 24 bits)
 };
 
 namespace cb {
@@ -146,7 +148,8 @@ static long long plane_px_for(int max_batch, int H) {
     return GUARD + np + GUARD;
 }
 
-static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool planes, bool lo, bool stream) {
+// lo: allocate the split planes beyond hi; nsplit = 3 (hi, mid, lo: forward activations) or 2 (hi, mid: gradients)
+static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool planes, bool lo, bool stream, int nsplit = 3) {
     a.C = C; a.H = H;
     const int chunks = (C + 7) / 8;
     if (planes) {
@@ -158,8 +161,10 @@ static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool planes, bool lo, bool
         if (lo) {
             if (dev_alloc(c, &p, bytes)) return -1;
             a.pl.mid = (bf16*)p + (long long)GUARD * 8;
-            if (dev_alloc(c, &p, bytes)) return -1;
-            a.pl.lo = (bf16*)p + (long long)GUARD * 8;
+            if (nsplit == 3) {
+                if (dev_alloc(c, &p, bytes)) return -1;
+                a.pl.lo = (bf16*)p + (long long)GUARD * 8;
+            }
         }
     }
     if (stream) {
@@ -190,6 +195,7 @@ struct ProfScope {
     }
 };
 static double planes_bytes(const ConvGeom& g, int chunks, bool lo) { return (double)g.NP * chunks * 8 * (lo ? 6 : 2); }
+static double planes_bytes(const ConvGeom& g, int chunks, const Planes& p) { return (double)g.NP * chunks * 8 * 2 * (p.lo ? 3 : (p.mid ? 2 : 1)); }
 static double stream_bytes(const ConvGeom& g, int chunks) { return (double)g.NP * chunks * 8 * 4; }
 
 static int refresh_weights(cb_ctx* c, cudaStream_t st) {
@@ -221,9 +227,9 @@ static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
     char name[96];
     snprintf(name, sizeof(name), "%s<cin%d,cout%d>@%dx%d", a.transpose ? "conv_dgrad" : "conv_fwd", a.cin_real, a.cout, a.g.H, a.g.W);
     const double flops = 2.0 * a.g.n * a.g.H * a.g.W * 9.0 * a.cin_real * a.cout;
-    double bytes = planes_bytes(a.g, a.cin_chunks, a.in.lo != nullptr);
+    double bytes = planes_bytes(a.g, a.cin_chunks, a.in);
     if (a.ep.out_s) bytes += stream_bytes(a.g, a.cout / 8);
-    if (a.ep.out.hi) bytes += planes_bytes(a.g, a.cout / 8, true);
+    if (a.ep.out.hi) bytes += planes_bytes(a.g, a.cout / 8, a.ep.out);
     if (a.ep.res) bytes += stream_bytes(a.g, a.cout / 8);
     if (a.ep.mask_hi) bytes += planes_bytes(a.g, a.cout / 8, false);
     ProfScope ps(c, name, flops, bytes, st);
@@ -240,7 +246,7 @@ static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, cons
     char name[96];
     snprintf(name, sizeof(name), "conv_wgrad<cin%d,cout%d>@%dx%d", L.cin, L.cout, g.H, g.W);
     ProfScope ps(c, name, 2.0 * g.n * g.H * g.W * 9.0 * L.cin * L.cout,
-                 planes_bytes(g, w.cin_chunks, x.pl.lo != nullptr) + planes_bytes(g, L.cout / 8, true), st);
+                 planes_bytes(g, w.cin_chunks, x.pl) + planes_bytes(g, L.cout / 8, gy.pl), st);
     if (c->cfg.conv_backend == CB_CONV_SIMT) return launch_wgrad_simt(w, c->wg_partial, 296, st);
     return launch_wgrad_umma(w, c->wg_partial, c->num_sms, st);
 }
@@ -411,6 +417,7 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->A = cfg->num_actions;
     c->leaves = build_leaves(c->A);
+    if (const char* gp = getenv("CLEANBA_GRAD_PLANES")) c->grad_planes = (atoi(gp) == 3) ? 3 : 2;
     c->nparam = c->leaves.back().offset + c->leaves.back().size();
     bool ok = false;
     do {
@@ -474,10 +481,11 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
                 void* ap;
                 if (dev_alloc(c, &ap, (size_t)cfg->max_batch * (Ho + 2) * (Ho + 2) * C)) { fail = true; break; }
                 S.amax = (uint8_t*)ap;
-                fail |= alloc_act(c, S.gA, C, Ho, true, true, true) != 0;
-                fail |= alloc_act(c, S.gB, C, Ho, true, true, false) != 0;
-                fail |= alloc_act(c, S.gC, C, Ho, true, true, true) != 0;
-                fail |= alloc_act(c, S.gBin, C, Hin, true, true, false) != 0;
+                const int gs = c->grad_planes;
+                fail |= alloc_act(c, S.gA, C, Ho, true, true, true, gs) != 0;
+                fail |= alloc_act(c, S.gB, C, Ho, true, true, false, gs) != 0;
+                fail |= alloc_act(c, S.gC, C, Ho, true, true, true, gs) != 0;
+                fail |= alloc_act(c, S.gBin, C, Hin, true, true, false, gs) != 0;
             }
         }
         if (fail) break;

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_dense_bwd_x(DenseArgs a, const float* _
         long long ooff = ((long long)chunk * out.plane_px + q) * 8 + e0;
         *reinterpret_cast<uint2*>(out.hi + ooff) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
         *reinterpret_cast<uint2*>(out.mid + ooff) = make_uint2(pack_bf16x2(md[0], md[1]), pack_bf16x2(md[2], md[3]));
-        *reinterpret_cast<uint2*>(out.lo + ooff) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+        if (out.lo) *reinterpret_cast<uint2*>(out.lo + ooff) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
     }
 }
 
@@ -208,7 +208,7 @@ int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, float* out_s, Plan
         size_t npr = (size_t)((NP + 127) / 128 * 128);   // zero up to the 128-pixel tile boundary (wgrad reads it)
         CB_CUDA(cudaMemsetAsync(out.hi + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
         CB_CUDA(cudaMemsetAsync(out.mid + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
-        CB_CUDA(cudaMemsetAsync(out.lo + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
+        if (out.lo) CB_CUDA(cudaMemsetAsync(out.lo + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
     }
     dim3 grid((a.n + TM - 1) / TM, (DK + TN - 1) / TN);
     k_dense_bwd_x<<<grid, 256, 0, st>>>(a, dpre, out_s, out);

