@@ -145,10 +145,20 @@ class Cycle:
         Bl = N_ENVS * N_THREADS
         self.Bl = Bl
         self.learner = PPOLearner(self.dev, PPOHyper(), T=T_STEPS, Bl=Bl, world_learners=world, allreduce=allreduce)
-        self.actor = ag.Context(self.dev, max_batch=N_ENVS, train=False)
         params = init_params(seed)
         self.learner.ctx.set_params(params)
-        self.learner.ctx.publish_to(self.actor)
+        from cleanba_b200.prng import first_key
+        # one actor context + CUDA-graphed step per actor thread, each on its own stream (the reference runs
+        # num_actor_threads = 2 Python threads per actor device, cleanba_ppo.py:670-686)
+        self.actors, self.graphed = [], []
+        for th in range(N_THREADS):
+            a = ag.Context(self.dev, max_batch=N_ENVS, train=False)
+            self.learner.ctx.publish_to(a)
+            torch.cuda.synchronize()
+            key = ag.key_tensor(first_key(seed), self.dev)
+            self.actors.append(a)
+            self.graphed.append(ag.GraphedActor(a, N_ENVS, key))
+        self.actor = self.actors[0]
         d = self.dev
         self.obs = torch.zeros(T_STEPS, Bl, 4, 84, 84, dtype=torch.uint8, device=d)
         self.actions = torch.zeros(T_STEPS, Bl, dtype=torch.int32, device=d)
@@ -158,9 +168,8 @@ class Cycle:
         self.rew_pool = (torch.multinomial(torch.tensor([.05, .9, .05]), 8 * T_STEPS * Bl, True, generator=g).float() - 1).reshape(8, T_STEPS, Bl).to(d)
         self.done_pool = (torch.rand(8, T_STEPS, Bl, generator=g) < 1 / 500).to(d)
         self.next_done = torch.zeros(Bl, dtype=torch.bool, device=d)
-        from cleanba_b200.prng import first_key
-        self.keys = [ag.key_tensor(first_key(seed), d) for _ in range(N_THREADS)]
         self.lkey = ag.key_tensor(first_key(seed), d)
+        self.act_host = [torch.empty(N_ENVS, dtype=torch.int32).pin_memory() for _ in range(N_THREADS)]
         # frame pools: 256 distinct [60,4,84,84] batches = 433 MB (> 126 MB L2); host copy pinned for the e2e path
         rng = np.random.Generator(np.random.PCG64(seed))
         host = torch.empty(256, N_ENVS, 4, 84, 84, dtype=torch.uint8).pin_memory()
@@ -173,20 +182,32 @@ class Cycle:
     def step(self, e2e: bool):
         torch = self.torch
         pool = self.host_pool if e2e else self.dev_pool
+        main = torch.cuda.current_stream(self.dev)
+        for g in self.graphed:
+            g.stream.wait_stream(main)                 # new parameters (publish) are visible before the rollout starts
         for t in range(T_STEPS):
-            for th in range(N_THREADS):
+            for th, g in enumerate(self.graphed):
                 c = slice(th * N_ENVS, (th + 1) * N_ENVS)
-                slot = self.obs[t, c]
-                slot.copy_(pool[self.cursor % 256], non_blocking=True)     # env frame -> rollout storage (H2D when e2e)
+                g.step(pool[self.cursor % 256])                         # frame -> device (H2D from pinned memory when e2e) + graph replay
                 self.cursor += 1
-                self.actor.actor_step(slot, self.keys[th], out=(self.actions[t, c], self.logprobs[t, c], self.values[t, c], None))
-                if e2e:
-                    _ = self.actions[t, c].cpu()                           # np.array(action): the per-step sync (cleanba_ppo.py:317)
-                    self.h2d += slot.numel(); self.d2h += N_ENVS * 4
+                with torch.cuda.stream(g.stream):                       # this step's transition -> rollout storage row t
+                    self.obs[t, c].copy_(g.obs, non_blocking=True)
+                    self.actions[t, c].copy_(g.action, non_blocking=True)
+                    self.logprobs[t, c].copy_(g.logprob, non_blocking=True)
+                    self.values[t, c].copy_(g.value, non_blocking=True)
+                    if e2e:
+                        self.act_host[th].copy_(g.action, non_blocking=True)
+            if e2e:
+                for th, g in enumerate(self.graphed):
+                    g.stream.synchronize()                              # np.array(action): the per-step sync (cleanba_ppo.py:317)
+                    self.h2d += g.obs.numel(); self.d2h += N_ENVS * 4
+        for g in self.graphed:
+            main.wait_stream(g.stream)
         k = (self.cursor // 256) % 8
         stats = self.learner.update(self.obs, self.done_pool[k], self.actions, self.logprobs, self.values, self.rew_pool[k],
                                     self.obs[0], self.next_done, self.lkey)
-        self.learner.ctx.publish_to(self.actor)                            # params_queue.put(device_params) (cleanba_ppo.py:721-725)
+        for a in self.actors:
+            self.learner.ctx.publish_to(a)                             # params_queue.put(device_params) (cleanba_ppo.py:721-725)
         if e2e:
             _ = stats.cpu(); self.d2h += 20
         return stats
@@ -207,7 +228,9 @@ def run_our_arm(args):
     from cleanba_b200 import lib
     cyc = Cycle(f"cuda:{local_rank}", world, allreduce)
     if world > 1:   # identical initial parameters on every learner (the reference relies on equal seeds, cleanba_ppo.py:468)
-        pv = cyc.learner.ctx.params_view(); dist.broadcast(pv, 0); cyc.learner.ctx.refresh_weights(); cyc.learner.ctx.publish_to(cyc.actor)
+        pv = cyc.learner.ctx.params_view(); dist.broadcast(pv, 0); cyc.learner.ctx.refresh_weights()
+        for a in cyc.actors:
+            cyc.learner.ctx.publish_to(a)
 
     def barrier():
         if world > 1:
@@ -218,14 +241,16 @@ def run_our_arm(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         if profile:
-            cyc.learner.ctx.profile(True); cyc.actor.profile(True)
+            cyc.learner.ctx.profile(True)
         l0 = lib.load().cb_launch_count()
+        r0 = sum(g.replays for g in cyc.graphed)
         ev0.record()
         for _ in range(steps):
             cyc.step(e2e)
         ev1.record()
         barrier()
-        launches = lib.load().cb_launch_count() - l0
+        # kernels of libcleanba_b200 in the timed region: eager launches + kernels inside the CUDA-graph replays
+        launches = lib.load().cb_launch_count() - l0 + (sum(g.replays for g in cyc.graphed) - r0) * cyc.graphed[0].kernels_per_replay
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
@@ -239,8 +264,8 @@ def run_our_arm(args):
         sampler.start()
     ms, launches = timed(False, args.steps)                      # `value`: no instrumentation in the timed region
     ms_prof, _ = timed(False, args.steps, profile=True)           # same region again with per-kernel CUDA-event brackets
-    rep = cyc.learner.ctx.profile_report() + cyc.actor.profile_report()
-    cyc.learner.ctx.profile(False); cyc.actor.profile(False)
+    rep = cyc.learner.ctx.profile_report()        # (the actor steps are CUDA-graph replays: no per-kernel brackets inside)
+    cyc.learner.ctx.profile(False)
     cyc.h2d = cyc.d2h = 0
     ms_e2e, _ = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -252,8 +277,8 @@ def run_our_arm(args):
     peaks = load_peaks()
     agg = {}
     for r in rep:
-        a = agg.setdefault(r["name"], dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
-        a["ms"] += r["ms"]; a["calls"] += r["calls"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]
+        a = agg.setdefault(r["name"], dict(ms=0.0, calls=0, records=0, flops=0.0, bytes=0.0))
+        a["ms"] += r["ms"]; a["calls"] += r["calls"]; a["records"] += r["records"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]
     top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     name, a = top
     ai = a["flops"] / max(a["bytes"], 1.0)
@@ -267,7 +292,7 @@ def run_our_arm(args):
     else:
         roof = dict(bound="hbm", achieved=a["bytes"] / (a["ms"] * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=name, kernel_share_of_step=a["ms"] / ms_prof,
-                algorithmic_bytes_per_launch=a["bytes"] / max(a["calls"], 1), profiled_ms_per_step=ms_prof / args.steps,
+                algorithmic_bytes_per_launch=a["bytes"] / max(a["records"], 1), profiled_ms_per_step=ms_prof / args.steps,
                 peak_source=peaks["src"], launches=a["calls"],
                 algorithmic_tflops=a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["flops"] else 0.0,
                 kernels={k: round(v["ms"] / args.steps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]})

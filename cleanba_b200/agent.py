@@ -200,6 +200,47 @@ class Context:
                                          _ptr(norm_out), _stream(self.device)))
 
 
+class GraphedActor:
+    """The actor step captured ONCE into a CUDA graph and replayed every environment step.
+
+    At N = 60 the ~25 kernels of get_action_and_value are microseconds each, so launch overhead and inter-kernel gaps
+    dominate an eager step; a replay costs one launch.  The graph reads a static observation buffer and the device-side
+    PRNG key (advanced in place by every replay) and writes static output buffers; `step()` copies the frame in
+    (host -> device or device -> device) on the actor's own stream and replays."""
+
+    def __init__(self, ctx: Context, n: int, key: torch.Tensor, want_logits: bool = False, stream: Optional[torch.cuda.Stream] = None):
+        d = ctx.device
+        self.ctx, self.n, self.key = ctx, n, key
+        self.stream = stream or torch.cuda.Stream(d)
+        self.obs = torch.zeros(n, 4, 84, 84, dtype=torch.uint8, device=d)
+        self.action = torch.zeros(n, dtype=torch.int32, device=d)
+        self.logprob = None if want_logits else torch.zeros(n, dtype=torch.float32, device=d)
+        self.value = None if want_logits else torch.zeros(n, dtype=torch.float32, device=d)
+        self.logits = torch.zeros(n, ctx.num_actions, dtype=torch.float32, device=d) if want_logits else None
+        out = (self.action, self.logprob, self.value, self.logits)
+        key_backup = key.clone()
+        with torch.cuda.device(d):
+            self.stream.wait_stream(torch.cuda.current_stream(d))
+            with torch.cuda.stream(self.stream):
+                ctx.actor_step(self.obs, key, out=out)        # warm-up (sets function attributes, touches every buffer)
+            self.stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            l0 = ctx.lib.cb_launch_count()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                ctx.actor_step(self.obs, key, out=out)
+            self.kernels_per_replay = int(ctx.lib.cb_launch_count() - l0)   # kernels of this library inside one replay
+            self.replays = 0
+            self.stream.synchronize()
+        key.copy_(key_backup)                                 # warm-up and capture do not consume randomness
+
+    def step(self, obs_src: torch.Tensor):
+        """Enqueue one actor step on self.stream; results are in self.action / logprob / value / logits."""
+        with torch.cuda.stream(self.stream):
+            self.obs.copy_(obs_src, non_blocking=True)
+            self.graph.replay()
+            self.replays += 1
+
+
 def _as_u8(t: torch.Tensor, device, name):
     if t.dtype == torch.bool:
         t = t.view(torch.uint8)

@@ -209,9 +209,16 @@ template <int CIN_CHUNKS, int COUT, int APL>
 static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
     ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, APL);
     CB_CHECK(L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
-    // always the device maximum: the attribute is per function and contexts on other host threads launch the same
-    // instantiation with other window sizes concurrently
-    CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // Opt in to the device maximum once per device: the attribute is per function (contexts on other host threads launch
+    // the same instantiation with other window sizes concurrently), and nothing but launches may happen while a
+    // CUDA graph is being captured.
+    static std::atomic<unsigned> attr_done{0};
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    if (!(attr_done.load() & (1u << dev))) {
+        CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done.fetch_or(1u << dev);
+    }
     int ntiles = (int)((a.g.NP + TILE_M - 1) / TILE_M);
     int ctas_per_sm = L.total <= 110 * 1024 ? 2 : 1;
     int grid = ntiles < num_sms * ctas_per_sm ? ntiles : num_sms * ctas_per_sm;
@@ -427,7 +434,13 @@ template <int CIN_CHUNKS, int COUT, int XPL, int GPL>
 static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st) {
     WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, XPL, GPL);
     CB_CHECK(L.total <= 227 * 1024, "wgrad_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
-    CB_CUDA(cudaFuncSetAttribute(k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    static std::atomic<unsigned> attr_done{0};
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    if (!(attr_done.load() & (1u << dev))) {
+        CB_CUDA(cudaFuncSetAttribute(k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done.fetch_or(1u << dev);
+    }
     int nblocks = (int)((a.g.NP + WG_BLOCK - 1) / WG_BLOCK);
     int grid = nblocks < num_sms ? nblocks : num_sms;
     k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);

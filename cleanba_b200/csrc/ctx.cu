@@ -103,7 +103,7 @@ struct Stage {
 
 using namespace cb;
 
-struct ProfAgg { long long launches = 0; double ms = 0, flops = 0, bytes = 0; };
+struct ProfAgg { long long launches = 0, records = 0; double ms = 0, flops = 0, bytes = 0; };
 struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; int launches; };
 
 struct cb_ctx {
@@ -649,7 +649,7 @@ int cb_ppo_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int mb, const
     h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
     h.idx = idx; h.actions = actions; h.old_logprobs = logprobs; h.advantages = advantages; h.returns = returns;
     h.clip_coef = clip_coef; h.ent_coef = ent_coef; h.vf_coef = vf_coef;
-    h.dpre = c->dpre; h.dlogits = c->dlogits; h.terms = c->terms; h.stats = stats;
+    h.dpre = c->dpre; h.dlogits = c->dlogits; h.terms = c->terms; h.stats = stats; h.wgrad_scratch = c->wg_partial;
     h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
     {
         ProfScope ps(c, "ppo_loss_head", 6.0 * mb * HIDDEN * (c->A + 1), (double)mb * (2 * HIDDEN * 4 + 92 + 76), st);
@@ -675,7 +675,7 @@ int cb_impala_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int T1, in
     h.idx = idx; h.actions = actions; h.behaviour_logits = behaviour_logits; h.rewards = rewards; h.dones = dones;
     h.firststeps = firststeps; h.gamma = gamma; h.vf_coef = vf_coef; h.ent_coef = ent_coef;
     h.logits_scratch = c->logits_scratch; h.cell_scratch = c->cell_scratch; h.dpre = c->dpre; h.dlogits = c->dlogits;
-    h.stats = stats;
+    h.stats = stats; h.wgrad_scratch = c->wg_partial;
     h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
     {
         ProfScope ps(c, "vtrace_loss_head", 6.0 * n * HIDDEN * (c->A + 1), (double)n * (2 * HIDDEN * 4 + 157 + 76), st);
@@ -730,14 +730,14 @@ int cb_profile_report(cb_ctx* c, char* buf, int cap) {
         float ms = 0.f;
         CB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
         ProfAgg& a = agg[r.name];
-        a.launches += r.launches; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+        a.launches += r.launches; a.records += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
     }
     std::string out = "[";
     bool first = true;
     for (auto& kv : agg) {
         char line[384];
-        snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"calls\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
-                 first ? "" : ", ", kv.first.c_str(), kv.second.launches, kv.second.ms, kv.second.flops, kv.second.bytes);
+        snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"calls\": %lld, \"records\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                 first ? "" : ", ", kv.first.c_str(), kv.second.launches, kv.second.records, kv.second.ms, kv.second.flops, kv.second.bytes);
         out += line;
         first = false;
     }

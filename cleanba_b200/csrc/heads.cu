@@ -211,20 +211,49 @@ __global__ void __launch_bounds__(256) k_ppo_stats(const float* __restrict__ ter
 }
 
 // Head weight gradients: dWa[k][a] = sum_b hidden[b][k] dl[b][a]; column A of dl is dvalue (critic); k == 256 is the bias.
-__global__ void __launch_bounds__(128) k_head_wgrad(const float* __restrict__ hidden, const float* __restrict__ dl, int n,
-                                                    int A, float* dwa, float* dba, float* dwc, float* dbc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int K1 = HIDDEN + 1;
-    if (t >= K1 * (A + 1)) return;
-    int a = t / K1, k = t % K1;
-    float s = 0.f;
-    if (k < HIDDEN) {
-        for (int b = 0; b < n; ++b) s = fmaf(hidden[(long long)b * HIDDEN + k], dl[(long long)b * (A + 1) + a], s);
-        if (a < A) dwa[k * A + a] = s; else dwc[k] = s;
-    } else {
-        for (int b = 0; b < n; ++b) s += dl[(long long)b * (A + 1) + a];
-        if (a < A) dba[a] = s; else dbc[0] = s;
+// Two deterministic stages: every block reduces a slice of HW_SLICE samples (hidden tile staged in shared memory, one
+// thread per hidden unit), then a second kernel adds the slices in a fixed order.
+constexpr int HW_SLICE = 32;
+__global__ void __launch_bounds__(HIDDEN) k_head_wgrad_partial(const float* __restrict__ hidden, const float* __restrict__ dl,
+                                                               int n, int A, float* __restrict__ partial) {
+    __shared__ float sh[HW_SLICE][HIDDEN];
+    __shared__ float sd[HW_SLICE][MAX_ACTIONS + 1];
+    const int b0 = blockIdx.x * HW_SLICE, k = threadIdx.x;
+    const int nb = min(HW_SLICE, n - b0);
+    for (int b = 0; b < nb; ++b) sh[b][k] = hidden[(long long)(b0 + b) * HIDDEN + k];
+    for (int t = threadIdx.x; t < nb * (A + 1); t += HIDDEN) sd[t / (A + 1)][t % (A + 1)] = dl[(long long)b0 * (A + 1) + t];
+    __syncthreads();
+    float* out = partial + (long long)blockIdx.x * (HIDDEN + 1) * (A + 1);
+    for (int a = 0; a <= A; ++a) {
+        float s = 0.f;
+        for (int b = 0; b < nb; ++b) s = fmaf(sh[b][k], sd[b][a], s);
+        out[k * (A + 1) + a] = s;
     }
+    if (k <= A) {   // bias row
+        float s = 0.f;
+        for (int b = 0; b < nb; ++b) s += sd[b][k];
+        out[HIDDEN * (A + 1) + k] = s;
+    }
+}
+__global__ void __launch_bounds__(128) k_head_wgrad_reduce(const float* __restrict__ partial, int nslices, int A, float* dwa,
+                                                           float* dba, float* dwc, float* dbc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (HIDDEN + 1) * (A + 1)) return;
+    int k = t / (A + 1), a = t % (A + 1);
+    float s = 0.f;
+    for (int i = 0; i < nslices; ++i) s += partial[(long long)i * (HIDDEN + 1) * (A + 1) + t];
+    if (k < HIDDEN) { if (a < A) dwa[k * A + a] = s; else dwc[k] = s; }
+    else { if (a < A) dba[a] = s; else dbc[0] = s; }
+}
+static int launch_head_wgrad(const float* hidden, const float* dl, int n, int A, float* scratch, float* dwa, float* dba,
+                             float* dwc, float* dbc, cudaStream_t st) {
+    int nslices = (n + HW_SLICE - 1) / HW_SLICE;
+    k_head_wgrad_partial<<<nslices, HIDDEN, 0, st>>>(hidden, dl, n, A, scratch);
+    CB_LAUNCH_CHECK();
+    int total = (HIDDEN + 1) * (A + 1);
+    k_head_wgrad_reduce<<<(total + 127) / 128, 128, 0, st>>>(scratch, nslices, A, dwa, dba, dwc, dbc);
+    CB_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
@@ -234,10 +263,7 @@ int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
     CB_LAUNCH_CHECK();
     k_ppo_stats<<<1, 256, 0, st>>>(a.terms, a.n, a.ent_coef, a.vf_coef, a.stats);
     CB_LAUNCH_CHECK();
-    int total = (HIDDEN + 1) * (a.num_actions + 1);
-    k_head_wgrad<<<(total + 127) / 128, 128, 0, st>>>(a.hidden, a.dlogits, a.n, a.num_actions, a.dwa, a.dba, a.dwc, a.dbc);
-    CB_LAUNCH_CHECK();
-    return 0;
+    return launch_head_wgrad(a.hidden, a.dlogits, a.n, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,11 +381,7 @@ int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st) {
     size_t smem = head_smem_bytes(a.num_actions) + (1 + 3 * 1024) * sizeof(float);
     k_impala_head<<<1, 1024, smem, st>>>(a);
     CB_LAUNCH_CHECK();
-    int total = (HIDDEN + 1) * (a.num_actions + 1);
-    k_head_wgrad<<<(total + 127) / 128, 128, 0, st>>>(a.hidden, a.dlogits, a.T1 * a.B, a.num_actions, a.dwa, a.dba,
-                                                       a.dwc, a.dbc);
-    CB_LAUNCH_CHECK();
-    return 0;
+    return launch_head_wgrad(a.hidden, a.dlogits, a.T1 * a.B, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
 }
 
 }  // namespace cb

@@ -63,6 +63,7 @@ struct PpoHeadArgs {
     float* dlogits;              // [n][num_actions + 1] (last column = dvalue) scratch for the head weight grads
     float* terms;                // [n][5] per-sample loss terms scratch
     float* stats;                // [5] loss, pg_loss, v_loss, entropy, approx_kl
+    float* wgrad_scratch;        // [ceil(n/32)][257][A+1] partial head weight gradients
     float *dwa, *dba, *dwc, *dbc;
 };
 int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st);
@@ -82,6 +83,7 @@ struct ImpalaHeadArgs {
     float* dpre;
     float* dlogits;
     float* stats;                // [4] total, pg, baseline, entropy
+    float* wgrad_scratch;
     float *dwa, *dba, *dwc, *dbc;
 };
 int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st);
