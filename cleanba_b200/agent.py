@@ -200,6 +200,11 @@ class Context:
                                          _ptr(norm_out), _stream(self.device)))
 
 
+import threading as _threading
+
+_CAPTURE_LOCK = _threading.Lock()
+
+
 class GraphedActor:
     """The actor step captured ONCE into a CUDA graph and replayed every environment step.
 
@@ -225,9 +230,10 @@ class GraphedActor:
                 ctx.actor_step(self.obs, key, out=out)        # warm-up (sets function attributes, touches every buffer)
             self.stream.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            l0 = ctx.lib.cb_launch_count()
-            with torch.cuda.graph(self.graph, stream=self.stream):
-                ctx.actor_step(self.obs, key, out=out)
+            with _CAPTURE_LOCK:      # one capture at a time; thread-local mode: other host threads keep using CUDA freely
+                l0 = ctx.lib.cb_launch_count()
+                with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+                    ctx.actor_step(self.obs, key, out=out)
             self.kernels_per_replay = int(ctx.lib.cb_launch_count() - l0)   # kernels of this library inside one replay
             self.replays = 0
             self.stream.synchronize()

@@ -256,7 +256,6 @@ constexpr int WG_STAGES = 3;
 constexpr int WG_WINX = WG_BLOCK + 2;     // pixels per shifted copy
 constexpr int WG_PLANE = WG_WINX * 16;    // bytes
 constexpr int WG_THREADS = 192;
-constexpr int WG_MROWS = 128;
 
 struct WgSmemLayout {
     int groups;        // real M groups = 3 * cin_chunks
@@ -265,8 +264,12 @@ struct WgSmemLayout {
     int a_bytes;       // one A region (one split plane): (groups + 1) copies (last = ones / zeros)
     int b_chunk;       // bytes of one (plane, chunk) of G
     int b_bytes;       // all of B: 3 planes x cout/8 chunks
-    int stage_bytes, total;
+    int stage_bytes, stages, total;
 };
+// Measured (tools/mma_microbench2.cu, profiles/): one thread can issue a tcgen05.mma every ~50 cycles; the tensor pipe
+// itself needs ~39 cycles for M=128 and <= 25 for M=64 (N <= 32).  wgrad therefore uses M = 64 whenever the stacked
+// (ky, ci) rows fit (<= 64) and runs two CTAs (two issuing threads) per SM whenever shared memory allows.
+__host__ __device__ constexpr int wg_mrows(int cin_chunks) { return (3 * cin_chunks + 1) * 8 <= 64 ? 64 : 128; }
 __host__ __device__ inline WgSmemLayout wg_smem_layout(int cin_chunks, int cout, int xpl, int gpl) {
     WgSmemLayout L;
     L.groups = 3 * cin_chunks;
@@ -276,8 +279,9 @@ __host__ __device__ inline WgSmemLayout wg_smem_layout(int cin_chunks, int cout,
     L.b_chunk = WG_BLOCK * 16;
     L.b_bytes = gpl * (cout / 8) * L.b_chunk;
     L.stage_bytes = L.xplanes * L.a_bytes + L.b_bytes;
-    // the M = 128 instruction reads 16 groups from the A base: pad so the unused groups stay inside the allocation
-    L.total = 1024 + WG_STAGES * L.stage_bytes + 16 * WG_PLANE;
+    L.stages = (1024 + WG_STAGES * L.stage_bytes + (wg_mrows(cin_chunks) / 8) * WG_PLANE <= 112 * 1024) ? WG_STAGES : 2;
+    // the MMA reads M/8 groups from the A base: pad so the unused groups stay inside the allocation
+    L.total = 1024 + L.stages * L.stage_bytes + (wg_mrows(cin_chunks) / 8) * WG_PLANE;
     return L;
 }
 
@@ -286,6 +290,8 @@ template <int CIN_CHUNKS, int COUT, int XPL, int GPL>
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblocks, float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, XPL, GPL);
+    const int NSTAGES = L.stages;
+    constexpr int WG_MROWS = wg_mrows(CIN_CHUNKS);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + WG_STAGES;
     uint64_t* done = empty + WG_STAGES;
@@ -298,12 +304,12 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     constexpr int NCOPY_A = XPL * GROUPS, NCOPY_B = GPL * (COUT / 8);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(done, 1);
         fence_barrier_init();
     }
     // constant "ones" group (hi region) and "zeros" groups (mid / lo regions) of every stage
-    for (int s = 0; s < WG_STAGES; ++s)
+    for (int s = 0; s < NSTAGES; ++s)
         for (int pl = 0; pl < XPL; ++pl) {
             uint32_t* g = reinterpret_cast<uint32_t*>(stages + s * L.stage_bytes + pl * L.a_bytes + GROUPS * WG_PLANE);
             const uint32_t val = pl == 0 ? 0x3F803F80u : 0u;   // bf16 1.0 x2
@@ -338,7 +344,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
                 }
             }
             __syncwarp();
-            if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+            if (++s == NSTAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 5) {
         constexpr uint32_t IDESC_A = make_idesc_bf16(WG_MROWS, GPL * COUT, 1, 1);                         // X plane 0
@@ -372,16 +378,18 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
                 mma_commit(&empty[s]);
             }
             __syncwarp();
-            if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+            if (++s == NSTAGES) { s = 0; ph ^= 1; }
         }
         if (lane == 0) mma_commit(done);
         __syncwarp();
     } else {
         mbar_wait(done, 0);
         tc_fence_after();
-        // D rows: m = ky*C + ci (and m = 3C .. 3C+7: bias rows);  thread = TMEM lane = m
-        const int m = warp * 32 + lane;
+        // D rows: m = ky*C + ci (and m = 3C .. 3C+7: bias rows).  M = 128: TMEM lane = m.  M = 64: row m lives in lane
+        // (m / 16) * 32 + m % 16, i.e. the first 16 lanes of every warp's quadrant (probed, profiles/r01_mma_m64_layout_probe.txt).
+        const int m = WG_MROWS == 128 ? warp * 32 + lane : (lane < 16 ? warp * 16 + lane : (1 << 30));
         constexpr int MROWS_USED = GROUPS * 8 + 8;
+        static_assert(MROWS_USED <= WG_MROWS, "stacked rows exceed the MMA M");
         float* out = partial + (long long)blockIdx.x * (3 * MROWS_USED * COUT);
         for (int kx = 0; kx < 3; ++kx) {
             float v[COUT];
@@ -442,7 +450,8 @@ static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, 
         attr_done.fetch_or(1u << dev);
     }
     int nblocks = (int)((a.g.NP + WG_BLOCK - 1) / WG_BLOCK);
-    int grid = nblocks < num_sms ? nblocks : num_sms;
+    int ctas_per_sm = (L.total <= 112 * 1024 && 3 * GPL * COUT <= 256) ? 2 : 1;   // two CTAs must also share the 512 TMEM columns
+    int grid = nblocks < num_sms * ctas_per_sm ? nblocks : num_sms * ctas_per_sm;
     k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);
     CB_LAUNCH_CHECK();
     int nw = 9 * a.cin_real * a.cout;

@@ -60,9 +60,12 @@ class CudaActor:
         self.key = ag.key_tensor(key, self.dev)
         self.act_host = torch.empty(N, dtype=torch.int32).pin_memory()
         self.staging = torch.empty(N, 4, 84, 84, dtype=torch.uint8).pin_memory()
+        self.graphed = None     # the actor step is captured into a CUDA graph after the first parameter publish
 
     def new_storage(self, rows):
-        with torch.cuda.device(self.dev):
+        # allocate on the actor's stream: the caching allocator recycles a block per allocation stream, and these buffers
+        # are written on self.stream (the learner, which reads them on its own stream, calls record_stream on the payload)
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             return _Storage(self, rows)
 
     def set_params(self, handle):
@@ -71,20 +74,26 @@ class CudaActor:
             self.stream.wait_event(event)
             self.ctx.set_params(snapshot if snapshot.device == self.dev else snapshot.to(self.dev, non_blocking=True))
             self.stream.synchronize()      # the reference blocks on the new params too (cleanba_ppo.py:294-300)
+        if self.graphed is None:
+            with torch.cuda.device(self.dev):
+                self.graphed = ag.GraphedActor(self.ctx, self.N, self.key, want_logits=self.impala, stream=self.stream)
 
     def step(self, storage, t, obs_host):
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             if isinstance(obs_host, np.ndarray):
                 self.staging.numpy()[...] = obs_host
                 obs_host = self.staging
-            slot = storage.obs[t]
-            slot.copy_(obs_host, non_blocking=True)
+            g = self.graphed
+            g.step(obs_host)                                   # H2D of the frame + one graph replay (all ~25 kernels)
+            storage.obs[t].copy_(g.obs, non_blocking=True)     # this step's transition -> row t of the rollout storage
+            storage.actions[t].copy_(g.action, non_blocking=True)
             if self.impala:
-                self.ctx.actor_step(slot, self.key, out=(storage.actions[t], None, None, storage.logitss[t]))
+                storage.logitss[t].copy_(g.logits, non_blocking=True)
             else:
-                self.ctx.actor_step(slot, self.key, out=(storage.actions[t], storage.logprobs[t], storage.values[t], None))
+                storage.logprobs[t].copy_(g.logprob, non_blocking=True)
+                storage.values[t].copy_(g.value, non_blocking=True)
             t0 = time.time()
-            self.act_host.copy_(storage.actions[t], non_blocking=True)
+            self.act_host.copy_(g.action, non_blocking=True)
             self.stream.synchronize()
             return self.act_host.numpy().copy(), time.time() - t0
 
