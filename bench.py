@@ -315,12 +315,24 @@ def run_our_arm(args):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(obj):
+    """The ONE JSON line on the real stdout (fd saved before libraries such as NCCL could write banners to it)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                 # anything else written to stdout (NCCL version banner, library prints) goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -332,14 +344,14 @@ def main():
         if int(os.environ.get("RANK", "0")) != 0:
             return
         r = run_cpu_arm(args.steps, args.warmup)
-        print(json.dumps({
+        _emit({
             "impl": "reference", "metric": "env-steps/sec (Breakout-v5 84x84x4, synthetic frames)", "value": r["value"],
             "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"] + " (PyTorch-CPU restatement of the reference path; the JAX reference cannot be installed here)"},
-            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
     run_our_arm(args)
 

@@ -56,6 +56,10 @@ struct ConvEpilogue {
     float* out_s;             // fp32 stream out, or null
     Planes out;               // bf16 planes out (hi may be null)
     int relu;
+    // optional second copy of the (relu'd) output in the sample-minor layout of the tcgen05 dense layer
+    // (dense_umma.cu): featT[plane][chunk][pixel (H*W, no padding ring)][sample (ft_npad)][8]
+    bf16 *ft_hi, *ft_mid, *ft_lo;
+    int ft_npad, ft_pixpad;
 };
 
 struct ConvArgs {
@@ -130,6 +134,19 @@ __device__ __forceinline__ bool interior(const ConvGeom& g, long long q) {
     return (y >= 1) & (y <= g.H) & (x >= 1) & (x <= g.W);
 }
 
+__device__ __forceinline__ void store_featT(bf16* ft_hi, bf16* ft_mid, bf16* ft_lo, int ft_npad, int ft_pixpad, const ConvGeom& g,
+                                            long long q, int oc, const float* v) {
+    const int b = (int)(q / g.P), r = (int)(q % g.P);
+    const int y = r / g.Wp - 1, x = r % g.Wp - 1;
+    const long long off = (((long long)oc * ft_pixpad + (y * g.W + x)) * ft_npad + b) * 8;
+    float x8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x8[e] = fmaxf(v[e], 0.f);
+    Planes p;
+    p.hi = ft_hi; p.mid = ft_mid; p.lo = ft_lo; p.plane_px = 0;
+    store_planes8(p, off, x8);
+}
+
 // Apply the epilogue to the 8 accumulators of (flat pixel q, output chunk oc) and store.
 __device__ __forceinline__ void conv_epilogue_store(const ConvEpilogue& ep, const ConvGeom& g, long long q, int oc,
                                                     float* acc) {
@@ -169,6 +186,7 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvEpilogue& ep, cons
         for (int e = 0; e < 8; ++e) x[e] = ep.relu ? fmaxf(v[e], 0.f) : v[e];
         store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, x);
     }
+    if (ep.ft_hi && in) store_featT(ep.ft_hi, ep.ft_mid, ep.ft_lo, ep.ft_npad, ep.ft_pixpad, g, q, oc, v);
 }
 
 // Split epilogue for the tcgen05 kernels: the residual / gate operands of a tile are fetched into registers BEFORE the
@@ -233,6 +251,7 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeo
             for (int e = 0; e < 8; ++e) x[e] = ep.relu ? fmaxf(v[e], 0.f) : v[e];
             store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, x);
         }
+        if (ep.ft_hi && p.in) store_featT(ep.ft_hi, ep.ft_mid, ep.ft_lo, ep.ft_npad, ep.ft_pixpad, g, q, oc, v);
     }
 }
 

@@ -130,6 +130,9 @@ struct cb_ctx {
     uint32_t* sort_keys = nullptr;
     int perm_cap = 0;
     int last_n = 0;
+    // tcgen05 dense layer (dense_umma.cu)
+    bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
+    int npad_max = 0;
     int grad_planes = 2;    // bf16 planes of gradient tensors (2 = 16 bits; CLEANBA_GRAD_PLANES=3 for 24 bits)
 };
 
@@ -200,7 +203,19 @@ static double stream_bytes(const ConvGeom& g, int chunks) { return (double)g.NP 
 
 static int refresh_weights(cb_ctx* c, cudaStream_t st) {
     ProfScope ps(c, "pack_weights", 0, 1089232.0 * (4 + 12), st);
-    return launch_pack_conv(c->pack_dev, 15, st);
+    if (launch_pack_conv(c->pack_dev, 15, st)) return -1;
+    if (c->wd_fwd) return launch_pack_dense(c->params + c->off_dense_w, c->wd_fwd, c->wd_dx, st);
+    return 0;
+}
+static DenseUmmaArgs dense_umma_args(cb_ctx* c, int n) {
+    DenseUmmaArgs u;
+    memset(&u, 0, sizeof(u));
+    u.n = n; u.npad = (n + 127) / 128 * 128; u.NP = (long long)n * 169;
+    u.ft_hi = c->ft[0]; u.ft_mid = c->ft[1]; u.ft_lo = c->ft[2];
+    u.dp_hi = c->dpT[0]; u.dp_mid = c->dpT[1];
+    u.w_fwd = c->wd_fwd; u.w_dx = c->wd_dx;
+    u.bias = c->params + c->off_dense_b; u.hidden = c->hidden; u.part = c->dense_part;
+    return u;
 }
 
 static ConvArgs conv_args(cb_ctx* c, int layer, const ConvGeom& g, const Act& in, bool transpose) {
@@ -295,12 +310,17 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             ConvArgs b = conv_args(c, base + 4, go, S.a1, false);
             b.ep.bias = c->params + c->conv[base + 4].off_b;
             b.ep.res = S.b0.s; b.ep.out = S.out.pl; b.ep.relu = (s == 2) ? 1 : 0;
+            if (s == 2 && c->wd_fwd) {   // sample-minor copy of the final features for the tcgen05 dense layer
+                b.ep.ft_hi = c->ft[0]; b.ep.ft_mid = c->ft[1]; b.ep.ft_lo = c->ft[2];
+                b.ep.ft_npad = (n + 127) / 128 * 128; b.ep.ft_pixpad = 124;
+            }
             if (run_conv(c, b, st)) return -1;
         }
     }
     DenseArgs d;
     d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
-    ProfScope ps(c, "dense_fwd", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 4 + (double)kFlat * HIDDEN * 4, st);
+    ProfScope ps(c, "dense_fwd", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 6 + (double)kFlat * HIDDEN * 6, st);
+    if (c->wd_fwd) return launch_dense_fwd_umma(dense_umma_args(c, n), st);
     return launch_dense_fwd(d, c->dense_part, st);
 }
 
@@ -308,13 +328,21 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
 static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
     DenseArgs d;
     d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
-    {
-        ProfScope ps(c, "dense_bwd_w", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 4 + (double)kFlat * HIDDEN * 4, st);
-        if (launch_dense_bwd_w(d, c->dpre, grads + c->off_dense_w, grads + c->off_dense_b, st)) return -1;
-    }
-    {
-        ProfScope ps(c, "dense_bwd_x", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 12 + (double)kFlat * HIDDEN * 4, st);
-        if (launch_dense_bwd_x(d, c->dpre, c->st[2].gA.s, c->st[2].gA.pl, st)) return -1;
+    if (c->wd_fwd) {
+        ProfScope ps(c, "dense_bwd", 4.0 * n * kFlat * HIDDEN, (double)n * kFlat * 12 + (double)kFlat * HIDDEN * 8, st);
+        DenseUmmaArgs u = dense_umma_args(c, n);
+        u.out_s = c->st[2].gA.s; u.out = c->st[2].gA.pl;
+        if (launch_dpre_transpose(c->dpre, n, u.npad, c->dpT[0], c->dpT[1], st)) return -1;
+        if (launch_dense_bwd_umma(u, c->dpre, grads + c->off_dense_w, grads + c->off_dense_b, c->dense_part, st)) return -1;
+    } else {
+        {
+            ProfScope ps(c, "dense_bwd_w", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 4 + (double)kFlat * HIDDEN * 4, st);
+            if (launch_dense_bwd_w(d, c->dpre, grads + c->off_dense_w, grads + c->off_dense_b, st)) return -1;
+        }
+        {
+            ProfScope ps(c, "dense_bwd_x", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 12 + (double)kFlat * HIDDEN * 4, st);
+            if (launch_dense_bwd_x(d, c->dpre, c->st[2].gA.s, c->st[2].gA.pl, st)) return -1;
+        }
     }
     for (int s = 2; s >= 0; --s) {
         Stage& S = c->st[s];
@@ -490,6 +518,27 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
         }
         if (fail) break;
         const size_t mb = (size_t)cfg->max_batch;
+        if (cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_DENSE_SIMT")) {
+            c->npad_max = (cfg->max_batch + 127) / 128 * 128;
+            bool bad = false;
+            for (int i = 0; i < 3 && !bad; ++i) {
+                if (dev_alloc(c, &p, dense_featT_elems(c->npad_max) * sizeof(bf16))) { bad = true; break; }
+                c->ft[i] = (bf16*)p;
+            }
+            if (bad) break;
+            if (dev_alloc(c, &p, dense_pack_fwd_elems() * sizeof(bf16))) break;
+            c->wd_fwd = (bf16*)p;
+            if (dev_alloc(c, &p, dense_pack_dx_elems() * sizeof(bf16))) break;
+            c->wd_dx = (bf16*)p;
+            if (cfg->train) {
+                for (int i = 0; i < 2 && !bad; ++i) {
+                    if (dev_alloc(c, &p, dense_dpreT_elems(c->npad_max) * sizeof(bf16))) { bad = true; break; }
+                    c->dpT[i] = (bf16*)p;
+                }
+                if (bad) break;
+            }
+            if (dense_umma_init()) break;
+        }
         if (dev_alloc(c, &p, mb * HIDDEN * sizeof(float))) break;
         c->hidden = (float*)p;
         size_t part = mb * HIDDEN;

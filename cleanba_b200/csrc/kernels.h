@@ -44,6 +44,29 @@ int launch_dense_bwd_w(const DenseArgs& a, const float* dpre, float* dw, float* 
 // dX -> gradient w.r.t. the (pre-relu) trunk output, masked by the forward relu, as fp32 stream + planes
 int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, float* out_s, Planes out, cudaStream_t st);
 
+// dense_umma.cu (tcgen05 dense layer on the sample-minor copies)
+struct DenseUmmaArgs {
+    int n, npad;                 // samples, samples rounded up to 128
+    long long NP;                // n * 169 (flat pixels of the 11x11 grid with its padding ring)
+    const bf16 *ft_hi, *ft_mid, *ft_lo;   // featT[chunk 4][pixel 124][npad][8]
+    const bf16 *dp_hi, *dp_mid;           // dpreT[256/8][npad][8]
+    const bf16 *w_fwd, *w_dx;             // packed weights (k_pack_dense)
+    const float* bias;
+    float* hidden;               // forward out [n][256]
+    float* part;                 // forward partial sums [psplit][n][256] when the pixels are split over CTAs
+    float* out_s;                // dX stream out
+    Planes out;                  // dX planes out (2 planes)
+};
+int dense_umma_init();
+int launch_pack_dense(const float* w, bf16* fwd, bf16* dx, cudaStream_t st);
+long long dense_pack_fwd_elems();
+long long dense_pack_dx_elems();
+long long dense_featT_elems(int npad);
+long long dense_dpreT_elems(int npad);
+int launch_dense_fwd_umma(const DenseUmmaArgs& a, cudaStream_t st);
+int launch_dense_bwd_umma(const DenseUmmaArgs& a, const float* dpre, float* dw, float* db, float* scratch, cudaStream_t st);
+int launch_dpre_transpose(const float* dpre, int n, int npad, bf16* dp_hi, bf16* dp_mid, cudaStream_t st);
+
 // heads.cu
 int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st);
 int launch_actor_head(const float* hidden, int n, int num_actions, const float* wa, const float* ba, const float* wc,

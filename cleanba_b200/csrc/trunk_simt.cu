@@ -156,45 +156,45 @@ int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int c
 // Backward of the pool in gather form (deterministic, no atomics): every input pixel visits the (<= 4) windows that
 // contain it and takes the window's gradient iff the stored arg-max slot is its own position in that window.
 //   amax: bytes from the forward pass;  dpool: gradient stream on the pooled grid;  out: gradient planes on the input grid
-__global__ void k_pool_bwd(const uint8_t* __restrict__ amax, const float* __restrict__ dpool, ConvGeom gi, ConvGeom go,
-                           int pad_lo, int chunks, Planes out) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long NPr = (gi.NP + 127) / 128 * 128;   // planes are zero-filled up to the 128-pixel tile boundary
-    if (t >= NPr * chunks) return;
-    int jc = (int)(t / NPr);
-    long long q = t % NPr;
-    int img = (int)(q / gi.P);
-    int rr = (int)(q % gi.P);
-    int yp = rr / gi.Wp, xp = rr % gi.Wp;
+// grid = (pixel blocks of one image, image * chunks): 32-bit index math only, no division by the image size.
+__global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ amax, const float* __restrict__ dpool,
+                                                  ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out) {
+    const int img = blockIdx.y / chunks, jc = blockIdx.y % chunks;
+    const int rr = blockIdx.x * blockDim.x + threadIdx.x;          // flat pixel inside the padded image
+    // the last image also zero-fills the planes up to the 128-pixel tile boundary (wgrad reads whole blocks)
+    const int limit = (img == gi.n - 1) ? (int)((gi.NP + 127) / 128 * 128 - (long long)img * gi.P) : gi.P;
+    if (rr >= limit) return;
+    const int yp = rr / gi.Wp, xp = rr - yp * gi.Wp;
     float g[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) g[e] = 0.f;
-    if (q < gi.NP && yp >= 1 && yp <= gi.H && xp >= 1 && xp <= gi.W) {
-        int r = yp - 1, c = xp - 1;
-        int i_lo = max(0, (r + pad_lo - 1) / 2), i_hi = min(go.H - 1, (r + pad_lo) / 2);
-        int j_lo = max(0, (c + pad_lo - 1) / 2), j_hi = min(go.W - 1, (c + pad_lo) / 2);
+    if (rr < gi.P && yp >= 1 && yp <= gi.H && xp >= 1 && xp <= gi.W) {
+        const int r = yp - 1, c = xp - 1;
+        const int i_lo = max(0, (r + pad_lo - 1) >> 1), i_hi = min(go.H - 1, (r + pad_lo) >> 1);
+        const int j_lo = max(0, (c + pad_lo - 1) >> 1), j_hi = min(go.W - 1, (c + pad_lo) >> 1);
+        const long long obase = ((long long)jc * go.NP + (long long)img * go.P) * 8;
         for (int i = i_lo; i <= i_hi; ++i)
             for (int j = j_lo; j <= j_hi; ++j) {
                 const int slot = (r - (2 * i - pad_lo)) * 3 + (c - (2 * j - pad_lo));   // my position inside window (i,j)
-                long long qo = (long long)img * go.P + (long long)(i + 1) * go.Wp + (j + 1);
-                uint2 pk = *reinterpret_cast<const uint2*>(amax + ((long long)jc * go.NP + qo) * 8);
-                const float4* p = reinterpret_cast<const float4*>(dpool + ((long long)jc * go.NP + qo) * 8);
-                float4 a = p[0], b = p[1];
-                float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                const long long o = obase + (long long)((i + 1) * go.Wp + (j + 1)) * 8;
+                const uint2 pk = *reinterpret_cast<const uint2*>(amax + o);
+                const float4* p = reinterpret_cast<const float4*>(dpool + o);
+                const float4 a = p[0], b = p[1];
+                const float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    int am = ((e < 4 ? pk.x : pk.y) >> (8 * (e & 3))) & 0xff;
+                    const int am = ((e < 4 ? pk.x : pk.y) >> (8 * (e & 3))) & 0xff;
                     g[e] += (am == slot) ? d[e] : 0.f;
                 }
             }
     }
-    store_planes8(out, ((long long)jc * out.plane_px + q) * 8, g);
+    store_planes8(out, ((long long)jc * out.plane_px + (long long)img * gi.P + rr) * 8, g);
 }
 
 int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
                     cudaStream_t st) {
-    long long total = (gi.NP + 127) / 128 * 128 * chunks;
-    k_pool_bwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(amax, dpool, gi, go, pad_lo, chunks, out);
+    dim3 grid((gi.P + 127 + 255) / 256, gi.n * chunks);
+    k_pool_bwd<<<grid, 256, 0, st>>>(amax, dpool, gi, go, pad_lo, chunks, out);
     CB_LAUNCH_CHECK();
     return 0;
 }
