@@ -153,48 +153,85 @@ int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int c
     return 0;
 }
 
-// Backward of the pool in gather form (deterministic, no atomics): every input pixel visits the (<= 4) windows that
-// contain it and takes the window's gradient iff the stored arg-max slot is its own position in that window.
+// Backward of the pool in gather form (deterministic, no atomics).  One thread owns the 2x2 input pixels that are the
+// slots (0..1, 0..1) of window (i, j); they can only be the arg-max of the four windows (i-1..i, j-1..j), so a thread loads
+// 4 windows (arg-max bytes + gradient) for 4 output pixels (the one-pixel-per-thread form loaded 4 windows per pixel).
+// Contributions are added in window order (i-1,j-1), (i-1,j), (i,j-1), (i,j).
 //   amax: bytes from the forward pass;  dpool: gradient stream on the pooled grid;  out: gradient planes on the input grid
-// grid = (pixel blocks of one image, image * chunks): 32-bit index math only, no division by the image size.
+// grid = (quad blocks of one image, image * chunks); quads cover the whole padded grid so the border ring is zero-filled too.
 __global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ amax, const float* __restrict__ dpool,
-                                                  ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out) {
+                                                  ConvGeom gi, ConvGeom go, int pad_lo, int chunks, int KQ, Planes out) {
     const int img = blockIdx.y / chunks, jc = blockIdx.y % chunks;
-    const int rr = blockIdx.x * blockDim.x + threadIdx.x;          // flat pixel inside the padded image
-    // the last image also zero-fills the planes up to the 128-pixel tile boundary (wgrad reads whole blocks)
-    const int limit = (img == gi.n - 1) ? (int)((gi.NP + 127) / 128 * 128 - (long long)img * gi.P) : gi.P;
-    if (rr >= limit) return;
-    const int yp = rr / gi.Wp, xp = rr - yp * gi.Wp;
-    float g[8];
+    const long long pbase = (long long)jc * out.plane_px;
+    if (img == gi.n - 1 && blockIdx.x == 0) {
+        // zero-fill the planes up to the 128-pixel tile boundary (wgrad / dgrad read whole blocks)
+        const long long np_pad = (gi.NP + 127) / 128 * 128;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (long long q = gi.NP + threadIdx.x; q < np_pad; q += blockDim.x) {
+            *reinterpret_cast<uint4*>(out.hi + (pbase + q) * 8) = z;
+            if (out.mid) *reinterpret_cast<uint4*>(out.mid + (pbase + q) * 8) = z;
+            if (out.lo) *reinterpret_cast<uint4*>(out.lo + (pbase + q) * 8) = z;
+        }
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= KQ * KQ) return;
+    const int k = t / KQ, l = t - k * KQ;
+    const int i = k - 1 + pad_lo, j = l - 1 + pad_lo;              // window whose first two rows / columns are this quad
+    const int yp0 = 2 * k - 1 + pad_lo, xp0 = 2 * l - 1 + pad_lo;  // padded coordinates of the quad's first pixel
+    // the four windows: w = di * 2 + dj  <->  (i - 1 + di, j - 1 + dj)
+    uint2 pk[4];
+    float d[4][8];
+    const long long obase = ((long long)jc * go.NP + (long long)img * go.P) * 8;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) g[e] = 0.f;
-    if (rr < gi.P && yp >= 1 && yp <= gi.H && xp >= 1 && xp <= gi.W) {
-        const int r = yp - 1, c = xp - 1;
-        const int i_lo = max(0, (r + pad_lo - 1) >> 1), i_hi = min(go.H - 1, (r + pad_lo) >> 1);
-        const int j_lo = max(0, (c + pad_lo - 1) >> 1), j_hi = min(go.W - 1, (c + pad_lo) >> 1);
-        const long long obase = ((long long)jc * go.NP + (long long)img * go.P) * 8;
-        for (int i = i_lo; i <= i_hi; ++i)
-            for (int j = j_lo; j <= j_hi; ++j) {
-                const int slot = (r - (2 * i - pad_lo)) * 3 + (c - (2 * j - pad_lo));   // my position inside window (i,j)
-                const long long o = obase + (long long)((i + 1) * go.Wp + (j + 1)) * 8;
-                const uint2 pk = *reinterpret_cast<const uint2*>(amax + o);
-                const float4* p = reinterpret_cast<const float4*>(dpool + o);
-                const float4 a = p[0], b = p[1];
-                const float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    for (int w = 0; w < 4; ++w) {
+        const int wi = i - 1 + (w >> 1), wj = j - 1 + (w & 1);
+        pk[w] = make_uint2(0x0f0f0f0fu, 0x0f0f0f0fu);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int am = ((e < 4 ? pk.x : pk.y) >> (8 * (e & 3))) & 0xff;
-                    g[e] += (am == slot) ? d[e] : 0.f;
+        for (int e = 0; e < 8; ++e) d[w][e] = 0.f;
+        if (wi >= 0 && wi < go.H && wj >= 0 && wj < go.W) {
+            const long long o = obase + (long long)((wi + 1) * go.Wp + (wj + 1)) * 8;
+            pk[w] = *reinterpret_cast<const uint2*>(amax + o);
+            const float4* p = reinterpret_cast<const float4*>(dpool + o);
+            const float4 a = p[0], b = p[1];
+            d[w][0] = a.x; d[w][1] = a.y; d[w][2] = a.z; d[w][3] = a.w;
+            d[w][4] = b.x; d[w][5] = b.y; d[w][6] = b.z; d[w][7] = b.w;
+        }
+    }
+    // slot of pixel (a, b) of the quad inside window w (di, dj): row slot = a + 2 * (1 - di) (valid if <= 2), same for columns
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int yp = yp0 + a;
+        if (yp < 0 || yp >= gi.Hp) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int xp = xp0 + b;
+            if (xp < 0 || xp >= gi.Wp) continue;
+            float g[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = 0.f;
+            if (yp >= 1 && yp <= gi.H && xp >= 1 && xp <= gi.W) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int sy = a + 2 * (1 - (w >> 1)), sx = b + 2 * (1 - (w & 1));
+                    if (sy > 2 || sx > 2) continue;
+                    const int slot = sy * 3 + sx;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int am = ((e < 4 ? pk[w].x : pk[w].y) >> (8 * (e & 3))) & 0xff;
+                        g[e] += (am == slot) ? d[w][e] : 0.f;
+                    }
                 }
             }
+            store_planes8(out, (pbase + (long long)img * gi.P + yp * gi.Wp + xp) * 8, g);
+        }
     }
-    store_planes8(out, ((long long)jc * out.plane_px + (long long)img * gi.P + rr) * 8, g);
 }
 
 int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
                     cudaStream_t st) {
-    dim3 grid((gi.P + 127 + 255) / 256, gi.n * chunks);
-    k_pool_bwd<<<grid, 256, 0, st>>>(amax, dpool, gi, go, pad_lo, chunks, out);
+    const int KQ = (gi.Hp + 2 - pad_lo) / 2;   // quads per image side: padded rows 2k - 1 + pad_lo, 2k + pad_lo
+    dim3 grid((KQ * KQ + 255) / 256, gi.n * chunks);
+    k_pool_bwd<<<grid, 256, 0, st>>>(amax, dpool, gi, go, pad_lo, chunks, KQ, out);
     CB_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,38 @@
+"""Developer probe (GPU box): ONE PPO minibatch gradient + optimizer step (mb from argv) inside cudaProfilerStart/Stop, for
+`ncu --profile-from-start off`; also one actor step at n=60 when argv[2] == "actor"."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from oracle import network as net
+from cleanba_b200 import agent as ag
+
+mb = int(sys.argv[1]) if len(sys.argv) > 1 else 3840
+what = sys.argv[2] if len(sys.argv) > 2 else "learner"
+params = net.init_params(1)
+rng = np.random.default_rng(0)
+obs = torch.from_numpy(rng.integers(0, 256, (mb, 4, 84, 84), dtype=np.uint8)).cuda()
+cudart = torch.cuda.cudart()
+if what == "learner":
+    actions = torch.from_numpy(rng.integers(0, 18, mb).astype(np.int32)).cuda()
+    oldlp = torch.full((mb,), float(np.log(1 / 18)), dtype=torch.float32).cuda()
+    adv = torch.randn(mb, device="cuda"); ret = torch.randn(mb, device="cuda")
+    idx = torch.from_numpy(rng.permutation(mb).astype(np.int32)).cuda()
+    ctx = ag.Context("cuda:0", max_batch=mb, train=True)
+    ctx.set_params(params)
+    grads = torch.zeros(ctx.num_params, device="cuda"); stats = torch.zeros(5, device="cuda")
+    def step():
+        ctx.ppo_grad(obs, idx, mb, actions, oldlp, adv, ret, 0.1, 0.01, 0.5, grads, stats)
+        ctx.optimizer_step(grads, 1.0, 2.5e-4, 0.5)
+else:
+    ctx = ag.Context("cuda:0", max_batch=mb)
+    ctx.set_params(params)
+    key = ag.key_tensor(np.array([1, 2], np.uint32), ctx.device)
+    def step():
+        ctx.actor_step(obs, key)
+for _ in range(2): step()
+torch.cuda.synchronize()
+cudart.cudaProfilerStart()
+step()
+torch.cuda.synchronize()
+cudart.cudaProfilerStop()
+print("done", what, mb)
