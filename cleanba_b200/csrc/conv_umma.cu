@@ -243,72 +243,86 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
 
 // =================================================================================================
 // wgrad on tcgen05:  dW[(ky,kx), ci, co] = sum_q X[q + d(ky,kx)][ci] * G[q][co],  db[co] = sum_q G[q][co].
-// GEMM view per 64-pixel block:  D_kx[m, co] += A_kx[m, q] * B[q, co]  with the reduction over pixels (K), where
-//   m = ky * C + ci  stacks the three filter ROWS (three bulk copies of the same planes shifted by one image row) and
-//   kx is a 16-byte shift of the start address.  A is MN-major (M = channels contiguous), B (= G) is MN-major too,
+// GEMM view per 128-pixel block:  D_kx[m, n] += A_kx[m, q] * B[q, n]  with the reduction over pixels (K), where
+//   m = (ky, ci) stacks the three filter ROWS (three bulk copies of the same planes shifted by one image row) and
+//   kx is a 16-byte shift of the A start address.  A is MN-major (M = channels contiguous), B (= G) is MN-major too,
 //   so both operands are again the untouched chunk planes.  One extra M group of bf16 ones yields the bias gradient.
-// Precision: same 3-way split as above, the three G planes are stacked along N (they are adjacent in shared memory):
-//   D += X_hi * [G_hi|G_mid|G_lo],  D[:, :2C] += X_mid * [G_hi|G_mid],  D[:, :C] += X_lo * [G_hi].
-// Three accumulators (kx) x 3*Cout columns stay in TMEM across ALL pixel blocks of a CTA; one partial per CTA is
-// written at the end and reduced in a fixed order by k_wgrad_umma_reduce (deterministic).
-constexpr int WG_BLOCK = 64;              // pixels per pipeline stage (K block)
-constexpr int WG_STAGES = 3;
+// Precision: X = hi + mid (16 significant bits are enough here: products are summed in fp32 over >= 10^5 pixels),
+//   G = hi + mid (gradient tensors are carried with 2 planes); n = (G plane, co) stacks the two G planes along N.
+// Measured limits that shape the kernel (profiles/r01_v5_*): the TMA unit retires one bulk copy per ~50 cycles per SM, so
+//   copies are >= 2 KB (128-pixel blocks); one thread issues at most one MMA per ~50 cycles and the tensor pipe needs
+//   (A bytes + B bytes) / 128 cycles per MMA, so the MMA count per block is minimised per shape:
+//   * Cin = 4 (frames, exact in bf16):  M = 64,  one MMA per (K step, kx), two CTAs per SM.
+//   * Cin = 16: the X planes are stacked along M as well ([X_hi groups | ones | X_mid groups | zeros] = 14 groups, M = 128):
+//     ONE MMA per (K step, kx) yields X_hi*G_hi, X_hi*G_mid, X_mid*G_hi (and X_mid*G_mid for free); two CTAs per SM.
+//   * Cin = 32: 13 groups per plane do not stack; two issuing threads instead, each with its own accumulators
+//     (X_hi * [G_hi|G_mid] and X_mid * [G_hi]), one CTA per SM with a 3-stage ring.
+// The accumulators stay in TMEM across ALL pixel blocks of a CTA; one partial per CTA is written at the end and
+// reduced in a fixed order by k_wgrad_umma_reduce (deterministic).
+constexpr int WG_BLOCK = 128;             // pixels per pipeline stage (K block)
 constexpr int WG_WINX = WG_BLOCK + 2;     // pixels per shifted copy
-constexpr int WG_PLANE = WG_WINX * 16;    // bytes
-constexpr int WG_THREADS = 192;
+constexpr int WG_PLANE = WG_WINX * 16;    // bytes of one copy (one M group)
+constexpr int WG_BCHUNK = WG_BLOCK * 16;  // bytes of one (plane, chunk) of G (one N group)
+constexpr int WG_THREADS = 224;           // warps 0-3 epilogue, 4 TMA producer, 5 / 6 MMA issuers
+constexpr int WG_MAXST = 4;
 
-struct WgSmemLayout {
-    int groups;        // real M groups = 3 * cin_chunks
-    int xplanes;       // X planes used: 1 (frames) .. 3
-    int gplanes;       // G planes (2 or 3), stacked along N
-    int a_bytes;       // one A region (one split plane): (groups + 1) copies (last = ones / zeros)
-    int b_chunk;       // bytes of one (plane, chunk) of G
-    int b_bytes;       // all of B: 3 planes x cout/8 chunks
-    int stage_bytes, stages, total;
+template <int CIN_CHUNKS>
+struct WgShape {
+    static constexpr int XPL = CIN_CHUNKS == 1 ? 1 : 2;         // X planes used
+    static constexpr bool MSTACK = CIN_CHUNKS == 2;             // both X planes in one MMA (stacked along M)
+    static constexpr bool DUAL = CIN_CHUNKS == 4;               // two issuers, separate accumulators per X plane
+    static constexpr int GROUPS = 3 * CIN_CHUNKS;               // real M groups per plane: (ky, chunk)
+    static constexpr int HROWS = (GROUPS + 1) * 8;              // rows per plane incl. the ones / zeros group
+    static constexpr int ROWS = MSTACK ? 2 * HROWS : HROWS;     // rows of D that are written to the partial
+    static constexpr int MMA_M = ROWS <= 64 ? 64 : 128;
 };
-// Measured (tools/mma_microbench2.cu, profiles/): one thread can issue a tcgen05.mma every ~50 cycles; the tensor pipe
-// itself needs ~39 cycles for M=128 and <= 25 for M=64 (N <= 32).  wgrad therefore uses M = 64 whenever the stacked
-// (ky, ci) rows fit (<= 64) and runs two CTAs (two issuing threads) per SM whenever shared memory allows.
-__host__ __device__ constexpr int wg_mrows(int cin_chunks) { return (3 * cin_chunks + 1) * 8 <= 64 ? 64 : 128; }
-__host__ __device__ inline WgSmemLayout wg_smem_layout(int cin_chunks, int cout, int xpl, int gpl) {
+
+struct WgSmemLayout { int a_bytes, b_bytes, stage_bytes, stages, total, ctas_per_sm; };
+template <int CIN_CHUNKS, int COUT>
+__host__ __device__ inline WgSmemLayout wg_smem_layout() {
+    using S = WgShape<CIN_CHUNKS>;
     WgSmemLayout L;
-    L.groups = 3 * cin_chunks;
-    L.xplanes = xpl;
-    L.gplanes = gpl;
-    L.a_bytes = (L.groups + 1) * WG_PLANE;
-    L.b_chunk = WG_BLOCK * 16;
-    L.b_bytes = gpl * (cout / 8) * L.b_chunk;
-    L.stage_bytes = L.xplanes * L.a_bytes + L.b_bytes;
-    L.stages = (1024 + WG_STAGES * L.stage_bytes + (wg_mrows(cin_chunks) / 8) * WG_PLANE <= 112 * 1024) ? WG_STAGES : 2;
-    // the MMA reads M/8 groups from the A base: pad so the unused groups stay inside the allocation
-    L.total = 1024 + L.stages * L.stage_bytes + (wg_mrows(cin_chunks) / 8) * WG_PLANE;
+    L.a_bytes = (S::GROUPS + 1) * WG_PLANE;                 // one X plane: real groups + ones (hi) / zeros (mid)
+    L.b_bytes = 2 * (COUT / 8) * WG_BCHUNK;
+    L.stage_bytes = S::XPL * L.a_bytes + L.b_bytes;
+    // the MMA reads MMA_M / 8 groups from its A base; the unused ones fall into the B region of the same stage (+ a pad
+    // after the last stage where B is smaller than the overrun)
+    const int over = (S::MMA_M / 8) * WG_PLANE - ((S::MSTACK ? 2 : 1) * L.a_bytes + L.b_bytes);
+    const int pad = over > 0 ? (over + 1023) / 1024 * 1024 : 0;
+    L.ctas_per_sm = S::DUAL ? 1 : 2;
+    const int budget = (S::DUAL ? 226 : 113) * 1024 - 1024 - pad;
+    int st = budget / L.stage_bytes;
+    L.stages = st > WG_MAXST ? WG_MAXST : st;
+    L.total = 1024 + L.stages * L.stage_bytes + pad;
     return L;
 }
 
-// XPL = planes of X used (1 frames, 2 or 3), GPL = planes of G (2 or 3); plane p of X multiplies the first GPL - p planes of G.
-template <int CIN_CHUNKS, int COUT, int XPL, int GPL>
+template <int CIN_CHUNKS, int COUT>
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblocks, float* __restrict__ partial) {
+    using S = WgShape<CIN_CHUNKS>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, XPL, GPL);
+    const WgSmemLayout L = wg_smem_layout<CIN_CHUNKS, COUT>();
     const int NSTAGES = L.stages;
-    constexpr int WG_MROWS = wg_mrows(CIN_CHUNKS);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + WG_STAGES;
-    uint64_t* done = empty + WG_STAGES;
+    uint64_t* empty = full + WG_MAXST;
+    uint64_t* done = empty + WG_MAXST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     uint8_t* stages = smem + 1024;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int ACC_COLS = GPL * COUT;
-    constexpr uint32_t TMEM_COLS = (3 * ACC_COLS <= 128) ? 128 : ((3 * ACC_COLS <= 256) ? 256 : 512);
-    constexpr int GROUPS = 3 * CIN_CHUNKS;
-    constexpr int NCOPY_A = XPL * GROUPS, NCOPY_B = GPL * (COUT / 8);
+    constexpr int XPL = S::XPL, GROUPS = S::GROUPS, NCH = COUT / 8;
+    constexpr int ACC0 = 2 * COUT;                             // columns of one kx accumulator: [G_hi | G_mid]
+    constexpr int ACC1 = S::DUAL ? COUT : 0;                   // second issuer: X_mid * G_hi
+    constexpr int COLS = 3 * (ACC0 + ACC1);
+    constexpr uint32_t TMEM_COLS = COLS <= 128 ? 128 : (COLS <= 256 ? 256 : 512);
+    constexpr int NCOPY_A = XPL * GROUPS, NCOPY_B = 2 * NCH;
+    constexpr int NISSUE = S::DUAL ? 2 : 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(done, 1);
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NISSUE); }
+        mbar_init(done, NISSUE);
         fence_barrier_init();
     }
-    // constant "ones" group (hi region) and "zeros" groups (mid / lo regions) of every stage
+    // constant "ones" group (hi region) and "zeros" group (mid region) of every stage
     for (int s = 0; s < NSTAGES; ++s)
         for (int pl = 0; pl < XPL; ++pl) {
             uint32_t* g = reinterpret_cast<uint32_t*>(stages + s * L.stage_bytes + pl * L.a_bytes + GROUPS * WG_PLANE);
@@ -324,55 +338,53 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     const int Wp = a.g.Wp;
 
     if (warp == 4) {
+        // ===================== TMA producer: one bulk copy per lane =====================
         int s = 0; uint32_t ph = 0;
-        const uint32_t tx = (uint32_t)(NCOPY_A * WG_PLANE + NCOPY_B * L.b_chunk);
+        const uint32_t tx = (uint32_t)(NCOPY_A * WG_PLANE + NCOPY_B * WG_BCHUNK);
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
             mbar_wait(&empty[s], ph ^ 1);
             if (lane == 0) mbar_arrive_expect_tx(&full[s], tx);
+            __syncwarp();
             uint8_t* dst = stages + s * L.stage_bytes;
             const long long q0 = (long long)blk * WG_BLOCK;
             for (int i = lane; i < NCOPY_A + NCOPY_B; i += 32) {
                 if (i < NCOPY_A) {
                     const int pl = i / GROUPS, g = i % GROUPS, ky = g / CIN_CHUNKS, j = g % CIN_CHUNKS;
-                    const bf16* src = pl == 0 ? a.x.hi : (pl == 1 ? a.x.mid : a.x.lo);
+                    const bf16* src = pl == 0 ? a.x.hi : a.x.mid;
                     const long long q = q0 + (ky - 1) * Wp - 1;
                     bulk_g2s(dst + pl * L.a_bytes + g * WG_PLANE, src + ((long long)j * a.x.plane_px + q) * 8, WG_PLANE, &full[s]);
                 } else {
-                    const int k = i - NCOPY_A, pl = k / (COUT / 8), j = k % (COUT / 8);
-                    const bf16* src = pl == 0 ? a.gy.hi : (pl == 1 ? a.gy.mid : a.gy.lo);
-                    bulk_g2s(dst + XPL * L.a_bytes + k * L.b_chunk, src + ((long long)j * a.gy.plane_px + q0) * 8, L.b_chunk, &full[s]);
+                    const int k = i - NCOPY_A, pl = k / NCH, j = k % NCH;
+                    const bf16* src = pl == 0 ? a.gy.hi : a.gy.mid;
+                    bulk_g2s(dst + XPL * L.a_bytes + k * WG_BCHUNK, src + ((long long)j * a.gy.plane_px + q0) * 8, WG_BCHUNK, &full[s]);
                 }
             }
             __syncwarp();
             if (++s == NSTAGES) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 5) {
-        constexpr uint32_t IDESC_A = make_idesc_bf16(WG_MROWS, GPL * COUT, 1, 1);                         // X plane 0
-        constexpr uint32_t IDESC_B = make_idesc_bf16(WG_MROWS, (GPL > 1 ? GPL - 1 : 1) * COUT, 1, 1);     // X plane 1
-        constexpr uint32_t IDESC_C = make_idesc_bf16(WG_MROWS, (GPL > 2 ? GPL - 2 : 1) * COUT, 1, 1);     // X plane 2
+    } else if (warp == 5 || (S::DUAL && warp == 6)) {
+        // ===================== MMA issuer(s) =====================
+        const int who = warp - 5;                               // 0: X_hi (or both planes when stacked), 1: X_mid (DUAL)
+        const uint32_t idesc = make_idesc_bf16(S::MMA_M, who == 0 ? 2 * COUT : COUT, 1, 1);
+        const uint32_t d0 = tmem_base + (who == 0 ? 0 : 3 * ACC0);
+        const uint32_t dstep = who == 0 ? ACC0 : ACC1;
         int s = 0; uint32_t ph = 0;
         uint32_t accum = 0;
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_base = smem_u32(stages + s * L.stage_bytes);
+                const uint32_t st_base = smem_u32(stages + s * L.stage_bytes);
                 // K step = 16 pixels = 2 core-matrix groups of 8 pixels (128 bytes each, LBO); M groups WG_PLANE apart,
-                // N groups (8 channels of one G plane chunk) b_chunk apart (SBO)
-                const uint32_t a_lo0 = desc_lo(a_base, 128), a_hi_w = desc_hi(WG_PLANE);
-                const uint32_t b_lo0 = desc_lo(a_base + XPL * L.a_bytes, 128), b_hi_w = desc_hi(L.b_chunk);
-                const uint32_t apl16 = (uint32_t)L.a_bytes >> 4;
+                // N groups (8 channels of one G plane chunk) WG_BCHUNK apart (SBO)
+                const uint32_t a_lo0 = desc_lo(st_base + who * L.a_bytes, 128), a_hi_w = desc_hi(WG_PLANE);
+                const uint32_t b_lo0 = desc_lo(st_base + XPL * L.a_bytes, 128), b_hi_w = desc_hi(WG_BCHUNK);
 #pragma unroll
                 for (int ks = 0; ks < WG_BLOCK / 16; ++ks) {
-                    const uint32_t b_lo = b_lo0 + ks * 16;
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const uint32_t d_tmem = tmem_base + kx * ACC_COLS;
-                        const uint32_t a_lo = a_lo0 + ks * 16 + kx;
-                        mma_bf16_parts(d_tmem, a_lo, a_hi_w, b_lo, b_hi_w, IDESC_A, ks == 0 ? accum : 1u);
-                        if (XPL > 1 && GPL > 1) mma_bf16_parts(d_tmem, a_lo + apl16, a_hi_w, b_lo, b_hi_w, IDESC_B, 1);
-                        if (XPL > 2 && GPL > 2) mma_bf16_parts(d_tmem, a_lo + 2 * apl16, a_hi_w, b_lo, b_hi_w, IDESC_C, 1);
-                    }
+                    for (int kx = 0; kx < 3; ++kx)
+                        mma_bf16_parts(d0 + kx * dstep, a_lo0 + ks * 16 + kx, a_hi_w, b_lo0 + ks * 16, b_hi_w, idesc,
+                                       ks == 0 ? accum : 1u);
                 }
                 accum = 1;
                 mma_commit(&empty[s]);
@@ -382,33 +394,32 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
         }
         if (lane == 0) mma_commit(done);
         __syncwarp();
-    } else {
+    } else if (warp < 4) {
         mbar_wait(done, 0);
         tc_fence_after();
-        // D rows: m = ky*C + ci (and m = 3C .. 3C+7: bias rows).  M = 128: TMEM lane = m.  M = 64: row m lives in lane
-        // (m / 16) * 32 + m % 16, i.e. the first 16 lanes of every warp's quadrant (probed, profiles/r01_mma_m64_layout_probe.txt).
-        const int m = WG_MROWS == 128 ? warp * 32 + lane : (lane < 16 ? warp * 16 + lane : (1 << 30));
-        constexpr int MROWS_USED = GROUPS * 8 + 8;
-        static_assert(MROWS_USED <= WG_MROWS, "stacked rows exceed the MMA M");
-        float* out = partial + (long long)blockIdx.x * (3 * MROWS_USED * COUT);
+        // D rows: M = 128: TMEM lane = row.  M = 64: row m lives in lane (m / 16) * 32 + m % 16, i.e. the first 16 lanes of
+        // every warp's quadrant (probed, profiles/r01_mma_m64_layout_probe.txt).
+        const int m = S::MMA_M == 128 ? warp * 32 + lane : (lane < 16 ? warp * 16 + lane : (1 << 30));
+        float* out = partial + (long long)blockIdx.x * (3 * S::ROWS * COUT);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int kx = 0; kx < 3; ++kx) {
-            float v[COUT];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + kx * ACC_COLS;
-            float t[16];
+            float v[COUT], t[16];
 #pragma unroll
             for (int h = 0; h < COUT / 16; ++h) {
-                tmem_ld16(taddr + (GPL - 1) * COUT + h * 16, v + h * 16);
+                tmem_ld16(lane_addr + kx * ACC0 + COUT + h * 16, v + h * 16);          // * G_mid
+                tmem_ld16(lane_addr + kx * ACC0 + h * 16, t);                          // * G_hi
 #pragma unroll
-                for (int blk = GPL - 2; blk >= 0; --blk) {
-                    tmem_ld16(taddr + blk * COUT + h * 16, t);
+                for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                if (S::DUAL) {
+                    tmem_ld16(lane_addr + 3 * ACC0 + kx * ACC1 + h * 16, t);           // X_mid * G_hi (same rows)
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
                 }
             }
-            if (m < MROWS_USED) {
+            if (m < S::ROWS) {
 #pragma unroll
                 for (int c = 0; c < COUT; c += 4)
-                    *reinterpret_cast<float4*>(out + ((long long)kx * MROWS_USED + m) * COUT + c) =
+                    *reinterpret_cast<float4*>(out + ((long long)kx * S::ROWS + m) * COUT + c) =
                         make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
             }
         }
@@ -418,64 +429,78 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// dW[(ky*3+kx)][ci][co] = scale * sum_cta partial[cta][kx][ky*Cpad + ci][co];  db[co] = sum_cta partial[cta][1][3*Cpad][co]
-__global__ void k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas, int cpad, int cin_real, int cout,
-                                    float scale, float* __restrict__ dw, float* __restrict__ db) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int nw = 9 * cin_real * cout;
-    if (i >= nw + cout) return;
-    const int mrows = 3 * cpad + 8;
-    long long src;
-    if (i < nw) {
-        int co = i % cout, ci = (i / cout) % cin_real, tap = i / (cout * cin_real);
-        int ky = tap / 3, kx = tap % 3;
-        src = ((long long)kx * mrows + ky * cpad + ci) * cout + co;
-    } else {
-        src = ((long long)1 * mrows + 3 * cpad) * cout + (i - nw);
-    }
+// dW[(ky*3+kx)][ci][co] = scale * sum_cta (P[cta][kx][ky*Cpad + ci][co] + P[cta][kx][hrows + ky*Cpad + ci][co] if stacked)
+// db[co] = sum_cta P[cta][1][3*Cpad][co]
+// One block per 32 consecutive outputs; warp w sums the partials of CTAs w, w+8, ... (coalesced 128-byte rows), the eight
+// warp sums are added in a fixed order.
+__global__ void __launch_bounds__(256) k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas, int cpad, int rows, int hrows,
+                                                           int stacked, int cin_real, int cout, float scale,
+                                                           float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float sm[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int nw = 9 * cin_real * cout;
     float s = 0.f;
-    for (int b = 0; b < nctas; ++b) s += partial[(long long)b * (3 * mrows * cout) + src];
-    if (i < nw) dw[i] = s * scale; else db[i - nw] = s;
+    if (i < nw + cout) {
+        long long src;
+        bool two = false;
+        if (i < nw) {
+            int co = i % cout, ci = (i / cout) % cin_real, tap = i / (cout * cin_real);
+            int ky = tap / 3, kx = tap % 3;
+            src = ((long long)kx * rows + ky * cpad + ci) * cout + co;
+            two = stacked != 0;
+        } else {
+            src = ((long long)1 * rows + 3 * cpad) * cout + (i - nw);
+        }
+        const long long stride = (long long)3 * rows * cout;
+        for (int b = w; b < nctas; b += 8) {
+            const float* p = partial + (long long)b * stride + src;
+            float v = p[0];
+            if (two) v += p[(long long)hrows * cout];
+            s += v;
+        }
+    }
+    sm[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < nw + cout) {
+        float t = sm[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sm[k][lane];
+        if (i < nw) dw[i] = t * scale; else db[i - nw] = t;
+    }
 }
 
-template <int CIN_CHUNKS, int COUT, int XPL, int GPL>
+template <int CIN_CHUNKS, int COUT>
 static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st) {
-    WgSmemLayout L = wg_smem_layout(CIN_CHUNKS, COUT, XPL, GPL);
-    CB_CHECK(L.total <= 227 * 1024, "wgrad_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
+    using S = WgShape<CIN_CHUNKS>;
+    WgSmemLayout L = wg_smem_layout<CIN_CHUNKS, COUT>();
+    CB_CHECK(L.stages >= 2 && L.total <= 227 * 1024, "wgrad_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
     static std::atomic<unsigned> attr_done{0};
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     if (!(attr_done.load() & (1u << dev))) {
-        CB_CUDA(cudaFuncSetAttribute(k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CB_CUDA(cudaFuncSetAttribute(k_wgrad_umma<CIN_CHUNKS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done.fetch_or(1u << dev);
     }
     int nblocks = (int)((a.g.NP + WG_BLOCK - 1) / WG_BLOCK);
-    int ctas_per_sm = (L.total <= 112 * 1024 && 3 * GPL * COUT <= 256) ? 2 : 1;   // two CTAs must also share the 512 TMEM columns
-    int grid = nblocks < num_sms * ctas_per_sm ? nblocks : num_sms * ctas_per_sm;
-    k_wgrad_umma<CIN_CHUNKS, COUT, XPL, GPL><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);
+    int grid = nblocks < num_sms * L.ctas_per_sm ? nblocks : num_sms * L.ctas_per_sm;
+    k_wgrad_umma<CIN_CHUNKS, COUT><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);
     CB_LAUNCH_CHECK();
     int nw = 9 * a.cin_real * a.cout;
-    k_wgrad_umma_reduce<<<(nw + a.cout + 255) / 256, 256, 0, st>>>(partial, grid, CIN_CHUNKS * 8, a.cin_real, a.cout, a.scale, a.dw, a.db);
+    k_wgrad_umma_reduce<<<(nw + a.cout + 31) / 32, 256, 0, st>>>(partial, grid, CIN_CHUNKS * 8, S::ROWS, S::HROWS, S::MSTACK ? 1 : 0,
+                                                                 a.cin_real, a.cout, a.scale, a.dw, a.db);
     CB_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_wgrad_umma(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st) {
-    CB_CHECK(TILE_M + a.g.Wp + 2 <= GUARD, "wgrad_umma: guard too small for Wp=%d", a.g.Wp);
-    // gradients are carried with 2 planes (16 bits): X_hi*[G_hi|G_mid] + X_mid*[G_hi]; with 3-plane G the full 6 products
-    const int gpl = a.gy.lo ? 3 : 2;
-    const int xpl = a.x.mid ? (gpl == 3 && a.x.lo ? 3 : 2) : 1;
-    if (gpl == 2) {
-        if (a.cin_chunks == 1 && a.cout == 16) return launch_wgrad_umma_t<1, 16, 1, 2>(a, partial, num_sms, st);
-        if (a.cin_chunks == 2 && a.cout == 16 && xpl == 2) return launch_wgrad_umma_t<2, 16, 2, 2>(a, partial, num_sms, st);
-        if (a.cin_chunks == 2 && a.cout == 32 && xpl == 2) return launch_wgrad_umma_t<2, 32, 2, 2>(a, partial, num_sms, st);
-        if (a.cin_chunks == 4 && a.cout == 32 && xpl == 2) return launch_wgrad_umma_t<4, 32, 2, 2>(a, partial, num_sms, st);
-    } else {
-        if (a.cin_chunks == 1 && a.cout == 16) return launch_wgrad_umma_t<1, 16, 1, 3>(a, partial, num_sms, st);
-        if (a.cin_chunks == 2 && a.cout == 16 && xpl == 3) return launch_wgrad_umma_t<2, 16, 3, 3>(a, partial, num_sms, st);
-        if (a.cin_chunks == 2 && a.cout == 32 && xpl == 3) return launch_wgrad_umma_t<2, 32, 3, 3>(a, partial, num_sms, st);
-        if (a.cin_chunks == 4 && a.cout == 32 && xpl == 3) return launch_wgrad_umma_t<4, 32, 3, 3>(a, partial, num_sms, st);
-    }
+    CB_CHECK(WG_BLOCK + a.g.Wp + 2 <= GUARD, "wgrad_umma: guard too small for Wp=%d", a.g.Wp);
+    CB_CHECK(a.gy.mid && !a.gy.lo, "wgrad_umma: gradient tensors carry two bf16 planes");
+    CB_CHECK(a.cin_chunks == 1 || a.x.mid, "wgrad_umma: activation planes hi and mid needed");
+    if (a.cin_chunks == 1 && a.cout == 16) return launch_wgrad_umma_t<1, 16>(a, partial, num_sms, st);
+    if (a.cin_chunks == 2 && a.cout == 16) return launch_wgrad_umma_t<2, 16>(a, partial, num_sms, st);
+    if (a.cin_chunks == 2 && a.cout == 32) return launch_wgrad_umma_t<2, 32>(a, partial, num_sms, st);
+    if (a.cin_chunks == 4 && a.cout == 32) return launch_wgrad_umma_t<4, 32>(a, partial, num_sms, st);
     CB_CHECK(false, "wgrad_umma: unsupported shape cin_chunks=%d cout=%d", a.cin_chunks, a.cout);
 }
 

@@ -133,7 +133,7 @@ struct cb_ctx {
     // tcgen05 dense layer (dense_umma.cu)
     bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
     int npad_max = 0;
-    int grad_planes = 2;    // bf16 planes of gradient tensors (2 = 16 bits; CLEANBA_GRAD_PLANES=3 for 24 bits)
+    static constexpr int grad_planes = 2;   // bf16 planes of gradient tensors (16 significant bits)
 };
 
 namespace cb {
@@ -445,7 +445,6 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->A = cfg->num_actions;
     c->leaves = build_leaves(c->A);
-    if (const char* gp = getenv("CLEANBA_GRAD_PLANES")) c->grad_planes = (atoi(gp) == 3) ? 3 : 2;
     c->nparam = c->leaves.back().offset + c->leaves.back().size();
     bool ok = false;
     do {
