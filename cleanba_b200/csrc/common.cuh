@@ -256,6 +256,18 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeo
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the forward / backward chain starts with griddep_launch() (its
+// successor in the stream may be scheduled as soon as all CTAs of this grid are running) and calls griddep_wait() before
+// its first access to memory produced by earlier kernels; whatever precedes the wait (barrier init, TMEM allocation, the
+// TMA load of the packed weights) overlaps the predecessor's tail.  Rules that keep this correct:
+//   * a kernel launched through launch_pdl() MUST call griddep_wait() before touching dependent memory;
+//   * the only global data read before the wait are the packed weights, and their writers (k_pack_conv / k_pack_dense,
+//     cudaMemcpy) are launched normally and never trigger early, so they are complete before any successor starts;
+//   * kernels launched with <<<>>> stay fully stream-ordered (they are barriers of the chain).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // error plumbing (host)
 void set_error(const char* fmt, ...);
 }  // namespace cb
@@ -283,5 +295,18 @@ extern std::atomic<long long> g_launches;
         cb::g_launches.fetch_add(1);      \
         CB_CUDA(cudaGetLastError());      \
     } while (0)
+
+bool pdl_enabled();   // ctx.cu: CLEANBA_PDL != "0"
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // errors are picked up by CB_LAUNCH_CHECK
+}
 
 }  // namespace cb

@@ -31,7 +31,8 @@ namespace cb {
 using namespace umma;
 
 constexpr int TILE_M = 128;
-constexpr int CONV_STAGES = 3;
+constexpr int CONV_MAXST = 8;        // stages of the input-window ring: as many as fit (memory latency, not bandwidth,
+                                     // bounds these kernels: profiles/r01_v5_ncu_sweep_learner_mb3840.txt)
 constexpr int CONV_THREADS = 320;   // warps 0-7: two epilogue groups (one per TMEM accumulator), warp 8: TMA, warp 9: MMA
 
 __host__ __device__ constexpr int conv_steps(int cin_chunks) { return cin_chunks == 1 ? 5 : 9 * (cin_chunks / 2); }
@@ -41,7 +42,7 @@ __host__ __device__ constexpr int conv_wbytes(int cin_chunks, int cout) { return
 long long packed_conv_elems(int cin_chunks, int cout) { return (long long)conv_wbytes(cin_chunks, cout) / 2; }
 
 struct ConvSmemLayout {
-    int win, plane_bytes, nplanes, stage_bytes, w_bytes, total;
+    int win, plane_bytes, nplanes, stage_bytes, w_bytes, stages, ctas_per_sm, total;
 };
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int cout, int Wp, int apl = 3) {
     ConvSmemLayout L;
@@ -51,7 +52,12 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int c
     L.nplanes = cin_chunks == 1 ? 1 : apl * cin_chunks;      // hi planes, mid planes[, lo planes] (frames: hi only, exact)
     L.stage_bytes = L.nplanes * L.plane_bytes;
     L.w_bytes = conv_wbytes(cin_chunks, cout);
-    L.total = 1024 + L.w_bytes + CONV_STAGES * L.stage_bytes;
+    // two CTAs per SM (two MMA-issuing threads) when three stages fit in half an SM, else one CTA with a deeper ring
+    L.ctas_per_sm = 1024 + L.w_bytes + 3 * L.stage_bytes <= 112 * 1024 ? 2 : 1;
+    const int budget = (L.ctas_per_sm == 2 ? 112 : 226) * 1024 - 1024 - L.w_bytes;
+    L.stages = budget / L.stage_bytes;
+    if (L.stages > CONV_MAXST) L.stages = CONV_MAXST;
+    L.total = 1024 + L.w_bytes + L.stages * L.stage_bytes;
     return L;
 }
 int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_layout(cin_chunks, cout, Wp, 3).total; }
@@ -61,11 +67,13 @@ int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_la
 template <int CIN_CHUNKS, int COUT, int APL>
 __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_launch();
     const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, APL);
     // [0,1024): barriers + tmem pointer; then the weight image; then the activation stages
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [CONV_STAGES]
-    uint64_t* empty = full + CONV_STAGES;                        // [CONV_STAGES]
-    uint64_t* tfull = empty + CONV_STAGES;                       // [2]
+    const int NSTAGES = L.stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [CONV_MAXST]
+    uint64_t* empty = full + CONV_MAXST;                         // [CONV_MAXST]
+    uint64_t* tfull = empty + CONV_MAXST;                        // [2]
     uint64_t* tempty = tfull + 2;                                // [2]
     uint64_t* wbar = tempty + 2;                                 // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
     constexpr int NPLANES = CIN_CHUNKS == 1 ? 1 : APL * CIN_CHUNKS;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CONV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         mbar_init(wbar, 1);
         fence_barrier_init();
@@ -90,13 +98,15 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the packed weights do not depend on the preceding kernels: their load is issued before the dependency wait
+    if (warp == 8 && lane == 0) {
+        mbar_arrive_expect_tx(wbar, (uint32_t)L.w_bytes);
+        bulk_g2s(wsm, a.wp, L.w_bytes, wbar);
+    }
+    griddep_wait();
 
     if (warp == 8) {
         // ===================== TMA producer (lanes share the bulk copies of a stage) =====================
-        if (lane == 0) {
-            mbar_arrive_expect_tx(wbar, (uint32_t)L.w_bytes);
-            bulk_g2s(wsm, a.wp, L.w_bytes, wbar);
-        }
         int s = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(&empty[s], ph ^ 1);
@@ -109,7 +119,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
                 bulk_g2s(dst + lane * L.plane_bytes, src + ((long long)j * a.in.plane_px + q_lo) * 8, L.plane_bytes, &full[s]);
             }
             __syncwarp();
-            if (++s == CONV_STAGES) { s = 0; ph ^= 1; }
+            if (++s == NSTAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
                 mma_commit(&tfull[acc]);    // accumulator complete
             }
             __syncwarp();
-            if (++s == CONV_STAGES) { s = 0; ph ^= 1; }
+            if (++s == NSTAGES) { s = 0; ph ^= 1; }
             if (++acc == 2) { acc = 0; aph ^= 1; }
         }
     } else {
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
 template <int CIN_CHUNKS, int COUT, int APL>
 static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
     ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, APL);
-    CB_CHECK(L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
+    CB_CHECK(L.stages >= 2 && L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
     // Opt in to the device maximum once per device: the attribute is per function (contexts on other host threads launch
     // the same instantiation with other window sizes concurrently), and nothing but launches may happen while a
     // CUDA graph is being captured.
@@ -220,9 +230,8 @@ static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
         attr_done.fetch_or(1u << dev);
     }
     int ntiles = (int)((a.g.NP + TILE_M - 1) / TILE_M);
-    int ctas_per_sm = L.total <= 110 * 1024 ? 2 : 1;
-    int grid = ntiles < num_sms * ctas_per_sm ? ntiles : num_sms * ctas_per_sm;
-    k_conv_umma<CIN_CHUNKS, COUT, APL><<<grid, CONV_THREADS, L.total, st>>>(a, ntiles);
+    int grid = ntiles < num_sms * L.ctas_per_sm ? ntiles : num_sms * L.ctas_per_sm;
+    launch_pdl(k_conv_umma<CIN_CHUNKS, COUT, APL>, dim3(grid), dim3(CONV_THREADS), (size_t)L.total, st, a, ntiles);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -301,6 +310,7 @@ template <int CIN_CHUNKS, int COUT>
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblocks, float* __restrict__ partial) {
     using S = WgShape<CIN_CHUNKS>;
     extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_launch();
     const WgSmemLayout L = wg_smem_layout<CIN_CHUNKS, COUT>();
     const int NSTAGES = L.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -336,6 +346,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int Wp = a.g.Wp;
+    griddep_wait();
 
     if (warp == 4) {
         // ===================== TMA producer: one bulk copy per lane =====================
@@ -437,6 +448,8 @@ __global__ void __launch_bounds__(256) k_wgrad_umma_reduce(const float* __restri
                                                            int stacked, int cin_real, int cout, float scale,
                                                            float* __restrict__ dw, float* __restrict__ db) {
     __shared__ float sm[8][32];
+    griddep_launch();
+    griddep_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
     const int nw = 9 * cin_real * cout;
@@ -484,11 +497,11 @@ static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, 
     }
     int nblocks = (int)((a.g.NP + WG_BLOCK - 1) / WG_BLOCK);
     int grid = nblocks < num_sms * L.ctas_per_sm ? nblocks : num_sms * L.ctas_per_sm;
-    k_wgrad_umma<CIN_CHUNKS, COUT><<<grid, WG_THREADS, L.total, st>>>(a, nblocks, partial);
+    launch_pdl(k_wgrad_umma<CIN_CHUNKS, COUT>, dim3(grid), dim3(WG_THREADS), (size_t)L.total, st, a, nblocks, partial);
     CB_LAUNCH_CHECK();
     int nw = 9 * a.cin_real * a.cout;
-    k_wgrad_umma_reduce<<<(nw + a.cout + 31) / 32, 256, 0, st>>>(partial, grid, CIN_CHUNKS * 8, S::ROWS, S::HROWS, S::MSTACK ? 1 : 0,
-                                                                 a.cin_real, a.cout, a.scale, a.dw, a.db);
+    launch_pdl(k_wgrad_umma_reduce, dim3((nw + a.cout + 31) / 32), dim3(256), 0, st, (const float*)partial, grid, CIN_CHUNKS * 8,
+               S::ROWS, S::HROWS, S::MSTACK ? 1 : 0, a.cin_real, a.cout, a.scale, a.dw, a.db);
     CB_LAUNCH_CHECK();
     return 0;
 }

@@ -17,6 +17,13 @@
 
 namespace cb {
 
+// PDL pays for launch-latency-bound chains (the actor's n = 60 step: 0.236 -> 0.193 ms) and costs ~1% on the learner's
+// large minibatches (early CTAs of the next kernel compete with the running one), so it is enabled per call by batch size.
+static thread_local bool g_pdl_scope = false;
+bool pdl_enabled() {
+    static const int mode = [] { const char* e = getenv("CLEANBA_PDL"); return e ? atoi(e) : 1; }();   // 0 off, 1 auto, 2 always
+    return mode == 2 || (mode == 1 && g_pdl_scope);
+}
 std::atomic<long long> g_launches{0};   // every kernel launch of this library (CB_LAUNCH_CHECK increments it)
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
@@ -270,6 +277,7 @@ static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, cons
 static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStream_t st) {
     CB_CHECK(n > 0 && n <= c->cfg.max_batch, "batch %d outside (0, max_batch=%d]", n, c->cfg.max_batch);
     c->last_n = n;
+    g_pdl_scope = n <= 512;
     {
         ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 86.0 * 86 * 16), st);
         if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st)) return -1;

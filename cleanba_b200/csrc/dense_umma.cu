@@ -64,6 +64,8 @@ constexpr int DF_SMEM = 1024 + DF_STAGES * DF_STAGE;
 
 __global__ void __launch_bounds__(DN_THREADS) k_dense_fwd_umma(DenseUmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_launch();
+    griddep_wait();
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + DF_STAGES;
     uint64_t* done = empty + DF_STAGES;
@@ -417,6 +419,8 @@ int dense_umma_init() {   // once per device, outside any graph capture
 
 __global__ void k_dense_finish_umma(const float* __restrict__ part, int nsplit, int n, const float* __restrict__ bias,
                                     float* __restrict__ hidden) {
+    griddep_launch();
+    griddep_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n * HIDDEN) return;
     float s = 0.f;
@@ -428,11 +432,11 @@ int launch_dense_fwd_umma(const DenseUmmaArgs& a, cudaStream_t st) {
     const int tiles = a.npad / 128;
     const int psplit = tiles >= 16 ? 1 : (tiles >= 4 ? 4 : 11);
     dim3 grid(tiles, 4, psplit);
-    k_dense_fwd_umma<<<grid, DN_THREADS, DF_SMEM, st>>>(a);
+    launch_pdl(k_dense_fwd_umma, grid, dim3(DN_THREADS), (size_t)DF_SMEM, st, a);
     CB_LAUNCH_CHECK();
     if (psplit > 1) {
         long long tot = (long long)a.n * HIDDEN;
-        k_dense_finish_umma<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a.part, psplit, a.n, a.bias, a.hidden);
+        launch_pdl(k_dense_finish_umma, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, (const float*)a.part, psplit, a.n, a.bias, a.hidden);
         CB_LAUNCH_CHECK();
     }
     return 0;

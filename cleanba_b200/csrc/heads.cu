@@ -62,6 +62,8 @@ __device__ __forceinline__ void head_forward(const HeadSmem& h, const float* hid
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_split_key(uint32_t* key, uint32_t* subkey) {
+    griddep_launch();
+    griddep_wait();
     if (threadIdx.x == 0) {
         uint32_t k0 = key[0], k1 = key[1], nk0, nk1, sk0, sk1;
         jax_split2(k0, k1, nk0, nk1, sk0, sk1);
@@ -69,7 +71,7 @@ __global__ void k_split_key(uint32_t* key, uint32_t* subkey) {
     }
 }
 int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st) {
-    k_split_key<<<1, 32, 0, st>>>(key_inout, subkey_out);
+    launch_pdl(k_split_key, dim3(1), dim3(32), 0, st, key_inout, subkey_out);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -81,7 +83,9 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hi
                                                     const uint32_t* __restrict__ subkey, float* logits_out,
                                                     float* value_out, int* action_out, float* logprob_out) {
     extern __shared__ float sm[];
-    HeadSmem h = load_head_smem(sm, wa, ba, wc, bc, A);
+    griddep_launch();
+    HeadSmem h = load_head_smem(sm, wa, ba, wc, bc, A);   // master parameters: not written by the preceding kernels
+    griddep_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const uint32_t k0 = subkey[0], k1 = subkey[1];
     const uint32_t total = (uint32_t)n * (uint32_t)A;
@@ -121,8 +125,8 @@ int launch_actor_head(const float* hidden, int n, int A, const float* wa, const 
                       float* logprob_out, cudaStream_t st) {
     int blocks = (n + 7) / 8;
     if (blocks > 296) blocks = 296;
-    k_actor_head<<<blocks, 256, head_smem_bytes(A), st>>>(hidden, n, A, wa, ba, wc, bc, subkey, logits_out, value_out,
-                                                         action_out, logprob_out);
+    launch_pdl(k_actor_head, dim3(blocks), dim3(256), (size_t)head_smem_bytes(A), st, hidden, n, A, wa, ba, wc, bc, subkey, logits_out,
+               value_out, action_out, logprob_out);
     CB_LAUNCH_CHECK();
     return 0;
 }

@@ -13,6 +13,8 @@ namespace cb {
 // One block per (image, padded row): the 4 channel rows are staged through shared memory with coalesced
 // 4-byte reads, then every thread emits one 16-byte pixel.
 __global__ void k_unpack_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, int n, bf16* __restrict__ out_hi) {
+    griddep_launch();
+    griddep_wait();
     const int H = 84, W = 84, Wp = 86, Hp = 86;
     int img = blockIdx.x / Hp;
     int yp = blockIdx.x % Hp;
@@ -42,7 +44,7 @@ __global__ void k_unpack_frames(const uint8_t* __restrict__ obs, const int* __re
 }
 
 int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st) {
-    k_unpack_frames<<<n * 86, 96, 0, st>>>(obs, idx, n, out_hi);
+    launch_pdl(k_unpack_frames, dim3(n * 86), dim3(96), 0, st, obs, idx, n, out_hi);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -99,6 +101,8 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 // order (XLA select_and_scatter with a `ge` select), which is all the backward pass needs.
 __global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks,
                            float* __restrict__ out_s, Planes out_relu, uint8_t* __restrict__ amax) {
+    griddep_launch();
+    griddep_wait();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= go.NP * chunks) return;
     int jc = (int)(t / go.NP);
@@ -148,7 +152,7 @@ __global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom g
 int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
                     uint8_t* amax, cudaStream_t st) {
     long long total = go.NP * chunks;
-    k_pool_fwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, gi, go, pad_lo, chunks, out_s, out_relu, amax);
+    launch_pdl(k_pool_fwd, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, in, gi, go, pad_lo, chunks, out_s, out_relu, amax);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -161,6 +165,8 @@ int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int c
 // grid = (quad blocks of one image, image * chunks); quads cover the whole padded grid so the border ring is zero-filled too.
 __global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ amax, const float* __restrict__ dpool,
                                                   ConvGeom gi, ConvGeom go, int pad_lo, int chunks, int KQ, Planes out) {
+    griddep_launch();
+    griddep_wait();
     const int img = blockIdx.y / chunks, jc = blockIdx.y % chunks;
     const long long pbase = (long long)jc * out.plane_px;
     if (img == gi.n - 1 && blockIdx.x == 0) {
@@ -231,7 +237,7 @@ int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGe
                     cudaStream_t st) {
     const int KQ = (gi.Hp + 2 - pad_lo) / 2;   // quads per image side: padded rows 2k - 1 + pad_lo, 2k + pad_lo
     dim3 grid((KQ * KQ + 255) / 256, gi.n * chunks);
-    k_pool_bwd<<<grid, 256, 0, st>>>(amax, dpool, gi, go, pad_lo, chunks, KQ, out);
+    launch_pdl(k_pool_bwd, grid, dim3(256), 0, st, amax, dpool, gi, go, pad_lo, chunks, KQ, out);
     CB_LAUNCH_CHECK();
     return 0;
 }
