@@ -107,6 +107,20 @@ class Context:
         check(self.lib.cb_get_opt_state(self.h, _ptr(m), _ptr(v), ctypes.byref(cnt), _stream(self.device)))
         return m, v, cnt.value
 
+    def set_opt_state(self, m, v, count: int):
+        """Restore the optimizer moments and step count (resume; the reference has no equivalent)."""
+        def dev(x):
+            if isinstance(x, np.ndarray):
+                x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            x = x.to(self.device, torch.float32).contiguous()
+            if x.numel() != self.num_params:
+                raise CleanbaError(f"expected {self.num_params} optimizer-state elements, got {x.numel()}")
+            return x
+        m, v = dev(m), dev(v)
+        with torch.cuda.device(self.device):
+            check(self.lib.cb_set_opt_state(self.h, _ptr(m), _ptr(v), ctypes.c_longlong(int(count)), _stream(self.device)))
+            torch.cuda.current_stream(self.device).synchronize()
+
     def profile(self, enable: bool):
         check(self.lib.cb_profile(self.h, int(enable)))
 

@@ -218,6 +218,24 @@ class CudaLearner:
             ev.record(torch.cuda.current_stream(lr.ctx.device))
         return snap, ev
 
+    def flat_params(self):
+        """Host copy of the (replicated) parameters: flax.jax_utils.unreplicate(agent_state).params (cleanba_ppo.py:756)."""
+        return self.learners[0].ctx.get_params().cpu().numpy()
+
+    def train_state(self):
+        """Everything needed to resume: parameters, optimizer moments + count, learner keys."""
+        lr = self.learners[0]
+        m, v, count = lr.ctx.get_opt_state()
+        return dict(params=self.flat_params(), m=m.cpu().numpy(), v=v.cpu().numpy(), count=count,
+                    key=ag.key_numpy(self.keys[0]), opt_count=lr.opt_count)
+
+    def load_train_state(self, st):
+        for l, lr in enumerate(self.learners):
+            lr.ctx.set_params(st["params"])
+            lr.ctx.set_opt_state(st["m"], st["v"], st["count"])
+            lr.opt_count = int(st["count"])
+            self.keys[l] = ag.key_tensor(np.asarray(st["key"], np.uint32), self.devices[l])
+
     def stats_to_host(self, stats):
         s = stats.detach().cpu().numpy()
         names = ("loss", "pg_loss", "v_loss", "entropy_loss") + (() if self.impala else ("approx_kl",))

@@ -66,6 +66,8 @@ class Args:
     algo: str = "ppo"
     max_updates: int = 0          # 0 = run to total_timesteps
     synthetic_env: bool = True    # envpool is not installable here; frames come from cleanba_b200.envs.SyntheticAtari
+    eval_max_steps: int = 27000   # step cap of one evaluation episode after --save-model (envpool's max_episode_steps)
+    resume_from: str = ""         # train-state sidecar written by --save-model (parameters + optimizer state + keys)
 
     # runtime arguments to be filled in (cleanba_ppo.py:106-118)
     local_batch_size: int = 0
@@ -270,6 +272,9 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
     writer = writer or _NullWriter()
     key = backend.first_key(args.seed)            # key, network_key, actor_key, critic_key = split(PRNGKey(seed), 4)
     learner = backend.make_learner(args, key, allreduce)
+    if getattr(args, "resume_from", ""):
+        from .checkpoint import load_train_state
+        learner.load_train_state(load_train_state(args.resume_from))
     params_queues, rollout_queues, threads = [], [], []
     stop = threading.Event()
     errors: list = []

@@ -71,6 +71,62 @@ def test_sebulba_loop_on_cuda_matches_cpu_plumbing(algo):
     assert np.abs(p_cuda - ro.learner.learner.params).max() < 5e-2 * np.abs(p_cuda).max()   # loose sanity bound (chaos, see above)
 
 
+def test_save_model_eval_and_resume(tmp_path, monkeypatch):
+    """--save-model writes runs/{run}/{exp}.cleanrl_model in the reference's flax msgpack layout (cleanba_ppo.py:753-771),
+    evaluates it (cleanrl_utils/evals/ppo_envpool_jax_eval.py), and the train-state sidecar resumes bit-exactly: a run of
+    2 updates + a resumed run of 1 update equals a run of 3 updates when the rollouts are the same."""
+    from cleanba_b200 import agent as ag, checkpoint as ck
+    from cleanba_b200.cleanba_ppo import main
+    from cleanba_b200.learner import PPOHyper, PPOLearner
+    from cleanba_b200.params import init_params
+    from cleanba_b200.sebulba import Args
+    monkeypatch.chdir(tmp_path)
+    a = Args(local_num_envs=8, num_actor_threads=1, num_steps=4, num_minibatches=2, update_epochs=1, total_timesteps=10 ** 6,
+             log_frequency=1000, max_updates=2, save_model=True, eval_max_steps=5, seed=2)
+    res = main(a)
+    assert os.path.exists(res.model_path) and len(res.eval_returns) == 10
+    saved_args, flat = ck.load_cleanrl_model(res.model_path)
+    assert saved_args["seed"] == 2 and saved_args["local_num_envs"] == 8
+    assert np.array_equal(flat, res.learner.flat_params())
+    st = ck.load_train_state(res.model_path + ".train_state.npz")
+    assert st["learner_policy_version"] == 2 and st["count"] == 4 and np.array_equal(st["params"], flat)   # 2 updates x 2 minibatches
+
+    # resume determinism at the learner level (fixed synthetic rollouts): 3 updates == 2 updates + restore + 1 update
+    T, Bl = 4, 8
+    rng = np.random.default_rng(0)
+    tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    rolls = [dict(obs=tt(rng.integers(0, 256, (T, Bl, 4, 84, 84), dtype=np.uint8)), dones=tt(rng.random((T, Bl)) < 0.1),
+                  actions=tt(rng.integers(0, 18, (T, Bl)).astype(np.int32)), logprobs=tt(np.full((T, Bl), np.log(1 / 18), np.float32)),
+                  values=tt((rng.standard_normal((T, Bl)) * 0.1).astype(np.float32)),
+                  rewards=tt(rng.choice([-1.0, 0.0, 1.0], size=(T, Bl)).astype(np.float32)),
+                  next_obs=tt(rng.integers(0, 256, (Bl, 4, 84, 84), dtype=np.uint8)), next_done=tt(np.zeros(Bl, bool))) for _ in range(3)]
+
+    def make():
+        L = PPOLearner("cuda:0", PPOHyper(update_epochs=1, num_minibatches=2, num_updates=10), T=T, Bl=Bl)
+        L.ctx.set_params(init_params(5))
+        return L, ag.key_tensor(np.array([7, 9], np.uint32), L.ctx.device)
+
+    def upd(L, key, r):
+        return L.update(r["obs"], r["dones"], r["actions"], r["logprobs"], r["values"], r["rewards"], r["next_obs"], r["next_done"], key)
+
+    A, ka = make()
+    for r in rolls:
+        upd(A, ka, r)
+    want = A.ctx.get_params().cpu().numpy()
+    B, kb = make()
+    for r in rolls[:2]:
+        upd(B, kb, r)
+    m, v, count = B.ctx.get_opt_state()
+    path = ck.save_train_state(str(tmp_path / "mid.npz"), B.ctx.get_params().cpu().numpy(), m.cpu().numpy(), v.cpu().numpy(), count,
+                               ag.key_numpy(kb), 2)
+    st = ck.load_train_state(path)
+    C, _ = make()
+    C.ctx.set_params(st["params"]); C.ctx.set_opt_state(st["m"], st["v"], st["count"]); C.opt_count = st["count"]
+    kc = ag.key_tensor(st["key"], C.ctx.device)
+    upd(C, kc, rolls[2])
+    assert np.array_equal(C.ctx.get_params().cpu().numpy(), want)
+
+
 WORKER = r"""
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})

@@ -1,5 +1,4 @@
-N="ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled"
-timeout 600 $N -k regex:'k_conv_umma<.int.4, .int.32, .int.3>' -s 1 -c 1 -o gpurun_out/prof_conv4323 -f python tests/gpu_ncu_step.py 3840 learner > gpurun_out/ncu1.log 2>&1
-timeout 600 $N -k regex:'k_wgrad_umma<.int.4, .int.32>' -s 1 -c 1 -o gpurun_out/prof_wgrad432 -f python tests/gpu_ncu_step.py 3840 learner > gpurun_out/ncu2.log 2>&1
-timeout 600 $N -k regex:'k_conv_umma<.int.2, .int.16, .int.3>' -s 1 -c 1 -o gpurun_out/prof_conv2163 -f python tests/gpu_ncu_step.py 3840 learner > gpurun_out/ncu3.log 2>&1
-tail -n 2 gpurun_out/ncu1.log gpurun_out/ncu2.log gpurun_out/ncu3.log; ls -la gpurun_out/*.ncu-rep
+python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_all.log
+tail -n 5 gpurun_out/t_all.log
+for f in 0 1; do echo "=== CLEANBA_FUSE_POOL_BWD=$f"; CLEANBA_FUSE_POOL_BWD=$f python tests/gpu_perf_probe.py 3840 2>&1 | grep -E "==|wgrad<cin4|pool_bwd@84|sum of"; done > gpurun_out/perf.log 2>&1
+cat gpurun_out/perf.log
