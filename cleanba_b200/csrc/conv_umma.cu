@@ -36,10 +36,11 @@ constexpr int CONV_MAXST = 8;        // stages of the input-window ring: as many
 constexpr int CONV_THREADS = 320;   // warps 0-7: two epilogue groups (one per TMEM accumulator), warp 8: TMA, warp 9: MMA
 
 __host__ __device__ constexpr int conv_steps(int cin_chunks) { return cin_chunks == 1 ? 5 : 9 * (cin_chunks / 2); }
-// bytes of the packed weight image: per step [kc(2)][3*cout][8] bf16
-__host__ __device__ constexpr int conv_wbytes(int cin_chunks, int cout) { return conv_steps(cin_chunks) * 2 * 3 * cout * 16; }
+// bytes of the packed weight image: per step [kc(2)][wpl*cout][8] bf16, wpl = 3 planes (forward) or 2 (dgrad)
+__host__ __device__ constexpr int conv_wbytes(int cin_chunks, int cout, int wpl) { return conv_steps(cin_chunks) * 2 * wpl * cout * 16; }
+__host__ __device__ constexpr int conv_wpl(int apl) { return apl == 2 ? 2 : 3; }
 
-long long packed_conv_elems(int cin_chunks, int cout) { return (long long)conv_wbytes(cin_chunks, cout) / 2; }
+long long packed_conv_elems(int cin_chunks, int cout, int wpl) { return (long long)conv_wbytes(cin_chunks, cout, wpl) / 2; }
 
 struct ConvSmemLayout {
     int win, plane_bytes, nplanes, stage_bytes, w_bytes, stages, ctas_per_sm, total;
@@ -51,7 +52,7 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int c
     L.plane_bytes = L.win * 16;
     L.nplanes = cin_chunks == 1 ? 1 : apl * cin_chunks;      // hi planes, mid planes[, lo planes] (frames: hi only, exact)
     L.stage_bytes = L.nplanes * L.plane_bytes;
-    L.w_bytes = conv_wbytes(cin_chunks, cout);
+    L.w_bytes = conv_wbytes(cin_chunks, cout, conv_wpl(apl));
     // two CTAs per SM (two MMA-issuing threads) when three stages fit in half an SM, else one CTA with a deeper ring
     L.ctas_per_sm = 1024 + L.w_bytes + 3 * L.stage_bytes <= 112 * 1024 ? 2 : 1;
     const int budget = (L.ctas_per_sm == 2 ? 112 : 226) * 1024 - 1024 - L.w_bytes;
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
         // issue loop below is fully unrolled and costs one integer add per operand per MMA).
         const uint32_t win16 = (uint32_t)L.win;                  // plane stride in 16-byte units
         const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
-        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 3 * COUT * 16);
+        constexpr int WPL = conv_wpl(APL);
+        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), WPL * COUT * 16);
         uint32_t a_rel[STEPS];
 #pragma unroll
         for (int step = 0; step < STEPS; ++step) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
 #pragma unroll
                 for (int step = 0; step < STEPS; ++step) {
                     const uint32_t a_lo = st16 + a_rel[step];
-                    const uint32_t b_lo = b_lo0 + step * (2 * 3 * COUT);
+                    const uint32_t b_lo = b_lo0 + step * (2 * WPL * COUT);
                     if (APL == 2) {
                         mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0);
                         mma_bf16_parts(d_tmem, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1);
@@ -239,6 +241,7 @@ static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
     CB_CHECK(a.g.Wp + 1 <= GUARD && TILE_M + a.g.Wp + 2 <= GUARD, "conv_umma: guard too small for Wp=%d", a.g.Wp);
     const int apl = a.in.lo ? 3 : (a.in.mid ? 2 : 1);
+    CB_CHECK((apl == 2) == (a.transpose != 0), "conv_umma: 2-plane inputs are gradient tensors (dgrad weight image), 1/3-plane inputs forward");
     if (a.cin_chunks == 1 && a.cout == 16 && apl == 1) return launch_conv_umma_t<1, 16, 1>(a, num_sms, st);
     if (a.cin_chunks == 2 && a.cout == 16 && apl == 3) return launch_conv_umma_t<2, 16, 3>(a, num_sms, st);
     if (a.cin_chunks == 2 && a.cout == 16 && apl == 2) return launch_conv_umma_t<2, 16, 2>(a, num_sms, st);

@@ -478,12 +478,12 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
                 L.cout = kStageC[s];
                 L.off_b = c->leaves[s * 10 + k * 2].offset;
                 L.off_w = c->leaves[s * 10 + k * 2 + 1].offset;
-                long long ef = packed_conv_elems((L.cin + 7) / 8, L.cout);
+                long long ef = packed_conv_elems((L.cin + 7) / 8, L.cout, 3);
                 if (dev_alloc(c, &p, ef * sizeof(bf16))) { fail = true; break; }
                 L.fwd = (bf16*)p;
                 L.dg = nullptr;
                 if (li != 0) {
-                    long long ed = packed_conv_elems(L.cout / 8, L.cin);
+                    long long ed = packed_conv_elems(L.cout / 8, L.cin, 2);
                     if (dev_alloc(c, &p, ed * sizeof(bf16))) { fail = true; break; }
                     L.dg = (bf16*)p;
                 }

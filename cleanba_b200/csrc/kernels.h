@@ -140,6 +140,6 @@ struct PackLayer {
     bf16* dg;                    // packed dgrad image (null for the first conv)
 };
 int launch_pack_conv(const PackLayer* layers_dev, int nlayers, cudaStream_t st);
-long long packed_conv_elems(int cin_chunks, int cout);
+long long packed_conv_elems(int cin_chunks, int cout, int wpl);
 
 }  // namespace cb

@@ -2,7 +2,8 @@
 // tcgen05 conv kernel (conv_umma.cu): per K=16 step a K-major SWIZZLE_NONE B tile  [kc(2)][n3(3*Cout)][8]  where the
 // N rows are the three bf16 split planes of the weights stacked: rows [0,Cout) = hi, [Cout,2Cout) = mid, [2Cout,3Cout) = lo,
 // so that B(n3,k) sits at n3*16 + (k/8)*3*Cout*16 + (k%8)*2 bytes (LBO = 3*Cout*16, SBO = 128) and an MMA with
-// N = 3*Cout, 2*Cout or Cout uses the hi|mid|lo, hi|mid or hi planes of the same image.
+// N = 3*Cout, 2*Cout or Cout uses the hi|mid|lo, hi|mid or hi planes of the same image.  The dgrad image carries the hi and
+// mid planes only (n3 = 2*Cout rows): its A operand (a 2-plane gradient tensor) never meets W_lo.
 //   forward : step = tap * (Cin/16) + pair,  k -> ci = pair*16 + k,  B[n=co][k] = W[tap][ci][co]
 //   dgrad   : conv of the output gradient with flipped taps and swapped channels:
 //             step = tap' * (Cout/16) + pair, k -> co = pair*16 + k, B[n=ci][k] = W[8 - tap'][ci][co]
@@ -23,7 +24,7 @@ __global__ void k_pack_conv(const PackLayer* __restrict__ layers) {
     const bool frames = (kin < 8);
     const int chunks = frames ? 1 : kin / 8;
     const int steps = frames ? 5 : 9 * (chunks / 2);
-    const int n3tot = 3 * nout;
+    const int n3tot = (variant ? 2 : 3) * nout;   // dgrad multiplies 2-plane gradients: only W_hi | W_mid are ever used
     const long long total = (long long)steps * 2 * n3tot * 8;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int k8 = (int)(e % 8);

@@ -10,41 +10,46 @@ namespace cb {
 // ------------------------------------------------------------------------------------------------
 // uint8 NCHW frame stack -> bf16 chunk plane (8 channels: 4 real + 4 zero), borders zero.
 // cleanba_ppo.py:180-181 (transpose + /255; the 1/255 is folded into the conv epilogue, 0..255 are exact in bf16).
-// One block per (image, padded row): the 4 channel rows are staged through shared memory with coalesced
-// 4-byte reads, then every thread emits one 16-byte pixel.
-__global__ void k_unpack_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, int n, bf16* __restrict__ out_hi) {
+// One block per (image, group of UNPACK_ROWS padded rows): the channel rows are staged through shared memory with
+// coalesced 4-byte reads, then every thread emits 16-byte pixels (consecutive threads -> consecutive pixels).
+constexpr int UNPACK_ROWS = 8;
+__global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, int n,
+                                                       bf16* __restrict__ out_hi) {
     griddep_launch();
     griddep_wait();
-    const int H = 84, W = 84, Wp = 86, Hp = 86;
-    int img = blockIdx.x / Hp;
-    int yp = blockIdx.x % Hp;
-    __shared__ uint32_t srow[4][W / 4];
-    bool row_in = (yp >= 1 && yp <= H);
-    if (row_in) {
-        long long src = idx ? (long long)idx[img] : (long long)img;
-        const uint8_t* base = obs + src * (4LL * H * W) + (long long)(yp - 1) * W;
-        for (int t = threadIdx.x; t < 4 * (W / 4); t += blockDim.x) {
-            int c = t / (W / 4), w4 = t % (W / 4);
-            srow[c][w4] = *reinterpret_cast<const uint32_t*>(base + (long long)c * H * W + w4 * 4);
-        }
+    constexpr int H = 84, W = 84, Wp = 86, Hp = 86, GROUPS = (Hp + UNPACK_ROWS - 1) / UNPACK_ROWS;
+    const int img = blockIdx.x / GROUPS;
+    const int yp0 = (blockIdx.x % GROUPS) * UNPACK_ROWS;
+    __shared__ uint32_t srow[UNPACK_ROWS][4][W / 4];
+    const long long src = idx ? (long long)idx[img] : (long long)img;
+    const uint8_t* base = obs + src * (4LL * H * W);
+    for (int t = threadIdx.x; t < UNPACK_ROWS * 4 * (W / 4); t += blockDim.x) {
+        const int w4 = t % (W / 4), c = (t / (W / 4)) % 4, ry = t / (4 * (W / 4));
+        const int yp = yp0 + ry;
+        if (yp >= 1 && yp <= H)
+            srow[ry][c][w4] = *reinterpret_cast<const uint32_t*>(base + ((long long)c * H + (yp - 1)) * W + w4 * 4);
     }
     __syncthreads();
-    for (int xp = threadIdx.x; xp < Wp; xp += blockDim.x) {
+    for (int t = threadIdx.x; t < UNPACK_ROWS * Wp; t += blockDim.x) {
+        const int ry = t / Wp, xp = t - ry * Wp;
+        const int yp = yp0 + ry;
+        if (yp >= Hp) break;
         uint4 o = make_uint4(0, 0, 0, 0);
-        if (row_in && xp >= 1 && xp <= W) {
-            int x = xp - 1;
-            const uint8_t* s = reinterpret_cast<const uint8_t*>(&srow[0][0]);
-            float c0 = s[0 * W + x], c1 = s[1 * W + x], c2 = s[2 * W + x], c3 = s[3 * W + x];
+        if (yp >= 1 && yp <= H && xp >= 1 && xp <= W) {
+            const int x = xp - 1;
+            const uint8_t* s = reinterpret_cast<const uint8_t*>(&srow[ry][0][0]);
+            const float c0 = s[0 * W + x], c1 = s[1 * W + x], c2 = s[2 * W + x], c3 = s[3 * W + x];
             o.x = pack_bf16x2(__float2bfloat16_rn(c0), __float2bfloat16_rn(c1));
             o.y = pack_bf16x2(__float2bfloat16_rn(c2), __float2bfloat16_rn(c3));
         }
-        long long q = (long long)img * (Hp * Wp) + (long long)yp * Wp + xp;
+        const long long q = (long long)img * (Hp * Wp) + (long long)yp * Wp + xp;
         *reinterpret_cast<uint4*>(out_hi + q * 8) = o;
     }
 }
 
 int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st) {
-    launch_pdl(k_unpack_frames, dim3(n * 86), dim3(96), 0, st, obs, idx, n, out_hi);
+    const int groups = (86 + UNPACK_ROWS - 1) / UNPACK_ROWS;
+    launch_pdl(k_unpack_frames, dim3(n * groups), dim3(256), 0, st, obs, idx, n, out_hi);
     CB_LAUNCH_CHECK();
     return 0;
 }
