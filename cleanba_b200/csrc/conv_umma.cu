@@ -254,6 +254,243 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
 }
 
 // =================================================================================================
+// First ConvSequence, forward: the frame conv FUSED with its max-pool (cleanba_ppo.py:167-168).
+// The 84x84x16 fp32 conv output (473 KB per frame: the largest tensor of the network) is never written to HBM.  A CTA
+// processes BANDS of 3 pooled rows = 7 consecutive conv rows = 602 consecutive flat pixels = 5 MMA tiles of 128 (the
+// flat-shifted-window trick needs consecutive pixels, and whole rows ARE consecutive).  The epilogue warps move each
+// accumulator (x 1/255 + bias) into a shared-memory band buffer instead of HBM; after the 5th tile they pool the band
+// (3x3 stride 2, SAME: windows (2i..2i+2, 2j..2j+2) clipped at 84, first maximum in row-major order like k_pool_fwd) and
+// write what the separate pool kernel wrote: the fp32 stream, the relu'd 3-way split planes and the arg-max bytes of the
+// pooled 44x44 padded grid (borders zero).  The TMA producer and the MMA issuer run ahead of the pooling by the two
+// TMEM accumulators.  HBM traffic per frame: 118 KB in + 340 KB out instead of 1.4 MB through the two kernels.
+constexpr int C0_HP = 86, C0_P = C0_HP * C0_HP, C0_HO = 42, C0_WPO = 44, C0_PO = C0_WPO * C0_WPO;
+constexpr int C0_BAND_K = 3;                                   // pooled rows per band
+constexpr int C0_BANDS = C0_HO / C0_BAND_K;                    // 14 bands per frame
+constexpr int C0_BAND_TILES = 5;                               // ceil(7 * 86 / 128)
+constexpr int C0_BAND_PX = C0_BAND_TILES * TILE_M;             // 640 pixels in the band buffer
+constexpr int C0_COUT = 16;
+constexpr int C0_STAGES = 8;
+constexpr int C0_WIN = TILE_M + 2 * C0_HP + 3;                 // 303 pixels per input window (see conv_smem_layout)
+constexpr int C0_STAGE_BYTES = C0_WIN * 16;
+constexpr int C0_W_BYTES = conv_wbytes(1, C0_COUT, 3);
+constexpr int C0_BAND_BYTES = C0_BAND_PX * C0_COUT * 4;
+constexpr int C0_SMEM = 1024 + C0_W_BYTES + C0_STAGES * C0_STAGE_BYTES + C0_BAND_BYTES;
+static_assert(C0_HO % C0_BAND_K == 0, "bands must tile the pooled rows");
+static_assert(2 * C0_SMEM <= 226 * 1024, "two CTAs per SM");
+
+struct Conv0PoolArgs {
+    int n;                    // frames
+    const bf16* x_hi;         // unpacked frames: chunk plane [n * 86 * 86][8] (4 real channels), flat pixel 0
+    const bf16* wp;           // packed forward weight image of the frame conv
+    const float* bias;        // [16]
+    float acc_scale;          // 1/255
+    float* out_s;             // pooled fp32 stream [2][n * 44 * 44][8]
+    Planes out;               // relu'd pooled planes (hi, mid, lo)
+    uint8_t* amax;            // arg-max bytes [2][n * 44 * 44][8] or null (actor contexts)
+};
+
+// 16-byte chunk c (0..3) of band pixel pb, swizzled so that the epilogue's per-lane pixel stores are conflict free
+__device__ __forceinline__ float4* c0_band_ptr(uint8_t* band, int pb, int c) {
+    return reinterpret_cast<float4*>(band + pb * 64 + ((c ^ ((pb >> 1) & 3)) << 4));
+}
+
+__global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_launch();
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [C0_STAGES]
+    uint64_t* empty = full + C0_STAGES;                          // [C0_STAGES]
+    uint64_t* tfull = empty + C0_STAGES;                         // [2]
+    uint64_t* tempty = tfull + 2;                                // [2]
+    uint64_t* wbar = tempty + 2;                                 // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint8_t* wsm = smem + 1024;
+    uint8_t* stages = wsm + C0_W_BYTES;
+    uint8_t* band = stages + C0_STAGES * C0_STAGE_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int STEPS = conv_steps(1);
+    constexpr int ACC_COLS = 3 * C0_COUT;
+    constexpr uint32_t TMEM_COLS = 128;
+    const int nbands = a.n * C0_BANDS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C0_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 8 && lane == 0) {
+        mbar_arrive_expect_tx(wbar, (uint32_t)C0_W_BYTES);
+        bulk_g2s(wsm, a.wp, C0_W_BYTES, wbar);
+    }
+    griddep_wait();
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
+                const int img = bnd / C0_BANDS, b = bnd - img * C0_BANDS;
+                const long long qb = (long long)img * C0_P + (2 * C0_BAND_K * b + 1) * C0_HP;     // first conv row of the band
+                for (int t = 0; t < C0_BAND_TILES; ++t) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)C0_STAGE_BYTES);
+                    const long long q_lo = qb + t * TILE_M - C0_HP - 1;
+                    bulk_g2s(stages + s * C0_STAGE_BYTES, a.x_hi + q_lo * 8, C0_STAGE_BYTES, &full[s]);
+                    if (++s == C0_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer (frames: one exact bf16 plane, two taps per K = 16 step) =====================
+        constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * C0_COUT, 0, 0);
+        mbar_wait(wbar, 0);
+        int s = 0; uint32_t ph = 0;
+        int acc = 0; uint32_t aph = 0;
+        const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
+        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 3 * C0_COUT * 16);
+        uint32_t a_rel[STEPS];
+#pragma unroll
+        for (int step = 0; step < STEPS; ++step) {
+            if (step < 3) a_rel[step] = (uint32_t)(step * C0_HP) | (1u << 16);
+            else if (step == 3) a_rel[step] = 2u | ((uint32_t)C0_HP << 16);
+            else a_rel[step] = (uint32_t)(2 * C0_HP + 2) | (1u << 16);
+        }
+        for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x)
+            for (int t = 0; t < C0_BAND_TILES; ++t) {
+                mbar_wait(&tempty[acc], aph ^ 1);
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                    const uint32_t st16 = (smem_u32(stages + s * C0_STAGE_BYTES) >> 4);
+#pragma unroll
+                    for (int step = 0; step < STEPS; ++step)
+                        mma_bf16_parts(d_tmem, st16 + a_rel[step], a_hi, b_lo0 + step * (2 * 3 * C0_COUT), b_hi, IDESC3, step > 0);
+                    mma_commit(&empty[s]);
+                    mma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++s == C0_STAGES) { s = 0; ph ^= 1; }
+                if (++acc == 2) { acc = 0; aph ^= 1; }
+            }
+    } else {
+        // ===================== epilogue warps 0-7: accumulators -> band buffer, then pool the band =====================
+        const int grp = warp >> 2, quad = warp & 3;
+        const int etid = threadIdx.x;                            // 0..255
+        uint32_t aph = 0;                                        // phase of this group's accumulator
+        long long cnt = 0;                                       // tiles seen so far by the CTA (parity = accumulator)
+        float bias[C0_COUT];
+#pragma unroll
+        for (int e = 0; e < C0_COUT; ++e) bias[e] = a.bias[e];
+        for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
+            const int img = bnd / C0_BANDS, b = bnd - img * C0_BANDS;
+            for (int t = 0; t < C0_BAND_TILES; ++t, ++cnt) {
+                if ((int)(cnt & 1) != grp) continue;
+                mbar_wait(&tfull[grp], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * ACC_COLS;
+                float v[C0_COUT], u[16];
+                tmem_ld16(taddr + 2 * C0_COUT, v);
+                tmem_ld16(taddr + C0_COUT, u);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += u[i];
+                tmem_ld16(taddr, u);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += u[i];
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[grp]);
+                aph ^= 1;
+                const int pb = t * TILE_M + quad * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *c0_band_ptr(band, pb, c) = make_float4(v[c * 4 + 0] * a.acc_scale + bias[c * 4 + 0], v[c * 4 + 1] * a.acc_scale + bias[c * 4 + 1],
+                                                            v[c * 4 + 2] * a.acc_scale + bias[c * 4 + 2], v[c * 4 + 3] * a.acc_scale + bias[c * 4 + 3]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // the band is complete in shared memory
+            // pooled padded rows of this band: 3b+1 .. 3b+3, plus the border rows 0 / 43 for the first / last band
+            const int r_lo = (b == 0) ? -1 : 0, r_hi = (b == C0_BANDS - 1) ? C0_BAND_K + 1 : C0_BAND_K;
+            const int nitems = (r_hi - r_lo) * C0_WPO * 2;
+            for (int it = etid; it < nitems; it += 256) {
+                const int xp = it % C0_WPO;
+                const int jc = (it / C0_WPO) & 1;
+                const int r = r_lo + it / (2 * C0_WPO);
+                const int ypo = C0_BAND_K * b + r + 1;
+                float v[8];
+                int am[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { v[e] = 0.f; am[e] = 15; }
+                if (r >= 0 && r < C0_BAND_K && xp >= 1 && xp <= C0_HO) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = -INFINITY;
+                    const int j = xp - 1, y0 = 2 * (C0_BAND_K * b + r);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        if (y0 + dy >= 84) continue;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            if (2 * j + dx >= 84) continue;
+                            const int pb = (2 * r + dy) * C0_HP + 2 * j + dx + 1;
+                            const float4 f0 = *c0_band_ptr(band, pb, 2 * jc), f1 = *c0_band_ptr(band, pb, 2 * jc + 1);
+                            const float o[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (o[e] > v[e]) { v[e] = o[e]; am[e] = dy * 3 + dx; }
+                        }
+                    }
+                }
+                const long long qo = (long long)img * C0_PO + ypo * C0_WPO + xp;
+                const long long so = ((long long)jc * a.n * C0_PO + qo) * 8;
+                float4* o = reinterpret_cast<float4*>(a.out_s + so);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                float rl[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
+                store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, rl);
+                if (a.amax) {
+                    uint2 pk;
+                    pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                    pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                    *reinterpret_cast<uint2*>(a.amax + so) = pk;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // band buffer free for the next band
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int launch_conv0_pool_umma(const ConvArgs& a, float* out_s, Planes out, uint8_t* amax, int num_sms, cudaStream_t st) {
+    CB_CHECK(a.g.H == 84 && a.g.W == 84 && a.cin_chunks == 1 && a.cout == C0_COUT && !a.transpose,
+             "conv0_pool_umma: frame conv (84x84, 4 -> 16 channels) only");
+    CB_CHECK(C0_HP + 1 <= GUARD && TILE_M + C0_HP + 2 + TILE_M <= GUARD + 128, "conv0_pool_umma: guard too small");
+    static std::atomic<unsigned> attr_done{0};
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    if (!(attr_done.load() & (1u << dev))) {
+        CB_CUDA(cudaFuncSetAttribute(k_conv0_pool_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM));
+        attr_done.fetch_or(1u << dev);
+    }
+    Conv0PoolArgs p;
+    p.n = a.g.n; p.x_hi = a.in.hi; p.wp = a.wp; p.bias = a.ep.bias; p.acc_scale = a.ep.acc_scale;
+    p.out_s = out_s; p.out = out; p.amax = amax;
+    const int nbands = a.g.n * C0_BANDS;
+    const int grid = nbands < 2 * num_sms ? nbands : 2 * num_sms;
+    launch_pdl(k_conv0_pool_umma, dim3(grid), dim3(CONV_THREADS), (size_t)C0_SMEM, st, p);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+// =================================================================================================
 // wgrad on tcgen05:  dW[(ky,kx), ci, co] = sum_q X[q + d(ky,kx)][ci] * G[q][co],  db[co] = sum_q G[q][co].
 // GEMM view per 128-pixel block:  D_kx[m, n] += A_kx[m, q] * B[q, n]  with the reduction over pixels (K), where
 //   m = (ky, ci) stacks the three filter ROWS (three bulk copies of the same planes shifted by one image row) and

@@ -386,6 +386,13 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             if (run_conv(c, a, st)) return -1;
         }
         // ---- max-pool backward, then the sequence conv
+        if (s == 0 && c->cfg.conv_backend == CB_CONV_TCGEN05) {
+            // frames need no dX: the pooled gradient goes straight into the frame conv's weight gradient (trunk_simt.cu)
+            ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), st);
+            if (launch_pool_bwd_wgrad0(S.amax, S.gA.s, S.x.pl.hi, gi, go, 1.0f / 255.0f, grads + c->conv[0].off_w,
+                                       grads + c->conv[0].off_b, c->wg_partial, c->num_sms, st)) return -1;
+            continue;
+        }
         {
             ProfScope ps(c, "pool_bwd@" + std::to_string(kStageHin[s]), 0,
                          (double)go.NP * kStageC[s] * 5 + planes_bytes(gi, kStageC[s] / 8, true), st);

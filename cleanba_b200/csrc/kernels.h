@@ -23,11 +23,16 @@ int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int c
 int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
                     cudaStream_t st);
 int launch_wgrad_simt(const WgradArgs& a, float* partial, int max_blocks, cudaStream_t st);
+// first ConvSequence: pool backward fused with the frame conv's weight gradient (no 84x84 gradient tensor)
+int launch_pool_bwd_wgrad0(const uint8_t* amax, const float* dpool, const bf16* x_hi, ConvGeom gi, ConvGeom go, float scale,
+                           float* dw, float* db, float* partial, int num_sms, cudaStream_t st);
 
 // conv_umma.cu (tcgen05 + TMA bulk copies)
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st);
 int launch_wgrad_umma(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st);
 int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp);
+// frame conv fused with its max-pool (84x84x4 -> pooled 42x42x16: stream, relu'd planes, arg-max bytes)
+int launch_conv0_pool_umma(const ConvArgs& a, float* out_s, Planes out, uint8_t* amax, int num_sms, cudaStream_t st);
 
 // dense.cu
 struct DenseArgs {
