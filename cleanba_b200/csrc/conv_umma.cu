@@ -289,9 +289,13 @@ struct Conv0PoolArgs {
     uint8_t* amax;            // arg-max bytes [2][n * 44 * 44][8] or null (actor contexts)
 };
 
-// 16-byte chunk c (0..3) of band pixel pb, swizzled so that the epilogue's per-lane pixel stores are conflict free
+// 16-byte chunk c (0..3) of band pixel pb.  A pixel PAIR is one 128-byte row (all 32 banks); the 3-bit index (pixel parity, c)
+// is XOR-swizzled with the pair index, a Latin square: the epilogue's stores (8 lanes = 8 consecutive pixels, same c) and the
+// pool's loads (8 lanes = 8 consecutive pooled columns = pixel stride 2, same parity and c) both touch 8 distinct 16-byte
+// bank groups, i.e. both are conflict free.
 __device__ __forceinline__ float4* c0_band_ptr(uint8_t* band, int pb, int c) {
-    return reinterpret_cast<float4*>(band + pb * 64 + ((c ^ ((pb >> 1) & 3)) << 4));
+    const int pair = pb >> 1;
+    return reinterpret_cast<float4*>(band + (pair << 7) + (((((pb & 1) << 2) | c) ^ (pair & 7)) << 4));
 }
 
 __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs a) {
@@ -299,9 +303,9 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
     griddep_launch();
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [C0_STAGES]
     uint64_t* empty = full + C0_STAGES;                          // [C0_STAGES]
-    uint64_t* tfull = empty + C0_STAGES;                         // [2]
-    uint64_t* tempty = tfull + 2;                                // [2]
-    uint64_t* wbar = tempty + 2;                                 // [1]
+    uint64_t* tfull = empty + C0_STAGES;                         // [C0_BAND_TILES]: one TMEM accumulator per tile of a band
+    uint64_t* tempty = tfull + C0_BAND_TILES;                    // [C0_BAND_TILES]
+    uint64_t* wbar = tempty + C0_BAND_TILES;                     // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     uint8_t* wsm = smem + 1024;
     uint8_t* stages = wsm + C0_W_BYTES;
@@ -310,12 +314,12 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(1);
     constexpr int ACC_COLS = 3 * C0_COUT;
-    constexpr uint32_t TMEM_COLS = 128;
-    const int nbands = a.n * C0_BANDS;
+    constexpr uint32_t TMEM_COLS = 256;                          // 5 accumulators x 48 columns: the MMAs of the NEXT band run
+    const int nbands = a.n * C0_BANDS;                           // while this band is being pooled
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C0_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < C0_BAND_TILES; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
         constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * C0_COUT, 0, 0);
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
-        int acc = 0; uint32_t aph = 0;
+        uint32_t aph = 0;                                        // accumulator phase: flips once per band
         const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
         const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 3 * C0_COUT * 16);
         uint32_t a_rel[STEPS];
@@ -361,40 +365,64 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
             else if (step == 3) a_rel[step] = 2u | ((uint32_t)C0_HP << 16);
             else a_rel[step] = (uint32_t)(2 * C0_HP + 2) | (1u << 16);
         }
-        for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x)
+        for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
             for (int t = 0; t < C0_BAND_TILES; ++t) {
-                mbar_wait(&tempty[acc], aph ^ 1);
+                mbar_wait(&tempty[t], aph ^ 1);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                    const uint32_t d_tmem = tmem_base + t * ACC_COLS;
                     const uint32_t st16 = (smem_u32(stages + s * C0_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int step = 0; step < STEPS; ++step)
                         mma_bf16_parts(d_tmem, st16 + a_rel[step], a_hi, b_lo0 + step * (2 * 3 * C0_COUT), b_hi, IDESC3, step > 0);
                     mma_commit(&empty[s]);
-                    mma_commit(&tfull[acc]);
+                    mma_commit(&tfull[t]);
                 }
                 __syncwarp();
                 if (++s == C0_STAGES) { s = 0; ph ^= 1; }
-                if (++acc == 2) { acc = 0; aph ^= 1; }
             }
+            aph ^= 1;
+        }
     } else {
         // ===================== epilogue warps 0-7: accumulators -> band buffer, then pool the band =====================
         const int grp = warp >> 2, quad = warp & 3;
         const int etid = threadIdx.x;                            // 0..255
-        uint32_t aph = 0;                                        // phase of this group's accumulator
-        long long cnt = 0;                                       // tiles seen so far by the CTA (parity = accumulator)
+        uint32_t aph = 0;                                        // accumulator phase: flips once per band
         float bias[C0_COUT];
 #pragma unroll
         for (int e = 0; e < C0_COUT; ++e) bias[e] = a.bias[e];
+        // stream + relu'd planes + arg-max bytes of one (pooled pixel, chunk)
+        auto emit = [&](int img, int ypo, int xp, int jc, const float* v, const int* am) {
+            const long long qo = (long long)img * C0_PO + ypo * C0_WPO + xp;
+            const long long so = ((long long)jc * a.n * C0_PO + qo) * 8;
+            float4* o = reinterpret_cast<float4*>(a.out_s + so);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            float rl[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
+            store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, rl);
+            if (a.amax) {
+                uint2 pk;
+                pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                *reinterpret_cast<uint2*>(a.amax + so) = pk;
+            }
+        };
+        auto emit_zero = [&](int img, int ypo, int xp, int jc) {
+            float v[8];
+            int am[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[e] = 0.f; am[e] = 15; }
+            emit(img, ypo, xp, jc, v, am);
+        };
         for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
             const int img = bnd / C0_BANDS, b = bnd - img * C0_BANDS;
-            for (int t = 0; t < C0_BAND_TILES; ++t, ++cnt) {
-                if ((int)(cnt & 1) != grp) continue;
-                mbar_wait(&tfull[grp], aph);
+            for (int t = grp; t < C0_BAND_TILES; t += 2) {        // group 0: tiles 0, 2, 4; group 1: tiles 1, 3
+                mbar_wait(&tfull[t], aph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * ACC_COLS;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + t * ACC_COLS;
                 float v[C0_COUT], u[16];
                 tmem_ld16(taddr + 2 * C0_COUT, v);
                 tmem_ld16(taddr + C0_COUT, u);
@@ -405,62 +433,45 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
                 for (int i = 0; i < 16; ++i) v[i] += u[i];
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[grp]);
-                aph ^= 1;
+                if (lane == 0) mbar_arrive(&tempty[t]);
                 const int pb = t * TILE_M + quad * 32 + lane;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     *c0_band_ptr(band, pb, c) = make_float4(v[c * 4 + 0] * a.acc_scale + bias[c * 4 + 0], v[c * 4 + 1] * a.acc_scale + bias[c * 4 + 1],
                                                             v[c * 4 + 2] * a.acc_scale + bias[c * 4 + 2], v[c * 4 + 3] * a.acc_scale + bias[c * 4 + 3]);
             }
+            aph ^= 1;
             asm volatile("bar.sync 1, 256;" ::: "memory");       // the band is complete in shared memory
-            // pooled padded rows of this band: 3b+1 .. 3b+3, plus the border rows 0 / 43 for the first / last band
-            const int r_lo = (b == 0) ? -1 : 0, r_hi = (b == C0_BANDS - 1) ? C0_BAND_K + 1 : C0_BAND_K;
-            const int nitems = (r_hi - r_lo) * C0_WPO * 2;
-            for (int it = etid; it < nitems; it += 256) {
-                const int xp = it % C0_WPO;
-                const int jc = (it / C0_WPO) & 1;
-                const int r = r_lo + it / (2 * C0_WPO);
-                const int ypo = C0_BAND_K * b + r + 1;
+            // 3 pooled rows x 42 interior columns x 2 chunks = 252 items, one per thread; threads 252..255 write the 12 border
+            // pixels of these rows, and the first / last band of a frame also writes the border row 0 / 43.
+            if (etid < C0_BAND_K * C0_HO * 2) {
+                const int j = etid % C0_HO, jc = (etid / C0_HO) & 1, r = etid / (2 * C0_HO);
                 float v[8];
                 int am[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { v[e] = 0.f; am[e] = 15; }
-                if (r >= 0 && r < C0_BAND_K && xp >= 1 && xp <= C0_HO) {
+                for (int e = 0; e < 8; ++e) { v[e] = -INFINITY; am[e] = 15; }
+                const int y0 = 2 * (C0_BAND_K * b + r);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = -INFINITY;
-                    const int j = xp - 1, y0 = 2 * (C0_BAND_K * b + r);
+                for (int dy = 0; dy < 3; ++dy) {
+                    if (y0 + dy >= 84) continue;
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        if (y0 + dy >= 84) continue;
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (2 * j + dx >= 84) continue;
+                        const int pb = (2 * r + dy) * C0_HP + 2 * j + dx + 1;
+                        const float4 f0 = *c0_band_ptr(band, pb, 2 * jc), f1 = *c0_band_ptr(band, pb, 2 * jc + 1);
+                        const float o[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            if (2 * j + dx >= 84) continue;
-                            const int pb = (2 * r + dy) * C0_HP + 2 * j + dx + 1;
-                            const float4 f0 = *c0_band_ptr(band, pb, 2 * jc), f1 = *c0_band_ptr(band, pb, 2 * jc + 1);
-                            const float o[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (o[e] > v[e]) { v[e] = o[e]; am[e] = dy * 3 + dx; }
-                        }
+                        for (int e = 0; e < 8; ++e)
+                            if (o[e] > v[e]) { v[e] = o[e]; am[e] = dy * 3 + dx; }
                     }
                 }
-                const long long qo = (long long)img * C0_PO + ypo * C0_WPO + xp;
-                const long long so = ((long long)jc * a.n * C0_PO + qo) * 8;
-                float4* o = reinterpret_cast<float4*>(a.out_s + so);
-                o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                o[1] = make_float4(v[4], v[5], v[6], v[7]);
-                float rl[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
-                store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, rl);
-                if (a.amax) {
-                    uint2 pk;
-                    pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
-                    pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
-                    *reinterpret_cast<uint2*>(a.amax + so) = pk;
-                }
+                emit(img, C0_BAND_K * b + r + 1, j + 1, jc, v, am);
+            } else {
+                for (int k = etid - C0_BAND_K * C0_HO * 2; k < C0_BAND_K * 4; k += 4)      // (row, left | right, chunk)
+                    emit_zero(img, C0_BAND_K * b + (k >> 2) + 1, (k & 2) ? C0_WPO - 1 : 0, k & 1);
             }
+            if ((b == 0 || b == C0_BANDS - 1) && etid < 2 * C0_WPO)
+                emit_zero(img, b == 0 ? 0 : C0_WPO - 1, etid % C0_WPO, etid / C0_WPO);
             asm volatile("bar.sync 1, 256;" ::: "memory");       // band buffer free for the next band
         }
     }

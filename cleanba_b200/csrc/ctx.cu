@@ -141,6 +141,7 @@ struct cb_ctx {
     bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
     int npad_max = 0;
     static constexpr int grad_planes = 2;   // bf16 planes of gradient tensors (16 significant bits)
+    bool fuse0 = false;                     // first ConvSequence: conv + pool (forward) and pool + wgrad (backward) fused
 };
 
 namespace cb {
@@ -287,7 +288,16 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
         const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
         const ConvGeom go = make_geom(n, kStageHout[s], kStageHout[s]);
         const int base = s * 5;
-        {   // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
+        if (s == 0 && c->fuse0) {
+            // frame conv + max-pool in one kernel: the 84x84x16 conv output never reaches HBM (conv_umma.cu)
+            ConvArgs a = conv_args(c, 0, gi, S.x, false);
+            a.ep.bias = c->params + c->conv[0].off_b;
+            a.ep.acc_scale = 1.0f / 255.0f;                       // x / 255.0 (cleanba_ppo.py:181) folded into the epilogue
+            ProfScope ps(c, "conv0_pool_fwd@84", 2.0 * n * 84 * 84 * 9.0 * 4 * 16,
+                         planes_bytes(gi, 1, false) + stream_bytes(go, 2) + planes_bytes(go, 2, true) + (S.amax ? (double)go.NP * 16 : 0.0), st);
+            if (launch_conv0_pool_umma(a, S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
+        } else {
+            // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
             ConvArgs a = conv_args(c, base + 0, gi, S.x, false);
             a.ep.bias = c->params + c->conv[base].off_b;
             a.ep.acc_scale = (s == 0) ? (1.0f / 255.0f) : 1.0f;   // x / 255.0 (cleanba_ppo.py:181) folded into the epilogue
@@ -295,7 +305,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             if (run_conv(c, a, st)) return -1;
         }
         // x = nn.max_pool(x, (3,3), strides=(2,2), padding="SAME")              (cleanba_ppo.py:168)
-        {
+        if (!(s == 0 && c->fuse0)) {
             ProfScope ps(c, "pool_fwd@" + std::to_string(kStageHin[s]), 0,
                          stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(go, kStageC[s] / 8, true), st);
             if (launch_pool_fwd(S.y.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.p.s, S.p.pl, S.amax, st)) return -1;
@@ -386,7 +396,7 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             if (run_conv(c, a, st)) return -1;
         }
         // ---- max-pool backward, then the sequence conv
-        if (s == 0 && c->cfg.conv_backend == CB_CONV_TCGEN05) {
+        if (s == 0 && c->fuse0) {
             // frames need no dX: the pooled gradient goes straight into the frame conv's weight gradient (trunk_simt.cu)
             ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), st);
             if (launch_pool_bwd_wgrad0(S.amax, S.gA.s, S.x.pl.hi, gi, go, 1.0f / 255.0f, grads + c->conv[0].off_w,
@@ -459,6 +469,7 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
     c->cfg = *cfg;
     c->num_sms = prop.multiProcessorCount;
     c->A = cfg->num_actions;
+    c->fuse0 = cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_NO_FUSE0");
     c->leaves = build_leaves(c->A);
     c->nparam = c->leaves.back().offset + c->leaves.back().size();
     bool ok = false;
@@ -832,7 +843,10 @@ long long cb_debug_tensor(cb_ctx* c, const char* name, float* host_out, long lon
     bool want_stream = false;
     if (name[0] == 's') {
         if (!strcmp(f, "x")) a = &S.x;
-        else if (!strcmp(f, "y")) { a = &S.y; want_stream = true; }
+        else if (!strcmp(f, "y")) {
+            CB_CHECK(!(s == 0 && c->fuse0), "tensor s0.y is not materialised (frame conv fused with its max-pool)");
+            a = &S.y; want_stream = true;
+        }
         else if (!strcmp(f, "p")) { a = &S.p; want_stream = true; }
         else if (!strcmp(f, "pr")) a = &S.p;
         else if (!strcmp(f, "a0")) a = &S.a0;
