@@ -758,14 +758,46 @@ int cb_impala_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int T1, in
     return trunk_backward(c, n, grads, st);
 }
 
+static int optimizer_step(cb_ctx* c, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
+                          float* norm_out, cb_stream stream);
+
 int cb_optimizer_step(cb_ctx* c, const float* grads, float grad_scale, float lr, float max_norm, float* norm_out,
                       cb_stream stream) {
     CB_CHECK(c && grads, "null argument");
+    return optimizer_step(c, &grads, 1, grad_scale, lr, max_norm, norm_out, stream);
+}
+
+int cb_optimizer_step_peers(cb_ctx* c, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
+                            float* norm_out, cb_stream stream) {
+    CB_CHECK(c && grads, "null argument");
+    CB_CHECK(num_grads >= 1 && num_grads <= OPT_MAX_PEERS, "num_grads must be in [1,%d]", OPT_MAX_PEERS);
+    for (int k = 0; k < num_grads; ++k) CB_CHECK(grads[k], "null gradient buffer %d", k);
+    return optimizer_step(c, grads, num_grads, grad_scale, lr, max_norm, norm_out, stream);
+}
+
+int cb_enable_peer_access(cb_ctx* c, int peer_device) {
+    CB_CHECK(c, "null argument");
+    if (peer_device == c->cfg.device) return 0;
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    int can = 0;
+    CB_CUDA(cudaDeviceCanAccessPeer(&can, c->cfg.device, peer_device));
+    CB_CHECK(can, "device %d cannot access peer device %d", c->cfg.device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return 0; }
+    CB_CUDA(e);
+    return 0;
+}
+
+static int optimizer_step(cb_ctx* c, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
+                          float* norm_out, cb_stream stream) {
     CB_CHECK(c->cfg.train, "cb_optimizer_step needs a learner context (train=1)");
     CB_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     OptArgs o;
-    o.n = c->nparam; o.p = c->params; o.g = grads; o.m = c->m; o.v = c->v;
+    memset(&o, 0, sizeof(o));
+    o.n = c->nparam; o.p = c->params; o.g = grads[0]; o.m = c->m; o.v = c->v;
+    o.ng = num_grads;
+    for (int k = 0; k < num_grads; ++k) o.gp[k] = grads[k];
     o.grad_scale = grad_scale; o.max_norm = max_norm; o.lr = lr;
     o.partials = c->opt_partials; o.norm_out = norm_out;
     c->opt_count += 1;

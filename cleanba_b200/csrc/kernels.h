@@ -133,7 +133,13 @@ struct OptArgs {
     float max_norm, lr, b1, b2, eps, bc1, bc2;
     float* partials;             // [OPT_BLOCKS]
     float* norm_out;             // [1] global norm (after grad_scale), optional
+    // Fused gradient exchange: when ng > 1 the gradient is the fixed-order sum gp[0][i] + gp[1][i] + ... of the flat gradient
+    // buffers of ALL learner replicas, read straight from peer memory over NVLink (g is ignored); every replica evaluates the
+    // same sum in the same order, so the replicas stay bit-identical without a separate allreduce pass.
+    const float* gp[8];
+    int ng;
 };
+constexpr int OPT_MAX_PEERS = 8;
 constexpr int OPT_BLOCKS = 296;
 int launch_optimizer(const OptArgs& a, cudaStream_t st);
 

@@ -174,13 +174,23 @@ int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tm
 // ------------------------------------------------------------------------------------------------
 // Optimizer: pass 1 writes OPT_BLOCKS partial sums of (g * grad_scale)^2; pass 2 re-reduces them in a fixed order,
 // applies clip_by_global_norm and the Adam / RMSProp update on the flat parameter vector.
-__global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, long long n, float scale, float* __restrict__ partials) {
+// gradient element i: the local buffer, or the fixed-order sum over the replicas' buffers (peer memory)
+__device__ __forceinline__ float opt_grad(const OptArgs& a, long long i) {
+    if (a.ng <= 1) return a.g[i];
+    float g = a.gp[0][i];
+#pragma unroll 1
+    for (int k = 1; k < a.ng; ++k) g += a.gp[k][i];
+    return g;
+}
+
+__global__ void __launch_bounds__(256) k_sumsq(OptArgs a) {
     __shared__ float red[256];
+    const long long n = a.n;
     long long per = (n + gridDim.x - 1) / gridDim.x;
     long long lo = (long long)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
     float s = 0.f;
     for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-        float x = g[i] * scale;
+        float x = opt_grad(a, i) * a.grad_scale;
         s = fmaf(x, x, s);
     }
     red[threadIdx.x] = s;
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, long
         if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+    if (threadIdx.x == 0) a.partials[blockIdx.x] = red[0];
 }
 
 __global__ void __launch_bounds__(256) k_opt_apply(OptArgs a) {
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(256) k_opt_apply(OptArgs a) {
     const float norm = s_norm;
     const bool clip = !(norm < a.max_norm);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (long long)gridDim.x * 256) {
-        float g = a.g[i] * a.grad_scale;
+        float g = opt_grad(a, i) * a.grad_scale;
         if (clip) g = (g / norm) * a.max_norm;      // optax.clip_by_global_norm: (g / norm) * max_norm
         float p = a.p[i];
         if (a.kind == 0) {
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(256) k_opt_apply(OptArgs a) {
 }
 
 int launch_optimizer(const OptArgs& a, cudaStream_t st) {
-    k_sumsq<<<OPT_BLOCKS, 256, 0, st>>>(a.g, a.n, a.grad_scale, a.partials);
+    k_sumsq<<<OPT_BLOCKS, 256, 0, st>>>(a);
     CB_LAUNCH_CHECK();
     k_opt_apply<<<OPT_BLOCKS, 256, 0, st>>>(a);
     CB_LAUNCH_CHECK();

@@ -178,3 +178,31 @@ def test_two_gpu_nccl_allreduce_matches_shard_emulation(tmp_path):
     ol.update(shards, tf.split(tf.PRNGKey(1), 4)[0])
     got = np.load(out)
     assert np.abs(got - ol.params).max() < 1e-3 * np.abs(ol.params).max()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_in_process_two_learner_devices_match_shard_emulation():
+    """`--actor-device-ids 0 --learner-device-ids 0 1` in ONE process (the reference's pmap over local learner devices,
+    cleanba_ppo.py:656-660): the actor splits every payload's env axis over the two learner GPUs (:278,357-363), the
+    gradients are averaged once per minibatch, the replicas stay bit-identical and agree with the oracle's 2-shard
+    emulation on the same plumbing."""
+    from cleanba_b200.cuda_backend import CudaBackend
+    from cleanba_b200.sebulba import Args, derive_sizes, train
+    from oracle.backend import OracleBackend
+
+    def args():
+        a = Args(local_num_envs=8, num_actor_threads=2, num_steps=4, num_minibatches=2, update_epochs=1, total_timesteps=10 ** 6,
+                 log_frequency=1000, max_updates=2, actor_device_ids=[0], learner_device_ids=[0, 1])
+        a.concurrency = False
+        return derive_sizes(a, 1)
+
+    got, want = [], []
+    rc = train(args(), CudaBackend(), _make_env, on_update=lambda v, gs, st: got.append(st.detach().cpu().numpy().astype(np.float64)))
+    ro = train(args(), OracleBackend(), _make_env, on_update=lambda v, gs, st: want.append(np.asarray(st, np.float64)))
+    assert rc.updates == ro.updates == 2 and rc.global_step == ro.global_step
+    p0 = rc.learner.learners[0].ctx.get_params().cpu().numpy()
+    p1 = rc.learner.learners[1].ctx.get_params().cpu().numpy()
+    assert np.array_equal(p0, p1), "learner replicas diverged"
+    rel = np.abs(got[0][:4] - want[0][:4]) / np.maximum(np.abs(want[0][:4]), 1e-6)
+    assert rel.max() < 5e-3, (got[0], want[0])       # chained optimizer steps on tiny minibatches: see the test above
+    assert np.abs(p0 - ro.learner.learner.params).max() < 5e-2 * np.abs(p0).max()
