@@ -214,6 +214,18 @@ class Context:
                                          _ptr(norm_out), _stream(self.device)))
 
 
+    def enable_peer_access(self, peer: "Context"):
+        check(self.lib.cb_enable_peer_access(self.h, int(peer.device.index)))
+
+    def optimizer_step_peers(self, grads_list, grad_scale, lr, max_norm, norm_out=None):
+        """clip + Adam / RMSProp on the fixed-order SUM of the replicas' flat gradient buffers, read from peer memory inside
+        the optimizer kernels (the fused form of pmean + apply_gradients, cleanba_ppo.py:628-629).  The caller orders the
+        replicas' streams with events (see cuda_backend.CudaLearner)."""
+        arr = (ctypes.c_void_p * len(grads_list))(*[g.data_ptr() for g in grads_list])
+        check(self.lib.cb_optimizer_step_peers(self.h, arr, len(grads_list), float(grad_scale), float(lr), float(max_norm),
+                                               _ptr(norm_out), _stream(self.device)))
+
+
 import threading as _threading
 
 _CAPTURE_LOCK = _threading.Lock()

@@ -6,6 +6,7 @@ libcleanba_b200 on CUDA devices.  There is no CPU path here; constructing it wit
   env axis is split into L contiguous slices and each slice is copied to its learner GPU on the actor's side stream
   (cudaMemcpyAsync / peer copy); an event travels with the payload.
 """
+import os
 import threading
 import time
 from typing import List
@@ -154,6 +155,17 @@ class CudaLearner:
         self.keys = [ag.key_tensor(key, d) for d in self.devices]    # learner_keys = device_put_replicated(key) (cleanba_ppo.py:470)
         self.barrier = threading.Barrier(L) if L > 1 else None
         self.hyper = h
+        # Several learner GPUs in ONE process and no cross-process exchange: the gradient mean is fused into the optimizer
+        # kernels, which read every replica's flat gradient buffer from peer memory over NVLink (cb_optimizer_step_peers);
+        # the replicas' streams are ordered with events, the host threads only rendezvous (no device synchronisation).
+        self.peer_fused = L > 1 and allreduce is None and os.environ.get("CLEANBA_PEER_FUSED", "1") != "0"
+        if self.peer_fused:
+            for a in self.learners:
+                for b in self.learners:
+                    a.ctx.enable_peer_access(b.ctx)
+            self.ev_done, self.ev_read = [None] * L, [None] * L
+            for l, lr in enumerate(self.learners):
+                lr.fused_step = self._make_fused(l)
 
     def _make_hook(self, l):
         """Gradient sum over all learner devices: local devices rendezvous on device 0, device 0 joins the cross-process
@@ -179,6 +191,28 @@ class CudaLearner:
                 torch.cuda.current_stream(g.device).synchronize()
             self.barrier.wait()
         return hook
+
+    def _make_fused(self, l):
+        L = len(self.devices)
+
+        def fused(lr, grad_scale, lrate, max_norm):
+            st = torch.cuda.current_stream(self.devices[l])
+            ev = torch.cuda.Event()
+            ev.record(st)                                   # this replica's backward is complete
+            self.ev_done[l] = ev
+            self.barrier.wait()                             # host rendezvous only: every replica's event exists
+            for k in range(L):
+                if k != l:
+                    st.wait_event(self.ev_done[k])
+            lr.ctx.optimizer_step_peers([x.grads for x in self.learners], grad_scale, lrate, max_norm)
+            ev = torch.cuda.Event()
+            ev.record(st)                                   # this replica has read every peer buffer
+            self.ev_read[l] = ev
+            self.barrier.wait()
+            for k in range(L):
+                if k != l:
+                    st.wait_event(self.ev_read[k])          # the next backward may overwrite this replica's buffer
+        return fused
 
     def _update_one(self, l, payloads, out):
         lr, d = self.learners[l], self.devices[l]
@@ -208,7 +242,18 @@ class CudaLearner:
             ths = [threading.Thread(target=self._update_one, args=(l, payloads, out)) for l in range(L)]
             [t.start() for t in ths]
             [t.join() for t in ths]
-        return out[-1]     # the reference logs the scalars of the last learner device (cleanba_ppo.py:745-749)
+        if L == 1:
+            return out[0]
+        # loss scalars are pmean'ed over the learner devices (cleanba_ppo.py:649-653; cleanba_impala.py:635-638); the
+        # reference then logs device [-1]'s copy of that mean (cleanba_ppo.py:745-749)
+        d = self.devices[-1]
+        with torch.cuda.device(d):
+            st = torch.cuda.current_stream(d)
+            for l in range(L - 1):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.devices[l]))
+                st.wait_event(ev)
+            return torch.stack([o.to(d, non_blocking=True) for o in out]).mean(0)
 
     def params_for_actor(self, actor_device_id):
         lr = self.learners[0]

@@ -59,6 +59,7 @@ class PPOLearner:
         self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
         self.stats = torch.zeros(hyper.update_epochs * hyper.num_minibatches, 5, dtype=torch.float32, device=d)
         self.opt_count = 0
+        self.fused_step = None      # f(learner, grad_scale, lr, max_norm): gradient exchange fused into the optimizer step
 
     def update(self, obs, dones, actions, logprobs, values, rewards, next_obs, next_done, key) -> torch.Tensor:
         """single_device_update (cleanba_ppo.py:579-654).  Fields are [T,Bl,...] device tensors (the hstack of the actor
@@ -79,11 +80,14 @@ class PPOLearner:
                 idx = perm[j * self.mb:(j + 1) * self.mb]
                 c.ppo_grad(obs_f, idx, self.mb, act_f, lp_f, adv_f, ret_f, h.clip_coef, h.ent_coef, h.vf_coef,
                            self.grads, self.stats[k])
-                if self.allreduce is not None and self.world_learners > 1:
-                    self.allreduce(self.grads)                        # lax.pmean(grads) (cleanba_ppo.py:628)
                 lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches * h.update_epochs,
                                      h.num_updates, h.anneal_lr)
-                c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
+                if self.fused_step is not None:                       # pmean + apply_gradients in one pass over peer memory
+                    self.fused_step(self, 1.0 / self.world_learners, lr, h.max_grad_norm)
+                else:
+                    if self.allreduce is not None and self.world_learners > 1:
+                        self.allreduce(self.grads)                    # lax.pmean(grads) (cleanba_ppo.py:628)
+                    c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
                 self.opt_count += 1
                 k += 1
         return self.stats.mean(0)
@@ -118,6 +122,7 @@ class ImpalaLearner:
         self.stats = torch.zeros(hyper.num_minibatches, 4, dtype=torch.float32, device=d)
         # contiguous env-column blocks, never shuffled (cleanba_impala.py:626-633): idx[j][t*B+b] = t*Bl + j*B + b
         t = torch.arange(T1, device=d, dtype=torch.int32)[:, None] * Bl
+        self.fused_step = None
         self.idx = [(t + (j * self.B + torch.arange(self.B, device=d, dtype=torch.int32))[None, :]).reshape(-1).contiguous()
                     for j in range(hyper.num_minibatches)]
         self.opt_count = 0
@@ -132,9 +137,12 @@ class ImpalaLearner:
         for j in range(h.num_minibatches):
             c.impala_grad(obs_f, self.idx[j], T1, self.B, actions.reshape(-1), logitss.reshape(-1, A), rewards.reshape(-1),
                           dones.reshape(-1), firststeps.reshape(-1), h.gamma, h.vf_coef, h.ent_coef, self.grads, self.stats[j])
-            if self.allreduce is not None and self.world_learners > 1:
-                self.allreduce(self.grads)                            # lax.pmean(grads) (cleanba_impala.py:619)
             lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches, h.num_updates, h.anneal_lr)
-            c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
+            if self.fused_step is not None:                           # pmean + apply_gradients in one pass over peer memory
+                self.fused_step(self, 1.0 / self.world_learners, lr, h.max_grad_norm)
+            else:
+                if self.allreduce is not None and self.world_learners > 1:
+                    self.allreduce(self.grads)                        # lax.pmean(grads) (cleanba_impala.py:619)
+                c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
             self.opt_count += 1
         return self.stats.mean(0)

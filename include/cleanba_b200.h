@@ -103,6 +103,17 @@ int cb_impala_grad(cb_ctx* ctx, const uint8_t* obs, const int32_t* idx, int T1, 
  * may be NULL) receives the pre-clip global norm.  Refreshes the packed bf16 weights. */
 int cb_optimizer_step(cb_ctx* ctx, const float* grads, float grad_scale, float lr, float max_norm, float* norm_out,
                       cb_stream stream);
+/* The same step with the gradient exchange FUSED in: the gradient is the fixed-order sum grads[0] + ... + grads[n-1] of the
+ * flat gradient buffers of all learner replicas of this process, read directly from peer memory over NVLink / NVSwitch inside
+ * the norm and the update kernels -- `jax.lax.pmean(grads, "local_devices")` (cleanba_ppo.py:628) without a separate
+ * allreduce pass or a host rendezvous.  Every replica calls this with the SAME pointer list, so all replicas apply bit-identical
+ * updates.  The caller orders the streams with events: every replica's backward must have finished before any replica's step
+ * starts, and every step must have finished before a replica's next backward overwrites its buffer.  grads is a HOST array of
+ * 1..8 device pointers; peer devices must have been opened with cb_enable_peer_access. */
+int cb_optimizer_step_peers(cb_ctx* ctx, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
+                            float* norm_out, cb_stream stream);
+/* cudaDeviceEnablePeerAccess from ctx's device to peer_device (no-op if already enabled or the same device). */
+int cb_enable_peer_access(cb_ctx* ctx, int peer_device);
 
 /* ---- measurement ---------------------------------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all contexts, all threads). */
