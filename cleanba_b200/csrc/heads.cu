@@ -271,22 +271,39 @@ int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// IMPALA / V-trace loss head (one block; a minibatch is [T1 = T+1, B] frames ordered f = t*B + b).
-__global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a) {
+// IMPALA / V-trace loss head (a minibatch is [T1 = T+1, B] frames ordered f = t*B + b), three launches of one kernel:
+//   phases = 1: logits + value of every frame            (one warp per frame, all SMs)
+//   phases = 2: per-cell terms, the V-trace scan along T, loss scalars, d/dlogits, d/dvalue   (ONE block: the scan is a
+//               sequential recurrence per column and the whole minibatch is <= a few thousand cells)
+//   phases = 4: gradient w.r.t. the pre-relu dense output (one warp per frame, all SMs)
+__global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a, int phases) {
     extern __shared__ float sm[];
     const int A = a.num_actions, T1 = a.T1, B = a.B, T = T1 - 1;
     HeadSmem h = load_head_smem(sm, a.wa, a.ba, a.wc, a.bc, A);
     float* red = h.ba + A + 1;   // [3][1024]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int nf = T1 * B, nc = T * B;
-    // phase 0: logits + value of every frame
-    for (int f = warp; f < nf; f += nwarp) {
-        float hreg[8], logit, value;
-        head_forward(h, a.hidden + (long long)f * HIDDEN, A, lane, hreg, logit, value);
-        if (lane < A) a.logits_scratch[(long long)f * (A + 1) + lane] = logit;
-        if (lane == 0) a.logits_scratch[(long long)f * (A + 1) + A] = value;
+    if (phases & 1) {
+        // phase 0: logits + value of every frame
+        for (int f = blockIdx.x * nwarp + warp; f < nf; f += gridDim.x * nwarp) {
+            float hreg[8], logit, value;
+            head_forward(h, a.hidden + (long long)f * HIDDEN, A, lane, hreg, logit, value);
+            if (lane < A) a.logits_scratch[(long long)f * (A + 1) + lane] = logit;
+            if (lane == 0) a.logits_scratch[(long long)f * (A + 1) + A] = value;
+        }
     }
-    __syncthreads();
+    if (phases & 4) {
+        // phase 4: gradient w.r.t. the pre-relu dense output
+        for (int f = blockIdx.x * nwarp + warp; f < nf; f += gridDim.x * nwarp) {
+            float hreg[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hreg[i] = a.hidden[(long long)f * HIDDEN + lane + 32 * i];
+            float dl = lane < A ? a.dlogits[(long long)f * (A + 1) + lane] : 0.f;
+            float dv = a.dlogits[(long long)f * (A + 1) + A];
+            head_backward_hidden(h, A, lane, hreg, dl, dv, a.dpre + (long long)f * HIDDEN);
+        }
+    }
+    if (!(phases & 2) || blockIdx.x != 0) return;
     // phase 1: per cell log pi(a), rho, entropy
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
         const int src = a.idx ? a.idx[c] : c;
@@ -370,20 +387,18 @@ __global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a) {
         a.stats[0] = pg + a.vf_coef * bl + a.ent_coef * en;
         a.stats[1] = pg; a.stats[2] = bl; a.stats[3] = en;
     }
-    // phase 4: gradient w.r.t. the pre-relu dense output
-    for (int f = warp; f < nf; f += nwarp) {
-        float hreg[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hreg[i] = a.hidden[(long long)f * HIDDEN + lane + 32 * i];
-        float dl = lane < A ? a.dlogits[(long long)f * (A + 1) + lane] : 0.f;
-        float dv = a.dlogits[(long long)f * (A + 1) + A];
-        head_backward_hidden(h, A, lane, hreg, dl, dv, a.dpre + (long long)f * HIDDEN);
-    }
 }
 
 int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st) {
     size_t smem = head_smem_bytes(a.num_actions) + (1 + 3 * 1024) * sizeof(float);
-    k_impala_head<<<1, 1024, smem, st>>>(a);
+    const int nf = a.T1 * a.B;
+    int blocks = (nf + 7) / 8;                       // 8 warps (frames) per block
+    if (blocks > 592) blocks = 592;
+    k_impala_head<<<blocks, 256, smem, st>>>(a, 1);
+    CB_LAUNCH_CHECK();
+    k_impala_head<<<1, 1024, smem, st>>>(a, 2);
+    CB_LAUNCH_CHECK();
+    k_impala_head<<<blocks, 256, smem, st>>>(a, 4);
     CB_LAUNCH_CHECK();
     return launch_head_wgrad(a.hidden, a.dlogits, a.T1 * a.B, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
 }
