@@ -214,6 +214,10 @@ class Context:
                                          _ptr(norm_out), _stream(self.device)))
 
 
+    def set_sm_budget(self, num_sms: int):
+        """Size this context's persistent grids for an SM partition (see cleanba_b200.partition)."""
+        check(self.lib.cb_set_sm_budget(self.h, int(num_sms)))
+
     def enable_peer_access(self, peer: "Context"):
         check(self.lib.cb_enable_peer_access(self.h, int(peer.device.index)))
 

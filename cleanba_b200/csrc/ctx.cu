@@ -18,7 +18,8 @@
 namespace cb {
 
 // PDL pays for launch-latency-bound chains (the actor's n = 60 step: 0.236 -> 0.193 ms) and costs ~1% on the learner's
-// large minibatches (early CTAs of the next kernel compete with the running one), so it is enabled per call by batch size.
+// large minibatches (early CTAs of the next kernel compete with the running one), so it is enabled per call by batch size
+// (n <= CLEANBA_PDL_MAX_BATCH, default 1024: covers the actor step and the 630-frame IMPALA minibatch, +3% on config 3).
 static thread_local bool g_pdl_scope = false;
 bool pdl_enabled() {
     static const int mode = [] { const char* e = getenv("CLEANBA_PDL"); return e ? atoi(e) : 1; }();   // 0 off, 1 auto, 2 always
@@ -278,7 +279,8 @@ static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, cons
 static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStream_t st) {
     CB_CHECK(n > 0 && n <= c->cfg.max_batch, "batch %d outside (0, max_batch=%d]", n, c->cfg.max_batch);
     c->last_n = n;
-    g_pdl_scope = n <= 512;
+    static const int pdl_max = [] { const char* e = getenv("CLEANBA_PDL_MAX_BATCH"); return e ? atoi(e) : 1024; }();
+    g_pdl_scope = n <= pdl_max;
     {
         ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 86.0 * 86 * 16), st);
         if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st)) return -1;
@@ -773,6 +775,16 @@ int cb_optimizer_step_peers(cb_ctx* c, const float* const* grads, int num_grads,
     CB_CHECK(num_grads >= 1 && num_grads <= OPT_MAX_PEERS, "num_grads must be in [1,%d]", OPT_MAX_PEERS);
     for (int k = 0; k < num_grads; ++k) CB_CHECK(grads[k], "null gradient buffer %d", k);
     return optimizer_step(c, grads, num_grads, grad_scale, lr, max_norm, norm_out, stream);
+}
+
+int cb_set_sm_budget(cb_ctx* c, int num_sms) {
+    CB_CHECK(c, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaDeviceProp prop;
+    CB_CUDA(cudaGetDeviceProperties(&prop, c->cfg.device));
+    CB_CHECK(num_sms >= 1 && num_sms <= prop.multiProcessorCount, "num_sms must be in [1,%d]", prop.multiProcessorCount);
+    c->num_sms = num_sms;
+    return 0;
 }
 
 int cb_enable_peer_access(cb_ctx* c, int peer_device) {

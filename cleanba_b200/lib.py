@@ -47,6 +47,7 @@ SIGNATURES = {
     "cb_optimizer_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P]),
     "cb_optimizer_step_peers": (c_int, [_P, POINTER(_P), c_int, c_float, c_float, c_float, _P, _P]),
     "cb_enable_peer_access": (c_int, [_P, c_int]),
+    "cb_set_sm_budget": (c_int, [_P, c_int]),
     "cb_launch_count": (c_longlong, []),
     "cb_profile": (c_int, [_P, c_int]),
     "cb_profile_report": (c_int, [_P, c_char_p, c_int]),

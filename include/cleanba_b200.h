@@ -112,6 +112,10 @@ int cb_optimizer_step(cb_ctx* ctx, const float* grads, float grad_scale, float l
  * 1..8 device pointers; peer devices must have been opened with cb_enable_peer_access. */
 int cb_optimizer_step_peers(cb_ctx* ctx, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
                             float* norm_out, cb_stream stream);
+/* Size the persistent grids of this context for num_sms SMs instead of the whole device: for contexts whose streams live on an
+ * SM partition (a CUDA green context), e.g. actor replicas on a small partition running beside the learner (the reference runs
+ * actor and learner threads concurrently on one GPU in the a0-l0 topology, cleanba_ppo.py:669-686). */
+int cb_set_sm_budget(cb_ctx* ctx, int num_sms);
 /* cudaDeviceEnablePeerAccess from ctx's device to peer_device (no-op if already enabled or the same device). */
 int cb_enable_peer_access(cb_ctx* ctx, int peer_device);
 

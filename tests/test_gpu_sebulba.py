@@ -206,3 +206,38 @@ def test_in_process_two_learner_devices_match_shard_emulation():
     rel = np.abs(got[0][:4] - want[0][:4]) / np.maximum(np.abs(want[0][:4]), 1e-6)
     assert rel.max() < 5e-3, (got[0], want[0])       # chained optimizer steps on tiny minibatches: see the test above
     assert np.abs(p0 - ro.learner.learner.params).max() < 5e-2 * np.abs(p0).max()
+
+
+def test_sm_partition_actor_step_is_bit_identical():
+    """cleanba_b200.partition.SmPartition (CUDA green contexts): an actor step launched into the 16-SM actor partition, with
+    its grids sized by set_sm_budget, returns bit-identical actions / log-probs / values / key to the whole-GPU launch."""
+    from cleanba_b200 import agent as ag
+    from cleanba_b200.params import init_params
+    from cleanba_b200.partition import SmPartition
+    try:
+        part = SmPartition("cuda:0", 16)
+    except Exception as e:      # driver without green-context support
+        pytest.skip(f"green contexts unavailable: {e}")
+    assert part.actor_sms >= 8 and part.actor_sms + part.learner_sms <= torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(3)
+    obs = torch.from_numpy(rng.integers(0, 256, (60, 4, 84, 84), dtype=np.uint8)).cuda()
+    outs = []
+    for partitioned in (False, True):
+        ctx = ag.Context("cuda:0", max_batch=60)
+        ctx.set_params(init_params(4))
+        key = ag.key_tensor(np.array([5, 6], np.uint32), ctx.device)
+        torch.cuda.synchronize()
+        if partitioned:
+            ctx.set_sm_budget(part.actor_sms)
+            st = part.actor_stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                a, lp, v, _ = ctx.actor_step(obs, key)
+            st.synchronize()
+        else:
+            a, lp, v, _ = ctx.actor_step(obs, key)
+            torch.cuda.synchronize()
+        outs.append((a.cpu().numpy(), lp.cpu().numpy(), v.cpu().numpy(), ag.key_numpy(key)))
+        ctx.close()
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)
