@@ -693,12 +693,13 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
 
 // dW[(ky*3+kx)][ci][co] = scale * sum_cta (P[cta][kx][ky*Cpad + ci][co] + P[cta][kx][hrows + ky*Cpad + ci][co] if stacked)
 // db[co] = sum_cta P[cta][1][3*Cpad][co]
-// One block per 32 consecutive outputs; warp w sums the partials of CTAs w, w+8, ... (coalesced 128-byte rows), the eight
-// warp sums are added in a fixed order.
-__global__ void __launch_bounds__(256) k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas, int cpad, int rows, int hrows,
-                                                           int stacked, int cin_real, int cout, float scale,
-                                                           float* __restrict__ dw, float* __restrict__ db) {
-    __shared__ float sm[8][32];
+// One block per 32 consecutive outputs; warp w of 32 sums the partials of CTAs w, w+32, ... (coalesced 128-byte rows, loads of
+// four CTAs in flight), the 32 warp sums are added in a fixed order (deterministic).
+constexpr int WG_RED_WARPS = 32;
+__global__ void __launch_bounds__(WG_RED_WARPS * 32) k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas, int cpad, int rows,
+                                                                          int hrows, int stacked, int cin_real, int cout, float scale,
+                                                                          float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float sm[WG_RED_WARPS][32];
     griddep_launch();
     griddep_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -717,10 +718,12 @@ __global__ void __launch_bounds__(256) k_wgrad_umma_reduce(const float* __restri
             src = ((long long)1 * rows + 3 * cpad) * cout + (i - nw);
         }
         const long long stride = (long long)3 * rows * cout;
-        for (int b = w; b < nctas; b += 8) {
+        const long long off2 = two ? (long long)hrows * cout : 0;
+#pragma unroll 4
+        for (int b = w; b < nctas; b += WG_RED_WARPS) {
             const float* p = partial + (long long)b * stride + src;
             float v = p[0];
-            if (two) v += p[(long long)hrows * cout];
+            if (two) v += p[off2];
             s += v;
         }
     }
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(256) k_wgrad_umma_reduce(const float* __restri
     if (w == 0 && i < nw + cout) {
         float t = sm[0][lane];
 #pragma unroll
-        for (int k = 1; k < 8; ++k) t += sm[k][lane];
+        for (int k = 1; k < WG_RED_WARPS; ++k) t += sm[k][lane];
         if (i < nw) dw[i] = t * scale; else db[i - nw] = t;
     }
 }
@@ -751,7 +754,7 @@ static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, 
     launch_pdl(k_wgrad_umma<CIN_CHUNKS, COUT>, dim3(grid), dim3(WG_THREADS), (size_t)L.total, st, a, nblocks, partial);
     CB_LAUNCH_CHECK();
     int nw = 9 * a.cin_real * a.cout;
-    launch_pdl(k_wgrad_umma_reduce, dim3((nw + a.cout + 31) / 32), dim3(256), 0, st, (const float*)partial, grid, CIN_CHUNKS * 8,
+    launch_pdl(k_wgrad_umma_reduce, dim3((nw + a.cout + 31) / 32), dim3(WG_RED_WARPS * 32), 0, st, (const float*)partial, grid, CIN_CHUNKS * 8,
                S::ROWS, S::HROWS, S::MSTACK ? 1 : 0, a.cin_real, a.cout, a.scale, a.dw, a.db);
     CB_LAUNCH_CHECK();
     return 0;

@@ -358,24 +358,26 @@ __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_
     }
 }
 
-// out[i] = sum_b partial[b][i] in a fixed order: warp w adds partials w, w + 8, ..., then the 8 warp sums are added in order.
-// The first nw outputs are scaled and go to dw, the rest to db.
-__global__ void __launch_bounds__(256) k_partial_reduce(const float* __restrict__ partial, int nparts, int count, int nw, float scale,
-                                                        float* __restrict__ dw, float* __restrict__ db) {
-    __shared__ float sm[8][32];
+// out[i] = sum_b partial[b][i] in a fixed order: warp w of 32 adds partials w, w + 32, ..., then the 32 warp sums are added in
+// order.  The first nw outputs are scaled and go to dw, the rest to db.
+__global__ void __launch_bounds__(1024) k_partial_reduce(const float* __restrict__ partial, int nparts, int count, int nw, float scale,
+                                                         float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float sm[32][32];
     griddep_launch();
     griddep_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
     float s = 0.f;
-    if (i < count)
-        for (int b = w; b < nparts; b += 8) s += partial[(long long)b * count + i];
+    if (i < count) {
+#pragma unroll 4
+        for (int b = w; b < nparts; b += 32) s += partial[(long long)b * count + i];
+    }
     sm[w][lane] = s;
     __syncthreads();
     if (w == 0 && i < count) {
         float t = sm[0][lane];
 #pragma unroll
-        for (int k = 1; k < 8; ++k) t += sm[k][lane];
+        for (int k = 1; k < 32; ++k) t += sm[k][lane];
         if (i < nw) dw[i] = t * scale; else db[i - nw] = t;
     }
 }
@@ -393,7 +395,7 @@ int launch_pool_bwd_wgrad0(const uint8_t* amax, const float* dpool, const bf16* 
     const int grid = gi.n < 3 * num_sms ? gi.n : 3 * num_sms;
     launch_pdl(k_pool_bwd_wgrad0, dim3(grid), dim3(PW0_THREADS), (size_t)PW0_SMEM, st, amax, dpool, x_hi, gi.n, go.NP, partial);
     CB_LAUNCH_CHECK();
-    launch_pdl(k_partial_reduce, dim3((PW0_OUT + 31) / 32), dim3(256), 0, st, (const float*)partial, grid, PW0_OUT, 36 * 16, scale, dw, db);
+    launch_pdl(k_partial_reduce, dim3((PW0_OUT + 31) / 32), dim3(1024), 0, st, (const float*)partial, grid, PW0_OUT, 36 * 16, scale, dw, db);
     CB_LAUNCH_CHECK();
     return 0;
 }
