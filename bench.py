@@ -157,7 +157,7 @@ class Cycle:
             torch.cuda.synchronize()
             key = ag.key_tensor(first_key(seed), self.dev)
             self.actors.append(a)
-            self.graphed.append(ag.GraphedActor(a, N_ENVS, key))
+            self.graphed.append(ag.RolloutActor(a, N_ENVS, key))        # writes straight into the rollout storage rows
         self.actor = self.actors[0]
         d = self.dev
         self.obs = torch.zeros(T_STEPS, Bl, 4, 84, 84, dtype=torch.uint8, device=d)
@@ -183,24 +183,22 @@ class Cycle:
         torch = self.torch
         pool = self.host_pool if e2e else self.dev_pool
         main = torch.cuda.current_stream(self.dev)
-        for g in self.graphed:
+        for th, g in enumerate(self.graphed):
             g.stream.wait_stream(main)                 # new parameters (publish) are visible before the rollout starts
+            c = slice(th * N_ENVS, (th + 1) * N_ENVS)
+            g.begin(self.obs[:, c], self.actions[:, c], self.logprobs[:, c], self.values[:, c])   # this thread's storage columns
         for t in range(T_STEPS):
             for th, g in enumerate(self.graphed):
                 c = slice(th * N_ENVS, (th + 1) * N_ENVS)
-                g.step(pool[self.cursor % 256])                         # frame -> device (H2D from pinned memory when e2e) + graph replay
-                self.cursor += 1
-                with torch.cuda.stream(g.stream):                       # this step's transition -> rollout storage row t
-                    self.obs[t, c].copy_(g.obs, non_blocking=True)
-                    self.actions[t, c].copy_(g.action, non_blocking=True)
-                    self.logprobs[t, c].copy_(g.logprob, non_blocking=True)
-                    self.values[t, c].copy_(g.value, non_blocking=True)
-                    if e2e:
-                        self.act_host[th].copy_(g.action, non_blocking=True)
+                g.step(pool[self.cursor % 256], t)     # frames -> storage row t (H2D from pinned memory when e2e) + graph replay:
+                self.cursor += 1                       # the step reads row t and writes action / logprob / value into row t
+                if e2e:
+                    with torch.cuda.stream(g.stream):
+                        self.act_host[th].copy_(self.actions[t, c], non_blocking=True)
             if e2e:
                 for th, g in enumerate(self.graphed):
                     g.stream.synchronize()                              # np.array(action): the per-step sync (cleanba_ppo.py:317)
-                    self.h2d += g.obs.numel(); self.d2h += N_ENVS * 4
+                    self.h2d += N_ENVS * 4 * 84 * 84; self.d2h += N_ENVS * 4
         for g in self.graphed:
             main.wait_stream(g.stream)
         k = (self.cursor // 256) % 8

@@ -277,6 +277,87 @@ class GraphedActor:
             self.replays += 1
 
 
+class RolloutActor:
+    """The actor step captured ONCE into a CUDA graph that reads its frames from, and writes its outputs to, the current ROW
+    of the rollout storage (cb_actor_step_cursor): per environment step the host copies the frames into their storage row and
+    replays the graph -- the reference's list append + stack (`prepare_data`, cleanba_ppo.py:276-278, 342-356) without a staging
+    buffer or per-field copies.  `begin()` points the device-side cursor at a rollout's storage views, `step()` runs row t."""
+
+    def __init__(self, ctx: Context, n: int, key: torch.Tensor, want_logits: bool = False, stream: Optional[torch.cuda.Stream] = None):
+        d = ctx.device
+        self.ctx, self.n, self.key, self.want_logits = ctx, n, key, want_logits
+        self.stream = stream or torch.cuda.Stream(d)
+        self.cursor = torch.zeros(8, dtype=torch.int64, device=d)                 # struct cb_rollout_cursor (64 bytes)
+        self._cursor_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self._cursor_event = None
+        A = ctx.num_actions
+        scratch = dict(obs=torch.zeros(1, n, 4, 84, 84, dtype=torch.uint8, device=d), action=torch.zeros(1, n, dtype=torch.int32, device=d),
+                       logprob=None if want_logits else torch.zeros(1, n, dtype=torch.float32, device=d),
+                       value=None if want_logits else torch.zeros(1, n, dtype=torch.float32, device=d),
+                       logits=torch.zeros(1, n, A, dtype=torch.float32, device=d) if want_logits else None)
+        self._scratch = scratch
+        key_backup = key.clone()
+        with torch.cuda.device(d):
+            self.stream.wait_stream(torch.cuda.current_stream(d))
+            self.begin(first_row=0, **scratch)
+            with torch.cuda.stream(self.stream):
+                self._launch()                                # warm-up (sets function attributes, touches every buffer)
+            self.stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with _CAPTURE_LOCK:
+                l0 = ctx.lib.cb_launch_count()
+                with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+                    self._launch()
+            self.kernels_per_replay = int(ctx.lib.cb_launch_count() - l0)
+            self.replays = 0
+            self.stream.synchronize()
+        key.copy_(key_backup)                                 # warm-up and capture do not consume randomness
+        self._obs = None
+
+    def _launch(self):
+        check(self.ctx.lib.cb_actor_step_cursor(self.ctx.h, _ptr(self.cursor), self.n, _ptr(self.key),
+                                                ctypes.c_void_p(self.stream.cuda_stream)))
+
+    def begin(self, obs, action, logprob=None, value=None, logits=None, first_row: int = 0):
+        """Point the cursor at this rollout's storage: obs uint8 [rows, n, 4, 84, 84], action int32 [rows, n], logprob / value
+        float32 [rows, n] (PPO) or logits float32 [rows, n, A] (IMPALA); views of a wider [rows, N_total, ...] storage are fine
+        as long as every row of n entries is contiguous.  Enqueued on self.stream."""
+        n, A, d = self.n, self.ctx.num_actions, self.ctx.device
+        def chk(t, dtype, inner):
+            if t is None:
+                return 0
+            if t.dtype != dtype or t.device != d or t.shape[1] != n or (n > 1 and t.stride(1) != inner) or not t[0].is_contiguous():
+                raise CleanbaError(f"rollout storage view: expected {dtype} [rows, {n}, ...] on {d} with contiguous rows, got "
+                                   f"{t.dtype} {tuple(t.shape)} strides {t.stride()} on {t.device}")
+            return t.data_ptr()
+        po = chk(obs, torch.uint8, 4 * 84 * 84)
+        pa, pl, pv, pg = chk(action, torch.int32, 1), chk(logprob, torch.float32, 1), chk(value, torch.float32, 1), chk(logits, torch.float32, A)
+        ors = action.stride(0)
+        for t, mult in ((logprob, 1), (value, 1), (logits, A)):
+            if t is not None and t.stride(0) != ors * mult:
+                raise CleanbaError("rollout storage views must share one row stride (logits: row stride x num_actions)")
+        if self._cursor_event is not None:
+            self._cursor_event.synchronize()                  # the pinned mirror is free again
+        h = self._cursor_host.numpy()
+        h[:7] = [po, pa, pl, pv, pg, obs.stride(0), ors]
+        h[7] = int(np.array([first_row - 1, 0], np.int32).view(np.int64)[0])
+        with torch.cuda.stream(self.stream):
+            self.cursor.copy_(self._cursor_host, non_blocking=True)
+            self._cursor_event = torch.cuda.Event()
+            self._cursor_event.record(self.stream)
+        self._obs, self._next_row = obs, first_row
+
+    def step(self, obs_src: torch.Tensor, t: int):
+        """Enqueue the actor step of storage row t on self.stream: frames (host or device) -> row t, then one graph replay."""
+        if t != self._next_row:
+            raise CleanbaError(f"rollout rows must be stepped in order: expected row {self._next_row}, got {t}")
+        with torch.cuda.stream(self.stream):
+            self._obs[t].copy_(obs_src, non_blocking=True)
+            self.graph.replay()
+        self.replays += 1
+        self._next_row += 1
+
+
 def _as_u8(t: torch.Tensor, device, name):
     if t.dtype == torch.bool:
         t = t.view(torch.uint8)

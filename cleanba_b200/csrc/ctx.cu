@@ -142,6 +142,7 @@ struct cb_ctx {
     bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
     int npad_max = 0;
     static constexpr int grad_planes = 2;   // bf16 planes of gradient tensors (16 significant bits)
+    const cb_rollout_cursor* cursor = nullptr;   // set for the duration of a cb_actor_step_cursor call
     bool fuse0 = false;                     // first ConvSequence: conv + pool (forward) and pool + wgrad (backward) fused
 };
 
@@ -283,7 +284,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
     g_pdl_scope = n <= pdl_max;
     {
         ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 86.0 * 86 * 16), st);
-        if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st)) return -1;
+        if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st, c->cursor)) return -1;
     }
     for (int s = 0; s < 3; ++s) {
         Stage& S = c->st[s];
@@ -658,6 +659,22 @@ int cb_actor_step(cb_ctx* c, const uint8_t* obs, int n, uint32_t* key, int32_t* 
     return launch_actor_head(c->hidden, n, c->A, c->params + c->off_actor_w, c->params + c->off_actor_b,
                              c->params + c->off_critic_w, c->params + c->off_critic_b, c->subkey, logits, value, action,
                              logprob, st);
+}
+
+int cb_actor_step_cursor(cb_ctx* c, cb_rollout_cursor* cursor, int n, uint32_t* key, cb_stream stream) {
+    CB_CHECK(c && cursor && key, "null argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // key, subkey = jax.random.split(key); the same kernel advances cursor->row, which unpack and the head then read
+    if (launch_split_key(key, c->subkey, st, cursor)) return -1;
+    c->cursor = cursor;
+    const int rc = trunk_forward(c, nullptr, nullptr, n, st);
+    c->cursor = nullptr;
+    if (rc) return -1;
+    ProfScope ps(c, "actor_head", 2.0 * n * HIDDEN * (c->A + 1), (double)n * (HIDDEN * 4 + 12), st);
+    return launch_actor_head(c->hidden, n, c->A, c->params + c->off_actor_w, c->params + c->off_actor_b,
+                             c->params + c->off_critic_w, c->params + c->off_critic_b, c->subkey, nullptr, nullptr,
+                             reinterpret_cast<int*>(c->dense_part), nullptr, st, cursor);
 }
 
 // forward-only heads (no sampling): reuse the actor head kernel with a scratch action buffer

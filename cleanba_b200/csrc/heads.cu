@@ -61,17 +61,18 @@ __device__ __forceinline__ void head_forward(const HeadSmem& h, const float* hid
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void k_split_key(uint32_t* key, uint32_t* subkey) {
+__global__ void k_split_key(uint32_t* key, uint32_t* subkey, cb_rollout_cursor* cursor) {
     griddep_launch();
     griddep_wait();
     if (threadIdx.x == 0) {
+        if (cursor) cursor->row += 1;          // first kernel of a cursor step: the row every later kernel of the step uses
         uint32_t k0 = key[0], k1 = key[1], nk0, nk1, sk0, sk1;
         jax_split2(k0, k1, nk0, nk1, sk0, sk1);
         key[0] = nk0; key[1] = nk1; subkey[0] = sk0; subkey[1] = sk1;
     }
 }
-int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st) {
-    launch_pdl(k_split_key, dim3(1), dim3(32), 0, st, key_inout, subkey_out);
+int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st, cb_rollout_cursor* cursor) {
+    launch_pdl(k_split_key, dim3(1), dim3(32), 0, st, key_inout, subkey_out, cursor);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -81,11 +82,19 @@ int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st)
 __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hidden, int n, int A, const float* wa,
                                                     const float* ba, const float* wc, const float* bc,
                                                     const uint32_t* __restrict__ subkey, float* logits_out,
-                                                    float* value_out, int* action_out, float* logprob_out) {
+                                                    float* value_out, int* action_out, float* logprob_out,
+                                                    const cb_rollout_cursor* __restrict__ cursor) {
     extern __shared__ float sm[];
     griddep_launch();
     HeadSmem h = load_head_smem(sm, wa, ba, wc, bc, A);   // master parameters: not written by the preceding kernels
     griddep_wait();
+    if (cursor) {   // outputs go to row cursor->row of the rollout storages
+        const long long r = (long long)cursor->row * cursor->out_row_stride;
+        action_out = reinterpret_cast<int*>(cursor->action) + r;
+        logprob_out = cursor->logprob ? reinterpret_cast<float*>(cursor->logprob) + r : nullptr;
+        value_out = cursor->value ? reinterpret_cast<float*>(cursor->value) + r : nullptr;
+        logits_out = cursor->logits ? reinterpret_cast<float*>(cursor->logits) + r * A : nullptr;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const uint32_t k0 = subkey[0], k1 = subkey[1];
     const uint32_t total = (uint32_t)n * (uint32_t)A;
@@ -122,11 +131,11 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hi
 
 int launch_actor_head(const float* hidden, int n, int A, const float* wa, const float* ba, const float* wc,
                       const float* bc, const uint32_t* subkey, float* logits_out, float* value_out, int* action_out,
-                      float* logprob_out, cudaStream_t st) {
+                      float* logprob_out, cudaStream_t st, const cb_rollout_cursor* cursor) {
     int blocks = (n + 7) / 8;
     if (blocks > 296) blocks = 296;
     launch_pdl(k_actor_head, dim3(blocks), dim3(256), (size_t)head_smem_bytes(A), st, hidden, n, A, wa, ba, wc, bc, subkey, logits_out,
-               value_out, action_out, logprob_out);
+               value_out, action_out, logprob_out, cursor);
     CB_LAUNCH_CHECK();
     return 0;
 }

@@ -1,6 +1,7 @@
 // Internal launcher declarations (host side) for libcleanba_b200.
 #pragma once
 #include "common.cuh"
+#include "../../include/cleanba_b200.h"
 
 namespace cb {
 
@@ -16,7 +17,7 @@ struct WgradArgs {
 };
 
 // trunk_simt.cu
-int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st);
+int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
                     uint8_t* amax, cudaStream_t st);
@@ -73,10 +74,10 @@ int launch_dense_bwd_umma(const DenseUmmaArgs& a, const float* dpre, float* dw, 
 int launch_dpre_transpose(const float* dpre, int n, int npad, bf16* dp_hi, bf16* dp_mid, cudaStream_t st);
 
 // heads.cu
-int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st);
+int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st, cb_rollout_cursor* cursor = nullptr);
 int launch_actor_head(const float* hidden, int n, int num_actions, const float* wa, const float* ba, const float* wc,
                       const float* bc, const uint32_t* subkey, float* logits_out, float* value_out, int* action_out,
-                      float* logprob_out, cudaStream_t st);
+                      float* logprob_out, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr);
 struct PpoHeadArgs {
     int n, num_actions;
     const float* hidden;         // [n][256]

@@ -14,9 +14,10 @@ namespace cb {
 // coalesced 4-byte reads, then every thread emits 16-byte pixels (consecutive threads -> consecutive pixels).
 constexpr int UNPACK_ROWS = 8;
 __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, int n,
-                                                       bf16* __restrict__ out_hi) {
+                                                       bf16* __restrict__ out_hi, const cb_rollout_cursor* __restrict__ cursor) {
     griddep_launch();
     griddep_wait();
+    if (cursor) obs = reinterpret_cast<const uint8_t*>(cursor->obs) + (long long)cursor->row * cursor->obs_row_stride;
     constexpr int H = 84, W = 84, Wp = 86, Hp = 86, GROUPS = (Hp + UNPACK_ROWS - 1) / UNPACK_ROWS;
     const int img = blockIdx.x / GROUPS;
     const int yp0 = (blockIdx.x % GROUPS) * UNPACK_ROWS;
@@ -47,9 +48,9 @@ __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict
     }
 }
 
-int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st) {
+int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor) {
     const int groups = (86 + UNPACK_ROWS - 1) / UNPACK_ROWS;
-    launch_pdl(k_unpack_frames, dim3(n * groups), dim3(256), 0, st, obs, idx, n, out_hi);
+    launch_pdl(k_unpack_frames, dim3(n * groups), dim3(256), 0, st, obs, idx, n, out_hi, cursor);
     CB_LAUNCH_CHECK();
     return 0;
 }

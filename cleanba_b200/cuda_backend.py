@@ -77,7 +77,8 @@ class CudaActor:
             self.stream.synchronize()      # the reference blocks on the new params too (cleanba_ppo.py:294-300)
         if self.graphed is None:
             with torch.cuda.device(self.dev):
-                self.graphed = ag.GraphedActor(self.ctx, self.N, self.key, want_logits=self.impala, stream=self.stream)
+                self.graphed = ag.RolloutActor(self.ctx, self.N, self.key, want_logits=self.impala, stream=self.stream)
+                self._cur_storage = None
 
     def step(self, storage, t, obs_host):
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
@@ -85,16 +86,15 @@ class CudaActor:
                 self.staging.numpy()[...] = obs_host
                 obs_host = self.staging
             g = self.graphed
-            g.step(obs_host)                                   # H2D of the frame + one graph replay (all ~25 kernels)
-            storage.obs[t].copy_(g.obs, non_blocking=True)     # this step's transition -> row t of the rollout storage
-            storage.actions[t].copy_(g.action, non_blocking=True)
-            if self.impala:
-                storage.logitss[t].copy_(g.logits, non_blocking=True)
-            else:
-                storage.logprobs[t].copy_(g.logprob, non_blocking=True)
-                storage.values[t].copy_(g.value, non_blocking=True)
-            t0 = time.time()
-            self.act_host.copy_(g.action, non_blocking=True)
+            if storage is not self._cur_storage:               # new rollout: point the device-side cursor at its storage
+                if self.impala:
+                    g.begin(storage.obs, storage.actions, logits=storage.logitss, first_row=t)
+                else:
+                    g.begin(storage.obs, storage.actions, storage.logprobs, storage.values, first_row=t)
+                self._cur_storage = storage
+            g.step(obs_host, t)                                # H2D of the frames into row t + one graph replay (~25 kernels),
+            t0 = time.time()                                   # which writes this step's transition into row t
+            self.act_host.copy_(storage.actions[t], non_blocking=True)
             self.stream.synchronize()
             return self.act_host.numpy().copy(), time.time() - t0
 

@@ -38,6 +38,7 @@ SIGNATURES = {
     "cb_get_opt_state": (c_int, [_P, _P, _P, POINTER(c_longlong), _P]),
     "cb_set_opt_state": (c_int, [_P, _P, _P, c_longlong, _P]),
     "cb_actor_step": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "cb_actor_step_cursor": (c_int, [_P, _P, c_int, _P, _P]),
     "cb_policy_value": (c_int, [_P, _P, _P, c_int, _P, _P, _P]),
     "cb_gae": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, c_int, _P, _P, _P]),
     "cb_split_key": (c_int, [_P, _P, _P, _P]),

@@ -69,6 +69,24 @@ int cb_set_opt_state(cb_ctx* ctx, const float* m, const float* v, long long coun
  * Outputs (device): action int32[n]; logprob, value float[n] (may be NULL); logits float[n,num_actions] (may be NULL). */
 int cb_actor_step(cb_ctx* ctx, const uint8_t* obs, int n, uint32_t* key, int32_t* action, float* logprob, float* value,
                   float* logits, cb_stream stream);
+
+/* Rollout-storage form of cb_actor_step (prepare_data without the stack, cleanba_ppo.py:276-278, 342-356): the step reads its n
+ * frames from row `row` of a frame storage and writes action / logprob / value / logits into row `row` of the rollout storages
+ * described by a cursor that lives in DEVICE memory.  The step itself advances cursor->row BEFORE using it (initialise it to
+ * first_row - 1), so ONE captured CUDA graph serves every step of every rollout: per step the host only copies the frames into
+ * their storage row and replays the graph -- no staging buffers, no per-field copies.  Null (0) output pointers are skipped. */
+typedef struct cb_rollout_cursor {
+    unsigned long long obs;        /* uint8 frames of this actor: row r = obs + r * obs_row_stride bytes, n*4*84*84 bytes each */
+    unsigned long long action;     /* int32: row r = action + r * out_row_stride elements */
+    unsigned long long logprob;    /* float or 0 */
+    unsigned long long value;      /* float or 0 */
+    unsigned long long logits;     /* float, rows out_row_stride * num_actions elements apart, or 0 */
+    long long obs_row_stride;      /* bytes */
+    long long out_row_stride;      /* elements */
+    int row;
+    int reserved;
+} cb_rollout_cursor;
+int cb_actor_step_cursor(cb_ctx* ctx, cb_rollout_cursor* cursor_dev, int n, uint32_t* key, cb_stream stream);
 /* Network + heads only (bootstrap value in compute_gae, cleanba_ppo.py:550-552). idx (int32[n], may be NULL) gathers
  * frames obs[idx[i]]. logits / value may be NULL. */
 int cb_policy_value(cb_ctx* ctx, const uint8_t* obs, const int32_t* idx, int n, float* logits, float* value, cb_stream stream);

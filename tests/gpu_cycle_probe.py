@@ -22,22 +22,25 @@ def phase(fn, reps=1):
     return (t1 - t0) * 1e3 / reps, (t2 - t0) * 1e3 / reps
 
 
-def rollout(nthreads=2, copies=True):
+def rollout(nthreads=2, e2e=False):
     main = torch.cuda.current_stream(cyc.dev)
     gs = cyc.graphed[:nthreads]
-    for g in gs:
+    pool = cyc.host_pool if e2e else cyc.dev_pool
+    for th, g in enumerate(gs):
         g.stream.wait_stream(main)
+        c = slice(th * bench.N_ENVS, (th + 1) * bench.N_ENVS)
+        g.begin(cyc.obs[:, c], cyc.actions[:, c], cyc.logprobs[:, c], cyc.values[:, c])
     for t in range(bench.T_STEPS):
         for th, g in enumerate(gs):
             c = slice(th * bench.N_ENVS, (th + 1) * bench.N_ENVS)
-            g.step(cyc.dev_pool[cyc.cursor % 256])
+            g.step(pool[cyc.cursor % 256], t)
             cyc.cursor += 1
-            if copies:
+            if e2e:
                 with torch.cuda.stream(g.stream):
-                    cyc.obs[t, c].copy_(g.obs, non_blocking=True)
-                    cyc.actions[t, c].copy_(g.action, non_blocking=True)
-                    cyc.logprobs[t, c].copy_(g.logprob, non_blocking=True)
-                    cyc.values[t, c].copy_(g.value, non_blocking=True)
+                    cyc.act_host[th].copy_(cyc.actions[t, c], non_blocking=True)
+        if e2e:
+            for g in gs:
+                g.stream.synchronize()
     for g in gs:
         main.wait_stream(g.stream)
 
@@ -54,8 +57,11 @@ def publish():
 
 def replay_only():
     g = cyc.graphed[0]
+    g.begin(cyc.obs[:, :bench.N_ENVS], cyc.actions[:, :bench.N_ENVS], cyc.logprobs[:, :bench.N_ENVS], cyc.values[:, :bench.N_ENVS])
     with torch.cuda.stream(g.stream):
-        for _ in range(256):
+        for r in range(256):
+            if r == 128:      # the cursor must stay inside the storage
+                g.begin(cyc.obs[:, :bench.N_ENVS], cyc.actions[:, :bench.N_ENVS], cyc.logprobs[:, :bench.N_ENVS], cyc.values[:, :bench.N_ENVS])
             g.graph.replay()
 
 
@@ -68,8 +74,8 @@ def gae_part():
         c.permutation(sub, bench.T_STEPS * cyc.Bl)
 
 
-for name, fn in [("rollout 2 threads (256 steps + storage copies)", rollout),
-                 ("rollout 2 threads, no storage copies", lambda: rollout(2, False)),
+for name, fn in [("rollout 2 threads (256 steps into storage rows)", rollout),
+                 ("rollout 2 threads, host frames + per-step sync", lambda: rollout(2, True)),
                  ("rollout 1 thread (128 steps)", lambda: rollout(1)),
                  ("256 graph replays on one stream", replay_only),
                  ("update (GAE + 16 minibatches)", update),

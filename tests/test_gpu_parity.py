@@ -419,3 +419,40 @@ def test_full_size_minibatch_properties(agent, params):
     gerr = float((out[0][0] - out[1][0]).norm() / out[1][0].norm())
     _diag("full_size_mb3840", stats_tcgen05_vs_simt=serr, grad_tcgen05_vs_simt=gerr)
     assert serr < 1e-5 and gerr < 1e-3
+
+
+def test_rollout_actor_rows_match_plain_actor_steps(agent, params):
+    """cb_actor_step_cursor through agent.RolloutActor (one CUDA graph, outputs written straight into rows of a column-sliced
+    [T, Bl, ...] rollout storage) is bit-identical to consecutive cb_actor_step calls: actions, log-probs, values, PRNG key,
+    and the frames land in their storage rows; a second rollout re-points the cursor (first_row = 1, the IMPALA carry row)."""
+    rng = np.random.default_rng(21)
+    n, T, Bl = 6, 4, 16
+    dev = torch.device("cuda:0")
+    frames = [torch.from_numpy(_frames(rng, n)).pin_memory() for _ in range(2 * T)]
+    ref = agent.Context(dev, max_batch=n); ref.set_params(params)
+    kr = agent.key_tensor(np.array([11, 12], np.uint32), dev)
+    want = [tuple(x.cpu().numpy() for x in ref.actor_step(f.to(dev), kr)[:3]) for f in frames[:2 * T - 1]]
+    ctx = agent.Context(dev, max_batch=n); ctx.set_params(params)
+    key = agent.key_tensor(np.array([11, 12], np.uint32), dev)
+    ra = agent.RolloutActor(ctx, n, key)
+    obs = torch.zeros(T, Bl, 4, 84, 84, dtype=torch.uint8, device=dev)
+    act = torch.full((T, Bl), -1, dtype=torch.int32, device=dev)
+    lp = torch.zeros(T, Bl, device=dev); val = torch.zeros(T, Bl, device=dev)
+    c = slice(5, 5 + n)                                  # a column block in the middle of the storage
+    k = 0
+    for first_row in (0, 1):                             # second rollout: row 0 is a carried row, steps start at row 1
+        ra.stream.wait_stream(torch.cuda.current_stream(dev))
+        ra.begin(obs[:, c], act[:, c], lp[:, c], val[:, c], first_row=first_row)
+        for t in range(first_row, T):
+            ra.step(frames[k], t)
+            ra.stream.synchronize()
+            a, l, v = want[k]
+            assert np.array_equal(act[t, c].cpu().numpy(), a), (first_row, t)
+            assert np.array_equal(lp[t, c].cpu().numpy(), l) and np.array_equal(val[t, c].cpu().numpy(), v)
+            assert torch.equal(obs[t, c].cpu(), frames[k])
+            k += 1
+    assert (act[:, :5] == -1).all() and (act[:, 5 + n:] == -1).all(), "wrote outside its storage columns"
+    assert agent.key_numpy(key).tolist() == agent.key_numpy(kr).tolist()
+    with pytest.raises(agent.CleanbaError):
+        ra.step(frames[0], 0)                            # rows must be stepped in order
+    ref.close(); ctx.close()
