@@ -190,15 +190,18 @@ class Cycle:
         for t in range(T_STEPS):
             for th, g in enumerate(self.graphed):
                 c = slice(th * N_ENVS, (th + 1) * N_ENVS)
+                if e2e and t > 0:
+                    g.stream.synchronize()             # np.array(action) of this thread's previous step: the per-step sync of
+                                                       # cleanba_ppo.py:317 (each actor thread waits for ITS OWN step only)
                 g.step(pool[self.cursor % 256], t)     # frames -> storage row t (H2D from pinned memory when e2e) + graph replay:
                 self.cursor += 1                       # the step reads row t and writes action / logprob / value into row t
                 if e2e:
                     with torch.cuda.stream(g.stream):
                         self.act_host[th].copy_(self.actions[t, c], non_blocking=True)
-            if e2e:
-                for th, g in enumerate(self.graphed):
-                    g.stream.synchronize()                              # np.array(action): the per-step sync (cleanba_ppo.py:317)
                     self.h2d += N_ENVS * 4 * 84 * 84; self.d2h += N_ENVS * 4
+        if e2e:
+            for g in self.graphed:
+                g.stream.synchronize()                 # actions of the last step
         for g in self.graphed:
             main.wait_stream(g.stream)
         k = (self.cursor // 256) % 8
