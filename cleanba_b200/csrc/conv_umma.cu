@@ -502,6 +502,310 @@ int launch_conv0_pool_umma(const ConvArgs& a, float* out_s, Planes out, uint8_t*
 }
 
 // =================================================================================================
+// Second / third ConvSequence, forward: the sequence conv (16 -> 32 at 42x42, 32 -> 32 at 21x21; 3-plane activations, three MMAs
+// per K step as in k_conv_umma) FUSED with its max-pool, by the band scheme of k_conv0_pool_umma: a band = CP_K pooled rows =
+// 2*CP_K + 1 conv rows = consecutive flat pixels = up to CP_MAXT tiles, each with its own TMEM accumulator (96 columns), so
+// the MMAs of the next band overlap the pooling of this one.  The last band of an image may be shorter (21 = 4*5 + 1,
+// 11 = 2*5 + 1).  pad_lo = 0 (42 -> 21: windows 2i .. 2i+2) or 1 (21 -> 11: windows 2i-1 .. 2i+1), clipped to the image.
+// Band shapes (template parameters K = pooled rows per band, MAXT = tiles per band):
+//   42x42 (Wp = 44): K = 2 -> 5 conv rows = 220 px = 2 tiles; 2 accumulators = 256 TMEM columns and ~100 KB of shared memory,
+//                    so TWO CTAs (16 epilogue warps, two MMA issuers) share an SM -- with K = 5 (4 tiles, 512 columns, one CTA per
+//                    SM) the 8 epilogue warps were the bottleneck (0.78 ms vs 0.83 ms unfused);
+//   21x21 (Wp = 23): K = 5 -> 11 conv rows = 253 px = 2 tiles, one CTA per SM (the 55 KB weight image leaves no room for two).
+constexpr int CP_COUT = 32;
+constexpr int CP_ACC_COLS = 3 * CP_COUT;
+
+struct ConvPoolArgs {
+    ConvGeom gi, go;          // conv grid (input of the pool) and pooled grid
+    int pad_lo;
+    int bands_per_img;        // ceil(go.H / K)
+    Planes in;                // 3-plane input activations of the conv
+    const bf16* wp;           // packed forward weight image
+    const float* bias;        // [32]
+    float* out_s;             // pooled fp32 stream
+    Planes out;               // relu'd pooled planes (hi, mid, lo)
+    uint8_t* amax;            // arg-max bytes or null
+};
+
+struct ConvPoolSmem { int win, plane_bytes, stage_bytes, w_bytes, stages, band_bytes, total, ctas_per_sm; };
+__host__ __device__ inline ConvPoolSmem conv_pool_smem(int cin_chunks, int Wp, int K, int MAXT) {
+    ConvPoolSmem L;
+    L.win = TILE_M + 2 * Wp + 2;
+    L.plane_bytes = L.win * 16;
+    L.stage_bytes = 3 * cin_chunks * L.plane_bytes;
+    L.w_bytes = conv_wbytes(cin_chunks, CP_COUT, 3);
+    const int band_px = ((2 * K + 1) * Wp + TILE_M - 1) / TILE_M * TILE_M;
+    L.band_bytes = band_px * CP_COUT * 4;
+    // two CTAs per SM when the accumulators fit 256 TMEM columns AND two stages fit half an SM's shared memory
+    const int fixed = 1024 + L.w_bytes + L.band_bytes;
+    const int st2 = (113 * 1024 - fixed) / L.stage_bytes;
+    L.ctas_per_sm = (MAXT * CP_ACC_COLS <= 256 && st2 >= 2) ? 2 : 1;
+    int st = L.ctas_per_sm == 2 ? st2 : (226 * 1024 - fixed) / L.stage_bytes;
+    L.stages = st > 4 ? 4 : st;
+    L.total = 1024 + L.w_bytes + L.stages * L.stage_bytes + L.band_bytes;
+    return L;
+}
+
+// 16-byte chunk c (0..7) of band pixel pb (one pixel = 32 channels = one 128-byte row): XOR with the pixel index keeps the
+// epilogue's per-lane pixel stores conflict free; the pool's stride-2 pixel loads see a 2-way conflict.
+__device__ __forceinline__ float4* cp_band_ptr(uint8_t* band, int pb, int c) {
+    return reinterpret_cast<float4*>(band + (pb << 7) + ((c ^ (pb & 7)) << 4));
+}
+
+template <int CIN_CHUNKS, int CP_K, int CP_MAXT>
+__global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_launch();
+    const ConvPoolSmem L = conv_pool_smem(CIN_CHUNKS, a.gi.Wp, CP_K, CP_MAXT);
+    const int NSTAGES = L.stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [4]
+    uint64_t* empty = full + 4;                                  // [4]
+    uint64_t* tfull = empty + 4;                                 // [CP_MAXT]
+    uint64_t* tempty = tfull + CP_MAXT;                          // [CP_MAXT]
+    uint64_t* wbar = tempty + CP_MAXT;                           // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint8_t* wsm = smem + 1024;
+    uint8_t* stages = wsm + L.w_bytes;
+    uint8_t* band = stages + NSTAGES * L.stage_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int STEPS = conv_steps(CIN_CHUNKS);
+    constexpr uint32_t TMEM_COLS = CP_MAXT * CP_ACC_COLS <= 256 ? 256 : 512;   // CP_MAXT accumulators x 96 columns
+    constexpr int NPLANES = 3 * CIN_CHUNKS;
+    const int Wp = a.gi.Wp, Ho = a.go.H;
+    const int nbands = a.gi.n * a.bands_per_img;
+    // band b of an image: pooled rows [b*CP_K, b*CP_K + kb), conv rows from padded row 2*b*CP_K - pad_lo + 1, (2*kb + 1) of them
+    auto band_rows = [&](int b) { const int r = Ho - b * CP_K; return r < CP_K ? r : CP_K; };
+    auto band_tiles = [&](int kb) { return ((2 * kb + 1) * Wp + TILE_M - 1) / TILE_M; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < CP_MAXT; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 8 && lane == 0) {
+        mbar_arrive_expect_tx(wbar, (uint32_t)L.w_bytes);
+        bulk_g2s(wsm, a.wp, L.w_bytes, wbar);
+    }
+    griddep_wait();
+
+    if (warp == 8) {
+        // ===================== TMA producer (lanes share the bulk copies of a stage) =====================
+        int s = 0; uint32_t ph = 0;
+        for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
+            const int img = bnd / a.bands_per_img, b = bnd - img * a.bands_per_img;
+            const long long qb = (long long)img * a.gi.P + (long long)(2 * b * CP_K - a.pad_lo + 1) * Wp;
+            const int nt = band_tiles(band_rows(b));
+            for (int t = 0; t < nt; ++t) {
+                mbar_wait(&empty[s], ph ^ 1);
+                if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)L.stage_bytes);
+                const long long q_lo = qb + t * TILE_M - Wp - 1;
+                uint8_t* dst = stages + s * L.stage_bytes;
+                if (lane < NPLANES) {
+                    const int pl = lane / CIN_CHUNKS, j = lane % CIN_CHUNKS;      // pl: 0 hi, 1 mid, 2 lo
+                    const bf16* src = pl == 0 ? a.in.hi : (pl == 1 ? a.in.mid : a.in.lo);
+                    bulk_g2s(dst + lane * L.plane_bytes, src + ((long long)j * a.in.plane_px + q_lo) * 8, L.plane_bytes, &full[s]);
+                }
+                __syncwarp();
+                if (++s == NSTAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer: three MMAs per K step (see k_conv_umma) =====================
+        constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * CP_COUT, 0, 0);
+        constexpr uint32_t IDESC2 = make_idesc_bf16(TILE_M, 2 * CP_COUT, 0, 0);
+        constexpr uint32_t IDESC1 = make_idesc_bf16(TILE_M, CP_COUT, 0, 0);
+        mbar_wait(wbar, 0);
+        int s = 0; uint32_t ph = 0;
+        uint32_t accph = 0;                                      // bit t: phase of accumulator t (flips each time it is used)
+        const uint32_t win16 = (uint32_t)L.win;
+        const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
+        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 3 * CP_COUT * 16);
+        uint32_t a_rel[STEPS];
+#pragma unroll
+        for (int step = 0; step < STEPS; ++step) {
+            constexpr int HALF = CIN_CHUNKS / 2;
+            const int tap = step / HALF, pair = step % HALF;
+            a_rel[step] = ((uint32_t)(pair * 2) * win16 + (uint32_t)((tap / 3) * Wp + (tap % 3))) | (win16 << 16);
+        }
+        const uint32_t mid16 = CIN_CHUNKS * win16, lo16 = 2 * CIN_CHUNKS * win16;
+        for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
+            const int b = bnd % a.bands_per_img;
+            const int nt = band_tiles(band_rows(b));
+            for (int t = 0; t < nt; ++t) {
+                mbar_wait(&tempty[t], ((accph >> t) & 1) ^ 1);
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d_tmem = tmem_base + t * CP_ACC_COLS;
+                    const uint32_t st16 = (smem_u32(stages + s * L.stage_bytes) >> 4);
+#pragma unroll
+                    for (int step = 0; step < STEPS; ++step) {
+                        const uint32_t a_lo = st16 + a_rel[step];
+                        const uint32_t b_lo = b_lo0 + step * (2 * 3 * CP_COUT);
+                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC3, step > 0);
+                        mma_bf16_parts(d_tmem, a_lo + mid16, a_hi, b_lo, b_hi, IDESC2, 1);
+                        mma_bf16_parts(d_tmem, a_lo + lo16, a_hi, b_lo, b_hi, IDESC1, 1);
+                    }
+                    mma_commit(&empty[s]);
+                    mma_commit(&tfull[t]);
+                }
+                __syncwarp();
+                accph ^= 1u << t;
+                if (++s == NSTAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps 0-7: accumulators -> band buffer, then pool the band =====================
+        const int grp = warp >> 2, quad = warp & 3;
+        const int etid = threadIdx.x;                            // 0..255
+        uint32_t accph = 0;
+        const int Wo = a.go.W, Wpo = a.go.Wp;
+        constexpr int NCH = CP_COUT / 8;
+        float bias[CP_COUT];
+#pragma unroll
+        for (int e = 0; e < CP_COUT; ++e) bias[e] = a.bias[e];
+        auto emit = [&](int img, int ypo, int xp, int jc, const float* v, const int* am) {
+            const long long qo = (long long)img * a.go.P + ypo * Wpo + xp;
+            const long long so = ((long long)jc * a.go.NP + qo) * 8;
+            float4* o = reinterpret_cast<float4*>(a.out_s + so);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            float rl[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
+            store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, rl);
+            if (a.amax) {
+                uint2 pk;
+                pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                *reinterpret_cast<uint2*>(a.amax + so) = pk;
+            }
+        };
+        auto emit_zero = [&](int img, int ypo, int xp, int jc) {
+            float v[8];
+            int am[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[e] = 0.f; am[e] = 15; }
+            emit(img, ypo, xp, jc, v, am);
+        };
+        for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
+            const int img = bnd / a.bands_per_img, b = bnd - img * a.bands_per_img;
+            const int kb = band_rows(b), nt = band_tiles(kb);
+            for (int t = grp; t < nt; t += 2) {
+                mbar_wait(&tfull[t], (accph >> t) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + t * CP_ACC_COLS;
+                const int pb = t * TILE_M + quad * 32 + lane;
+#pragma unroll
+                for (int h = 0; h < CP_COUT / 16; ++h) {
+                    float v[16], u[16];
+                    tmem_ld16(taddr + 2 * CP_COUT + h * 16, v);
+                    tmem_ld16(taddr + CP_COUT + h * 16, u);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += u[i];
+                    tmem_ld16(taddr + h * 16, u);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += u[i];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *cp_band_ptr(band, pb, h * 4 + c) = make_float4(v[c * 4 + 0] + bias[h * 16 + c * 4 + 0], v[c * 4 + 1] + bias[h * 16 + c * 4 + 1],
+                                                                        v[c * 4 + 2] + bias[h * 16 + c * 4 + 2], v[c * 4 + 3] + bias[h * 16 + c * 4 + 3]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[t]);
+                accph ^= 1u << t;
+            }
+            // accumulators this group did not touch in this band keep their phase; the other group's bits are tracked by that group
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // the band is complete in shared memory
+            const int nitems = kb * Wo * NCH;
+            for (int it = etid; it < nitems; it += 256) {
+                const int j = it % Wo, jc = (it / Wo) % NCH, r = it / (Wo * NCH);
+                float v[8];
+                int am[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { v[e] = -INFINITY; am[e] = 15; }
+                const int y0 = 2 * (b * CP_K + r) - a.pad_lo, x0 = 2 * j - a.pad_lo;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    if (y0 + dy < 0 || y0 + dy >= a.gi.H) continue;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (x0 + dx < 0 || x0 + dx >= a.gi.W) continue;
+                        const int pb = (2 * r + dy) * Wp + x0 + dx + 1;
+                        const float4 f0 = *cp_band_ptr(band, pb, 2 * jc), f1 = *cp_band_ptr(band, pb, 2 * jc + 1);
+                        const float o[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (o[e] > v[e]) { v[e] = o[e]; am[e] = dy * 3 + dx; }
+                    }
+                }
+                emit(img, b * CP_K + r + 1, j + 1, jc, v, am);
+            }
+            // zero border of the pooled grid: left / right pixels of this band's rows, plus the top / bottom row of the image
+            const int nside = kb * 2 * NCH;
+            const int ntop = (b == 0) ? Wpo * NCH : 0, nbot = (b == a.bands_per_img - 1) ? Wpo * NCH : 0;
+            for (int it = etid; it < nside + ntop + nbot; it += 256) {
+                if (it < nside) {
+                    emit_zero(img, b * CP_K + it / (2 * NCH) + 1, ((it / NCH) & 1) ? Wpo - 1 : 0, it % NCH);
+                } else if (it < nside + ntop) {
+                    const int k = it - nside;
+                    emit_zero(img, 0, k % Wpo, k / Wpo);
+                } else {
+                    const int k = it - nside - ntop;
+                    emit_zero(img, Ho + 1, k % Wpo, k / Wpo);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // band buffer free for the next band
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int CIN_CHUNKS, int CP_K, int CP_MAXT>
+static int launch_conv_pool_umma_t(ConvPoolArgs p, int num_sms, cudaStream_t st) {
+    const ConvPoolSmem L = conv_pool_smem(CIN_CHUNKS, p.gi.Wp, CP_K, CP_MAXT);
+    CB_CHECK(L.stages >= 2 && L.total <= 227 * 1024, "conv_pool_umma<%d>: %d bytes of shared memory needed", CIN_CHUNKS, L.total);
+    CB_CHECK(((2 * CP_K + 1) * p.gi.Wp + TILE_M - 1) / TILE_M <= CP_MAXT, "conv_pool_umma: band of %d rows x %d does not fit %d tiles",
+             2 * CP_K + 1, p.gi.Wp, CP_MAXT);
+    p.bands_per_img = (p.go.H + CP_K - 1) / CP_K;
+    static std::atomic<unsigned> attr_done{0};
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    if (!(attr_done.load() & (1u << dev))) {
+        CB_CUDA(cudaFuncSetAttribute(k_conv_pool_umma<CIN_CHUNKS, CP_K, CP_MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done.fetch_or(1u << dev);
+    }
+    const int nbands = p.gi.n * p.bands_per_img;
+    const int per_sm = L.ctas_per_sm;
+    const int grid = nbands < per_sm * num_sms ? nbands : per_sm * num_sms;
+    launch_pdl(k_conv_pool_umma<CIN_CHUNKS, CP_K, CP_MAXT>, dim3(grid), dim3(CONV_THREADS), (size_t)L.total, st, p);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, float* out_s, Planes out, uint8_t* amax, int num_sms,
+                          cudaStream_t st) {
+    CB_CHECK(a.cout == CP_COUT && !a.transpose && a.in.lo && (a.cin_chunks == 2 || a.cin_chunks == 4),
+             "conv_pool_umma: 3-plane 16|32 -> 32 channel sequence convs only");
+    CB_CHECK(a.g.Wp + 1 <= GUARD && 2 * TILE_M + a.g.Wp + 2 <= GUARD + 128, "conv_pool_umma: guard too small for Wp=%d", a.g.Wp);
+    ConvPoolArgs p;
+    p.gi = a.g; p.go = go; p.pad_lo = pad_lo; p.bands_per_img = 0;
+    p.in = a.in; p.wp = a.wp; p.bias = a.ep.bias; p.out_s = out_s; p.out = out; p.amax = amax;
+    if (a.cin_chunks == 2) return launch_conv_pool_umma_t<2, 2, 2>(p, num_sms, st);
+    return launch_conv_pool_umma_t<4, 5, 2>(p, num_sms, st);
+}
+
+// =================================================================================================
 // wgrad on tcgen05:  dW[(ky,kx), ci, co] = sum_q X[q + d(ky,kx)][ci] * G[q][co],  db[co] = sum_q G[q][co].
 // GEMM view per 128-pixel block:  D_kx[m, n] += A_kx[m, q] * B[q, n]  with the reduction over pixels (K), where
 //   m = (ky, ci) stacks the three filter ROWS (three bulk copies of the same planes shifted by one image row) and

@@ -143,7 +143,8 @@ struct cb_ctx {
     int npad_max = 0;
     static constexpr int grad_planes = 2;   // bf16 planes of gradient tensors (16 significant bits)
     const cb_rollout_cursor* cursor = nullptr;   // set for the duration of a cb_actor_step_cursor call
-    bool fuse0 = false;                     // first ConvSequence: conv + pool (forward) and pool + wgrad (backward) fused
+    bool fuse0 = false;
+    bool fuse12 = false;                    // second / third ConvSequence: conv + pool (forward) fused                     // first ConvSequence: conv + pool (forward) and pool + wgrad (backward) fused
 };
 
 namespace cb {
@@ -299,6 +300,16 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             ProfScope ps(c, "conv0_pool_fwd@84", 2.0 * n * 84 * 84 * 9.0 * 4 * 16,
                          planes_bytes(gi, 1, false) + stream_bytes(go, 2) + planes_bytes(go, 2, true) + (S.amax ? (double)go.NP * 16 : 0.0), st);
             if (launch_conv0_pool_umma(a, S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
+        } else if (s > 0 && c->fuse12) {
+            // sequence conv + max-pool in one kernel (conv_umma.cu: k_conv_pool_umma)
+            ConvArgs a = conv_args(c, base, gi, S.x, false);
+            a.ep.bias = c->params + c->conv[base].off_b;
+            char name[96];
+            snprintf(name, sizeof(name), "conv_pool_fwd<cin%d,cout%d>@%d", a.cin_real, a.cout, gi.H);
+            ProfScope ps(c, name, 2.0 * n * gi.H * gi.W * 9.0 * a.cin_real * a.cout,
+                         planes_bytes(gi, a.cin_chunks, a.in) + stream_bytes(go, a.cout / 8) + planes_bytes(go, a.cout / 8, true) +
+                             (S.amax ? (double)go.NP * a.cout : 0.0), st);
+            if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
         } else {
             // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
             ConvArgs a = conv_args(c, base + 0, gi, S.x, false);
@@ -308,7 +319,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             if (run_conv(c, a, st)) return -1;
         }
         // x = nn.max_pool(x, (3,3), strides=(2,2), padding="SAME")              (cleanba_ppo.py:168)
-        if (!(s == 0 && c->fuse0)) {
+        if (!(s == 0 && c->fuse0) && !(s > 0 && c->fuse12)) {
             ProfScope ps(c, "pool_fwd@" + std::to_string(kStageHin[s]), 0,
                          stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(go, kStageC[s] / 8, true), st);
             if (launch_pool_fwd(S.y.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.p.s, S.p.pl, S.amax, st)) return -1;
@@ -473,6 +484,7 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->A = cfg->num_actions;
     c->fuse0 = cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_NO_FUSE0");
+    c->fuse12 = cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_NO_FUSE12");
     c->leaves = build_leaves(c->A);
     c->nparam = c->leaves.back().offset + c->leaves.back().size();
     bool ok = false;
@@ -905,7 +917,7 @@ long long cb_debug_tensor(cb_ctx* c, const char* name, float* host_out, long lon
     if (name[0] == 's') {
         if (!strcmp(f, "x")) a = &S.x;
         else if (!strcmp(f, "y")) {
-            CB_CHECK(!(s == 0 && c->fuse0), "tensor s0.y is not materialised (frame conv fused with its max-pool)");
+            CB_CHECK(!(s == 0 && c->fuse0) && !(s > 0 && c->fuse12), "tensor s%d.y is not materialised (conv fused with its max-pool)", s);
             a = &S.y; want_stream = true;
         }
         else if (!strcmp(f, "p")) { a = &S.p; want_stream = true; }
