@@ -135,6 +135,7 @@ struct cb_ctx {
     uint32_t* subkey = nullptr;
     uint32_t* key_tmp = nullptr;
     int* perm_tmp = nullptr;
+    int* perm_rank = nullptr;
     uint32_t* sort_keys = nullptr;
     int perm_cap = 0;
     int last_n = 0;
@@ -731,13 +732,15 @@ int cb_permutation(cb_ctx* c, const uint32_t* key, int n, int32_t* out, cb_strea
         c->perm_tmp = (int*)p;
         if (dev_alloc(c, &p, (size_t)n * sizeof(uint32_t))) return -1;
         c->sort_keys = (uint32_t*)p;
+        if (dev_alloc(c, &p, (size_t)n * sizeof(int))) return -1;
+        c->perm_rank = (int*)p;
         c->perm_cap = n;
     }
     // num_rounds = ceil(3 ln n / ln(2^32 - 1))  (jax._src.random._shuffle)
     int rounds = (int)ceil(3.0 * log((double)(n > 1 ? n : 1)) / log(4294967295.0));
     if (copy_any(c->key_tmp, key, 2 * sizeof(uint32_t), st)) return -1;
     ProfScope ps(c, "permutation", 0, 12.0 * n, st);
-    return launch_permutation(c->key_tmp, n, rounds, out, c->perm_tmp, c->sort_keys, c->subkey, st);
+    return launch_permutation(c->key_tmp, n, rounds, out, c->perm_tmp, c->sort_keys, c->perm_rank, c->subkey, st);
 }
 
 int cb_ppo_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int mb, const int32_t* actions, const float* logprobs,

@@ -124,7 +124,7 @@ int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st);
 int launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* next_value,
                const uint8_t* next_done, int T, int B, float gamma, float lambda, int num_groups, float* adv, float* ret,
                cudaStream_t st);
-int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tmp, uint32_t* sort_keys,
+int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tmp, uint32_t* sort_keys, int* rank,
                        uint32_t* subkey, cudaStream_t st);
 struct OptArgs {
     int kind;                    // 0 = Adam, 1 = RMSProp (PyTorch style)

@@ -134,26 +134,35 @@ __global__ void k_random_bits(const uint32_t* __restrict__ subkey, int n, uint32
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = jax_random_bits_elem(subkey[0], subkey[1], (uint32_t)i, (uint32_t)n);
 }
-__global__ void __launch_bounds__(256) k_rank_scatter(const uint32_t* __restrict__ keys, const int* __restrict__ xin,
-                                                      int* __restrict__ xout, int n) {
+// Stable rank-by-counting sort of n <= a few 10^4 (key, index) pairs: rank[i] = #{j : key[j] < key[i] or (key[j] == key[i] and j < i)}.
+// The n^2 comparisons are split over blockIdx.y key segments (integer atomicAdd: exact, order independent) so that the grid
+// covers the GPU (n = 15,360: 60 x 8 blocks instead of 60; 0.22 -> 0.04 ms per round); k_scatter_by_rank then permutes.
+constexpr int RANK_SEGS = 8;
+__global__ void __launch_bounds__(256) k_rank_count(const uint32_t* __restrict__ keys, int n, int* __restrict__ rank) {
     __shared__ uint32_t tile[2048];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t ki = i < n ? keys[i] : 0u;
-    int rank = 0;
-    for (int j0 = 0; j0 < n; j0 += 2048) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ki = i < n ? keys[i] : 0u;
+    const int seg = (n + RANK_SEGS - 1) / RANK_SEGS;
+    const int jlo = blockIdx.y * seg, jhi = min(n, jlo + seg);
+    int r = 0;
+    for (int j0 = jlo; j0 < jhi; j0 += 2048) {
         __syncthreads();
-        for (int t = threadIdx.x; t < 2048; t += 256) tile[t] = (j0 + t < n) ? keys[j0 + t] : 0xffffffffu;
+        for (int t = threadIdx.x; t < 2048; t += 256) tile[t] = (j0 + t < jhi) ? keys[j0 + t] : 0xffffffffu;
         __syncthreads();
-        int lim = min(2048, n - j0);
+        const int lim = min(2048, jhi - j0);
         for (int t = 0; t < lim; ++t) {
-            uint32_t kj = tile[t];
-            rank += (kj < ki) || (kj == ki && (j0 + t) < i);
+            const uint32_t kj = tile[t];
+            r += (kj < ki) || (kj == ki && (j0 + t) < i);
         }
     }
-    if (i < n) xout[rank] = xin[i];
+    if (i < n && r) atomicAdd(rank + i, r);
+}
+__global__ void k_scatter_by_rank(const int* __restrict__ rank, const int* __restrict__ xin, int* __restrict__ xout, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) xout[rank[i]] = xin[i];
 }
 
-int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tmp, uint32_t* sort_keys, uint32_t* subkey,
+int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tmp, uint32_t* sort_keys, int* rank, uint32_t* subkey,
                        cudaStream_t st) {
     int blocks = (n + 255) / 256;
     int* cur = (rounds % 2 == 0) ? out : tmp;   // after `rounds` swaps the result lands in `out`
@@ -164,7 +173,10 @@ int launch_permutation(uint32_t* key_inout, int n, int rounds, int* out, int* tm
         if (launch_split_key(key_inout, subkey, st)) return -1;
         k_random_bits<<<blocks, 256, 0, st>>>(subkey, n, sort_keys);
         CB_LAUNCH_CHECK();
-        k_rank_scatter<<<blocks, 256, 0, st>>>(sort_keys, cur, nxt, n);
+        CB_CUDA(cudaMemsetAsync(rank, 0, (size_t)n * sizeof(int), st));
+        k_rank_count<<<dim3(blocks, RANK_SEGS), 256, 0, st>>>(sort_keys, n, rank);
+        CB_LAUNCH_CHECK();
+        k_scatter_by_rank<<<blocks, 256, 0, st>>>(rank, cur, nxt, n);
         CB_LAUNCH_CHECK();
         int* t = cur; cur = nxt; nxt = t;
     }

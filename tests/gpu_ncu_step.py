@@ -20,7 +20,16 @@ if what == "learner":
     ctx = ag.Context("cuda:0", max_batch=mb, train=True)
     ctx.set_params(params)
     grads = torch.zeros(ctx.num_params, device="cuda"); stats = torch.zeros(5, device="cuda")
+    # the once-per-update kernels too: bootstrap value is skipped, GAE scan + advantage normalisation at [T=128, Bl=120] and one
+    # permutation of the 15,360 sample indices (cleanba_ppo.py:532-560, 592-595, 599-606)
+    T, Bl = 128, 120
+    rew = torch.randn(T, Bl, device="cuda"); val = torch.randn(T, Bl, device="cuda")
+    dones = torch.rand(T, Bl, device="cuda") < 0.01
+    nv = torch.randn(Bl, device="cuda"); nd = torch.zeros(Bl, dtype=torch.bool, device="cuda")
+    lkey = ag.key_tensor(np.array([3, 4], np.uint32), ctx.device)
     def step():
+        ctx.gae(rew, val, dones, nv, nd, 0.99, 0.95, 4)
+        ctx.permutation(ctx.split_key(lkey), T * Bl)
         ctx.ppo_grad(obs, idx, mb, actions, oldlp, adv, ret, 0.1, 0.01, 0.5, grads, stats)
         ctx.optimizer_step(grads, 1.0, 2.5e-4, 0.5)
 else:

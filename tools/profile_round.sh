@@ -1,6 +1,6 @@
 # Round profile (GPU box, one GPU): bench line, ncu launch list of the bench command, ncu metric sweep of one learner minibatch
 # and one actor step.  Outputs land in gpurun_out/ (copy the summaries to profiles/).
-TAG=${1:-r01_v8}
+TAG=${1:-r01_v9}
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -c 600 gpurun_out/${TAG}_bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2>> gpurun_out/${TAG}_bench.err
