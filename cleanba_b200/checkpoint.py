@@ -121,6 +121,8 @@ def _plain_args(args: Any) -> Dict[str, Any]:
     d = dict(vars(args)) if not isinstance(args, Mapping) else dict(args)
     out = {}
     for k, v in d.items():
+        if k.startswith("_"):      # runtime handles (e.g. the tracer) are not hyper-parameters
+            continue
         if isinstance(v, (np.ndarray, np.generic, str, int, float, bool, type(None), list, tuple, dict)):
             out[k] = v
         else:

@@ -62,7 +62,7 @@ def main(args: Args):
         try:
             from torch.utils.tensorboard import SummaryWriter
             writer = SummaryWriter(f"runs/{run_name}")
-            writer.add_text("hyperparameters", "|param|value|\n|-|-|\n%s" % ("\n".join([f"|{k}|{v}|" for k, v in vars(args).items()])))
+            writer.add_text("hyperparameters", "|param|value|\n|-|-|\n%s" % ("\n".join([f"|{k}|{v}|" for k, v in vars(args).items() if not k.startswith("_")])))
         except Exception:
             writer = None
     backend = CudaBackend()

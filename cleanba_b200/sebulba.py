@@ -21,6 +21,8 @@ from typing import Callable, List, Optional
 
 import numpy as np
 
+from .trace import NullTracer, Tracer
+
 
 @dataclass
 class Args:
@@ -68,6 +70,7 @@ class Args:
     synthetic_env: bool = True    # envpool is not installable here; frames come from cleanba_b200.envs.SyntheticAtari
     eval_max_steps: int = 27000   # step cap of one evaluation episode after --save-model (envpool's max_episode_steps)
     resume_from: str = ""         # train-state sidecar written by --save-model (parameters + optimizer state + keys)
+    trace_path: str = ""          # write a Chrome / Perfetto timeline of the actor and learner threads here (cleanba_b200.trace)
 
     # runtime arguments to be filled in (cleanba_ppo.py:106-118)
     local_batch_size: int = 0
@@ -148,6 +151,9 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
              device_thread_id: int, actor_device_id: int, stop: threading.Event, key):
     """Actor thread (cleanba_ppo.py:226-406 / cleanba_impala.py:268-447)."""
     impala = args.algo == "impala"
+    tracer = getattr(args, "_tracer", None) or NullTracer()
+    tid = 1 + device_thread_id
+    tracer.thread_name(tid, f"actor thread {device_thread_id} (device {actor_device_id})")
     envs = make_env(args.env_id, args.seed + args.local_rank + device_thread_id, args.local_num_envs)()
     len_actor_device_ids = len(args.actor_device_ids)
     N = args.local_num_envs
@@ -180,18 +186,22 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
         t0 = time.time()
         if not args.concurrency or update != 2:
             params = None
-            while not stop.is_set():
-                try:
-                    params = params_queue.get(timeout=0.5)
-                    break
-                except queue.Empty:
-                    continue
+            with tracer.span("params_queue.get", tid, update=update):
+                while not stop.is_set():
+                    try:
+                        params = params_queue.get(timeout=0.5)
+                        break
+                    except queue.Empty:
+                        continue
+                if params is not None:
+                    actor.set_params(params)      # includes the block_until_ready of the reference
             if params is None:                    # shutdown (sentinel from train() or stop flag)
                 break
-            actor.set_params(params)              # includes the block_until_ready of the reference
             actor_policy_version += 1
         params_queue_get_time.append(time.time() - t0)
         rollout_time_start = time.time()
+        rollout_span = tracer.span("rollout", tid, update=update, policy_version=actor_policy_version)
+        rollout_span.__enter__()
         T = args.num_steps
         rows = T + 1 if impala else T
         storage = actor.new_storage(rows)
@@ -231,18 +241,21 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
             episode_lengths[env_id] *= (1 - info["terminated"]) * (1 - truncated)
             storage_time += time.time() - t1
         rollout_time.append(time.time() - rollout_time_start)
+        rollout_span.__exit__(None, None, None)
         avg_episodic_return = np.mean(returned_episode_returns)
         # prepare_data + device_put_sharded (cleanba_ppo.py:357-363): split the env axis over the learner devices
-        sharded = actor.shard_to_learners(storage, None if impala else next_obs, None if impala else next_done,
-                                          len(args.learner_device_ids))
+        with tracer.span("shard_to_learners", tid, update=update):
+            sharded = actor.shard_to_learners(storage, None if impala else next_obs, None if impala else next_done,
+                                              len(args.learner_device_ids))
         payload = (global_step, actor_policy_version, update, sharded, np.mean(params_queue_get_time), device_thread_id)
         t1 = time.time()
-        while not stop.is_set():
-            try:
-                rollout_queue.put(payload, timeout=0.5)
-                break
-            except queue.Full:
-                continue
+        with tracer.span("rollout_queue.put", tid, update=update):
+            while not stop.is_set():
+                try:
+                    rollout_queue.put(payload, timeout=0.5)
+                    break
+                except queue.Full:
+                    continue
         rollout_queue_put_time.append(time.time() - t1)
         if impala:
             carry = storage.take_carry()
@@ -270,6 +283,9 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
     path; `allreduce(flat_grad)` sums gradients over the learner devices of other processes (None = single process).
     Returns a SimpleNamespace with the learner handle, the last stats and the measured SPS."""
     writer = writer or _NullWriter()
+    tracer = Tracer(f"{args.exp_name} ({args.algo})") if getattr(args, "trace_path", "") else NullTracer()
+    args._tracer = tracer
+    tracer.thread_name(0, "learner (main thread)")
     key = backend.first_key(args.seed)            # key, network_key, actor_key, critic_key = split(PRNGKey(seed), 4)
     learner = backend.make_learner(args, key, allreduce)
     if getattr(args, "resume_from", ""):
@@ -310,18 +326,21 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
             learner_policy_version += 1
             t0 = time.time()
             payloads = []
-            for d_idx, d_id in enumerate(args.actor_device_ids):
-                for thread_id in range(args.num_actor_threads):
-                    (global_step, actor_policy_version, update, sharded, avg_params_queue_get_time,
-                     device_thread_id) = get_payload(rollout_queues[d_idx * args.num_actor_threads + thread_id])
-                    payloads.append(sharded)
+            with tracer.span("rollout_queue.get", 0, learner_policy_version=learner_policy_version):
+                for d_idx, d_id in enumerate(args.actor_device_ids):
+                    for thread_id in range(args.num_actor_threads):
+                        (global_step, actor_policy_version, update, sharded, avg_params_queue_get_time,
+                         device_thread_id) = get_payload(rollout_queues[d_idx * args.num_actor_threads + thread_id])
+                        payloads.append(sharded)
             rollout_queue_get_time.append(time.time() - t0)
             training_time_start = time.time()
-            stats = learner.update(payloads)      # multi_device_update (cleanba_ppo.py:714-720)
-            for d_idx, d_id in enumerate(args.actor_device_ids):
-                device_params = learner.params_for_actor(d_id)
-                for thread_id in range(args.num_actor_threads):
-                    params_queues[d_idx * args.num_actor_threads + thread_id].put(device_params)
+            with tracer.span("multi_device_update", 0, learner_policy_version=learner_policy_version, actor_policy_version=actor_policy_version):
+                stats = learner.update(payloads)      # multi_device_update (cleanba_ppo.py:714-720)
+            with tracer.span("params_queue.put", 0, learner_policy_version=learner_policy_version):
+                for d_idx, d_id in enumerate(args.actor_device_ids):
+                    device_params = learner.params_for_actor(d_id)
+                    for thread_id in range(args.num_actor_threads):
+                        params_queues[d_idx * args.num_actor_threads + thread_id].put(device_params)
             result.stats, result.updates = stats, learner_policy_version
             result.versions.append((actor_policy_version, update, learner_policy_version))
             if on_update is not None:
@@ -353,8 +372,10 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
                 pass
         for th in threads:        # actor threads leave on `stop`; never let daemon threads die inside CUDA calls at exit
             th.join(timeout=10)
+        args.__dict__.pop("_tracer", None)
         if errors:
             raise RuntimeError("an actor thread failed") from errors[0]
     result.sps = global_step / max(time.time() - start, 1e-9)
     result.global_step = global_step
+    result.trace_path = tracer.save(args.trace_path) if getattr(args, "trace_path", "") else None
     return result

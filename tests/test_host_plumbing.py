@@ -158,3 +158,32 @@ def test_world_size_2_gloo_replicas_stay_identical(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK 62500 16 8" in r.stdout, r.stdout[-500:]
     assert np.isfinite(np.load(out)).all()
+
+
+def test_trace_export_records_actor_and_learner_phases(tmp_path):
+    """--trace-path: the Sebulba loop writes a Chrome / Perfetto timeline with one track per actor thread and one for the
+    learner; spans carry the policy versions, so the one-version lag of the concurrent mode is visible (cleanba_ppo.py:287-304)."""
+    import json
+    from cleanba_b200.envs import SyntheticAtari
+    from cleanba_b200.sebulba import Args, derive_sizes, train
+    from oracle.backend import OracleBackend
+    path = str(tmp_path / "trace.json")
+    a = Args(local_num_envs=4, num_actor_threads=2, num_steps=2, num_minibatches=2, update_epochs=1, total_timesteps=10 ** 6,
+             log_frequency=1000, max_updates=3, trace_path=path)
+    a.concurrency = True
+    a = derive_sizes(a, 1)
+    res = train(a, OracleBackend(), lambda env_id, seed, n: (lambda: SyntheticAtari(n, seed=seed, pool_batches=2)))
+    assert res.trace_path == path and not hasattr(a, "_tracer")
+    doc = json.load(open(path))
+    evs = [e for e in doc["traceEvents"] if e["ph"] == "X"]
+    names = {(e["tid"], e["name"]) for e in evs}
+    for tid in (1, 2):
+        assert (tid, "rollout") in names and (tid, "rollout_queue.put") in names and (tid, "params_queue.get") in names
+    assert (0, "multi_device_update") in names and (0, "rollout_queue.get") in names and (0, "params_queue.put") in names
+    upd = [e for e in evs if e["name"] == "multi_device_update"]
+    assert len(upd) == 3 and all(e["dur"] > 0 for e in upd)
+    # concurrency: the second rollout of an actor thread starts before the first learner update has finished
+    r2 = min(e["ts"] for e in evs if e["name"] == "rollout" and e["args"]["update"] == 2)
+    assert r2 < upd[0]["ts"] + upd[0]["dur"]
+    tracks = {e["tid"]: e["args"]["name"] for e in doc["traceEvents"] if e["ph"] == "M" and e["name"] == "thread_name"}
+    assert tracks[0].startswith("learner") and tracks[1].startswith("actor thread 0")
