@@ -113,9 +113,9 @@ def cpu_sample(T_s, threads=N_THREADS, n_envs=N_ENVS, seed=1):
 cpu_sample.state = None
 
 
-def run_cpu_arm(steps, warmup, budget_s=150.0):
+def run_cpu_arm(steps, warmup, budget_s=150.0, threads=None):
     import torch
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     t0 = time.time(); cpu_sample(1); t1 = time.time() - t0          # calibration (also warms torch)
     per_T = max(t1, 1e-3)
@@ -302,6 +302,9 @@ def run_our_arm(args):
         r = run_cpu_arm(1, 0, budget_s=25.0)
         cpu = dict(value=r["value"], unit="env-steps/s", cores=r["cores"], kind="port", sample=r["sample"] +
                    " (CPU restatement of the reference path in PyTorch-CPU fp32, not JAX: jax/flax/optax are not installable here)")
+        # the reference pins XLA:CPU to ONE thread (XLA_FLAGS intra_op_parallelism_threads=1, cleanba_ppo.py:28): same sample, 1 thread
+        r1 = run_cpu_arm(1, 0, budget_s=4.0, threads=1)
+        cpu["single_thread"] = dict(value=r1["value"], cores=1, sample=r1["sample"])
     out = {
         "metric": "env-steps/sec (Breakout-v5 84x84x4, synthetic frames)", "value": value, "unit": "env-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
