@@ -293,7 +293,8 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
         const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
         const ConvGeom go = make_geom(n, kStageHout[s], kStageHout[s]);
         const int base = s * 5;
-        if (s == 0 && c->fuse0) {
+        const bool fused = (s == 0) ? c->fuse0 : c->fuse12;       // sequence conv + max-pool in ONE tcgen05 kernel
+        if (fused && s == 0) {
             // frame conv + max-pool in one kernel: the 84x84x16 conv output never reaches HBM (conv_umma.cu)
             ConvArgs a = conv_args(c, 0, gi, S.x, false);
             a.ep.bias = c->params + c->conv[0].off_b;
@@ -301,7 +302,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             ProfScope ps(c, "conv0_pool_fwd@84", 2.0 * n * 84 * 84 * 9.0 * 4 * 16,
                          planes_bytes(gi, 1, false) + stream_bytes(go, 2) + planes_bytes(go, 2, true) + (S.amax ? (double)go.NP * 16 : 0.0), st);
             if (launch_conv0_pool_umma(a, S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
-        } else if (s > 0 && c->fuse12) {
+        } else if (fused) {
             // sequence conv + max-pool in one kernel (conv_umma.cu: k_conv_pool_umma)
             ConvArgs a = conv_args(c, base, gi, S.x, false);
             a.ep.bias = c->params + c->conv[base].off_b;
@@ -320,7 +321,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             if (run_conv(c, a, st)) return -1;
         }
         // x = nn.max_pool(x, (3,3), strides=(2,2), padding="SAME")              (cleanba_ppo.py:168)
-        if (!(s == 0 && c->fuse0) && !(s > 0 && c->fuse12)) {
+        if (!fused) {
             ProfScope ps(c, "pool_fwd@" + std::to_string(kStageHin[s]), 0,
                          stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(go, kStageC[s] / 8, true), st);
             if (launch_pool_fwd(S.y.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.p.s, S.p.pl, S.amax, st)) return -1;

@@ -149,7 +149,9 @@ int cb_profile_report(cb_ctx* ctx, char* json, int cap);
 
 /* ---- diagnostics (tests only) ------------------------------------------------------------------------------ */
 /* Copy an internal tensor of the last forward/backward to the host as dense NHWC fp32 [n,H,W,C] (or [n,256] for
- * "hidden").  Names: "s{0,1,2}.{x,y,p,a0,b0,a1,out}", gradients "g{0,1,2}.{A,B,C,Bin}", "hidden", "dpre".
+ * "hidden").  Names: "s{0,1,2}.{x,y,p,a0,b0,a1,out}", gradients "g{0,1,2}.{A,B,C,Bin}", "hidden", "dpre".  The pre-pool
+ * conv outputs "s*.y" (and "g0.Bin") exist on the CB_CONV_SIMT cross-check backend only: the tcgen05 backend fuses every
+ * sequence conv with its max-pool and never materialises them.
  * Returns the number of floats written (<= cap) or -1. Synchronises the device. */
 long long cb_debug_tensor(cb_ctx* ctx, const char* name, float* host_out, long long cap);
 
