@@ -351,6 +351,8 @@ class RolloutActor:
         """Enqueue the actor step of storage row t on self.stream: frames (host or device) -> row t, then one graph replay."""
         if t != self._next_row:
             raise CleanbaError(f"rollout rows must be stepped in order: expected row {self._next_row}, got {t}")
+        if t >= self._obs.shape[0]:
+            raise CleanbaError(f"row {t} is outside the rollout storage ({self._obs.shape[0]} rows): call begin() for the next rollout")
         with torch.cuda.stream(self.stream):
             self._obs[t].copy_(obs_src, non_blocking=True)
             self.graph.replay()

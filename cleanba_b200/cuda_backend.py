@@ -34,6 +34,7 @@ class _Storage:
         self.host = {k: np.zeros((rows, N), dt) for k, dt in (("dones", bool), ("rewards", np.float32), ("firststeps", bool),
                                                               ("truncations", bool), ("terminations", np.int32), ("env_ids", np.int32))}
         self.impala = actor.impala
+        self.stream = actor.stream
 
     def put_host(self, t, **fields):
         for k, v in fields.items():
@@ -46,7 +47,8 @@ class _Storage:
         return c
 
     def put_carry(self, c):
-        self.obs[0].copy_(c["obs"]); self.actions[0].copy_(c["actions"]); self.logitss[0].copy_(c["logitss"])
+        with torch.cuda.stream(self.stream):      # same stream as the actor steps that fill the other rows
+            self.obs[0].copy_(c["obs"]); self.actions[0].copy_(c["actions"]); self.logitss[0].copy_(c["logitss"])
         for k, v in c["host"].items():
             self.host[k][0] = v
 
