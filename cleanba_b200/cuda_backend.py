@@ -155,7 +155,7 @@ class CudaLearner:
         for lr in self.learners:
             lr.ctx.set_params(params)
         self.keys = [ag.key_tensor(key, d) for d in self.devices]    # learner_keys = device_put_replicated(key) (cleanba_ppo.py:470)
-        self.barrier = threading.Barrier(L) if L > 1 else None
+        self.barrier = threading.Barrier(L, timeout=300) if L > 1 else None   # a failed replica thread breaks the barrier instead of hanging the others
         self.hyper = h
         # Several learner GPUs in ONE process and no cross-process exchange: the gradient mean is fused into the optimizer
         # kernels, which read every replica's flat gradient buffer from peer memory over NVLink (cb_optimizer_step_peers);
@@ -241,9 +241,20 @@ class CudaLearner:
         if L == 1:
             self._update_one(0, payloads, out)
         else:
-            ths = [threading.Thread(target=self._update_one, args=(l, payloads, out)) for l in range(L)]
+            errs = []
+
+            def run(l):
+                try:
+                    self._update_one(l, payloads, out)
+                except BaseException as e:      # surface replica failures in the caller instead of losing them with the thread
+                    errs.append(e)
+                    self.barrier.abort()
+            ths = [threading.Thread(target=run, args=(l,)) for l in range(L)]
             [t.start() for t in ths]
             [t.join() for t in ths]
+            if errs:
+                first = next((e for e in errs if not isinstance(e, threading.BrokenBarrierError)), errs[0])
+                raise RuntimeError("a learner replica failed") from first
         if L == 1:
             return out[0]
         # loss scalars are pmean'ed over the learner devices (cleanba_ppo.py:649-653; cleanba_impala.py:635-638); the
