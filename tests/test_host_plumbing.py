@@ -187,3 +187,26 @@ def test_trace_export_records_actor_and_learner_phases(tmp_path):
     assert r2 < upd[0]["ts"] + upd[0]["dur"]
     tracks = {e["tid"]: e["args"]["name"] for e in doc["traceEvents"] if e["ph"] == "M" and e["name"] == "thread_name"}
     assert tracks[0].startswith("learner") and tracks[1].startswith("actor thread 0")
+
+
+def test_header_is_plain_c_and_a_c_program_can_drive_the_abi(tmp_path):
+    """include/cleanba_b200.h compiles as C99 and examples/abi_smoke.c (dlopen, no Python, no torch types) reaches the library:
+    without a GPU cb_create fails with a message from cb_last_error() (exit status 2); on a B200 it runs one actor step (0)."""
+    import shutil
+    import subprocess
+    import torch
+    from cleanba_b200 import build as b
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    so = b.build()
+    exe = str(tmp_path / "abi_smoke")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "abi_smoke.c"),
+                        "-o", exe, "-ldl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, so], capture_output=True, text=True, timeout=300)
+    assert "parameters: 1094115 floats" in r.stdout
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "actions:" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 2 and "cb_create failed" in r.stdout and "cuda" in r.stdout.lower(), r.stdout + r.stderr
