@@ -19,4 +19,9 @@ PARITY PINNING STATUS
   pinned upstream versions and are anchored by closed-form identities and autograd checks
   (tests/test_oracle_*.py).  The golden vectors in tests/golden/ are produced BY THIS ORACLE
   (tests/golden/make_golden.py) and pin it against regressions, not against JAX.
+* tests/test_oracle_crosscheck.py compares each restated third-party semantic with an INDEPENDENT implementation or
+  derivation (torch.optim.RMSprop / Adam, the IMPALA paper's closed-form V-trace, explicit GAE sums, an explicit conv
+  loop, torch.distributions.Categorical, a chi-square test of the Gumbel-max sampler).
+* `oracle.carriers` restates the tensor-core operand carriers (bf16 x 3, bf16 x 2, fp16 x 2) bit for bit;
+  tests/test_oracle_carriers.py states the accuracy each one guarantees.
 """
