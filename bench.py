@@ -29,9 +29,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_ENVS, N_THREADS, T_STEPS, N_MB, N_EPOCHS = 60, 2, 128, 4, 4
-FLOP_PER_ENV_STEP = 1.4108e9            # actor fwd + 4 epochs x 3 x fwd
-WORKLOAD = "cleanba_ppo a0-l0-d1 Breakout-v5-shaped synthetic frames, local_num_envs=60, 2 actor threads, num_steps=128"
+N_ENVS, N_THREADS, N_MB, N_EPOCHS = 60, 2, 4, 4
+FWD_FLOP = 108.46e6                     # trunk + heads forward per frame
+# --workload: BASELINE.json configs[1] (PPO, the configuration the metric is quoted on; default) and configs[2] (IMPALA, V-trace)
+WORKLOADS = {
+    "ppo": dict(script="cleanba_ppo", T=128, ref_T=8, flop_per_env_step=FWD_FLOP * (1 + 3 * N_EPOCHS)),
+    "impala": dict(script="cleanba_impala", T=20, ref_T=20, flop_per_env_step=FWD_FLOP * (1 + 3 * 21 / 20)),
+}
+
+
+def workload_name(wl, T):
+    return (f"{WORKLOADS[wl]['script']} a0-l0-d1 Breakout-v5-shaped synthetic frames, local_num_envs={N_ENVS}, {N_THREADS} actor threads, "
+            f"num_steps={T}")
+
+
+DTYPE = "bf16x3 (fp32-compensated bf16 tensor-core products, fp32 accumulate/state)"
 
 
 def load_peaks():
@@ -82,19 +94,35 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_sample(T_s, threads=N_THREADS, n_envs=N_ENVS, seed=1):
+def cpu_sample(T_s, workload="ppo", threads=N_THREADS, n_envs=N_ENVS, seed=1):
     """One bounded sample of the workload on the CPU oracle: a T_s-step rollout of `threads` x `n_envs` envs through
-    get_action_and_value, then a full single_device_update on it.  Returns env steps processed."""
-    from oracle import network as net, ppo as oppo, threefry as tf
+    get_action_and_value / get_action, then a full single_device_update on it.  Returns env steps processed."""
+    from oracle import impala as oimpala, network as net, ppo as oppo, threefry as tf
     st = cpu_sample.state
     if st is None:
         rng = np.random.Generator(np.random.PCG64(seed))
         st = cpu_sample.state = dict(params=net.init_params(seed), rng=rng, key=tf.split(tf.PRNGKey(seed), 4)[0])
     rng, params = st["rng"], st["params"]
     Bl = threads * n_envs
+    keys = [st["key"].copy() for _ in range(threads)]
+    if workload == "impala":
+        T1 = T_s + 1                                  # row 0 is the row carried over from the previous rollout
+        obs = rng.integers(0, 256, (T1, Bl, 4, 84, 84), dtype=np.uint8)
+        act = np.zeros((T1, Bl), np.int32); lg = np.zeros((T1, Bl, 18), np.float32)
+        for t in range(1, T1):
+            for th in range(threads):
+                c = slice(th * n_envs, (th + 1) * n_envs)
+                _, a, l, keys[th] = oimpala.get_action(params, obs[t, c], keys[th])
+                act[t, c], lg[t, c] = a, l
+        shard = oimpala.Shard(obs=obs, dones=rng.random((T1, Bl)) < 0.002, actions=act, logitss=lg,
+                              rewards=rng.choice(np.array([-1, 0, 1], np.float32), size=(T1, Bl), p=[.05, .9, .05]),
+                              firststeps=np.zeros((T1, Bl), bool))
+        learner = oimpala.ImpalaLearner(params, oimpala.ImpalaConfig(num_minibatches=N_MB))
+        learner.update([shard])
+        st["params"] = learner.params
+        return T_s * Bl
     obs = np.zeros((T_s, Bl, 4, 84, 84), np.uint8)
     act = np.zeros((T_s, Bl), np.int32); lp = np.zeros((T_s, Bl), np.float32); val = np.zeros((T_s, Bl), np.float32)
-    keys = [st["key"].copy() for _ in range(threads)]
     for t in range(T_s):
         for th in range(threads):
             c = slice(th * n_envs, (th + 1) * n_envs)
@@ -113,60 +141,69 @@ def cpu_sample(T_s, threads=N_THREADS, n_envs=N_ENVS, seed=1):
 cpu_sample.state = None
 
 
-def run_cpu_arm(steps, warmup, budget_s=150.0, threads=None):
+def run_cpu_arm(steps, warmup, workload="ppo", threads=None, T_s=None):
+    """The CPU arm.  The sample is FIXED (no calibration, identical in every run): a `ref_T`-step rollout (PPO: 8 of the
+    workload's 128 steps; IMPALA: the full 20) x 2 actor threads x 60 envs + one complete learner update on it per bench step."""
     import torch
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
-    t0 = time.time(); cpu_sample(1); t1 = time.time() - t0          # calibration (also warms torch)
-    per_T = max(t1, 1e-3)
-    T_s = int(max(1, min(T_STEPS, budget_s / max(1, steps + warmup) / per_T)))
+    T_s = T_s or WORKLOADS[workload]["ref_T"]
     for _ in range(warmup):
-        cpu_sample(T_s)
+        cpu_sample(T_s, workload)
     t0 = time.time(); n = 0
     for _ in range(steps):
-        n += cpu_sample(T_s)
+        n += cpu_sample(T_s, workload)
     dt = time.time() - t0
-    return dict(value=n / dt, cores=cores, T_s=T_s, ms_per_step=1e3 * dt / steps,
-                sample=f"{T_s}-step rollout x {N_THREADS} actor threads x {N_ENVS} envs + one PPO update "
-                       f"({N_EPOCHS} epochs x {N_MB} minibatches) = {T_s * N_THREADS * N_ENVS} env steps per bench step")
+    upd = f"one PPO update ({N_EPOCHS} epochs x {N_MB} minibatches)" if workload == "ppo" else f"one IMPALA update ({N_MB} minibatches of [{T_s + 1},{N_ENVS * N_THREADS // N_MB}])"
+    return dict(value=n / dt, cores=cores, T_s=T_s, ms_per_step=1e3 * dt / max(steps, 1),
+                sample=f"{T_s}-step rollout x {N_THREADS} actor threads x {N_ENVS} envs + {upd} "
+                       f"= {T_s * N_THREADS * N_ENVS} env steps per bench step (fixed sample, no calibration)")
 
 
 # ------------------------------------------------------------------------------------------------ our arm
 class Cycle:
-    """One actor (2 logical threads) + one learner replica on one GPU; PPO a0-l0 topology."""
+    """One actor device (2 logical actor threads, one CUDA-graphed step each) + one learner replica on one GPU: the a0-l0
+    topology of BASELINE configs[1] (PPO) / configs[2] (IMPALA).  One step() = rollout of T steps + single_device_update +
+    parameter publish."""
 
-    def __init__(self, device, world, allreduce, seed=1):
+    def __init__(self, device, world, allreduce, workload="ppo", seed=1):
         import torch
         from cleanba_b200 import agent as ag
-        from cleanba_b200.learner import PPOHyper, PPOLearner
+        from cleanba_b200.learner import ImpalaHyper, ImpalaLearner, PPOHyper, PPOLearner
         from cleanba_b200.params import init_params
-        self.torch, self.ag = torch, ag
-        self.dev = torch.device(device)
-        Bl = N_ENVS * N_THREADS
-        self.Bl = Bl
-        self.learner = PPOLearner(self.dev, PPOHyper(), T=T_STEPS, Bl=Bl, world_learners=world, allreduce=allreduce)
-        params = init_params(seed)
-        self.learner.ctx.set_params(params)
         from cleanba_b200.prng import first_key
+        self.torch, self.ag = torch, ag
+        self.dev = d = torch.device(device)
+        self.impala = workload == "impala"
+        self.T = T = WORKLOADS[workload]["T"]
+        self.rows = rows = T + 1 if self.impala else T          # IMPALA: row 0 is carried over from the previous rollout
+        Bl = self.Bl = N_ENVS * N_THREADS
+        if self.impala:
+            self.learner = ImpalaLearner(d, ImpalaHyper(), T1=rows, Bl=Bl, world_learners=world, allreduce=allreduce)
+        else:
+            self.learner = PPOLearner(d, PPOHyper(), T=T, Bl=Bl, world_learners=world, allreduce=allreduce)
+        self.learner.ctx.set_params(init_params(seed))
         # one actor context + CUDA-graphed step per actor thread, each on its own stream (the reference runs
         # num_actor_threads = 2 Python threads per actor device, cleanba_ppo.py:670-686)
         self.actors, self.graphed = [], []
         for th in range(N_THREADS):
-            a = ag.Context(self.dev, max_batch=N_ENVS, train=False)
+            a = ag.Context(d, max_batch=N_ENVS, train=False, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO)
             self.learner.ctx.publish_to(a)
             torch.cuda.synchronize()
-            key = ag.key_tensor(first_key(seed), self.dev)
+            key = ag.key_tensor(first_key(seed), d)
             self.actors.append(a)
-            self.graphed.append(ag.RolloutActor(a, N_ENVS, key))        # writes straight into the rollout storage rows
-        self.actor = self.actors[0]
-        d = self.dev
-        self.obs = torch.zeros(T_STEPS, Bl, 4, 84, 84, dtype=torch.uint8, device=d)
-        self.actions = torch.zeros(T_STEPS, Bl, dtype=torch.int32, device=d)
-        self.logprobs = torch.zeros(T_STEPS, Bl, dtype=torch.float32, device=d)
-        self.values = torch.zeros(T_STEPS, Bl, dtype=torch.float32, device=d)
+            self.graphed.append(ag.RolloutActor(a, N_ENVS, key, want_logits=self.impala))   # writes straight into the storage rows
+        self.obs = torch.zeros(rows, Bl, 4, 84, 84, dtype=torch.uint8, device=d)
+        self.actions = torch.zeros(rows, Bl, dtype=torch.int32, device=d)
+        if self.impala:
+            self.logitss = torch.zeros(rows, Bl, 18, dtype=torch.float32, device=d)
+            self.first = torch.zeros(rows, Bl, dtype=torch.bool, device=d)
+        else:
+            self.logprobs = torch.zeros(rows, Bl, dtype=torch.float32, device=d)
+            self.values = torch.zeros(rows, Bl, dtype=torch.float32, device=d)
         g = torch.Generator(device="cpu"); g.manual_seed(seed)
-        self.rew_pool = (torch.multinomial(torch.tensor([.05, .9, .05]), 8 * T_STEPS * Bl, True, generator=g).float() - 1).reshape(8, T_STEPS, Bl).to(d)
-        self.done_pool = (torch.rand(8, T_STEPS, Bl, generator=g) < 1 / 500).to(d)
+        self.rew_pool = (torch.multinomial(torch.tensor([.05, .9, .05]), 8 * rows * Bl, True, generator=g).float() - 1).reshape(8, rows, Bl).to(d)
+        self.done_pool = (torch.rand(8, rows, Bl, generator=g) < 1 / 500).to(d)
         self.next_done = torch.zeros(Bl, dtype=torch.bool, device=d)
         self.lkey = ag.key_tensor(first_key(seed), d)
         self.act_host = [torch.empty(N_ENVS, dtype=torch.int32).pin_memory() for _ in range(N_THREADS)]
@@ -183,14 +220,21 @@ class Cycle:
         torch = self.torch
         pool = self.host_pool if e2e else self.dev_pool
         main = torch.cuda.current_stream(self.dev)
+        row0 = 1 if self.impala else 0
         for th, g in enumerate(self.graphed):
             g.stream.wait_stream(main)                 # new parameters (publish) are visible before the rollout starts
             c = slice(th * N_ENVS, (th + 1) * N_ENVS)
-            g.begin(self.obs[:, c], self.actions[:, c], self.logprobs[:, c], self.values[:, c])   # this thread's storage columns
-        for t in range(T_STEPS):
+            if self.impala:                            # this thread's storage columns; the carried row first (cleanba_impala.py:327-329)
+                with torch.cuda.stream(g.stream):
+                    for buf in (self.obs, self.actions, self.logitss):
+                        buf[0, c].copy_(buf[self.rows - 1, c], non_blocking=True)
+                g.begin(self.obs[:, c], self.actions[:, c], logits=self.logitss[:, c], first_row=1)
+            else:
+                g.begin(self.obs[:, c], self.actions[:, c], self.logprobs[:, c], self.values[:, c])
+        for t in range(row0, self.rows):
             for th, g in enumerate(self.graphed):
                 c = slice(th * N_ENVS, (th + 1) * N_ENVS)
-                if e2e and t > 0:
+                if e2e and t > row0:
                     g.stream.synchronize()             # np.array(action) of this thread's previous step: the per-step sync of
                                                        # cleanba_ppo.py:317 (each actor thread waits for ITS OWN step only)
                 g.step(pool[self.cursor % 256], t)     # frames -> storage row t (H2D from pinned memory when e2e) + graph replay:
@@ -205,12 +249,15 @@ class Cycle:
         for g in self.graphed:
             main.wait_stream(g.stream)
         k = (self.cursor // 256) % 8
-        stats = self.learner.update(self.obs, self.done_pool[k], self.actions, self.logprobs, self.values, self.rew_pool[k],
-                                    self.obs[0], self.next_done, self.lkey)
+        if self.impala:
+            stats = self.learner.update(self.obs, self.done_pool[k], self.actions, self.logitss, self.rew_pool[k], self.first)
+        else:
+            stats = self.learner.update(self.obs, self.done_pool[k], self.actions, self.logprobs, self.values, self.rew_pool[k],
+                                        self.obs[0], self.next_done, self.lkey)
         for a in self.actors:
             self.learner.ctx.publish_to(a)                             # params_queue.put(device_params) (cleanba_ppo.py:721-725)
         if e2e:
-            _ = stats.cpu(); self.d2h += 20
+            _ = stats.cpu(); self.d2h += 4 * stats.numel()
         return stats
 
 
@@ -227,7 +274,9 @@ def run_our_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
     from cleanba_b200 import lib
-    cyc = Cycle(f"cuda:{local_rank}", world, allreduce)
+    wl = args.workload
+    T_STEPS = WORKLOADS[wl]["T"]
+    cyc = Cycle(f"cuda:{local_rank}", world, allreduce, workload=wl)
     if world > 1:   # identical initial parameters on every learner (the reference relies on equal seeds, cleanba_ppo.py:468)
         pv = cyc.learner.ctx.params_view(); dist.broadcast(pv, 0); cyc.learner.ctx.refresh_weights()
         for a in cyc.actors:
@@ -278,41 +327,49 @@ def run_our_arm(args):
     peaks = load_peaks()
     agg = {}
     for r in rep:
-        a = agg.setdefault(r["name"], dict(ms=0.0, calls=0, records=0, flops=0.0, bytes=0.0))
-        a["ms"] += r["ms"]; a["calls"] += r["calls"]; a["records"] += r["records"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]
+        a = agg.setdefault(r["name"], dict(ms=0.0, calls=0, records=0, flops=0.0, bytes=0.0, abytes=0.0))
+        for k in ("ms", "calls", "records", "flops", "bytes", "abytes"):
+            a[k] += r[k]
     top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     name, a = top
-    ai = a["flops"] / max(a["bytes"], 1.0)
+    # `achieved` uses the SURVEY 8(d) ALGORITHMIC bytes (every operand tensor of the operator once, unpadded fp32), not the
+    # bytes of this library's own storage formats; those (`moved_bytes_per_launch`) and the ncu DRAM traffic are reported beside it.
+    ai = a["flops"] / max(a["abytes"], 1.0)
     balance = peaks["tf"] * 1e12 / (peaks["hbm"] * 1e9)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(name)
+    nrec = max(a["records"], 1)
     if a["flops"] > 0 and ai >= balance:
         roof = dict(bound="tensor", achieved=a["flops"] / (a["ms"] * 1e-3) / 1e12, peak=peaks["tf"], unit="TFLOP/s")
     else:
-        roof = dict(bound="hbm", achieved=a["bytes"] / (a["ms"] * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
+        roof = dict(bound="hbm", achieved=a["abytes"] / (a["ms"] * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=name, kernel_share_of_step=a["ms"] / ms_prof,
-                algorithmic_bytes_per_launch=a["bytes"] / max(a["records"], 1), profiled_ms_per_step=ms_prof / args.steps,
+                algorithmic_bytes_per_launch=a["abytes"] / nrec, algorithmic_bytes_basis="fp32, each operand tensor once, unpadded (SURVEY 8d)",
+                moved_bytes_per_launch=a["bytes"] / nrec, moved_gbs=a["bytes"] / (a["ms"] * 1e-3) / 1e9,
+                traffic_over_algorithmic=(traffic / (a["abytes"] / nrec)) if traffic else None,
+                ms_per_launch=a["ms"] / nrec, profiled_ms_per_step=ms_prof / args.steps,
                 peak_source=peaks["src"], launches=a["calls"],
                 algorithmic_tflops=a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["flops"] else 0.0,
+                tensor_frac=(a["flops"] / (a["ms"] * 1e-3) / 1e12 / peaks["tf"]) if a["flops"] else 0.0,
                 kernels={k: round(v["ms"] / args.steps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]})
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = run_cpu_arm(1, 0, budget_s=25.0)
+        r = run_cpu_arm(4 if wl == "ppo" else 2, 0, workload=wl)
         cpu = dict(value=r["value"], unit="env-steps/s", cores=r["cores"], kind="port", sample=r["sample"] +
                    " (CPU restatement of the reference path in PyTorch-CPU fp32, not JAX: jax/flax/optax are not installable here)")
         # the reference pins XLA:CPU to ONE thread (XLA_FLAGS intra_op_parallelism_threads=1, cleanba_ppo.py:28): same sample, 1 thread
-        r1 = run_cpu_arm(1, 0, budget_s=4.0, threads=1)
+        r1 = run_cpu_arm(1, 0, workload=wl, threads=1, T_s=2)
         cpu["single_thread"] = dict(value=r1["value"], cores=1, sample=r1["sample"])
     out = {
         "metric": "env-steps/sec (Breakout-v5 84x84x4, synthetic frames)", "value": value, "unit": "env-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32-compensated bf16 tensor-core products, fp32 accumulate/state)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": WORKLOAD, "env_steps_per_bench_step": env_steps, "topology": f"a0-l0-d{world}",
+        "config": {"workload": workload_name(wl, T_STEPS), "env_steps_per_bench_step": env_steps, "topology": f"a0-l0-d{world}",
                    "cache": "inputs larger than L2: 433 MB device frame pool cycled, 433 MB rollout storage per update",
-                   "tensor_roof_frac_end_to_end": value * FLOP_PER_ENV_STEP / (peaks["tf"] * 1e12 * world)},
+                   "tensor_roof_frac_end_to_end": value * WORKLOADS[wl]["flop_per_env_step"] / (peaks["tf"] * 1e12 * world)},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": cyc.h2d // args.steps,
                 "d2h_bytes_per_step": cyc.d2h // args.steps, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
@@ -343,16 +400,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ppo", choices=sorted(WORKLOADS), help="ppo = BASELINE configs[1] (default), impala = configs[2]")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        r = run_cpu_arm(args.steps, args.warmup)
+        r = run_cpu_arm(args.steps, args.warmup, workload=args.workload)
         _emit({
             "impl": "reference", "metric": "env-steps/sec (Breakout-v5 84x84x4, synthetic frames)", "value": r["value"],
             "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD},
+            # the ACTUAL rollout length of the timed sample (PPO: 8 of the workload's 128 steps, fixed; IMPALA: the full 20)
+            "config": {"workload": workload_name(args.workload, r["T_s"]), "env_steps_per_bench_step": r["T_s"] * N_THREADS * N_ENVS,
+                       "sample_of": workload_name(args.workload, WORKLOADS[args.workload]["T"])},
             "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"] + " (PyTorch-CPU restatement of the reference path; the JAX reference cannot be installed here)"},
             "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})

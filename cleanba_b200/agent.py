@@ -230,6 +230,29 @@ class Context:
                                                _ptr(norm_out), _stream(self.device)))
 
 
+    def reduce_peers(self, grads_list, out: torch.Tensor):
+        """out = fixed-order sum of the replicas' flat gradient buffers (peer memory); see cb_reduce_peers."""
+        arr = (ctypes.c_void_p * len(grads_list))(*[g.data_ptr() for g in grads_list])
+        check(self.lib.cb_reduce_peers(self.h, arr, len(grads_list), _ptr(out), _stream(self.device)))
+
+
+def copy_columns(dst: torch.Tensor, src: torch.Tensor, stream: torch.cuda.Stream):
+    """dst[r] <- src[r] for every row r of a [rows, ...] pair where each ROW is contiguous but the row pitch may differ (src is
+    a column block `storage[:, c]` of a wider rollout storage): one cudaMemcpy2DAsync on `stream`, any device pair."""
+    if dst.shape != src.shape or dst.dtype != src.dtype:
+        raise CleanbaError(f"copy_columns: shape / dtype mismatch {tuple(dst.shape)} {dst.dtype} vs {tuple(src.shape)} {src.dtype}")
+    rows = src.shape[0]
+    if rows == 0 or src.numel() == 0:
+        return
+    if not (src[0].is_contiguous() and dst[0].is_contiguous()):
+        raise CleanbaError("copy_columns: rows must be contiguous")
+    es = src.element_size()
+    width = src[0].numel() * es
+    sp = src.stride(0) * es if rows > 1 else width
+    dp = dst.stride(0) * es if rows > 1 else width
+    check(_lib.load().cb_memcpy_2d(_ptr(dst), dp, _ptr(src), sp, width, rows, ctypes.c_void_p(stream.cuda_stream)))
+
+
 import threading as _threading
 
 _CAPTURE_LOCK = _threading.Lock()

@@ -2,6 +2,7 @@
 --actor-device-ids / --learner-device-ids / --distributed / --local-num-envs / --num-actor-threads / --concurrency ...),
 with the hot path on libcleanba_b200.  One process drives the listed local GPUs; `--distributed` joins the processes
 started by torchrun (or SLURM, as jax.distributed does in the reference) into one data-parallel learner group."""
+import sys
 import time
 import uuid
 
@@ -63,8 +64,13 @@ def main(args: Args):
             from torch.utils.tensorboard import SummaryWriter
             writer = SummaryWriter(f"runs/{run_name}")
             writer.add_text("hyperparameters", "|param|value|\n|-|-|\n%s" % ("\n".join([f"|{k}|{v}|" for k, v in vars(args).items() if not k.startswith("_")])))
-        except Exception:
+        except Exception as e:  # noqa: BLE001
+            print(f"warning: TensorBoard logging disabled ({type(e).__name__}: {e})", file=sys.stderr)
             writer = None
+        for flag in ("track", "capture_video", "upload_model"):
+            if getattr(args, flag):
+                print(f"warning: --{flag.replace('_', '-')} is accepted for CLI compatibility but not implemented "
+                      "(wandb / video capture / HF upload are outside the hot path, DESIGN.md section 7)", file=sys.stderr)
     backend = CudaBackend()
     t0 = time.time()
     res = train(args, backend, make_env, writer=writer, allreduce=allreduce)

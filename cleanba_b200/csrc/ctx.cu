@@ -111,8 +111,10 @@ struct Stage {
 
 using namespace cb;
 
-struct ProfAgg { long long launches = 0, records = 0; double ms = 0, flops = 0, bytes = 0; };
-struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; int launches; };
+// bytes  = what the kernel moves in THIS library's storage formats (carrier planes, padded grids);
+// abytes = SURVEY 8(d) algorithmic bytes: every operand tensor of the operator read / written once as unpadded fp32.
+struct ProfAgg { long long launches = 0, records = 0; double ms = 0, flops = 0, bytes = 0, abytes = 0; };
+struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes, abytes; int launches; };
 
 struct cb_ctx {
     cb_config cfg;
@@ -195,8 +197,10 @@ static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool planes, bool lo, bool
 // launching stream, with the kernel's algorithmic flops / bytes, for bench.py's roofline.
 struct ProfScope {
     cb_ctx* c; cudaStream_t st; ProfRec r; bool on; long long l0;
-    ProfScope(cb_ctx* c_, const std::string& name, double flops, double bytes, cudaStream_t st_) : c(c_), st(st_), on(c_->prof_on) {
+    ProfScope(cb_ctx* c_, const std::string& name, double flops, double bytes, cudaStream_t st_, double abytes = -1.0)
+        : c(c_), st(st_), on(c_->prof_on) {
         if (!on) return;
+        r.abytes = abytes >= 0 ? abytes : bytes;
         auto get = [&]() { cudaEvent_t e; if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(&e); return e; };
         r.name = name; r.flops = flops; r.bytes = bytes; r.a = get(); r.b = get();
         l0 = g_launches.load();
@@ -209,6 +213,7 @@ struct ProfScope {
         c->prof_recs.push_back(r);
     }
 };
+static double f32_once(const ConvGeom& g, int channels) { return 4.0 * g.n * g.H * g.W * channels; }   // unpadded fp32 tensor
 static double planes_bytes(const ConvGeom& g, int chunks, bool lo) { return (double)g.NP * chunks * 8 * (lo ? 6 : 2); }
 static double planes_bytes(const ConvGeom& g, int chunks, const Planes& p) { return (double)g.NP * chunks * 8 * 2 * (p.lo ? 3 : (p.mid ? 2 : 1)); }
 static double stream_bytes(const ConvGeom& g, int chunks) { return (double)g.NP * chunks * 8 * 4; }
@@ -259,7 +264,8 @@ static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
     if (a.ep.out.hi) bytes += planes_bytes(a.g, a.cout / 8, a.ep.out);
     if (a.ep.res) bytes += stream_bytes(a.g, a.cout / 8);
     if (a.ep.mask_hi) bytes += planes_bytes(a.g, a.cout / 8, false);
-    ProfScope ps(c, name, flops, bytes, st);
+    const double abytes = f32_once(a.g, a.cin_real) + f32_once(a.g, a.cout) * (1 + (a.ep.res ? 1 : 0) + (a.ep.mask_hi ? 1 : 0));
+    ProfScope ps(c, name, flops, bytes, st, abytes);
     if (c->cfg.conv_backend == CB_CONV_SIMT) return launch_conv_simt(a, st);
     return launch_conv_umma(a, c->num_sms, st);
 }
@@ -273,7 +279,7 @@ static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, cons
     char name[96];
     snprintf(name, sizeof(name), "conv_wgrad<cin%d,cout%d>@%dx%d", L.cin, L.cout, g.H, g.W);
     ProfScope ps(c, name, 2.0 * g.n * g.H * g.W * 9.0 * L.cin * L.cout,
-                 planes_bytes(g, w.cin_chunks, x.pl) + planes_bytes(g, L.cout / 8, gy.pl), st);
+                 planes_bytes(g, w.cin_chunks, x.pl) + planes_bytes(g, L.cout / 8, gy.pl), st, f32_once(g, L.cin) + f32_once(g, L.cout));
     if (c->cfg.conv_backend == CB_CONV_SIMT) return launch_wgrad_simt(w, c->wg_partial, 296, st);
     return launch_wgrad_umma(w, c->wg_partial, c->num_sms, st);
 }
@@ -300,7 +306,8 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             a.ep.bias = c->params + c->conv[0].off_b;
             a.ep.acc_scale = 1.0f / 255.0f;                       // x / 255.0 (cleanba_ppo.py:181) folded into the epilogue
             ProfScope ps(c, "conv0_pool_fwd@84", 2.0 * n * 84 * 84 * 9.0 * 4 * 16,
-                         planes_bytes(gi, 1, false) + stream_bytes(go, 2) + planes_bytes(go, 2, true) + (S.amax ? (double)go.NP * 16 : 0.0), st);
+                         planes_bytes(gi, 1, false) + stream_bytes(go, 2) + planes_bytes(go, 2, true) + (S.amax ? (double)go.NP * 16 : 0.0), st,
+                         (double)n * 28224.0 + f32_once(go, 16));      // uint8 frames in, pooled fp32 out
             if (launch_conv0_pool_umma(a, S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
         } else if (fused) {
             // sequence conv + max-pool in one kernel (conv_umma.cu: k_conv_pool_umma)
@@ -310,7 +317,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             snprintf(name, sizeof(name), "conv_pool_fwd<cin%d,cout%d>@%d", a.cin_real, a.cout, gi.H);
             ProfScope ps(c, name, 2.0 * n * gi.H * gi.W * 9.0 * a.cin_real * a.cout,
                          planes_bytes(gi, a.cin_chunks, a.in) + stream_bytes(go, a.cout / 8) + planes_bytes(go, a.cout / 8, true) +
-                             (S.amax ? (double)go.NP * a.cout : 0.0), st);
+                             (S.amax ? (double)go.NP * a.cout : 0.0), st, f32_once(gi, a.cin_real) + f32_once(go, a.cout));
             if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
         } else {
             // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
@@ -728,6 +735,15 @@ int cb_permutation(cb_ctx* c, const uint32_t* key, int n, int32_t* out, cb_strea
     CB_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     if (n > c->perm_cap) {
+        // growth replaces the scratch buffers: the old ones are released once the stream has drained
+        if (c->perm_cap) {
+            CB_CUDA(cudaStreamSynchronize(st));
+            for (void* old : {(void*)c->perm_tmp, (void*)c->sort_keys, (void*)c->perm_rank}) {
+                for (size_t i = 0; i < c->allocs.size(); ++i)
+                    if (c->allocs[i] == old) { c->allocs.erase(c->allocs.begin() + i); break; }
+                cudaFree(old);
+            }
+        }
         void* p;
         if (dev_alloc(c, &p, (size_t)n * sizeof(int))) return -1;
         c->perm_tmp = (int*)p;
@@ -810,6 +826,27 @@ int cb_optimizer_step_peers(cb_ctx* c, const float* const* grads, int num_grads,
     return optimizer_step(c, grads, num_grads, grad_scale, lr, max_norm, norm_out, stream);
 }
 
+int cb_reduce_peers(cb_ctx* c, const float* const* grads, int num_grads, float* out, cb_stream stream) {
+    CB_CHECK(c && grads && out, "null argument");
+    CB_CHECK(num_grads >= 1 && num_grads <= OPT_MAX_PEERS, "num_grads must be in [1,%d]", OPT_MAX_PEERS);
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    OptArgs o;
+    memset(&o, 0, sizeof(o));
+    o.n = c->nparam; o.ng = num_grads;
+    for (int k = 0; k < num_grads; ++k) { CB_CHECK(grads[k], "null gradient buffer %d", k); o.gp[k] = grads[k]; }
+    CB_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+    ProfScope ps(c, "grad_reduce_peers", 0, (double)c->nparam * 4 * (num_grads + 1), (cudaStream_t)stream);
+    return launch_reduce_peers(o, out, (cudaStream_t)stream);
+}
+
+int cb_memcpy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, cb_stream stream) {
+    CB_CHECK(dst && src, "null argument");
+    CB_CHECK(width_bytes <= dst_pitch && width_bytes <= src_pitch, "row width %zu exceeds a pitch (%zu, %zu)", width_bytes, dst_pitch, src_pitch);
+    if (!width_bytes || !rows) return 0;
+    CB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
 int cb_set_sm_budget(cb_ctx* c, int num_sms) {
     CB_CHECK(c, "null argument");
     CB_CUDA(cudaSetDevice(c->cfg.device));
@@ -881,14 +918,15 @@ int cb_profile_report(cb_ctx* c, char* buf, int cap) {
         float ms = 0.f;
         CB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
         ProfAgg& a = agg[r.name];
-        a.launches += r.launches; a.records += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+        a.launches += r.launches; a.records += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.abytes += r.abytes;
     }
     std::string out = "[";
     bool first = true;
     for (auto& kv : agg) {
         char line[384];
-        snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"calls\": %lld, \"records\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
-                 first ? "" : ", ", kv.first.c_str(), kv.second.launches, kv.second.records, kv.second.ms, kv.second.flops, kv.second.bytes);
+        snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"calls\": %lld, \"records\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e, \"abytes\": %.6e}",
+                 first ? "" : ", ", kv.first.c_str(), kv.second.launches, kv.second.records, kv.second.ms, kv.second.flops, kv.second.bytes,
+                 kv.second.abytes);
         out += line;
         first = false;
     }

@@ -146,6 +146,7 @@ struct OptArgs {
 constexpr int OPT_MAX_PEERS = 8;
 constexpr int OPT_BLOCKS = 296;
 int launch_optimizer(const OptArgs& a, cudaStream_t st);
+int launch_reduce_peers(const OptArgs& a, float* out, cudaStream_t st);   // needs n, gp, ng only
 
 // pack.cu
 struct PackLayer {

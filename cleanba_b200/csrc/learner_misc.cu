@@ -250,6 +250,32 @@ __global__ void __launch_bounds__(256) k_opt_apply(OptArgs a) {
     }
 }
 
+// out[i] = gp[0][i] + gp[1][i] + ... (fixed order, peer memory): the in-process stage of a two-level gradient exchange
+__global__ void __launch_bounds__(256) k_reduce_peers(OptArgs a, float* __restrict__ out) {
+    for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < a.n; i += (long long)gridDim.x * 256 * 4) {
+        if (i + 4 <= a.n) {
+            float4 s = *reinterpret_cast<const float4*>(a.gp[0] + i);
+#pragma unroll 1
+            for (int k = 1; k < a.ng; ++k) {
+                const float4 t = *reinterpret_cast<const float4*>(a.gp[k] + i);
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
+            *reinterpret_cast<float4*>(out + i) = s;
+        } else {
+            for (long long j = i; j < a.n; ++j) {
+                float s = a.gp[0][j];
+                for (int k = 1; k < a.ng; ++k) s += a.gp[k][j];
+                out[j] = s;
+            }
+        }
+    }
+}
+int launch_reduce_peers(const OptArgs& a, float* out, cudaStream_t st) {
+    k_reduce_peers<<<OPT_BLOCKS, 256, 0, st>>>(a, out);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_optimizer(const OptArgs& a, cudaStream_t st) {
     k_sumsq<<<OPT_BLOCKS, 256, 0, st>>>(a);
     CB_LAUNCH_CHECK();

@@ -38,11 +38,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.  The bound is
+// wall-clock (%globaltimer, 20 s), not a spin count: a legitimate long stall (time slicing between green contexts or
+// processes, a profiler replaying the kernel) must not kill the context.  The timer is only read every 2^16 failed polls.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if ((++spins & 0xffffu) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
     }
 }
 

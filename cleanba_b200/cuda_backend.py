@@ -60,6 +60,8 @@ class CudaActor:
         self.impala = args.algo == "impala"
         self.ctx = ag.Context(self.dev, max_batch=N, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO)
         self.stream = torch.cuda.Stream(self.dev)
+        self.copy_stream = torch.cuda.Stream(self.dev)      # actor -> learner payload copies (overlap the next rollout)
+        self._peers, self._payload_log, self._land = set(), [], {}
         self.key = ag.key_tensor(key, self.dev)
         self.act_host = torch.empty(N, dtype=torch.int32).pin_memory()
         self.staging = torch.empty(N, 4, 84, 84, dtype=torch.uint8).pin_memory()
@@ -101,31 +103,68 @@ class CudaActor:
             return self.act_host.numpy().copy(), time.time() - t0
 
     def shard_to_learners(self, storage, next_obs, next_done, L, learner_devices=None):
+        """prepare_data + jax.device_put_sharded (cleanba_ppo.py:276-278, 357-363): learner l receives env columns
+        [l*N/L, (l+1)*N/L) of every field.  The column blocks go straight from the [T, N, ...] storage to the learner GPUs as
+        strided block copies (cb_memcpy_2d: no contiguous temporary) on this actor's COPY stream, which only waits for the
+        rollout's last step: the actor stream is free at once, so the next rollout overlaps the hand-off.  An event recorded
+        on the copy stream travels with the payload."""
         N = self.N
+        cs = self.copy_stream
         shards = []
-        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
-            for l in range(L):
-                c = slice(l * N // L, (l + 1) * N // L)
-                ld = self.learner_devices[l]
-                sh = {"obs": storage.obs[:, c].to(ld, non_blocking=True) if (L > 1 or ld != self.dev) else storage.obs,
-                      "actions": storage.actions[:, c].to(ld, non_blocking=True)}
-                if self.impala:
-                    sh["logitss"] = storage.logitss[:, c].to(ld, non_blocking=True)
-                else:
-                    sh["logprobs"] = storage.logprobs[:, c].to(ld, non_blocking=True)
-                    sh["values"] = storage.values[:, c].to(ld, non_blocking=True)
-                for k in ("dones", "rewards", "firststeps"):
-                    sh[k] = torch.from_numpy(np.ascontiguousarray(storage.host[k][:, c])).to(ld, non_blocking=True)
-                if next_obs is not None:
-                    no = next_obs if torch.is_tensor(next_obs) else torch.from_numpy(next_obs)
-                    sh["next_obs"] = no[c].to(ld, non_blocking=True)
-                    sh["next_done"] = torch.from_numpy(np.ascontiguousarray(next_done[c])).to(ld, non_blocking=True)
-                shards.append(sh)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
+        with torch.cuda.device(self.dev):
+            done = torch.cuda.Event()
+            done.record(self.stream)                      # the rollout (every step's writes into the storage rows)
+            cs.wait_event(done)
+            t0 = torch.cuda.Event(enable_timing=True); t0.record(cs)
+        nbytes = 0
+        for l in range(L):
+            c = slice(l * N // L, (l + 1) * N // L)
+            ld = self.learner_devices[l]
+            local = L == 1 and ld == self.dev              # the only learner is this GPU: hand the storage itself over
+            if ld != self.dev and ld not in self._peers:
+                self.ctx.lib.cb_enable_peer_access(self.ctx.h, int(ld.index))    # DMA over NVLink instead of staging through the host
+                self._peers.add(ld)                        # (a refusal only makes the copy slower: not an error)
+            sh = {}
+            fields = ["obs", "actions"] + (["logitss"] if self.impala else ["logprobs", "values"])
+            for k in fields:
+                src = getattr(storage, k)
+                if local:
+                    sh[k] = src
+                    continue
+                view = src[:, c]
+                # allocate from a pool no compute stream frees into (this actor's copy stream / a landing stream on the learner
+                # GPU): a recycled block is then only handed out once every stream that used it (record_stream) has drained,
+                # so the unordered copy below can never overwrite memory another stream is still reading
+                ls = cs if ld == self.dev else self._land.setdefault(ld, torch.cuda.Stream(ld))
+                with torch.cuda.stream(ls):
+                    dst = torch.empty(view.shape, dtype=view.dtype, device=ld)
+                ag.copy_columns(dst, view, cs)
+                src.record_stream(cs)                      # the storage block may not be recycled before the copy has run
+                nbytes += dst.numel() * dst.element_size()
+                sh[k] = dst
+            for k in ("dones", "rewards", "firststeps"):
+                sh[k] = torch.from_numpy(np.ascontiguousarray(storage.host[k][:, c])).to(ld, non_blocking=True)
+            if next_obs is not None:
+                no = next_obs if torch.is_tensor(next_obs) else torch.from_numpy(next_obs)
+                sh["next_obs"] = no[c].to(ld, non_blocking=True)
+                sh["next_done"] = torch.from_numpy(np.ascontiguousarray(next_done[c])).to(ld, non_blocking=True)
+            shards.append(sh)
+        with torch.cuda.device(self.dev):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(cs)
         for sh in shards:
             sh["event"] = ev
+        if nbytes:
+            self._payload_log.append((t0, ev, nbytes))
         return shards
+
+    def payload_bandwidth(self):
+        """[(GB/s, bytes)] of the finished payload hand-offs (device-timed on the copy stream)."""
+        out = []
+        for t0, t1, nb in self._payload_log:
+            if t1.query():
+                out.append((nb / (t0.elapsed_time(t1) * 1e-3) / 1e9, nb))
+        return out
 
 
 class CudaLearner:
@@ -160,14 +199,19 @@ class CudaLearner:
         # Several learner GPUs in ONE process and no cross-process exchange: the gradient mean is fused into the optimizer
         # kernels, which read every replica's flat gradient buffer from peer memory over NVLink (cb_optimizer_step_peers);
         # the replicas' streams are ordered with events, the host threads only rendezvous (no device synchronisation).
-        self.peer_fused = L > 1 and allreduce is None and os.environ.get("CLEANBA_PEER_FUSED", "1") != "0"
+        # With `--distributed` on top (allreduce given), the exchange has two levels and still no device synchronisation:
+        # replica 0 sums its process' buffers from peer memory (cb_reduce_peers), joins ONE NCCL allreduce on that sum, and
+        # every replica applies the optimizer step on replica 0's reduced buffer (peer loads again).
+        self.peer_fused = L > 1 and os.environ.get("CLEANBA_PEER_FUSED", "1") != "0"
         if self.peer_fused:
             for a in self.learners:
                 for b in self.learners:
                     a.ctx.enable_peer_access(b.ctx)
-            self.ev_done, self.ev_read = [None] * L, [None] * L
+            self.ev_done, self.ev_read, self.ev_sum = [None] * L, [None] * L, None
+            if allreduce is not None:
+                self.gsum = torch.zeros_like(self.learners[0].grads)
             for l, lr in enumerate(self.learners):
-                lr.fused_step = self._make_fused(l)
+                lr.fused_step = self._make_fused(l) if allreduce is None else self._make_fused_cross(l)
 
     def _make_hook(self, l):
         """Gradient sum over all learner devices: local devices rendezvous on device 0, device 0 joins the cross-process
@@ -216,6 +260,38 @@ class CudaLearner:
                     st.wait_event(self.ev_read[k])          # the next backward may overwrite this replica's buffer
         return fused
 
+    def _make_fused_cross(self, l):
+        """pmean over ALL global learner devices (cleanba_ppo.py:628 under jax.distributed): in-process sum over peer memory
+        -> one NCCL allreduce issued by replica 0 -> optimizer step of every replica on the reduced buffer."""
+        L = len(self.devices)
+
+        def fused(lr, grad_scale, lrate, max_norm):
+            st = torch.cuda.current_stream(self.devices[l])
+            ev = torch.cuda.Event()
+            ev.record(st)                                   # this replica's backward is complete
+            self.ev_done[l] = ev
+            self.barrier.wait()                             # host rendezvous only: every replica's event exists
+            if l == 0:
+                for k in range(1, L):
+                    st.wait_event(self.ev_done[k])
+                lr.ctx.reduce_peers([x.grads for x in self.learners], self.gsum)
+                self.cross(self.gsum)                       # ONE NCCL allreduce per minibatch on the flat gradient buffer
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self.ev_sum = ev
+            self.barrier.wait()
+            if l != 0:
+                st.wait_event(self.ev_sum)
+            lr.ctx.optimizer_step_peers([self.gsum], grad_scale, lrate, max_norm)
+            ev = torch.cuda.Event()
+            ev.record(st)                                   # this replica has read the reduced buffer
+            self.ev_read[l] = ev
+            self.barrier.wait()
+            if l == 0:
+                for k in range(1, L):
+                    st.wait_event(self.ev_read[k])          # the next reduction may overwrite gsum
+        return fused
+
     def _update_one(self, l, payloads, out):
         lr, d = self.learners[l], self.devices[l]
         with torch.cuda.device(d):
@@ -226,12 +302,13 @@ class CudaLearner:
                 for v in s.values():      # payload memory was allocated on the actor's stream: tell the caching allocator
                     if torch.is_tensor(v) and v.is_cuda:   # that this stream uses it too, so it is not recycled early
                         v.record_stream(st)
-            cat = (lambda k: shards[0][k]) if len(shards) == 1 else (lambda k: torch.cat([s[k] for s in shards], dim=1).contiguous())
+            # a same-device shard is a strided column view of the actor's storage (`.to(ld)` is a no-op there): make it dense
+            cat = (lambda k: shards[0][k].contiguous()) if len(shards) == 1 else (lambda k: torch.cat([s[k] for s in shards], dim=1).contiguous())
             if self.impala:
                 out[l] = lr.update(cat("obs"), cat("dones"), cat("actions"), cat("logitss"), cat("rewards"), cat("firststeps"))
             else:
-                nobs = shards[0]["next_obs"] if len(shards) == 1 else torch.cat([s["next_obs"] for s in shards]).contiguous()
-                ndone = shards[0]["next_done"] if len(shards) == 1 else torch.cat([s["next_done"] for s in shards]).contiguous()
+                nobs = shards[0]["next_obs"].contiguous() if len(shards) == 1 else torch.cat([s["next_obs"] for s in shards]).contiguous()
+                ndone = shards[0]["next_done"].contiguous() if len(shards) == 1 else torch.cat([s["next_done"] for s in shards]).contiguous()
                 out[l] = lr.update(cat("obs"), cat("dones"), cat("actions"), cat("logprobs"), cat("values"), cat("rewards"),
                                    nobs, ndone, self.keys[l])
 

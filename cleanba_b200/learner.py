@@ -22,7 +22,8 @@ def linear_schedule(count: int, base_lr: float, steps_per_update: int, num_updat
     if not anneal:
         return float(np.float32(base_lr))
     frac = 1.0 - (count // steps_per_update) / num_updates
-    return float(np.float32(base_lr * frac))
+    # the reference never steps past num_updates; a resumed run that does must not turn the step into gradient ascent
+    return float(np.float32(base_lr * max(frac, 0.0)))
 
 
 @dataclass
@@ -60,6 +61,8 @@ class PPOLearner:
         self.stats = torch.zeros(hyper.update_epochs * hyper.num_minibatches, 5, dtype=torch.float32, device=d)
         self.opt_count = 0
         self.fused_step = None      # f(learner, grad_scale, lr, max_norm): gradient exchange fused into the optimizer step
+        self.step_hook = None       # f(phase, k, learner), phase in "pre" | "grad" | "post" of minibatch step k: lets the parity
+                                    # tests pin every step of an update to the oracle's recorded state (no chained drift)
 
     def update(self, obs, dones, actions, logprobs, values, rewards, next_obs, next_done, key) -> torch.Tensor:
         """single_device_update (cleanba_ppo.py:579-654).  Fields are [T,Bl,...] device tensors (the hstack of the actor
@@ -78,8 +81,12 @@ class PPOLearner:
             perm = c.permutation(sub, T * Bl)                         # jax.random.permutation(subkey, .) (:606)
             for j in range(h.num_minibatches):
                 idx = perm[j * self.mb:(j + 1) * self.mb]
+                if self.step_hook is not None:
+                    self.step_hook("pre", k, self)
                 c.ppo_grad(obs_f, idx, self.mb, act_f, lp_f, adv_f, ret_f, h.clip_coef, h.ent_coef, h.vf_coef,
                            self.grads, self.stats[k])
+                if self.step_hook is not None:
+                    self.step_hook("grad", k, self)
                 lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches * h.update_epochs,
                                      h.num_updates, h.anneal_lr)
                 if self.fused_step is not None:                       # pmean + apply_gradients in one pass over peer memory
@@ -89,6 +96,8 @@ class PPOLearner:
                         self.allreduce(self.grads)                    # lax.pmean(grads) (cleanba_ppo.py:628)
                     c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
                 self.opt_count += 1
+                if self.step_hook is not None:
+                    self.step_hook("post", k, self)
                 k += 1
         return self.stats.mean(0)
 
@@ -123,6 +132,7 @@ class ImpalaLearner:
         # contiguous env-column blocks, never shuffled (cleanba_impala.py:626-633): idx[j][t*B+b] = t*Bl + j*B + b
         t = torch.arange(T1, device=d, dtype=torch.int32)[:, None] * Bl
         self.fused_step = None
+        self.step_hook = None       # see PPOLearner
         self.idx = [(t + (j * self.B + torch.arange(self.B, device=d, dtype=torch.int32))[None, :]).reshape(-1).contiguous()
                     for j in range(hyper.num_minibatches)]
         self.opt_count = 0
@@ -135,8 +145,12 @@ class ImpalaLearner:
         obs_f = obs.reshape(T1 * Bl, 4, 84, 84)
         A = c.num_actions
         for j in range(h.num_minibatches):
+            if self.step_hook is not None:
+                self.step_hook("pre", j, self)
             c.impala_grad(obs_f, self.idx[j], T1, self.B, actions.reshape(-1), logitss.reshape(-1, A), rewards.reshape(-1),
                           dones.reshape(-1), firststeps.reshape(-1), h.gamma, h.vf_coef, h.ent_coef, self.grads, self.stats[j])
+            if self.step_hook is not None:
+                self.step_hook("grad", j, self)
             lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches, h.num_updates, h.anneal_lr)
             if self.fused_step is not None:                           # pmean + apply_gradients in one pass over peer memory
                 self.fused_step(self, 1.0 / self.world_learners, lr, h.max_grad_norm)
@@ -145,4 +159,6 @@ class ImpalaLearner:
                     self.allreduce(self.grads)                        # lax.pmean(grads) (cleanba_impala.py:619)
                 c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
             self.opt_count += 1
+            if self.step_hook is not None:
+                self.step_hook("post", j, self)
         return self.stats.mean(0)

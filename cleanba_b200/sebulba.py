@@ -99,6 +99,7 @@ def derive_sizes(args: Args, world_size: int = 1, local_rank: int = 0) -> Args:
     if args.channels != [16, 32, 32] or args.hiddens != [256]:
         raise ValueError("libcleanba_b200 implements the reference's default IMPALA-ResNet (channels 16,32,32; hiddens 256)")
     if args.gradient_accumulation_steps != 1:
+        # cleanba_ppo.py:492-500 wraps the optimizer in optax.MultiSteps(every_k_schedule=k); only k = 1 (its default) is built
         raise ValueError("gradient_accumulation_steps != 1 is not supported (reference default: 1)")
     args.local_batch_size = int(args.local_num_envs * args.num_steps * args.num_actor_threads * len(args.actor_device_ids))
     args.local_minibatch_size = int(args.local_batch_size // args.num_minibatches)
@@ -157,7 +158,9 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
     envs = make_env(args.env_id, args.seed + args.local_rank + device_thread_id, args.local_num_envs)()
     len_actor_device_ids = len(args.actor_device_ids)
     N = args.local_num_envs
-    global_step = 0
+    # --resume-from: continue the update / step counters of the saved run (the learning-rate schedule and the logs depend on them)
+    first_update, global_step = getattr(args, "_resume", (0, 0))
+    start_step = global_step
     start_time = time.time()
     actor = backend.make_actor(actor_device_id, N, args, key)
     episode_returns = np.zeros((N,), dtype=np.float32)
@@ -167,7 +170,7 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
     params_queue_get_time = deque(maxlen=10)
     rollout_time = deque(maxlen=10)
     rollout_queue_put_time = deque(maxlen=10)
-    actor_policy_version = 0
+    actor_policy_version = first_update
     if impala:
         envs.async_reset()
         next_obs = next_done = None
@@ -176,7 +179,7 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
         next_done = np.zeros(N, dtype=bool)
     carry = None   # IMPALA: last transition of the previous rollout (cleanba_impala.py:416)
 
-    for update in range(1, args.num_updates + 2):
+    for update in range(first_update + 1, args.num_updates + 2):
         if stop.is_set():
             break
         update_time_start = time.time()
@@ -184,7 +187,7 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
         # NOTE: `update != 2` lets policy collection run concurrently with learning while keeping the actor's policy
         # exactly one version behind the learner's (cleanba_ppo.py:287-304)
         t0 = time.time()
-        if not args.concurrency or update != 2:
+        if not args.concurrency or update - first_update != 2:
             params = None
             with tracer.span("params_queue.get", tid, update=update):
                 while not stop.is_set():
@@ -262,7 +265,7 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
         if update % args.log_frequency == 0:
             if device_thread_id == 0:
                 print(f"global_step={global_step}, avg_episodic_return={avg_episodic_return}, rollout_time={np.mean(rollout_time)}")
-                print("SPS:", int(global_step / (time.time() - start_time)))
+                print("SPS:", int((global_step - start_step) / (time.time() - start_time)))
             writer.add_scalar("stats/rollout_time", np.mean(rollout_time), global_step)
             writer.add_scalar("charts/avg_episodic_return", avg_episodic_return, global_step)
             writer.add_scalar("charts/avg_episodic_length", np.mean(returned_episode_lengths), global_step)
@@ -273,7 +276,7 @@ def _rollout(args: Args, backend, make_env: Callable, rollout_queue: queue.Queue
             writer.add_scalar("stats/d2h_time", d2h_time, global_step)
             writer.add_scalar("stats/env_send_time", env_send_time, global_step)
             writer.add_scalar("stats/rollout_queue_put_time", np.mean(rollout_queue_put_time), global_step)
-            writer.add_scalar("charts/SPS", int(global_step / (time.time() - start_time)), global_step)
+            writer.add_scalar("charts/SPS", int((global_step - start_step) / (time.time() - start_time)), global_step)
             writer.add_scalar("charts/SPS_update", int(N * args.num_steps * len_actor_device_ids * args.num_actor_threads
                                                        * args.world_size / (time.time() - update_time_start)), global_step)
 
@@ -288,9 +291,16 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
     tracer.thread_name(0, "learner (main thread)")
     key = backend.first_key(args.seed)            # key, network_key, actor_key, critic_key = split(PRNGKey(seed), 4)
     learner = backend.make_learner(args, key, allreduce)
+    first_update = first_step = 0
     if getattr(args, "resume_from", ""):
         from .checkpoint import load_train_state
-        learner.load_train_state(load_train_state(args.resume_from))
+        st = load_train_state(args.resume_from)
+        learner.load_train_state(st)
+        first_update, first_step = int(st["learner_policy_version"]), int(st["global_step"])
+        if first_update >= args.num_updates:
+            raise ValueError(f"--resume-from: the saved run already finished {first_update} of {args.num_updates} updates "
+                             "(raise --total-timesteps to continue it)")
+    args._resume = (first_update, first_step)
     params_queues, rollout_queues, threads = [], [], []
     stop = threading.Event()
     errors: list = []
@@ -318,7 +328,8 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
             threads.append(th)
 
     rollout_queue_get_time = deque(maxlen=10)
-    learner_policy_version = 0
+    learner_policy_version = first_update
+    global_step = first_step
     start = time.time()
     result = SimpleNamespace(learner=learner, stats=None, sps=0.0, updates=0, versions=[])
     try:
@@ -361,7 +372,7 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
                 if "approx_kl" in s:
                     writer.add_scalar("losses/approx_kl", s["approx_kl"], global_step)
                 writer.add_scalar("losses/loss", s["loss"], global_step)
-            if learner_policy_version >= args.num_updates or (args.max_updates and learner_policy_version >= args.max_updates):
+            if learner_policy_version >= args.num_updates or (args.max_updates and learner_policy_version - first_update >= args.max_updates):
                 break
     finally:
         stop.set()
@@ -373,9 +384,10 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
         for th in threads:        # actor threads leave on `stop`; never let daemon threads die inside CUDA calls at exit
             th.join(timeout=10)
         args.__dict__.pop("_tracer", None)
+        args.__dict__.pop("_resume", None)
         if errors:
             raise RuntimeError("an actor thread failed") from errors[0]
-    result.sps = global_step / max(time.time() - start, 1e-9)
+    result.sps = (global_step - first_step) / max(time.time() - start, 1e-9)
     result.global_step = global_step
     result.trace_path = tracer.save(args.trace_path) if getattr(args, "trace_path", "") else None
     return result

@@ -130,6 +130,16 @@ int cb_optimizer_step(cb_ctx* ctx, const float* grads, float grad_scale, float l
  * 1..8 device pointers; peer devices must have been opened with cb_enable_peer_access. */
 int cb_optimizer_step_peers(cb_ctx* ctx, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
                             float* norm_out, cb_stream stream);
+/* out = grads[0] + ... + grads[n-1] (fixed order, read from peer memory): the in-process stage of the gradient exchange when
+ * the learner group ALSO spans processes (`--distributed` with several learner devices per process, cleanba_ppo.py:419-423,628):
+ * one replica sums its process' replicas into `out`, ONE NCCL allreduce on `out` follows, and every replica then applies
+ * cb_optimizer_step_peers on that single buffer.  Same stream-ordering rules as cb_optimizer_step_peers. */
+int cb_reduce_peers(cb_ctx* ctx, const float* const* grads, int num_grads, float* out, cb_stream stream);
+/* Strided block copy (cudaMemcpy2DAsync, cudaMemcpyDefault): `rows` rows of `width_bytes` from src (row pitch src_pitch) to
+ * dst (row pitch dst_pitch) on `stream`, between any two of host-pinned / device / peer-device memory.  The actor -> learner
+ * payload hand-off (`jax.device_put_sharded`, cleanba_ppo.py:357-363) uses it to move one learner's env-column block of the
+ * [T, N, ...] rollout storage straight to that learner's GPU on the actor's copy stream, without a contiguous temporary. */
+int cb_memcpy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, cb_stream stream);
 /* Size the persistent grids of this context for num_sms SMs instead of the whole device: for contexts whose streams live on an
  * SM partition (a CUDA green context), e.g. actor replicas on a small partition running beside the learner (the reference runs
  * actor and learner threads concurrently on one GPU in the a0-l0 topology, cleanba_ppo.py:669-686). */

@@ -153,9 +153,13 @@ class ImpalaLearner:
             if getattr(self, "cross_allreduce", None) is not None:
                 g = self.cross_allreduce(g)
             lr = optim.linear_schedule(self.opt.count, cfg.learning_rate, cfg.num_minibatches, cfg.num_updates, cfg.anneal_lr)
+            if record is not None:   # the complete pre-step state: lets a test replay THIS step alone (no chained drift)
+                pre = dict(params_before=self.params.copy(), nu_before=self.opt.nu.copy(), count_before=int(self.opt.count),
+                           raw_grad=g.copy(), cols=cols[j].copy(), shard_grads=[x.copy() for x in grads],
+                           shard_stats=[x.copy() for x in stats])
             g = optim.clip_by_global_norm(g, cfg.max_grad_norm)
             self.params = self.opt.step(self.params, g, lr)
             stats_all.append(np.mean(np.stack(stats), axis=0))
             if record is not None:
-                record.append(dict(grad=g.copy(), stats=stats_all[-1].copy(), lr=float(lr), params=self.params.copy()))
+                record.append(dict(grad=g.copy(), stats=stats_all[-1].copy(), lr=float(lr), params=self.params.copy(), **pre))
         return np.mean(np.stack(stats_all), axis=0)

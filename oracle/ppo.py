@@ -123,6 +123,27 @@ def ppo_loss_and_grad(flat_params: np.ndarray, obs_u8, actions, behavior_logprob
     return stats, fp.grad.detach().numpy().copy()
 
 
+def ppo_loss_and_grad_chunked(flat_params: np.ndarray, obs_u8, actions, behavior_logprobs, advantages, target_values,
+                              clip_coef=0.1, ent_coef=0.01, vf_coef=0.5, dtype=torch.float32, chunk=256):
+    """Same result as ppo_loss_and_grad for LARGE minibatches (config shape: 3840 frames) in bounded memory: every term of
+    ppo_loss is a mean over the minibatch, so loss = sum_c (n_c / n) * loss(chunk c); gradients are accumulated chunk by chunk."""
+    fp = torch.tensor(np.asarray(flat_params), dtype=dtype, requires_grad=True)
+    n = len(actions)
+    stats = np.zeros(5, np.float64)
+    for lo in range(0, n, chunk):
+        sl = slice(lo, min(n, lo + chunk))
+        w = (sl.stop - sl.start) / n
+        p = net.unflatten(fp)
+        lp, ent, val = logprob_entropy_value(p, torch.as_tensor(np.asarray(obs_u8[sl])), torch.as_tensor(np.asarray(actions[sl])))
+        loss, (pg, vl, el, kl) = ppo_loss_from_heads(
+            lp, ent, val, torch.as_tensor(np.asarray(behavior_logprobs[sl])).to(dtype),
+            torch.as_tensor(np.asarray(advantages[sl])).to(dtype), torch.as_tensor(np.asarray(target_values[sl])).to(dtype),
+            clip_coef, ent_coef, vf_coef)
+        (loss * w).backward()
+        stats += w * np.array([loss.item(), pg.item(), vl.item(), el.item(), kl.item()], np.float64)
+    return stats, fp.grad.detach().numpy().copy()
+
+
 # ----------------------------------------------------------------------------- learner update
 @dataclass
 class PPOConfig:
@@ -200,9 +221,13 @@ class PPOLearner:
                     g = self.cross_allreduce(g)
                 lr = optim.linear_schedule(self.opt.count, cfg.learning_rate, cfg.num_minibatches * cfg.update_epochs,
                                            cfg.num_updates, cfg.anneal_lr)
+                if record is not None:   # the complete pre-step state: lets a test replay THIS step alone (no chained drift)
+                    pre = dict(params_before=self.params.copy(), m_before=self.opt.m.copy(), v_before=self.opt.v.copy(),
+                               count_before=int(self.opt.count), raw_grad=g.copy(), idx=idx[j].copy(),
+                               shard_grads=[x.copy() for x in grads], shard_stats=[x.copy() for x in stats])
                 g = optim.clip_by_global_norm(g, cfg.max_grad_norm)
                 self.params = self.opt.step(self.params, g, lr)
                 stats_all.append(np.mean(np.stack(stats), axis=0))
                 if record is not None:
-                    record.append(dict(grad=g.copy(), stats=stats_all[-1].copy(), lr=float(lr), params=self.params.copy()))
+                    record.append(dict(grad=g.copy(), stats=stats_all[-1].copy(), lr=float(lr), params=self.params.copy(), **pre))
         return np.mean(np.stack(stats_all), axis=0), key

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: config-shape comparison against the CPU oracle (tens of seconds of host time)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -15,7 +15,7 @@ def test_reference_arm_json_line(monkeypatch, capfd):
     sys.path.insert(0, ROOT)
     import bench
     orig = bench.run_cpu_arm
-    monkeypatch.setattr(bench, "run_cpu_arm", lambda steps, warmup, budget_s=150.0, threads=None: orig(1, 0, budget_s=2.0, threads=threads))
+    monkeypatch.setattr(bench, "run_cpu_arm", lambda steps, warmup, workload="ppo", threads=None, T_s=None: orig(1, 0, workload=workload, threads=threads, T_s=1))
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"])
     monkeypatch.delenv("RANK", raising=False)
     bench.main()

@@ -322,10 +322,14 @@ def test_optimizer_step(agent, params, algo):
     ctx.close()
 
 
-# --------------------------------------------------------------------------------------------- end-to-end update
+# --------------------------------------------------------------------------------------------- whole updates, step by step
+from _pin import pin_hook as _pin_hook  # noqa: E402  (tests/_pin.py)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_ppo_update_end_to_end(agent, params, backend):
-    """A whole single_device_update (GAE -> norm -> 2 epochs x 4 shuffled minibatches -> Adam) vs the oracle."""
+def test_ppo_update_every_step_pinned_to_oracle(agent, params, backend):
+    """PPOLearner.update = single_device_update (cleanba_ppo.py:579-654): bootstrap value -> GAE -> normalisation -> 2 epochs x 4
+    shuffled minibatches -> clip + Adam, with EVERY minibatch step started from the oracle's recorded state."""
     from cleanba_b200.learner import PPOLearner, PPOHyper
     rng = np.random.default_rng(17)
     T, B = 8, 8
@@ -338,25 +342,151 @@ def test_ppo_update_end_to_end(agent, params, backend):
     key = tf.split(tf.PRNGKey(1), 4)[0]
     cfg = oppo.PPOConfig(update_epochs=2, num_updates=10)
     ol = oppo.PPOLearner(params, cfg)
-    ostats, okey = ol.update([shard], key)
+    record = []
+    ostats, okey = ol.update([shard], key, record=record)
     hyper = PPOHyper(update_epochs=2, num_updates=10)
     L = PPOLearner("cuda:0", hyper, T=T, Bl=B, conv_backend=backend)
     L.ctx.set_params(params)
+    diag = []
+    L.step_hook = _pin_hook(record, diag, "ppo")
     dev = L.ctx.device
     tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     kt = agent.key_tensor(key, dev)
     stats = L.update(tt(shard.obs), tt(shard.dones), tt(shard.actions), tt(shard.logprobs), tt(shard.values),
                      tt(shard.rewards), tt(shard.next_obs), tt(shard.next_done), kt)
-    assert agent.key_numpy(kt).tolist() == okey.tolist()
+    assert agent.key_numpy(kt).tolist() == okey.tolist()                  # same shuffles (bit-exact permutations)
+    assert len(diag) == 16                                                # 8 steps x (grad, post)
     serr = [abs(float(stats[i]) - ostats[i]) / max(abs(ostats[i]), 1e-6) for i in range(4)]
-    perr = _relerr(L.ctx.get_params().cpu().numpy(), ol.params)
-    _diag(f"ppo_update_backend{backend}", stats_relerr=serr, params_relerr=perr, kl=[float(stats[4]), float(ostats[4])])
-    # Eight chained optimizer steps on 16-sample minibatches are chaotic at the 1e-3 level: the CPU oracle run twice
-    # (multi-threaded reductions) differs from itself by 2e-4 in these scalars, and perturbing its gradients by 1e-5
-    # relative moves them by 7e-4 .. 1.5e-3 (a relu / max-pool gate flips in a later minibatch).  Single-step parity at
-    # 1e-4 / 1e-5 is asserted by the gradient and optimizer tests above; here the bar is the oracle's own sensitivity.
-    assert max(serr) < 1e-2, (stats, ostats)
-    assert perr < 1e-2
+    _diag(f"ppo_update_pinned_backend{backend}", steps=diag, mean_stats_relerr=serr)
+    assert max(serr) < 1e-4, (stats, ostats)                              # the update's averaged scalars: 1e-4 relative
+    assert abs(float(stats[4]) - ostats[4]) < 1e-5
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_impala_update_every_step_pinned_to_oracle(agent, params, backend):
+    """ImpalaLearner.update = single_device_update (cleanba_impala.py:599-639): 2 contiguous column-block minibatches -> V-trace
+    loss -> clip + RMSProp, every step started from the oracle's recorded state."""
+    from cleanba_b200.learner import ImpalaLearner, ImpalaHyper
+    rng = np.random.default_rng(19)
+    T1, Bl = 6, 8
+    sh = oimpala.Shard(obs=rng.integers(0, 256, (T1, Bl, 4, 84, 84), dtype=np.uint8), dones=rng.random((T1, Bl)) < 0.15,
+                       actions=rng.integers(0, 18, (T1, Bl)).astype(np.int32),
+                       logitss=(rng.standard_normal((T1, Bl, 18)) * 0.3).astype(np.float32),
+                       rewards=rng.choice([-1.0, 0.0, 1.0], size=(T1, Bl)).astype(np.float32), firststeps=rng.random((T1, Bl)) < 0.15)
+    ol = oimpala.ImpalaLearner(params, oimpala.ImpalaConfig(num_minibatches=2, num_updates=10))
+    record = []
+    ostats = ol.update([sh], record=record)
+    L = ImpalaLearner("cuda:0", ImpalaHyper(num_minibatches=2, num_updates=10), T1=T1, Bl=Bl, conv_backend=backend)
+    L.ctx.set_params(params)
+    diag = []
+    # RMSProp's first steps move a weight by up to lr / (sqrt(1 - decay)) = 10 lr: 1% of that step at lr = 6e-4
+    L.step_hook = _pin_hook(record, diag, "impala", param_bar=6e-5)
+    dev = L.ctx.device
+    tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    stats = L.update(tt(sh.obs), tt(sh.dones), tt(sh.actions), tt(sh.logitss), tt(sh.rewards), tt(sh.firststeps))
+    serr = [abs(float(stats[i]) - ostats[i]) / max(abs(ostats[i]), 1e-6) for i in range(4)]
+    _diag(f"impala_update_pinned_backend{backend}", steps=diag, mean_stats_relerr=serr)
+    assert len(diag) == 4 and max(serr) < 1e-4, (stats, ostats)
+
+
+# --------------------------------------------------------------------------------------------- config shapes vs the oracle
+@pytest.mark.slow
+def test_ppo_grad_config2_shape_against_oracle(agent, params):
+    """BASELINE config 2: one 3840-frame minibatch of cb_ppo_grad against the fp32 oracle (chunked autograd on the host cores,
+    about a minute): loss scalars 1e-4 relative, gradient 1e-3."""
+    from cleanba_b200 import lib
+    rng = np.random.default_rng(41)
+    mb = 3840
+    obs = _frames(rng, mb)
+    actions = rng.integers(0, 18, mb).astype(np.int32)
+    oldlp = (np.log(1 / 18) + rng.standard_normal(mb) * 0.02).astype(np.float32)
+    adv = rng.standard_normal(mb).astype(np.float32)
+    ret = rng.standard_normal(mb).astype(np.float32)
+    ctx = agent.Context("cuda:0", max_batch=mb, train=True)
+    ctx.set_params(params)
+    tt = lambda x: torch.from_numpy(x).to(ctx.device)
+    grads = torch.zeros(ctx.num_params, dtype=torch.float32, device=ctx.device)
+    stats = torch.zeros(5, dtype=torch.float32, device=ctx.device)
+    ctx.ppo_grad(tt(obs), None, mb, tt(actions), tt(oldlp), tt(adv), tt(ret), 0.1, 0.01, 0.5, grads, stats)
+    torch.cuda.synchronize()
+    ostats, og = oppo.ppo_loss_and_grad_chunked(params, obs, actions, oldlp, adv, ret, chunk=256)
+    g = grads.cpu().numpy().astype(np.float64)
+    st = stats.cpu().numpy()
+    lw = _leafwise(g, og, lib.leaves())
+    tot = float(np.linalg.norm(g - og) / np.linalg.norm(og))
+    serr = [abs(st[i] - ostats[i]) / max(abs(ostats[i]), 1e-6) for i in range(4)]
+    _diag("ppo_grad_config2_mb3840_vs_oracle", total=tot, stats_relerr=serr, worst_leaf=max(lw, key=lw.get), worst=max(lw.values()))
+    assert max(serr) < 1e-4, (st, ostats)
+    assert tot < 1e-3, f"gradient relative error {tot}; per-leaf {lw}"
+    ctx.close()
+
+
+@pytest.mark.slow
+def test_impala_grad_config3_shape_against_oracle(agent, params):
+    """BASELINE config 3: one [T+1 = 21, B = 30] minibatch (630 frames) of cb_impala_grad against the fp32 oracle."""
+    from cleanba_b200 import lib
+    rng = np.random.default_rng(43)
+    T1, Bl, B = 21, 120, 30
+    obs = rng.integers(0, 256, (T1, Bl, 4, 84, 84), dtype=np.uint8)
+    a = rng.integers(0, 18, (T1, Bl)).astype(np.int32)
+    mu = (rng.standard_normal((T1, Bl, 18)) * 0.3).astype(np.float32)
+    r = rng.choice([-1.0, 0.0, 1.0], size=(T1, Bl), p=[.05, .9, .05]).astype(np.float32)
+    d = rng.random((T1, Bl)) < 0.02
+    fs = rng.random((T1, Bl)) < 0.02
+    cols = np.arange(60, 90)                             # the third minibatch's column block
+    idx = (np.arange(T1)[:, None] * Bl + cols[None, :]).astype(np.int32).ravel()
+    ctx = agent.Context("cuda:0", max_batch=T1 * B, algo=1, train=True)
+    ctx.set_params(params)
+    tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(ctx.device)
+    grads = torch.zeros(ctx.num_params, dtype=torch.float32, device=ctx.device)
+    stats = torch.zeros(4, dtype=torch.float32, device=ctx.device)
+    ctx.impala_grad(tt(obs.reshape(-1, 4, 84, 84)), tt(idx), T1, B, tt(a.ravel()), tt(mu.reshape(-1, 18)), tt(r.ravel()),
+                    tt(d.ravel()), tt(fs.ravel()), 0.99, 0.5, 0.01, grads, stats)
+    torch.cuda.synchronize()
+    ostats, og = oimpala.impala_loss_and_grad(params, obs[:, cols], a[:, cols], mu[:, cols], r[:, cols], d[:, cols], fs[:, cols])
+    g = grads.cpu().numpy().astype(np.float64)
+    st = stats.cpu().numpy()
+    lw = _leafwise(g, og, lib.leaves())
+    tot = float(np.linalg.norm(g - og) / np.linalg.norm(og))
+    serr = [abs(st[i] - ostats[i]) / max(abs(ostats[i]), 1e-6) for i in range(4)]
+    _diag("impala_grad_config3_21x30_vs_oracle", total=tot, stats_relerr=serr, worst_leaf=max(lw, key=lw.get), worst=max(lw.values()))
+    assert max(serr) < 1e-4, (st, ostats)
+    assert tot < 1e-3, f"gradient relative error {tot}; per-leaf {lw}"
+    ctx.close()
+
+
+# --------------------------------------------------------------------------------------------- parameter publish
+def test_publish_params_equals_set_params(agent, params):
+    """cb_publish_params (learner -> actor, cleanba_ppo.py:721-725; what bench.py and the Sebulba loop use after every update):
+    an actor fed by publish_to() behaves bit-identically to one fed by set_params(get_params()) -- parameters, packed weight
+    images (same logits) and the sampled step -- also after an optimizer step changed the learner's weights."""
+    rng = np.random.default_rng(23)
+    n = 16
+    learner = agent.Context("cuda:0", max_batch=n, train=True)
+    learner.set_params(params)
+    a_pub = agent.Context("cuda:0", max_batch=n)
+    a_set = agent.Context("cuda:0", max_batch=n)
+    obs = torch.from_numpy(_frames(rng, n)).cuda()
+    for rnd in range(2):
+        if rnd == 1:      # move the learner's weights first: publish must carry the NEW master weights and re-pack them
+            g = torch.from_numpy((rng.standard_normal(learner.num_params) * 1e-2).astype(np.float32)).cuda()
+            learner.optimizer_step(g, 1.0, 2.5e-4, 0.5)
+        learner.publish_to(a_pub)
+        a_set.set_params(learner.get_params())
+        torch.cuda.synchronize()
+        assert torch.equal(a_pub.get_params(), learner.get_params())
+        k1 = agent.key_tensor(np.array([3, 4], np.uint32), a_pub.device)
+        k2 = agent.key_tensor(np.array([3, 4], np.uint32), a_set.device)
+        o1 = a_pub.actor_step(obs, k1, True, True)
+        o2 = a_set.actor_step(obs, k2, True, True)
+        for x, y in zip(o1, o2):
+            assert torch.equal(x, y), "publish_to and set_params actors differ"
+        assert agent.key_numpy(k1).tolist() == agent.key_numpy(k2).tolist()
+        if rnd == 1:
+            assert not torch.equal(o1[3], first_logits), "the published weights did not change the actor's logits"
+        first_logits = o1[3].clone()
+    for c in (learner, a_pub, a_set):
+        c.close()
 
 
 # --------------------------------------------------------------------------------------------- golden fixtures

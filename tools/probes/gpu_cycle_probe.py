@@ -1,7 +1,7 @@
 """Developer probe (GPU box): where one bench cycle (bench.Cycle.step) spends its time -- rollout (256 actor steps on two
 streams), the PPO update, the parameter publish -- as host time to enqueue vs device time to finish."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 

@@ -1,6 +1,6 @@
 """Developer diagnostic (run on the GPU box): per-image, per-layer forward error table for several batch sizes."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import network as net
 from cleanba_b200 import agent as ag

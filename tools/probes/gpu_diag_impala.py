@@ -1,6 +1,6 @@
 """Developer diagnostic: per-minibatch IMPALA update, CUDA learner vs oracle learner on identical shards."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import impala as oimpala, network as net
 from cleanba_b200.learner import ImpalaHyper, ImpalaLearner

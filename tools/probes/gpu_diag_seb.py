@@ -1,6 +1,6 @@
 """Developer diagnostic: first two IMPALA payloads, CUDA backend vs oracle backend through the same plumbing."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from cleanba_b200.cuda_backend import CudaBackend
 from cleanba_b200.sebulba import Args, derive_sizes, impala_defaults, train

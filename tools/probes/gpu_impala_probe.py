@@ -3,7 +3,7 @@
 single_device_update (4 contiguous column minibatches of [21,30] = 630 frames: forward, V-trace, backward, clip + RMSProp)
 and the parameter publish = 2,400 env steps.  Prints env-steps/s and the per-kernel table of one update."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from cleanba_b200 import agent as ag
 from cleanba_b200.learner import ImpalaHyper, ImpalaLearner

@@ -3,7 +3,7 @@ process at the config-4 shapes (local_num_envs 60, 128 steps, 2 actor threads): 
 gradient exchange fused into the optimizer kernels over peer memory (default) and with the host-synchronised sum on
 device 0 (CLEANBA_PEER_FUSED=0)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from cleanba_b200.cuda_backend import CudaBackend
 from cleanba_b200.sebulba import Args, derive_sizes

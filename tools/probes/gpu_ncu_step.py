@@ -1,7 +1,7 @@
 """Developer probe (GPU box): ONE PPO minibatch gradient + optimizer step (mb from argv) inside cudaProfilerStart/Stop, for
 `ncu --profile-from-start off`; also one actor step at n=60 when argv[2] == "actor"."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import network as net
 from cleanba_b200 import agent as ag

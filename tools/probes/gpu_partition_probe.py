@@ -1,7 +1,7 @@
 """Developer probe (GPU box): PPO config-2 cycle with the GPU spatially partitioned between actor and learner (green contexts)
 and the rollout of update k+1 pipelined beside the learner step of update k, vs the serial cycle of bench.py."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bench
 from cleanba_b200 import agent as ag

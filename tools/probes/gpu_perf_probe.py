@@ -1,6 +1,6 @@
 """Developer probe (GPU box): per-kernel timing table of one PPO minibatch gradient + optimizer step and the actor step."""
 import sys, os, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import network as net
 from cleanba_b200 import agent as ag

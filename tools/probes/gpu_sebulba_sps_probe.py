@@ -2,7 +2,7 @@
 cleanba_b200.sebulba.train on the CUDA backend, synthetic Atari env) at config 2 / config 3 shapes; prints the steady-state
 SPS (the reference's charts/SPS definition) between the 3rd and the last update."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from cleanba_b200.cuda_backend import CudaBackend
 from cleanba_b200.sebulba import Args, derive_sizes, impala_defaults, train

@@ -8,9 +8,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 6000 -c
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__t_bytes.sum,lts__t_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size
 timeout 600 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_sweep_learner_raw.csv \
-    python tests/gpu_ncu_step.py 3840 learner > /dev/null 2>&1
+    python tools/probes/gpu_ncu_step.py 3840 learner > /dev/null 2>&1
 python tools/sweep_table.py gpurun_out/${TAG}_sweep_learner_raw.csv > gpurun_out/${TAG}_ncu_sweep_learner_mb3840.txt
 timeout 300 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_sweep_actor_raw.csv \
-    python tests/gpu_ncu_step.py 60 actor > /dev/null 2>&1
+    python tools/probes/gpu_ncu_step.py 60 actor > /dev/null 2>&1
 python tools/sweep_table.py gpurun_out/${TAG}_sweep_actor_raw.csv > gpurun_out/${TAG}_ncu_sweep_actor_n60.txt
 head -12 gpurun_out/${TAG}_ncu_sweep_learner_mb3840.txt
