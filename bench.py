@@ -43,7 +43,7 @@ def workload_name(wl, T):
             f"num_steps={T}")
 
 
-DTYPE = "bf16x3 (fp32-compensated bf16 tensor-core products, fp32 accumulate/state)"
+DTYPE = "fp16x2 carrier (two fp16 tensor-core operand planes per tensor = 22 significant bits; fp32 accumulate, fp32 master weights and optimizer state)"
 
 
 def load_peaks():

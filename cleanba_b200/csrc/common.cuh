@@ -5,30 +5,38 @@
 //   padded grid Hp = H + 2, Wp = W + 2 (the SAME-padding ring of the 3x3 convs, cleanba_ppo.py:156,167),
 //   flattened over (image, y', x') into NP = n * Hp * Wp "flat pixels", and split into C/8 planes of
 //   8 channels:   plane[c / 8][flat pixel][c % 8].
-//   * "planes"  = three bf16 arrays (hi, mid, lo) with x == hi + mid + lo to 24 significant bits (an exact
-//     3-way split of the fp32 value); each plane has GUARD zero pixels before and after so a 3x3 tap window
-//     of a 128-pixel tile is one contiguous, in-bounds byte range (a 1-D bulk TMA copy) and the tile itself
-//     is an UMMA operand.
-//   * "stream"  = one fp32 array [C/8][NP][8] (residual stream / pre-pool conv output / gradients).
+//   Every tensor is stored ONCE, as the fp16x2 CARRIER: two fp16 arrays
+//       hi  = fp16(x),     mid = fp16((x - hi) * 2^11)        x == hi + mid * 2^-11 to 22 significant bits
+//   (4 bytes per element, the size of the fp32 value it stands for).  Each plane has GUARD zero pixels before and after, so a
+//   3x3 tap window of a 128-pixel tile is one contiguous, in-bounds byte range (a 1-D bulk TMA copy) and the tile itself is a
+//   tcgen05 operand: no separate fp32 copy of any activation or gradient exists (round 1 kept three bf16 planes AND an fp32
+//   stream, 10 bytes per element).  Residual adds and relu gates read the same planes.  Tensors whose consumers need both
+//   the raw value (residual) and the rectified value (next conv's operand) are stored twice (raw planes + relu'd planes).
 //   Border pixels of every tensor are kept at exactly zero by the producing kernel.
+//   Gradient tensors use the same carrier, multiplied by a per-minibatch power-of-two LOSS SCALE (fp16 range): the scale is
+//   chosen on the device from max |dL/d(pre-relu hidden)| and divided out by the weight-gradient reductions (ctx.cu).
+//   The unpacked uint8 frames (0..255) are exact in fp16: one plane (mid == nullptr).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace cb {
 
-constexpr int GUARD = 256;          // zero pixels before / after every bf16 plane
+constexpr int GUARD = 256;          // zero pixels before / after every plane
 constexpr int NUM_TAPS = 9;
 constexpr int HIDDEN = 256;
 constexpr int MAX_ACTIONS = 32;
+constexpr float MID_SCALE = 2048.f;             // 2^11: the mid plane holds the fp16 rounding residual times this
+constexpr float MID_INV = 1.f / 2048.f;
 
-typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat16 bf16;         // dense layer operands (dense_umma.cu keeps the 3-way bf16 split of round 1)
+typedef __half f16;                 // carrier element of every trunk tensor
 
-struct Planes {           // bf16 hi/mid/lo chunk planes; pointers address flat pixel 0 (guard lies before it)
-    bf16* hi;
-    bf16* mid;            // 1 plane (hi only: exact-in-bf16 data, the unpacked uint8 frames), 2 planes (hi, mid: 16
-    bf16* lo;             // significant bits, gradient tensors) or 3 planes (hi, mid, lo: 24 bits, forward activations)
+struct Planes {           // fp16x2 carrier planes; pointers address flat pixel 0 (the guard lies before it)
+    f16* hi;
+    f16* mid;             // nullptr: single-plane tensor (the unpacked frames, exact in fp16)
     long long plane_px;   // pixels per plane INCLUDING both guards (plane stride = plane_px * 8 elements)
 };
 
@@ -46,17 +54,16 @@ __host__ __device__ inline ConvGeom make_geom(int n, int H, int W) {
 
 // Epilogue shared by the SIMT and the tcgen05 conv kernels (forward conv and dgrad):
 //   v = acc * acc_scale + bias;  v *= (mask_hi > 0);  v += res;  border -> 0
-//   out_s <- v ;  out planes <- split_bf16x3(relu ? max(v, 0) : v)
+//   out <- carrier(v) ;  out_r <- carrier(max(v, 0))
 struct ConvEpilogue {
     const float* bias;        // [Cout] or null
     float acc_scale;          // 1/255 for the first conv (cleanba_ppo.py:181), else 1
-    const bf16* mask_hi;      // planes (hi) of the forward activation whose sign gates the gradient, or null
+    const f16* mask_hi;       // hi plane of the (rectified) forward activation whose sign gates the gradient, or null
     long long mask_plane_px;
-    const float* res;         // fp32 stream added after the mask, or null
-    float* out_s;             // fp32 stream out, or null
-    Planes out;               // bf16 planes out (hi may be null)
-    int relu;
-    // optional second copy of the (relu'd) output in the sample-minor layout of the tcgen05 dense layer
+    Planes res;               // tensor added after the mask (residual input / residual gradient); res.hi null = none
+    Planes out;               // raw output planes (hi may be null)
+    Planes out_r;             // rectified output planes (hi may be null)
+    // optional third copy of the rectified output in the sample-minor bf16 layout of the tcgen05 dense layer
     // (dense_umma.cu): featT[plane][chunk][pixel (H*W, no padding ring)][sample (ft_npad)][8]
     bf16 *ft_hi, *ft_mid, *ft_lo;
     int ft_npad, ft_pixpad;
@@ -71,10 +78,68 @@ struct ConvArgs {
     const float* w;           // fp32 master kernel, HWIO [3][3][Cin_f][Cout_f] (SIMT path)
     int w_cin, w_cout;        // Cin_f, Cout_f of the master kernel
     int transpose;            // 0: forward conv; 1: dgrad (flipped taps, in/out channels swapped)
-    const bf16* wp;           // packed bf16 UMMA weight image ([hi|mid|lo] stacked along N), see pack.cu
+    const f16* wp;            // packed fp16 UMMA weight image ([hi|mid] stacked along N), see pack.cu
     ConvEpilogue ep;
 };
 
+// ---------------------------------------------------------------------------------------------- fp16x2 carrier
+__device__ __forceinline__ void split_f16(float x, f16& hi, f16& mid) {
+    hi = __float2half_rn(x);
+    mid = __float2half_rn((x - __half2float(hi)) * MID_SCALE);      // x - hi is exact in fp32
+}
+// two values -> packed (hi, hi) and (mid, mid) words
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uint32_t& mid2) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 m = __floats2half2_rn((a - hf.x) * MID_SCALE, (b - hf.y) * MID_SCALE);
+    hi2 = *reinterpret_cast<const uint32_t*>(&h);
+    mid2 = *reinterpret_cast<const uint32_t*>(&m);
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+// 8 fp16 (one uint4) -> 8 floats
+__device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
+    float2 t;
+    t = h2_to_f2(v.x); f[0] = t.x; f[1] = t.y;
+    t = h2_to_f2(v.y); f[2] = t.x; f[3] = t.y;
+    t = h2_to_f2(v.z); f[4] = t.x; f[5] = t.y;
+    t = h2_to_f2(v.w); f[6] = t.x; f[7] = t.y;
+}
+// relu gate from the hi plane of a rectified activation: bit pattern of a positive, non-zero fp16 (0x0001 .. 0x7fff)
+__device__ __forceinline__ bool h_pos(uint32_t bits16) { return ((bits16 - 1u) & 0xffffu) < 0x7fffu; }
+__device__ __forceinline__ void gate8h(const uint4& m, float* v) {
+    const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!h_pos(w[i] & 0xffffu)) v[2 * i] = 0.f;
+        if (!h_pos(w[i] >> 16)) v[2 * i + 1] = 0.f;
+    }
+}
+
+// 8 consecutive channels of one pixel-chunk (element offset `off`) <- -> fp32
+__device__ __forceinline__ void load_planes8(const Planes& p, long long off, float* f) {
+    unpack8h(*reinterpret_cast<const uint4*>(p.hi + off), f);
+    if (p.mid) {
+        float t[8];
+        unpack8h(*reinterpret_cast<const uint4*>(p.mid + off), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(t[e], MID_INV, f[e]);      // exact: both terms fit 24 bits
+    }
+}
+__device__ __forceinline__ void store_planes8(const Planes& p, long long off, const float* v) {
+    uint4 h, m;
+    split_f16x2(v[0], v[1], h.x, m.x);
+    split_f16x2(v[2], v[3], h.y, m.y);
+    split_f16x2(v[4], v[5], h.z, m.z);
+    split_f16x2(v[6], v[7], h.w, m.w);
+    *reinterpret_cast<uint4*>(p.hi + off) = h;
+    if (p.mid) *reinterpret_cast<uint4*>(p.mid + off) = m;
+}
+__device__ __forceinline__ void store_planes8_zero(const Planes& p, long long off) {
+    *reinterpret_cast<uint4*>(p.hi + off) = make_uint4(0, 0, 0, 0);
+    if (p.mid) *reinterpret_cast<uint4*>(p.mid + off) = make_uint4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------- bf16 x3 (dense layer operands)
 // exact 3-way split: x == hi + mid + lo up to 24 significant bits (each residual is exact in fp32)
 __device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& mid, bf16& lo) {
     hi = __float2bfloat16_rn(x);
@@ -82,14 +147,11 @@ __device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& mid, bf16& l
     mid = __float2bfloat16_rn(r1);
     lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
 }
-
 __device__ __forceinline__ uint32_t pack_bf16x2(bf16 a, bf16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-
 __device__ __forceinline__ float bf16lo_to_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi_to_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-
 // 8 bf16 (one uint4) -> 8 floats
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
     f[0] = bf16lo_to_f(v.x); f[1] = bf16hi_to_f(v.x);
@@ -97,33 +159,18 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
     f[4] = bf16lo_to_f(v.z); f[5] = bf16hi_to_f(v.z);
     f[6] = bf16lo_to_f(v.w); f[7] = bf16hi_to_f(v.w);
 }
-
-// 8 consecutive channels of one pixel-chunk (element offset `off`) <- -> fp32
-__device__ __forceinline__ void load_planes8(const Planes& p, long long off, float* f) {
-    unpack8(*reinterpret_cast<const uint4*>(p.hi + off), f);
-    if (p.mid) {
-        float t[8];
-        unpack8(*reinterpret_cast<const uint4*>(p.mid + off), t);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] += t[e];
-        if (p.lo) {
-            unpack8(*reinterpret_cast<const uint4*>(p.lo + off), t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] += t[e];
-        }
-    }
-}
-__device__ __forceinline__ void store_planes8(const Planes& p, long long off, const float* v) {
+// 8 floats -> hi / mid / lo bf16 arrays at element offset off (mid / lo optional)
+__device__ __forceinline__ void store_bf16_split8(bf16* hi, bf16* mid, bf16* lo, long long off, const float* v) {
     bf16 h[8], m[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], m[e], l[e]);
-    *reinterpret_cast<uint4*>(p.hi + off) =
+    *reinterpret_cast<uint4*>(hi + off) =
         make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    if (p.mid)
-        *reinterpret_cast<uint4*>(p.mid + off) =
+    if (mid)
+        *reinterpret_cast<uint4*>(mid + off) =
             make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
-    if (p.lo)
-        *reinterpret_cast<uint4*>(p.lo + off) =
+    if (lo)
+        *reinterpret_cast<uint4*>(lo + off) =
             make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
 }
 
@@ -142,15 +189,26 @@ __device__ __forceinline__ void store_featT(bf16* ft_hi, bf16* ft_mid, bf16* ft_
     float x8[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) x8[e] = fmaxf(v[e], 0.f);
-    Planes p;
-    p.hi = ft_hi; p.mid = ft_mid; p.lo = ft_lo; p.plane_px = 0;
-    store_planes8(p, off, x8);
+    store_bf16_split8(ft_hi, ft_mid, ft_lo, off, x8);
 }
 
-// Apply the epilogue to the 8 accumulators of (flat pixel q, output chunk oc) and store.
+// Stores of one (pixel, chunk) of 8 epilogue values: raw planes, rectified planes, sample-minor dense copy.
+__device__ __forceinline__ void epi_store8(const ConvEpilogue& ep, const ConvGeom& g, long long q, int oc, const float* v, bool in) {
+    if (ep.out.hi) store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, v);
+    if (ep.out_r.hi) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = fmaxf(v[e], 0.f);
+        store_planes8(ep.out_r, ((long long)oc * ep.out_r.plane_px + q) * 8, x);
+    }
+    if (ep.ft_hi && in) store_featT(ep.ft_hi, ep.ft_mid, ep.ft_lo, ep.ft_npad, ep.ft_pixpad, g, q, oc, v);
+}
+
+// Apply the epilogue to the 8 accumulators of (flat pixel q, output chunk oc) and store.  Pixels past the last image (rest of
+// the last 128-tile) and border pixels get zeros.
 __device__ __forceinline__ void conv_epilogue_store(const ConvEpilogue& ep, const ConvGeom& g, long long q, int oc,
                                                     float* acc) {
-    const bool tail = q >= g.NP;   // pixels past the last image (rest of the last 128-tile): planes get zeros
+    const bool tail = q >= g.NP;
     const bool in = !tail && interior(g, q);
     float v[8];
 #pragma unroll
@@ -161,39 +219,22 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvEpilogue& ep, cons
             float b = ep.bias ? ep.bias[oc * 8 + e] : 0.f;
             v[e] = acc[e] * ep.acc_scale + b;
         }
-        if (ep.mask_hi) {
-            uint4 m = *reinterpret_cast<const uint4*>(ep.mask_hi + ((long long)oc * ep.mask_plane_px + q) * 8);
-            float mf[8];
-            unpack8(m, mf);
+        if (ep.mask_hi) gate8h(*reinterpret_cast<const uint4*>(ep.mask_hi + ((long long)oc * ep.mask_plane_px + q) * 8), v);
+        if (ep.res.hi) {
+            float r[8];
+            load_planes8(ep.res, ((long long)oc * ep.res.plane_px + q) * 8, r);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = mf[e] > 0.f ? v[e] : 0.f;
-        }
-        if (ep.res) {
-            const float4* r = reinterpret_cast<const float4*>(ep.res + ((long long)oc * g.NP + q) * 8);
-            float4 r0 = r[0], r1 = r[1];
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+            for (int e = 0; e < 8; ++e) v[e] += r[e];
         }
     }
-    if (ep.out_s && !tail) {
-        float4* o = reinterpret_cast<float4*>(ep.out_s + ((long long)oc * g.NP + q) * 8);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    if (ep.out.hi) {
-        float x[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = ep.relu ? fmaxf(v[e], 0.f) : v[e];
-        store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, x);
-    }
-    if (ep.ft_hi && in) store_featT(ep.ft_hi, ep.ft_mid, ep.ft_lo, ep.ft_npad, ep.ft_pixpad, g, q, oc, v);
+    epi_store8(ep, g, q, oc, v, in);
 }
 
 // Split epilogue for the tcgen05 kernels: the residual / gate operands of a tile are fetched into registers BEFORE the
 // accumulator is waited for, so their global-memory latency overlaps the MMAs instead of following them.
 template <int COUT>
 struct EpiPrefetch {
-    float res[COUT];
+    uint4 res_hi[COUT / 8], res_mid[COUT / 8];
     uint4 mask[COUT / 8];
     bool in, tail;
 };
@@ -206,11 +247,10 @@ __device__ __forceinline__ void epi_prefetch(const ConvEpilogue& ep, const ConvG
 #pragma unroll
     for (int oc = 0; oc < COUT / 8; ++oc) {
         if (ep.mask_hi) p.mask[oc] = *reinterpret_cast<const uint4*>(ep.mask_hi + ((long long)oc * ep.mask_plane_px + q) * 8);
-        if (ep.res) {
-            const float4* r = reinterpret_cast<const float4*>(ep.res + ((long long)oc * g.NP + q) * 8);
-            float4 r0 = r[0], r1 = r[1];
-            p.res[oc * 8 + 0] = r0.x; p.res[oc * 8 + 1] = r0.y; p.res[oc * 8 + 2] = r0.z; p.res[oc * 8 + 3] = r0.w;
-            p.res[oc * 8 + 4] = r1.x; p.res[oc * 8 + 5] = r1.y; p.res[oc * 8 + 6] = r1.z; p.res[oc * 8 + 7] = r1.w;
+        if (ep.res.hi) {
+            const long long off = ((long long)oc * ep.res.plane_px + q) * 8;
+            p.res_hi[oc] = *reinterpret_cast<const uint4*>(ep.res.hi + off);
+            p.res_mid[oc] = *reinterpret_cast<const uint4*>(ep.res.mid + off);
         }
     }
 }
@@ -229,29 +269,16 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeo
                 float b = ep.bias ? ep.bias[oc * 8 + e] : 0.f;
                 v[e] = acc[oc * 8 + e] * ep.acc_scale + b;
             }
-            if (ep.mask_hi) {
-                float mf[8];
-                unpack8(p.mask[oc], mf);
+            if (ep.mask_hi) gate8h(p.mask[oc], v);
+            if (ep.res.hi) {
+                float rh[8], rm[8];
+                unpack8h(p.res_hi[oc], rh);
+                unpack8h(p.res_mid[oc], rm);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = mf[e] > 0.f ? v[e] : 0.f;
-            }
-            if (ep.res) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += p.res[oc * 8 + e];
+                for (int e = 0; e < 8; ++e) v[e] += fmaf(rm[e], MID_INV, rh[e]);
             }
         }
-        if (ep.out_s && !p.tail) {
-            float4* o = reinterpret_cast<float4*>(ep.out_s + ((long long)oc * g.NP + q) * 8);
-            o[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (ep.out.hi) {
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = ep.relu ? fmaxf(v[e], 0.f) : v[e];
-            store_planes8(ep.out, ((long long)oc * ep.out.plane_px + q) * 8, x);
-        }
-        if (ep.ft_hi && p.in) store_featT(ep.ft_hi, ep.ft_mid, ep.ft_lo, ep.ft_npad, ep.ft_pixpad, g, q, oc, v);
+        epi_store8(ep, g, q, oc, v, p.in);
     }
 }
 

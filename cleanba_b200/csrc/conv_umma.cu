@@ -8,17 +8,18 @@
 //   * the A operand of filter tap (ky,kx) is the same 128 rows shifted by (ky-1)*Wp + (kx-1) pixels, i.e. it is
 //     just a different START ADDRESS inside one contiguous window of 128 + 2*Wp + 2 pixels,
 //   * that window is ONE contiguous byte range per channel plane -> one 1-D bulk TMA copy per plane per tile,
-//   * a plane [pixel][8 ch] of bf16 is exactly a column of SWIZZLE_NONE 8x16-byte core matrices, both K-major
+//   * a plane [pixel][8 ch] of fp16 is exactly a column of SWIZZLE_NONE 8x16-byte core matrices, both K-major
 //     (conv / dgrad: K = channels) and MN-major (wgrad: K = pixels), so no data is ever re-laid out.
 //
 // Precision (parity bar: 1e-4 against an fp32 reference, with discontinuous relu / max-pool gates downstream):
-// every fp32 value is carried as an exact 3-way bf16 split x = hi + mid + lo (24 significant bits).  The six
-// significant cross products are obtained with THREE tcgen05.mma per K step by stacking the weight planes along N:
-//     D[:, 0:3C] += A_hi  * [W_hi | W_mid | W_lo]        (N = 3C)
-//     D[:, 0:2C] += A_mid * [W_hi | W_mid]               (N = 2C)
-//     D[:, 0:C ] += A_lo  * [W_hi]                       (N = C)
-// and the epilogue adds the three C-column blocks.  The MMAs are bound by the A-operand shared-memory fetch (ncu:
-// sm__pipe_tc_cycles_active ~80%), which does not depend on N, so the extra precision costs no tensor-pipe time.
+// every fp32 value is carried as the fp16x2 pair x = hi + mid * 2^-11 (22 significant bits, common.cuh); fp16 x fp16 products
+// are exact in the fp32 accumulator.  The three significant cross products cost TWO tcgen05.mma per K step by stacking the
+// weight planes along N:
+//     D[:, 0:2C] += A_hi  * [W_hi | W_mid]       (N = 2C)     column block 0: hi*hi,  block 1: hi*mid
+//     D[:, C:2C] += A_mid * [W_hi]               (N = C)      block 1 += mid*hi
+// and the epilogue evaluates  block0 + 2^-11 * block1  (the mid*mid term, 2^-22 relative, is dropped).  Round 1 carried three
+// bf16 planes and issued three MMAs per K step; the MMAs are bound by the A-operand shared-memory fetch (32 cycles per MMA
+// regardless of N), so two planes are 2/3 of the tensor-pipe time as well as 2/3 of the bytes.
 //
 // Warp roles (320 threads): warps 0-3 / 4-7 two epilogue groups, one per TMEM accumulator (TMEM lane quadrant = warp % 4),
 // which prefetch the residual / gate operands of their next tile before waiting for its accumulator; warp 8 TMA producer;
@@ -36,23 +37,23 @@ constexpr int CONV_MAXST = 8;        // stages of the input-window ring: as many
 constexpr int CONV_THREADS = 320;   // warps 0-7: two epilogue groups (one per TMEM accumulator), warp 8: TMA, warp 9: MMA
 
 __host__ __device__ constexpr int conv_steps(int cin_chunks) { return cin_chunks == 1 ? 5 : 9 * (cin_chunks / 2); }
-// bytes of the packed weight image: per step [kc(2)][wpl*cout][8] bf16, wpl = 3 planes (forward) or 2 (dgrad)
-__host__ __device__ constexpr int conv_wbytes(int cin_chunks, int cout, int wpl) { return conv_steps(cin_chunks) * 2 * wpl * cout * 16; }
-__host__ __device__ constexpr int conv_wpl(int apl) { return apl == 2 ? 2 : 3; }
+// bytes of the packed weight image: per step [kc(2)][2*cout][8] fp16 (hi | mid rows, pack.cu)
+__host__ __device__ constexpr int conv_wbytes(int cin_chunks, int cout) { return conv_steps(cin_chunks) * 2 * 2 * cout * 16; }
 
-long long packed_conv_elems(int cin_chunks, int cout, int wpl) { return (long long)conv_wbytes(cin_chunks, cout, wpl) / 2; }
+long long packed_conv_elems(int cin_chunks, int cout) { return (long long)conv_wbytes(cin_chunks, cout) / 2; }
 
 struct ConvSmemLayout {
     int win, plane_bytes, nplanes, stage_bytes, w_bytes, stages, ctas_per_sm, total;
 };
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int cout, int Wp, int apl = 3) {
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int cout, int Wp) {
+    const int apl = 2;
     ConvSmemLayout L;
     // frames path: the zero-weight half of the last K step reads one pixel past the 3x3 window -> load it too
     L.win = TILE_M + 2 * Wp + 2 + (cin_chunks == 1 ? 1 : 0);
     L.plane_bytes = L.win * 16;
-    L.nplanes = cin_chunks == 1 ? 1 : apl * cin_chunks;      // hi planes, mid planes[, lo planes] (frames: hi only, exact)
+    L.nplanes = cin_chunks == 1 ? 1 : apl * cin_chunks;      // hi planes, mid planes (frames: hi only, exact)
     L.stage_bytes = L.nplanes * L.plane_bytes;
-    L.w_bytes = conv_wbytes(cin_chunks, cout, conv_wpl(apl));
+    L.w_bytes = conv_wbytes(cin_chunks, cout);
     // two CTAs per SM (two MMA-issuing threads) when three stages fit in half an SM, else one CTA with a deeper ring
     L.ctas_per_sm = 1024 + L.w_bytes + 3 * L.stage_bytes <= 112 * 1024 ? 2 : 1;
     const int budget = (L.ctas_per_sm == 2 ? 112 : 226) * 1024 - 1024 - L.w_bytes;
@@ -61,15 +62,16 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int c
     L.total = 1024 + L.w_bytes + L.stages * L.stage_bytes;
     return L;
 }
-int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_layout(cin_chunks, cout, Wp, 3).total; }
+int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_layout(cin_chunks, cout, Wp).total; }
 
-// APL = bf16 planes of the A operand: 1 (frames, exact), 2 (gradient tensors, 16 bits: A_hi*[W_hi|W_mid] + A_mid*[W_hi])
-// or 3 (forward activations, 24 bits, the three MMAs above).
-template <int CIN_CHUNKS, int COUT, int APL>
+// One kernel for the forward conv and for dgrad (activations and gradients use the same carrier); CIN_CHUNKS == 1 is the
+// frame stack (one exact plane, ONE MMA per step: A_hi * [W_hi | W_mid]).
+template <int CIN_CHUNKS, int COUT>
 __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntiles) {
+    constexpr int APL = CIN_CHUNKS == 1 ? 1 : 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     griddep_launch();
-    const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, APL);
+    const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
     // [0,1024): barriers + tmem pointer; then the weight image; then the activation stages
     const int NSTAGES = L.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [CONV_MAXST]
@@ -83,8 +85,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(CIN_CHUNKS);
-    constexpr int NBLK = APL == 2 ? 2 : 3;                       // C-column blocks per accumulator
-    constexpr int ACC_COLS = NBLK * COUT;
+    constexpr int ACC_COLS = 2 * COUT;                           // column block 0: hi*hi, block 1: (hi*mid + mid*hi) * 2^11
     constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : ((2 * ACC_COLS <= 128) ? 128 : 256);
     constexpr int NPLANES = CIN_CHUNKS == 1 ? 1 : APL * CIN_CHUNKS;
 
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
             const long long q_lo = (long long)tile * TILE_M - a.g.Wp - 1;   // inside the front guard for tile 0
             uint8_t* dst = stages + s * L.stage_bytes;
             if (lane < NPLANES) {
-                const int pl = lane / CIN_CHUNKS, j = lane % CIN_CHUNKS;      // pl: 0 hi, 1 mid, 2 lo
-                const bf16* src = pl == 0 ? a.in.hi : (pl == 1 ? a.in.mid : a.in.lo);
+                const int pl = lane / CIN_CHUNKS, j = lane % CIN_CHUNKS;      // pl: 0 hi, 1 mid
+                const f16* src = pl == 0 ? a.in.hi : a.in.mid;
                 bulk_g2s(dst + lane * L.plane_bytes, src + ((long long)j * a.in.plane_px + q_lo) * 8, L.plane_bytes, &full[s]);
             }
             __syncwarp();
@@ -124,9 +125,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * COUT, 0, 0);
-        constexpr uint32_t IDESC2 = make_idesc_bf16(TILE_M, 2 * COUT, 0, 0);
-        constexpr uint32_t IDESC1 = make_idesc_bf16(TILE_M, COUT, 0, 0);
+        constexpr uint32_t IDESC2 = make_idesc_f16(TILE_M, 2 * COUT, 0, 0);
+        constexpr uint32_t IDESC1 = make_idesc_f16(TILE_M, COUT, 0, 0);
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         int acc = 0; uint32_t aph = 0;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
         // issue loop below is fully unrolled and costs one integer add per operand per MMA).
         const uint32_t win16 = (uint32_t)L.win;                  // plane stride in 16-byte units
         const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
-        constexpr int WPL = conv_wpl(APL);
+        constexpr int WPL = 2;
         const uint32_t b_lo0 = desc_lo(smem_u32(wsm), WPL * COUT * 16);
         uint32_t a_rel[STEPS];
 #pragma unroll
@@ -157,21 +157,13 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
             if (lane == 0) {
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 const uint32_t st16 = (smem_u32(stages + s * L.stage_bytes) >> 4);   // stage base (hi planes), 16-byte units
-                const uint32_t mid16 = CIN_CHUNKS * win16, lo16 = 2 * CIN_CHUNKS * win16;
+                const uint32_t mid16 = CIN_CHUNKS * win16;
 #pragma unroll
                 for (int step = 0; step < STEPS; ++step) {
                     const uint32_t a_lo = st16 + a_rel[step];
                     const uint32_t b_lo = b_lo0 + step * (2 * WPL * COUT);
-                    if (APL == 2) {
-                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0);
-                        mma_bf16_parts(d_tmem, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1);
-                    } else {
-                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC3, step > 0);
-                        if (APL == 3) {
-                            mma_bf16_parts(d_tmem, a_lo + mid16, a_hi, b_lo, b_hi, IDESC2, 1);
-                            mma_bf16_parts(d_tmem, a_lo + lo16, a_hi, b_lo, b_hi, IDESC1, 1);
-                        }
-                    }
+                    mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0);                 // A_hi * [W_hi | W_mid]
+                    if (APL == 2) mma_bf16_parts(d_tmem + COUT, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1);   // block 1 += A_mid * W_hi
                 }
                 mma_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
                 mma_commit(&tfull[acc]);    // accumulator complete
@@ -192,17 +184,14 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * ACC_COLS;
             float v[COUT];
-            {   // sum the column blocks, smallest contributions first
+            {   // block0 + 2^-11 * block1
                 float t[16];
 #pragma unroll
                 for (int h = 0; h < COUT / 16; ++h) {
-                    tmem_ld16(taddr + (NBLK - 1) * COUT + h * 16, v + h * 16);
+                    tmem_ld16(taddr + COUT + h * 16, t);
+                    tmem_ld16(taddr + h * 16, v + h * 16);
 #pragma unroll
-                    for (int blk = NBLK - 2; blk >= 0; --blk) {
-                        tmem_ld16(taddr + blk * COUT + h * 16, t);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
-                    }
+                    for (int i = 0; i < 16; ++i) v[h * 16 + i] = fmaf(t[i], MID_INV, v[h * 16 + i]);
                 }
             }
             tc_fence_before();
@@ -217,9 +206,9 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int CIN_CHUNKS, int COUT, int APL>
+template <int CIN_CHUNKS, int COUT>
 static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
-    ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, APL);
+    ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
     CB_CHECK(L.stages >= 2 && L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
     // Opt in to the device maximum once per device: the attribute is per function (contexts on other host threads launch
     // the same instantiation with other window sizes concurrently), and nothing but launches may happen while a
@@ -228,29 +217,25 @@ static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     if (!(attr_done.load() & (1u << dev))) {
-        CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done.fetch_or(1u << dev);
     }
     int ntiles = (int)((a.g.NP + TILE_M - 1) / TILE_M);
     int grid = ntiles < num_sms * L.ctas_per_sm ? ntiles : num_sms * L.ctas_per_sm;
-    launch_pdl(k_conv_umma<CIN_CHUNKS, COUT, APL>, dim3(grid), dim3(CONV_THREADS), (size_t)L.total, st, a, ntiles);
+    launch_pdl(k_conv_umma<CIN_CHUNKS, COUT>, dim3(grid), dim3(CONV_THREADS), (size_t)L.total, st, a, ntiles);
     CB_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
     CB_CHECK(a.g.Wp + 1 <= GUARD && TILE_M + a.g.Wp + 2 <= GUARD, "conv_umma: guard too small for Wp=%d", a.g.Wp);
-    const int apl = a.in.lo ? 3 : (a.in.mid ? 2 : 1);
-    CB_CHECK((apl == 2) == (a.transpose != 0), "conv_umma: 2-plane inputs are gradient tensors (dgrad weight image), 1/3-plane inputs forward");
-    if (a.cin_chunks == 1 && a.cout == 16 && apl == 1) return launch_conv_umma_t<1, 16, 1>(a, num_sms, st);
-    if (a.cin_chunks == 2 && a.cout == 16 && apl == 3) return launch_conv_umma_t<2, 16, 3>(a, num_sms, st);
-    if (a.cin_chunks == 2 && a.cout == 16 && apl == 2) return launch_conv_umma_t<2, 16, 2>(a, num_sms, st);
-    if (a.cin_chunks == 2 && a.cout == 32 && apl == 3) return launch_conv_umma_t<2, 32, 3>(a, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 16 && apl == 2) return launch_conv_umma_t<4, 16, 2>(a, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 16 && apl == 3) return launch_conv_umma_t<4, 16, 3>(a, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 32 && apl == 3) return launch_conv_umma_t<4, 32, 3>(a, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 32 && apl == 2) return launch_conv_umma_t<4, 32, 2>(a, num_sms, st);
-    CB_CHECK(false, "conv_umma: unsupported shape cin_chunks=%d cout=%d planes=%d", a.cin_chunks, a.cout, apl);
+    CB_CHECK((a.cin_chunks == 1) == (a.in.mid == nullptr), "conv_umma: single-plane inputs are the frame stack only");
+    if (a.cin_chunks == 1 && a.cout == 16) return launch_conv_umma_t<1, 16>(a, num_sms, st);
+    if (a.cin_chunks == 2 && a.cout == 16) return launch_conv_umma_t<2, 16>(a, num_sms, st);
+    if (a.cin_chunks == 2 && a.cout == 32) return launch_conv_umma_t<2, 32>(a, num_sms, st);
+    if (a.cin_chunks == 4 && a.cout == 16) return launch_conv_umma_t<4, 16>(a, num_sms, st);
+    if (a.cin_chunks == 4 && a.cout == 32) return launch_conv_umma_t<4, 32>(a, num_sms, st);
+    CB_CHECK(false, "conv_umma: unsupported shape cin_chunks=%d cout=%d", a.cin_chunks, a.cout);
 }
 
 // =================================================================================================
@@ -272,7 +257,7 @@ constexpr int C0_COUT = 16;
 constexpr int C0_STAGES = 8;
 constexpr int C0_WIN = TILE_M + 2 * C0_HP + 3;                 // 303 pixels per input window (see conv_smem_layout)
 constexpr int C0_STAGE_BYTES = C0_WIN * 16;
-constexpr int C0_W_BYTES = conv_wbytes(1, C0_COUT, 3);
+constexpr int C0_W_BYTES = conv_wbytes(1, C0_COUT);
 constexpr int C0_BAND_BYTES = C0_BAND_PX * C0_COUT * 4;
 constexpr int C0_SMEM = 1024 + C0_W_BYTES + C0_STAGES * C0_STAGE_BYTES + C0_BAND_BYTES;
 static_assert(C0_HO % C0_BAND_K == 0, "bands must tile the pooled rows");
@@ -280,12 +265,12 @@ static_assert(2 * C0_SMEM <= 226 * 1024, "two CTAs per SM");
 
 struct Conv0PoolArgs {
     int n;                    // frames
-    const bf16* x_hi;         // unpacked frames: chunk plane [n * 86 * 86][8] (4 real channels), flat pixel 0
-    const bf16* wp;           // packed forward weight image of the frame conv
+    const f16* x_hi;          // unpacked frames: chunk plane [n * 86 * 86][8] (4 real channels), flat pixel 0
+    const f16* wp;            // packed forward weight image of the frame conv
     const float* bias;        // [16]
     float acc_scale;          // 1/255
-    float* out_s;             // pooled fp32 stream [2][n * 44 * 44][8]
-    Planes out;               // relu'd pooled planes (hi, mid, lo)
+    Planes out;               // pooled planes (raw: the residual input of the first block)
+    Planes out_r;             // rectified pooled planes (the first block's conv operand)
     uint8_t* amax;            // arg-max bytes [2][n * 44 * 44][8] or null (actor contexts)
 };
 
@@ -313,8 +298,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(1);
-    constexpr int ACC_COLS = 3 * C0_COUT;
-    constexpr uint32_t TMEM_COLS = 256;                          // 5 accumulators x 48 columns: the MMAs of the NEXT band run
+    constexpr int ACC_COLS = 2 * C0_COUT;
+    constexpr uint32_t TMEM_COLS = 256;                          // 5 accumulators x 32 columns: the MMAs of the NEXT band run
     const int nbands = a.n * C0_BANDS;                           // while this band is being pooled
 
     if (threadIdx.x == 0) {
@@ -351,13 +336,13 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
             }
         }
     } else if (warp == 9) {
-        // ===================== MMA issuer (frames: one exact bf16 plane, two taps per K = 16 step) =====================
-        constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * C0_COUT, 0, 0);
+        // ===================== MMA issuer (frames: one exact fp16 plane, two taps per K = 16 step) =====================
+        constexpr uint32_t IDESC2 = make_idesc_f16(TILE_M, 2 * C0_COUT, 0, 0);
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         uint32_t aph = 0;                                        // accumulator phase: flips once per band
         const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
-        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 3 * C0_COUT * 16);
+        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 2 * C0_COUT * 16);
         uint32_t a_rel[STEPS];
 #pragma unroll
         for (int step = 0; step < STEPS; ++step) {
@@ -375,7 +360,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
                     const uint32_t st16 = (smem_u32(stages + s * C0_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int step = 0; step < STEPS; ++step)
-                        mma_bf16_parts(d_tmem, st16 + a_rel[step], a_hi, b_lo0 + step * (2 * 3 * C0_COUT), b_hi, IDESC3, step > 0);
+                        mma_bf16_parts(d_tmem, st16 + a_rel[step], a_hi, b_lo0 + step * (2 * 2 * C0_COUT), b_hi, IDESC2, step > 0);
                     mma_commit(&empty[s]);
                     mma_commit(&tfull[t]);
                 }
@@ -396,13 +381,11 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
         auto emit = [&](int img, int ypo, int xp, int jc, const float* v, const int* am) {
             const long long qo = (long long)img * C0_PO + ypo * C0_WPO + xp;
             const long long so = ((long long)jc * a.n * C0_PO + qo) * 8;
-            float4* o = reinterpret_cast<float4*>(a.out_s + so);
-            o[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, v);
             float rl[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
-            store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, rl);
+            store_planes8(a.out_r, ((long long)jc * a.out_r.plane_px + qo) * 8, rl);
             if (a.amax) {
                 uint2 pk;
                 pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
@@ -424,13 +407,10 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + t * ACC_COLS;
                 float v[C0_COUT], u[16];
-                tmem_ld16(taddr + 2 * C0_COUT, v);
                 tmem_ld16(taddr + C0_COUT, u);
+                tmem_ld16(taddr, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += u[i];
-                tmem_ld16(taddr, u);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += u[i];
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(u[i], MID_INV, v[i]);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[t]);
@@ -480,7 +460,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-int launch_conv0_pool_umma(const ConvArgs& a, float* out_s, Planes out, uint8_t* amax, int num_sms, cudaStream_t st) {
+int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t* amax, int num_sms, cudaStream_t st) {
     CB_CHECK(a.g.H == 84 && a.g.W == 84 && a.cin_chunks == 1 && a.cout == C0_COUT && !a.transpose,
              "conv0_pool_umma: frame conv (84x84, 4 -> 16 channels) only");
     CB_CHECK(C0_HP + 1 <= GUARD && TILE_M + C0_HP + 2 + TILE_M <= GUARD + 128, "conv0_pool_umma: guard too small");
@@ -493,7 +473,7 @@ int launch_conv0_pool_umma(const ConvArgs& a, float* out_s, Planes out, uint8_t*
     }
     Conv0PoolArgs p;
     p.n = a.g.n; p.x_hi = a.in.hi; p.wp = a.wp; p.bias = a.ep.bias; p.acc_scale = a.ep.acc_scale;
-    p.out_s = out_s; p.out = out; p.amax = amax;
+    p.out = out; p.out_r = out_r; p.amax = amax;
     const int nbands = a.g.n * C0_BANDS;
     const int grid = nbands < 2 * num_sms ? nbands : 2 * num_sms;
     launch_pdl(k_conv0_pool_umma, dim3(grid), dim3(CONV_THREADS), (size_t)C0_SMEM, st, p);
@@ -513,17 +493,17 @@ int launch_conv0_pool_umma(const ConvArgs& a, float* out_s, Planes out, uint8_t*
 //                    SM) the 8 epilogue warps were the bottleneck (0.78 ms vs 0.83 ms unfused);
 //   21x21 (Wp = 23): K = 5 -> 11 conv rows = 253 px = 2 tiles, one CTA per SM (the 55 KB weight image leaves no room for two).
 constexpr int CP_COUT = 32;
-constexpr int CP_ACC_COLS = 3 * CP_COUT;
+constexpr int CP_ACC_COLS = 2 * CP_COUT;
 
 struct ConvPoolArgs {
     ConvGeom gi, go;          // conv grid (input of the pool) and pooled grid
     int pad_lo;
     int bands_per_img;        // ceil(go.H / K)
-    Planes in;                // 3-plane input activations of the conv
-    const bf16* wp;           // packed forward weight image
+    Planes in;                // input activations of the conv (raw output of the previous stage)
+    const f16* wp;            // packed forward weight image
     const float* bias;        // [32]
-    float* out_s;             // pooled fp32 stream
-    Planes out;               // relu'd pooled planes (hi, mid, lo)
+    Planes out;               // pooled planes (raw)
+    Planes out_r;             // rectified pooled planes
     uint8_t* amax;            // arg-max bytes or null
 };
 
@@ -532,8 +512,8 @@ __host__ __device__ inline ConvPoolSmem conv_pool_smem(int cin_chunks, int Wp, i
     ConvPoolSmem L;
     L.win = TILE_M + 2 * Wp + 2;
     L.plane_bytes = L.win * 16;
-    L.stage_bytes = 3 * cin_chunks * L.plane_bytes;
-    L.w_bytes = conv_wbytes(cin_chunks, CP_COUT, 3);
+    L.stage_bytes = 2 * cin_chunks * L.plane_bytes;
+    L.w_bytes = conv_wbytes(cin_chunks, CP_COUT);
     const int band_px = ((2 * K + 1) * Wp + TILE_M - 1) / TILE_M * TILE_M;
     L.band_bytes = band_px * CP_COUT * 4;
     // two CTAs per SM when the accumulators fit 256 TMEM columns AND two stages fit half an SM's shared memory
@@ -570,8 +550,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(CIN_CHUNKS);
-    constexpr uint32_t TMEM_COLS = CP_MAXT * CP_ACC_COLS <= 256 ? 256 : 512;   // CP_MAXT accumulators x 96 columns
-    constexpr int NPLANES = 3 * CIN_CHUNKS;
+    constexpr uint32_t TMEM_COLS = CP_MAXT * CP_ACC_COLS <= 128 ? 128 : (CP_MAXT * CP_ACC_COLS <= 256 ? 256 : 512);   // CP_MAXT accumulators x 64 columns
+    constexpr int NPLANES = 2 * CIN_CHUNKS;
     const int Wp = a.gi.Wp, Ho = a.go.H;
     const int nbands = a.gi.n * a.bands_per_img;
     // band b of an image: pooled rows [b*CP_K, b*CP_K + kb), conv rows from padded row 2*b*CP_K - pad_lo + 1, (2*kb + 1) of them
@@ -608,8 +588,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
                 const long long q_lo = qb + t * TILE_M - Wp - 1;
                 uint8_t* dst = stages + s * L.stage_bytes;
                 if (lane < NPLANES) {
-                    const int pl = lane / CIN_CHUNKS, j = lane % CIN_CHUNKS;      // pl: 0 hi, 1 mid, 2 lo
-                    const bf16* src = pl == 0 ? a.in.hi : (pl == 1 ? a.in.mid : a.in.lo);
+                    const int pl = lane / CIN_CHUNKS, j = lane % CIN_CHUNKS;      // pl: 0 hi, 1 mid
+                    const f16* src = pl == 0 ? a.in.hi : a.in.mid;
                     bulk_g2s(dst + lane * L.plane_bytes, src + ((long long)j * a.in.plane_px + q_lo) * 8, L.plane_bytes, &full[s]);
                 }
                 __syncwarp();
@@ -617,16 +597,15 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
             }
         }
     } else if (warp == 9) {
-        // ===================== MMA issuer: three MMAs per K step (see k_conv_umma) =====================
-        constexpr uint32_t IDESC3 = make_idesc_bf16(TILE_M, 3 * CP_COUT, 0, 0);
-        constexpr uint32_t IDESC2 = make_idesc_bf16(TILE_M, 2 * CP_COUT, 0, 0);
-        constexpr uint32_t IDESC1 = make_idesc_bf16(TILE_M, CP_COUT, 0, 0);
+        // ===================== MMA issuer: two MMAs per K step (see k_conv_umma) =====================
+        constexpr uint32_t IDESC2 = make_idesc_f16(TILE_M, 2 * CP_COUT, 0, 0);
+        constexpr uint32_t IDESC1 = make_idesc_f16(TILE_M, CP_COUT, 0, 0);
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         uint32_t accph = 0;                                      // bit t: phase of accumulator t (flips each time it is used)
         const uint32_t win16 = (uint32_t)L.win;
         const uint32_t b_hi = desc_hi(128), a_hi = desc_hi(128);
-        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 3 * CP_COUT * 16);
+        const uint32_t b_lo0 = desc_lo(smem_u32(wsm), 2 * CP_COUT * 16);
         uint32_t a_rel[STEPS];
 #pragma unroll
         for (int step = 0; step < STEPS; ++step) {
@@ -634,7 +613,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
             const int tap = step / HALF, pair = step % HALF;
             a_rel[step] = ((uint32_t)(pair * 2) * win16 + (uint32_t)((tap / 3) * Wp + (tap % 3))) | (win16 << 16);
         }
-        const uint32_t mid16 = CIN_CHUNKS * win16, lo16 = 2 * CIN_CHUNKS * win16;
+        const uint32_t mid16 = CIN_CHUNKS * win16;
         for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
             const int b = bnd % a.bands_per_img;
             const int nt = band_tiles(band_rows(b));
@@ -648,10 +627,9 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
 #pragma unroll
                     for (int step = 0; step < STEPS; ++step) {
                         const uint32_t a_lo = st16 + a_rel[step];
-                        const uint32_t b_lo = b_lo0 + step * (2 * 3 * CP_COUT);
-                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC3, step > 0);
-                        mma_bf16_parts(d_tmem, a_lo + mid16, a_hi, b_lo, b_hi, IDESC2, 1);
-                        mma_bf16_parts(d_tmem, a_lo + lo16, a_hi, b_lo, b_hi, IDESC1, 1);
+                        const uint32_t b_lo = b_lo0 + step * (2 * 2 * CP_COUT);
+                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0);
+                        mma_bf16_parts(d_tmem + CP_COUT, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1);
                     }
                     mma_commit(&empty[s]);
                     mma_commit(&tfull[t]);
@@ -674,13 +652,11 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
         auto emit = [&](int img, int ypo, int xp, int jc, const float* v, const int* am) {
             const long long qo = (long long)img * a.go.P + ypo * Wpo + xp;
             const long long so = ((long long)jc * a.go.NP + qo) * 8;
-            float4* o = reinterpret_cast<float4*>(a.out_s + so);
-            o[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, v);
             float rl[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
-            store_planes8(a.out, ((long long)jc * a.out.plane_px + qo) * 8, rl);
+            store_planes8(a.out_r, ((long long)jc * a.out_r.plane_px + qo) * 8, rl);
             if (a.amax) {
                 uint2 pk;
                 pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
@@ -706,13 +682,10 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
 #pragma unroll
                 for (int h = 0; h < CP_COUT / 16; ++h) {
                     float v[16], u[16];
-                    tmem_ld16(taddr + 2 * CP_COUT + h * 16, v);
                     tmem_ld16(taddr + CP_COUT + h * 16, u);
+                    tmem_ld16(taddr + h * 16, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += u[i];
-                    tmem_ld16(taddr + h * 16, u);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += u[i];
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(u[i], MID_INV, v[i]);
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         *cp_band_ptr(band, pb, h * 4 + c) = make_float4(v[c * 4 + 0] + bias[h * 16 + c * 4 + 0], v[c * 4 + 1] + bias[h * 16 + c * 4 + 1],
@@ -793,14 +766,14 @@ static int launch_conv_pool_umma_t(ConvPoolArgs p, int num_sms, cudaStream_t st)
     return 0;
 }
 
-int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, float* out_s, Planes out, uint8_t* amax, int num_sms,
+int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out, Planes out_r, uint8_t* amax, int num_sms,
                           cudaStream_t st) {
-    CB_CHECK(a.cout == CP_COUT && !a.transpose && a.in.lo && (a.cin_chunks == 2 || a.cin_chunks == 4),
-             "conv_pool_umma: 3-plane 16|32 -> 32 channel sequence convs only");
+    CB_CHECK(a.cout == CP_COUT && !a.transpose && a.in.mid && (a.cin_chunks == 2 || a.cin_chunks == 4),
+             "conv_pool_umma: 16|32 -> 32 channel sequence convs only");
     CB_CHECK(a.g.Wp + 1 <= GUARD && 2 * TILE_M + a.g.Wp + 2 <= GUARD + 128, "conv_pool_umma: guard too small for Wp=%d", a.g.Wp);
     ConvPoolArgs p;
     p.gi = a.g; p.go = go; p.pad_lo = pad_lo; p.bands_per_img = 0;
-    p.in = a.in; p.wp = a.wp; p.bias = a.ep.bias; p.out_s = out_s; p.out = out; p.amax = amax;
+    p.in = a.in; p.wp = a.wp; p.bias = a.ep.bias; p.out = out; p.out_r = out_r; p.amax = amax;
     if (a.cin_chunks == 2) return launch_conv_pool_umma_t<2, 2, 2>(p, num_sms, st);
     return launch_conv_pool_umma_t<4, 5, 2>(p, num_sms, st);
 }
@@ -810,13 +783,13 @@ int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, float* out
 // GEMM view per 128-pixel block:  D_kx[m, n] += A_kx[m, q] * B[q, n]  with the reduction over pixels (K), where
 //   m = (ky, ci) stacks the three filter ROWS (three bulk copies of the same planes shifted by one image row) and
 //   kx is a 16-byte shift of the A start address.  A is MN-major (M = channels contiguous), B (= G) is MN-major too,
-//   so both operands are again the untouched chunk planes.  One extra M group of bf16 ones yields the bias gradient.
-// Precision: X = hi + mid (16 significant bits are enough here: products are summed in fp32 over >= 10^5 pixels),
-//   G = hi + mid (gradient tensors are carried with 2 planes); n = (G plane, co) stacks the two G planes along N.
+//   so both operands are again the untouched chunk planes.  One extra M group of fp16 ones yields the bias gradient.
+// Precision: X and G are fp16x2 carriers (22 bits); n = (G plane, co) stacks the two G planes along N; the blocks that involve
+//   one mid plane carry 2^11 and are folded in by the epilogue / the reduce kernel (G also carries the loss scale S).
 // Measured limits that shape the kernel (profiles/r01_v5_*): the TMA unit retires one bulk copy per ~50 cycles per SM, so
 //   copies are >= 2 KB (128-pixel blocks); one thread issues at most one MMA per ~50 cycles and the tensor pipe needs
 //   (A bytes + B bytes) / 128 cycles per MMA, so the MMA count per block is minimised per shape:
-//   * Cin = 4 (frames, exact in bf16):  M = 64,  one MMA per (K step, kx), two CTAs per SM.
+//   * Cin = 4 (frames, exact in fp16):  M = 64,  one MMA per (K step, kx), two CTAs per SM.
 //   * Cin = 16: the X planes are stacked along M as well ([X_hi groups | ones | X_mid groups | zeros] = 14 groups, M = 128):
 //     ONE MMA per (K step, kx) yields X_hi*G_hi, X_hi*G_mid, X_mid*G_hi (and X_mid*G_mid for free); two CTAs per SM.
 //   * Cin = 32: 13 groups per plane do not stack; two issuing threads instead, each with its own accumulators
@@ -891,7 +864,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     for (int s = 0; s < NSTAGES; ++s)
         for (int pl = 0; pl < XPL; ++pl) {
             uint32_t* g = reinterpret_cast<uint32_t*>(stages + s * L.stage_bytes + pl * L.a_bytes + GROUPS * WG_PLANE);
-            const uint32_t val = pl == 0 ? 0x3F803F80u : 0u;   // bf16 1.0 x2
+            const uint32_t val = pl == 0 ? 0x3C003C00u : 0u;   // fp16 1.0 x2
             for (int t = threadIdx.x; t < WG_PLANE / 4; t += WG_THREADS) g[t] = val;
         }
     fence_proxy_async();
@@ -916,12 +889,12 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
             for (int i = lane; i < NCOPY_A + NCOPY_B; i += 32) {
                 if (i < NCOPY_A) {
                     const int pl = i / GROUPS, g = i % GROUPS, ky = g / CIN_CHUNKS, j = g % CIN_CHUNKS;
-                    const bf16* src = pl == 0 ? a.x.hi : a.x.mid;
+                    const f16* src = pl == 0 ? a.x.hi : a.x.mid;
                     const long long q = q0 + (ky - 1) * Wp - 1;
                     bulk_g2s(dst + pl * L.a_bytes + g * WG_PLANE, src + ((long long)j * a.x.plane_px + q) * 8, WG_PLANE, &full[s]);
                 } else {
                     const int k = i - NCOPY_A, pl = k / NCH, j = k % NCH;
-                    const bf16* src = pl == 0 ? a.gy.hi : a.gy.mid;
+                    const f16* src = pl == 0 ? a.gy.hi : a.gy.mid;
                     bulk_g2s(dst + XPL * L.a_bytes + k * WG_BCHUNK, src + ((long long)j * a.gy.plane_px + q0) * 8, WG_BCHUNK, &full[s]);
                 }
             }
@@ -931,7 +904,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     } else if (warp == 5 || (S::DUAL && warp == 6)) {
         // ===================== MMA issuer(s) =====================
         const int who = warp - 5;                               // 0: X_hi (or both planes when stacked), 1: X_mid (DUAL)
-        const uint32_t idesc = make_idesc_bf16(S::MMA_M, who == 0 ? 2 * COUT : COUT, 1, 1);
+        const uint32_t idesc = make_idesc_f16(S::MMA_M, who == 0 ? 2 * COUT : COUT, 1, 1);
         const uint32_t d0 = tmem_base + (who == 0 ? 0 : 3 * ACC0);
         const uint32_t dstep = who == 0 ? ACC0 : ACC1;
         int s = 0; uint32_t ph = 0;
@@ -972,14 +945,14 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
             float v[COUT], t[16];
 #pragma unroll
             for (int h = 0; h < COUT / 16; ++h) {
-                tmem_ld16(lane_addr + kx * ACC0 + COUT + h * 16, v + h * 16);          // * G_mid
-                tmem_ld16(lane_addr + kx * ACC0 + h * 16, t);                          // * G_hi
+                tmem_ld16(lane_addr + kx * ACC0 + COUT + h * 16, t);                   // * G_mid (carries 2^11)
+                tmem_ld16(lane_addr + kx * ACC0 + h * 16, v + h * 16);                 // * G_hi
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                for (int i = 0; i < 16; ++i) v[h * 16 + i] = fmaf(t[i], MID_INV, v[h * 16 + i]);
                 if (S::DUAL) {
-                    tmem_ld16(lane_addr + 3 * ACC0 + kx * ACC1 + h * 16, t);           // X_mid * G_hi (same rows)
+                    tmem_ld16(lane_addr + 3 * ACC0 + kx * ACC1 + h * 16, t);           // X_mid * G_hi (same rows, carries 2^11)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[h * 16 + i] += t[i];
+                    for (int i = 0; i < 16; ++i) v[h * 16 + i] = fmaf(t[i], MID_INV, v[h * 16 + i]);
                 }
             }
             if (m < S::ROWS) {
@@ -995,14 +968,15 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// dW[(ky*3+kx)][ci][co] = scale * sum_cta (P[cta][kx][ky*Cpad + ci][co] + P[cta][kx][hrows + ky*Cpad + ci][co] if stacked)
-// db[co] = sum_cta P[cta][1][3*Cpad][co]
+// dW[(ky*3+kx)][ci][co] = scale / S * sum_cta (P[cta][kx][ky*Cpad + ci][co] + 2^-11 * P[cta][kx][hrows + ky*Cpad + ci][co] if stacked)
+// db[co] = 1 / S * sum_cta P[cta][1][3*Cpad][co]              (S = the minibatch's loss scale, *inv_scale = 1 / S)
 // One block per 32 consecutive outputs; warp w of 32 sums the partials of CTAs w, w+32, ... (coalesced 128-byte rows, loads of
 // four CTAs in flight), the 32 warp sums are added in a fixed order (deterministic).
 constexpr int WG_RED_WARPS = 32;
 __global__ void __launch_bounds__(WG_RED_WARPS * 32) k_wgrad_umma_reduce(const float* __restrict__ partial, int nctas, int cpad, int rows,
                                                                           int hrows, int stacked, int cin_real, int cout, float scale,
-                                                                          float* __restrict__ dw, float* __restrict__ db) {
+                                                                          const float* __restrict__ inv_scale, float* __restrict__ dw,
+                                                                          float* __restrict__ db) {
     __shared__ float sm[WG_RED_WARPS][32];
     griddep_launch();
     griddep_wait();
@@ -1027,7 +1001,7 @@ __global__ void __launch_bounds__(WG_RED_WARPS * 32) k_wgrad_umma_reduce(const f
         for (int b = w; b < nctas; b += WG_RED_WARPS) {
             const float* p = partial + (long long)b * stride + src;
             float v = p[0];
-            if (two) v += p[off2];
+            if (two) v = fmaf(p[off2], MID_INV, v);      // rows of the X_mid groups
             s += v;
         }
     }
@@ -1037,7 +1011,8 @@ __global__ void __launch_bounds__(WG_RED_WARPS * 32) k_wgrad_umma_reduce(const f
         float t = sm[0][lane];
 #pragma unroll
         for (int k = 1; k < WG_RED_WARPS; ++k) t += sm[k][lane];
-        if (i < nw) dw[i] = t * scale; else db[i - nw] = t;
+        const float inv = inv_scale ? *inv_scale : 1.f;
+        if (i < nw) dw[i] = t * scale * inv; else db[i - nw] = t * inv;
     }
 }
 
@@ -1059,14 +1034,14 @@ static int launch_wgrad_umma_t(const WgradArgs& a, float* partial, int num_sms, 
     CB_LAUNCH_CHECK();
     int nw = 9 * a.cin_real * a.cout;
     launch_pdl(k_wgrad_umma_reduce, dim3((nw + a.cout + 31) / 32), dim3(WG_RED_WARPS * 32), 0, st, (const float*)partial, grid, CIN_CHUNKS * 8,
-               S::ROWS, S::HROWS, S::MSTACK ? 1 : 0, a.cin_real, a.cout, a.scale, a.dw, a.db);
+               S::ROWS, S::HROWS, S::MSTACK ? 1 : 0, a.cin_real, a.cout, a.scale, a.inv_scale, a.dw, a.db);
     CB_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_wgrad_umma(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st) {
     CB_CHECK(WG_BLOCK + a.g.Wp + 2 <= GUARD, "wgrad_umma: guard too small for Wp=%d", a.g.Wp);
-    CB_CHECK(a.gy.mid && !a.gy.lo, "wgrad_umma: gradient tensors carry two bf16 planes");
+    CB_CHECK(a.gy.mid, "wgrad_umma: gradient tensors carry two fp16 planes");
     CB_CHECK(a.cin_chunks == 1 || a.x.mid, "wgrad_umma: activation planes hi and mid needed");
     if (a.cin_chunks == 1 && a.cout == 16) return launch_wgrad_umma_t<1, 16>(a, partial, num_sms, st);
     if (a.cin_chunks == 2 && a.cout == 16) return launch_wgrad_umma_t<2, 16>(a, partial, num_sms, st);

@@ -89,22 +89,24 @@ static std::vector<Leaf> build_leaves(int A) {
 struct ConvLayer {
     int cin, cout;          // real channels
     long long off_b, off_w; // offsets in the flat parameter vector
-    bf16 *fwd, *dg;         // packed [hi|mid|lo] weight images (forward / dgrad)
+    f16 *fwd, *dg;          // packed [hi|mid] weight images (forward / dgrad)
 };
 
-struct Act {                // one activation / gradient tensor
-    Planes pl = {nullptr, nullptr, nullptr, 0};
-    float* s = nullptr;
+struct Act {                // one activation / gradient tensor: fp16x2 carrier planes (common.cuh)
+    Planes pl = {nullptr, nullptr, 0};
     int C = 0, H = 0;
 };
 
 struct Stage {
-    Act x;                  // input planes of the sequence conv (stage 0: frames, hi only; else previous stage output)
-    Act y;                  // conv output (fp32 stream, pre-pool)
-    Act p;                  // pooled: stream + relu planes
+    Act x;                  // input of the sequence conv (stage 0: frames, hi only; else the previous stage's raw output)
+    Act y;                  // conv output before the pool (only when the conv is not fused with its pool)
+    Act p, pr;              // pooled: raw (residual input of block 0) and rectified (operand of its first conv)
     uint8_t* amax = nullptr; // arg-max slots of the pool (learner contexts)
-    Act a0, b0, a1, out;    // residual blocks (see trunk_forward)
-    Act gA, gB, gC, gBin;   // gradients (learner contexts)
+    Act a0;                 // relu(conv1(relu(p)))
+    Act b0, b0r;            // p + conv2(a0): raw and rectified
+    Act a1;                 // relu(conv3(relu(b0)))
+    Act out;                // b0 + conv4(a1): raw for stages 0 / 1 (the next ConvSequence is fed un-rectified), rectified for stage 2
+    Act gA, gB, gC, gBin;   // gradients (learner contexts), all scaled by the minibatch's loss scale
 };
 
 }  // namespace cb
@@ -144,7 +146,8 @@ struct cb_ctx {
     // tcgen05 dense layer (dense_umma.cu)
     bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
     int npad_max = 0;
-    static constexpr int grad_planes = 2;   // bf16 planes of gradient tensors (16 significant bits)
+    float* gscale = nullptr;                // device {S, 1 / S}: loss scale of the current minibatch's gradient tensors
+    unsigned* gs_work = nullptr;            // scratch of k_loss_scale
     const cb_rollout_cursor* cursor = nullptr;   // set for the duration of a cb_actor_step_cursor call
     bool fuse0 = false;
     bool fuse12 = false;                    // second / third ConvSequence: conv + pool (forward) fused                     // first ConvSequence: conv + pool (forward) and pool + wgrad (backward) fused
@@ -165,30 +168,18 @@ static long long plane_px_for(int max_batch, int H) {
     return GUARD + np + GUARD;
 }
 
-// lo: allocate the split planes beyond hi; nsplit = 3 (hi, mid, lo: forward activations) or 2 (hi, mid: gradients)
-static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool planes, bool lo, bool stream, int nsplit = 3) {
+// two = false: single-plane tensor (the unpacked frames)
+static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool two = true) {
     a.C = C; a.H = H;
     const int chunks = (C + 7) / 8;
-    if (planes) {
-        a.pl.plane_px = plane_px_for(c->cfg.max_batch, H);
-        size_t bytes = (size_t)chunks * a.pl.plane_px * 8 * sizeof(bf16);
-        void* p;
+    a.pl.plane_px = plane_px_for(c->cfg.max_batch, H);
+    size_t bytes = (size_t)chunks * a.pl.plane_px * 8 * sizeof(f16);
+    void* p;
+    if (dev_alloc(c, &p, bytes)) return -1;
+    a.pl.hi = (f16*)p + (long long)GUARD * 8;
+    if (two) {
         if (dev_alloc(c, &p, bytes)) return -1;
-        a.pl.hi = (bf16*)p + (long long)GUARD * 8;
-        if (lo) {
-            if (dev_alloc(c, &p, bytes)) return -1;
-            a.pl.mid = (bf16*)p + (long long)GUARD * 8;
-            if (nsplit == 3) {
-                if (dev_alloc(c, &p, bytes)) return -1;
-                a.pl.lo = (bf16*)p + (long long)GUARD * 8;
-            }
-        }
-    }
-    if (stream) {
-        size_t bytes = (size_t)chunks * c->cfg.max_batch * (H + 2) * (H + 2) * 8 * sizeof(float);
-        void* p;
-        if (dev_alloc(c, &p, bytes)) return -1;
-        a.s = (float*)p;
+        a.pl.mid = (f16*)p + (long long)GUARD * 8;
     }
     return 0;
 }
@@ -214,12 +205,11 @@ struct ProfScope {
     }
 };
 static double f32_once(const ConvGeom& g, int channels) { return 4.0 * g.n * g.H * g.W * channels; }   // unpadded fp32 tensor
-static double planes_bytes(const ConvGeom& g, int chunks, bool lo) { return (double)g.NP * chunks * 8 * (lo ? 6 : 2); }
-static double planes_bytes(const ConvGeom& g, int chunks, const Planes& p) { return (double)g.NP * chunks * 8 * 2 * (p.lo ? 3 : (p.mid ? 2 : 1)); }
-static double stream_bytes(const ConvGeom& g, int chunks) { return (double)g.NP * chunks * 8 * 4; }
+static double planes_bytes(const ConvGeom& g, int chunks, bool two = true) { return (double)g.NP * chunks * 8 * (two ? 4 : 2); }
+static double planes_bytes(const ConvGeom& g, int chunks, const Planes& p) { return p.hi ? planes_bytes(g, chunks, p.mid != nullptr) : 0.0; }
 
 static int refresh_weights(cb_ctx* c, cudaStream_t st) {
-    ProfScope ps(c, "pack_weights", 0, 1089232.0 * (4 + 12), st);
+    ProfScope ps(c, "pack_weights", 0, 1089232.0 * (4 + 8), st);
     if (launch_pack_conv(c->pack_dev, 15, st)) return -1;
     if (c->wd_fwd) return launch_pack_dense(c->params + c->off_dense_w, c->wd_fwd, c->wd_dx, st);
     return 0;
@@ -259,12 +249,10 @@ static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
     char name[96];
     snprintf(name, sizeof(name), "%s<cin%d,cout%d>@%dx%d", a.transpose ? "conv_dgrad" : "conv_fwd", a.cin_real, a.cout, a.g.H, a.g.W);
     const double flops = 2.0 * a.g.n * a.g.H * a.g.W * 9.0 * a.cin_real * a.cout;
-    double bytes = planes_bytes(a.g, a.cin_chunks, a.in);
-    if (a.ep.out_s) bytes += stream_bytes(a.g, a.cout / 8);
-    if (a.ep.out.hi) bytes += planes_bytes(a.g, a.cout / 8, a.ep.out);
-    if (a.ep.res) bytes += stream_bytes(a.g, a.cout / 8);
+    double bytes = planes_bytes(a.g, a.cin_chunks, a.in) + planes_bytes(a.g, a.cout / 8, a.ep.out) + planes_bytes(a.g, a.cout / 8, a.ep.out_r) +
+                   planes_bytes(a.g, a.cout / 8, a.ep.res);
     if (a.ep.mask_hi) bytes += planes_bytes(a.g, a.cout / 8, false);
-    const double abytes = f32_once(a.g, a.cin_real) + f32_once(a.g, a.cout) * (1 + (a.ep.res ? 1 : 0) + (a.ep.mask_hi ? 1 : 0));
+    const double abytes = f32_once(a.g, a.cin_real) + f32_once(a.g, a.cout) * (1 + (a.ep.res.hi ? 1 : 0) + (a.ep.mask_hi ? 1 : 0));
     ProfScope ps(c, name, flops, bytes, st, abytes);
     if (c->cfg.conv_backend == CB_CONV_SIMT) return launch_conv_simt(a, st);
     return launch_conv_umma(a, c->num_sms, st);
@@ -276,6 +264,7 @@ static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, cons
     w.g = g; w.x = x.pl; w.cin_chunks = (L.cin + 7) / 8; w.cin_real = L.cin; w.gy = gy.pl; w.cout = L.cout;
     w.dw = grads + L.off_w; w.db = grads + L.off_b;
     w.scale = (layer == 0) ? (1.0f / 255.0f) : 1.0f;
+    w.inv_scale = c->gscale + 1;
     char name[96];
     snprintf(name, sizeof(name), "conv_wgrad<cin%d,cout%d>@%dx%d", L.cin, L.cout, g.H, g.W);
     ProfScope ps(c, name, 2.0 * g.n * g.H * g.W * 9.0 * L.cin * L.cout,
@@ -299,6 +288,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
         const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
         const ConvGeom go = make_geom(n, kStageHout[s], kStageHout[s]);
         const int base = s * 5;
+        const int C = kStageC[s];
         const bool fused = (s == 0) ? c->fuse0 : c->fuse12;       // sequence conv + max-pool in ONE tcgen05 kernel
         if (fused && s == 0) {
             // frame conv + max-pool in one kernel: the 84x84x16 conv output never reaches HBM (conv_umma.cu)
@@ -306,9 +296,9 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             a.ep.bias = c->params + c->conv[0].off_b;
             a.ep.acc_scale = 1.0f / 255.0f;                       // x / 255.0 (cleanba_ppo.py:181) folded into the epilogue
             ProfScope ps(c, "conv0_pool_fwd@84", 2.0 * n * 84 * 84 * 9.0 * 4 * 16,
-                         planes_bytes(gi, 1, false) + stream_bytes(go, 2) + planes_bytes(go, 2, true) + (S.amax ? (double)go.NP * 16 : 0.0), st,
+                         planes_bytes(gi, 1, false) + 2 * planes_bytes(go, 2) + (S.amax ? (double)go.NP * 16 : 0.0), st,
                          (double)n * 28224.0 + f32_once(go, 16));      // uint8 frames in, pooled fp32 out
-            if (launch_conv0_pool_umma(a, S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
+            if (launch_conv0_pool_umma(a, S.p.pl, S.pr.pl, S.amax, c->num_sms, st)) return -1;
         } else if (fused) {
             // sequence conv + max-pool in one kernel (conv_umma.cu: k_conv_pool_umma)
             ConvArgs a = conv_args(c, base, gi, S.x, false);
@@ -316,41 +306,41 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             char name[96];
             snprintf(name, sizeof(name), "conv_pool_fwd<cin%d,cout%d>@%d", a.cin_real, a.cout, gi.H);
             ProfScope ps(c, name, 2.0 * n * gi.H * gi.W * 9.0 * a.cin_real * a.cout,
-                         planes_bytes(gi, a.cin_chunks, a.in) + stream_bytes(go, a.cout / 8) + planes_bytes(go, a.cout / 8, true) +
-                             (S.amax ? (double)go.NP * a.cout : 0.0), st, f32_once(gi, a.cin_real) + f32_once(go, a.cout));
-            if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.s, S.p.pl, S.amax, c->num_sms, st)) return -1;
+                         planes_bytes(gi, a.cin_chunks, a.in) + 2 * planes_bytes(go, a.cout / 8) + (S.amax ? (double)go.NP * a.cout : 0.0), st,
+                         f32_once(gi, a.cin_real) + f32_once(go, a.cout));
+            if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.pl, S.pr.pl, S.amax, c->num_sms, st)) return -1;
         } else {
             // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
             ConvArgs a = conv_args(c, base + 0, gi, S.x, false);
             a.ep.bias = c->params + c->conv[base].off_b;
             a.ep.acc_scale = (s == 0) ? (1.0f / 255.0f) : 1.0f;   // x / 255.0 (cleanba_ppo.py:181) folded into the epilogue
-            a.ep.out_s = S.y.s;
+            a.ep.out = S.y.pl;
             if (run_conv(c, a, st)) return -1;
-        }
-        // x = nn.max_pool(x, (3,3), strides=(2,2), padding="SAME")              (cleanba_ppo.py:168)
-        if (!fused) {
+            // x = nn.max_pool(x, (3,3), strides=(2,2), padding="SAME")          (cleanba_ppo.py:168)
             ProfScope ps(c, "pool_fwd@" + std::to_string(kStageHin[s]), 0,
-                         stream_bytes(gi, kStageC[s] / 8) + stream_bytes(go, kStageC[s] / 8) + planes_bytes(go, kStageC[s] / 8, true), st);
-            if (launch_pool_fwd(S.y.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.p.s, S.p.pl, S.amax, st)) return -1;
+                         planes_bytes(gi, C / 8) + 2 * planes_bytes(go, C / 8) + (S.amax ? (double)go.NP * C : 0.0), st,
+                         f32_once(gi, C) + f32_once(go, C));
+            if (launch_pool_fwd(S.y.pl, gi, go, kStagePadLo[s], C / 8, S.p.pl, S.pr.pl, S.amax, st)) return -1;
         }
         {   // ResidualBlock 0: x + Conv(relu(Conv(relu(x))))                    (cleanba_ppo.py:153-159)
-            ConvArgs a = conv_args(c, base + 1, go, S.p, false);
+            ConvArgs a = conv_args(c, base + 1, go, S.pr, false);
             a.ep.bias = c->params + c->conv[base + 1].off_b;
-            a.ep.out = S.a0.pl; a.ep.relu = 1;
+            a.ep.out_r = S.a0.pl;
             if (run_conv(c, a, st)) return -1;
             ConvArgs b = conv_args(c, base + 2, go, S.a0, false);
             b.ep.bias = c->params + c->conv[base + 2].off_b;
-            b.ep.res = S.p.s; b.ep.out_s = S.b0.s; b.ep.out = S.b0.pl; b.ep.relu = 1;
+            b.ep.res = S.p.pl; b.ep.out = S.b0.pl; b.ep.out_r = S.b0r.pl;
             if (run_conv(c, b, st)) return -1;
         }
         {   // ResidualBlock 1; its output feeds the next ConvSequence un-rectified, or the final nn.relu (cleanba_ppo.py:184)
-            ConvArgs a = conv_args(c, base + 3, go, S.b0, false);
+            ConvArgs a = conv_args(c, base + 3, go, S.b0r, false);
             a.ep.bias = c->params + c->conv[base + 3].off_b;
-            a.ep.out = S.a1.pl; a.ep.relu = 1;
+            a.ep.out_r = S.a1.pl;
             if (run_conv(c, a, st)) return -1;
             ConvArgs b = conv_args(c, base + 4, go, S.a1, false);
             b.ep.bias = c->params + c->conv[base + 4].off_b;
-            b.ep.res = S.b0.s; b.ep.out = S.out.pl; b.ep.relu = (s == 2) ? 1 : 0;
+            b.ep.res = S.b0.pl;
+            if (s < 2) b.ep.out = S.out.pl; else b.ep.out_r = S.out.pl;
             if (s == 2 && c->wd_fwd) {   // sample-minor copy of the final features for the tcgen05 dense layer
                 b.ep.ft_hi = c->ft[0]; b.ep.ft_mid = c->ft[1]; b.ep.ft_lo = c->ft[2];
                 b.ep.ft_npad = (n + 127) / 128 * 128; b.ep.ft_pixpad = 124;
@@ -360,19 +350,23 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
     }
     DenseArgs d;
     d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
-    ProfScope ps(c, "dense_fwd", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 6 + (double)kFlat * HIDDEN * 6, st);
+    ProfScope ps(c, "dense_fwd", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 6 + (double)kFlat * HIDDEN * 6, st,
+                 4.0 * ((double)n * kFlat + (double)kFlat * HIDDEN + (double)n * HIDDEN));
     if (c->wd_fwd) return launch_dense_fwd_umma(dense_umma_args(c, n), st);
     return launch_dense_fwd(d, c->dense_part, st);
 }
 
 // Backward of the trunk given c->dpre (gradient w.r.t. the pre-relu dense output); writes all trunk gradients.
 static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
+    // per-minibatch power-of-two loss scale of the fp16 gradient carriers (device side, no host sync)
+    if (launch_loss_scale(c->dpre, (long long)n * HIDDEN, c->gs_work, c->gscale, st)) return -1;
     DenseArgs d;
     d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
     if (c->wd_fwd) {
-        ProfScope ps(c, "dense_bwd", 4.0 * n * kFlat * HIDDEN, (double)n * kFlat * 12 + (double)kFlat * HIDDEN * 8, st);
+        ProfScope ps(c, "dense_bwd", 4.0 * n * kFlat * HIDDEN, (double)n * kFlat * 12 + (double)kFlat * HIDDEN * 8, st,
+                     4.0 * (2.0 * n * kFlat + 2.0 * kFlat * HIDDEN + (double)n * HIDDEN));
         DenseUmmaArgs u = dense_umma_args(c, n);
-        u.out_s = c->st[2].gA.s; u.out = c->st[2].gA.pl;
+        u.gscale = c->gscale; u.out = c->st[2].gA.pl;
         if (launch_dpre_transpose(c->dpre, n, u.npad, c->dpT[0], c->dpT[1], st)) return -1;
         if (launch_dense_bwd_umma(u, c->dpre, grads + c->off_dense_w, grads + c->off_dense_b, c->dense_part, st)) return -1;
     } else {
@@ -381,8 +375,8 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             if (launch_dense_bwd_w(d, c->dpre, grads + c->off_dense_w, grads + c->off_dense_b, st)) return -1;
         }
         {
-            ProfScope ps(c, "dense_bwd_x", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 12 + (double)kFlat * HIDDEN * 4, st);
-            if (launch_dense_bwd_x(d, c->dpre, c->st[2].gA.s, c->st[2].gA.pl, st)) return -1;
+            ProfScope ps(c, "dense_bwd_x", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 6 + (double)kFlat * HIDDEN * 4, st);
+            if (launch_dense_bwd_x(d, c->dpre, c->gscale, c->st[2].gA.pl, st)) return -1;
         }
     }
     for (int s = 2; s >= 0; --s) {
@@ -390,6 +384,7 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
         const ConvGeom go = make_geom(n, kStageHout[s], kStageHout[s]);
         const int base = s * 5;
+        const int C = kStageC[s];
         // ---- ResidualBlock 1: out = b0 + conv4(relu(conv3(relu(b0))))
         if (run_wgrad(c, base + 4, go, S.a1, S.gA, grads, st)) return -1;
         {
@@ -397,11 +392,11 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             a.ep.mask_hi = S.a1.pl.hi; a.ep.mask_plane_px = S.a1.pl.plane_px; a.ep.out = S.gB.pl;
             if (run_conv(c, a, st)) return -1;
         }
-        if (run_wgrad(c, base + 3, go, S.b0, S.gB, grads, st)) return -1;
+        if (run_wgrad(c, base + 3, go, S.b0r, S.gB, grads, st)) return -1;
         {
             ConvArgs a = conv_args(c, base + 3, go, S.gB, true);
-            a.ep.mask_hi = S.b0.pl.hi; a.ep.mask_plane_px = S.b0.pl.plane_px; a.ep.res = S.gA.s;
-            a.ep.out_s = S.gC.s; a.ep.out = S.gC.pl;
+            a.ep.mask_hi = S.b0r.pl.hi; a.ep.mask_plane_px = S.b0r.pl.plane_px; a.ep.res = S.gA.pl;
+            a.ep.out = S.gC.pl;
             if (run_conv(c, a, st)) return -1;
         }
         // ---- ResidualBlock 0: b0 = p + conv2(relu(conv1(relu(p))))
@@ -411,30 +406,31 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             a.ep.mask_hi = S.a0.pl.hi; a.ep.mask_plane_px = S.a0.pl.plane_px; a.ep.out = S.gB.pl;
             if (run_conv(c, a, st)) return -1;
         }
-        if (run_wgrad(c, base + 1, go, S.p, S.gB, grads, st)) return -1;
+        if (run_wgrad(c, base + 1, go, S.pr, S.gB, grads, st)) return -1;
         {
             ConvArgs a = conv_args(c, base + 1, go, S.gB, true);
-            a.ep.mask_hi = S.p.pl.hi; a.ep.mask_plane_px = S.p.pl.plane_px; a.ep.res = S.gC.s;
-            a.ep.out_s = S.gA.s;   // gradient w.r.t. the pooled tensor (gA.s is free again)
+            a.ep.mask_hi = S.pr.pl.hi; a.ep.mask_plane_px = S.pr.pl.plane_px; a.ep.res = S.gC.pl;
+            a.ep.out = S.gA.pl;    // gradient w.r.t. the pooled tensor (gA is free again)
             if (run_conv(c, a, st)) return -1;
         }
         // ---- max-pool backward, then the sequence conv
         if (s == 0 && c->fuse0) {
             // frames need no dX: the pooled gradient goes straight into the frame conv's weight gradient (trunk_simt.cu)
-            ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), st);
-            if (launch_pool_bwd_wgrad0(S.amax, S.gA.s, S.x.pl.hi, gi, go, 1.0f / 255.0f, grads + c->conv[0].off_w,
+            ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), st,
+                         f32_once(go, 16) + (double)n * 28224.0);
+            if (launch_pool_bwd_wgrad0(S.amax, S.gA.pl, S.x.pl.hi, gi, go, 1.0f / 255.0f, c->gscale + 1, grads + c->conv[0].off_w,
                                        grads + c->conv[0].off_b, c->wg_partial, c->num_sms, st)) return -1;
             continue;
         }
         {
             ProfScope ps(c, "pool_bwd@" + std::to_string(kStageHin[s]), 0,
-                         (double)go.NP * kStageC[s] * 5 + planes_bytes(gi, kStageC[s] / 8, true), st);
-            if (launch_pool_bwd(S.amax, S.gA.s, gi, go, kStagePadLo[s], kStageC[s] / 8, S.gBin.pl, st)) return -1;
+                         (double)go.NP * C * 5 + planes_bytes(gi, C / 8), st, f32_once(go, C) + f32_once(gi, C));
+            if (launch_pool_bwd(S.amax, S.gA.pl, gi, go, kStagePadLo[s], C / 8, S.gBin.pl, st)) return -1;
         }
         if (run_wgrad(c, base + 0, gi, S.x, S.gBin, grads, st)) return -1;
         if (s > 0) {
             ConvArgs a = conv_args(c, base + 0, gi, S.gBin, true);
-            a.ep.out_s = c->st[s - 1].gA.s; a.ep.out = c->st[s - 1].gA.pl;
+            a.ep.out = c->st[s - 1].gA.pl;
             if (run_conv(c, a, st)) return -1;
         }
     }
@@ -520,14 +516,14 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
                 L.cout = kStageC[s];
                 L.off_b = c->leaves[s * 10 + k * 2].offset;
                 L.off_w = c->leaves[s * 10 + k * 2 + 1].offset;
-                long long ef = packed_conv_elems((L.cin + 7) / 8, L.cout, 3);
-                if (dev_alloc(c, &p, ef * sizeof(bf16))) { fail = true; break; }
-                L.fwd = (bf16*)p;
+                long long ef = packed_conv_elems((L.cin + 7) / 8, L.cout);
+                if (dev_alloc(c, &p, ef * sizeof(f16))) { fail = true; break; }
+                L.fwd = (f16*)p;
                 L.dg = nullptr;
                 if (li != 0) {
-                    long long ed = packed_conv_elems(L.cout / 8, L.cin, 2);
-                    if (dev_alloc(c, &p, ed * sizeof(bf16))) { fail = true; break; }
-                    L.dg = (bf16*)p;
+                    long long ed = packed_conv_elems(L.cout / 8, L.cin);
+                    if (dev_alloc(c, &p, ed * sizeof(f16))) { fail = true; break; }
+                    L.dg = (f16*)p;
                 }
                 pl[li].w = c->params + L.off_w; pl[li].cin = L.cin; pl[li].cout = L.cout;
                 pl[li].fwd = L.fwd; pl[li].dg = L.dg;
@@ -546,23 +542,25 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
         for (int s = 0; s < 3 && !fail; ++s) {
             Stage& S = c->st[s];
             const int C = kStageC[s], Hin = kStageHin[s], Ho = kStageHout[s];
-            if (s == 0) fail |= alloc_act(c, S.x, 8, Hin, true, false, false) != 0;
-            fail |= alloc_act(c, S.y, C, Hin, false, false, true) != 0;
-            fail |= alloc_act(c, S.p, C, Ho, true, true, true) != 0;
-            fail |= alloc_act(c, S.a0, C, Ho, true, true, false) != 0;
-            fail |= alloc_act(c, S.b0, C, Ho, true, true, true) != 0;
-            fail |= alloc_act(c, S.a1, C, Ho, true, true, false) != 0;
-            fail |= alloc_act(c, S.out, C, Ho, true, true, false) != 0;
+            const bool fused = (s == 0) ? c->fuse0 : c->fuse12;
+            if (s == 0) fail |= alloc_act(c, S.x, 8, Hin, false) != 0;
+            if (!fused) fail |= alloc_act(c, S.y, C, Hin) != 0;
+            fail |= alloc_act(c, S.p, C, Ho) != 0;
+            fail |= alloc_act(c, S.pr, C, Ho) != 0;
+            fail |= alloc_act(c, S.a0, C, Ho) != 0;
+            fail |= alloc_act(c, S.b0, C, Ho) != 0;
+            fail |= alloc_act(c, S.b0r, C, Ho) != 0;
+            fail |= alloc_act(c, S.a1, C, Ho) != 0;
+            fail |= alloc_act(c, S.out, C, Ho) != 0;
             if (s < 2 && !fail) c->st[s + 1].x = S.out;
             if (cfg->train) {
                 void* ap;
                 if (dev_alloc(c, &ap, (size_t)cfg->max_batch * (Ho + 2) * (Ho + 2) * C)) { fail = true; break; }
                 S.amax = (uint8_t*)ap;
-                const int gs = c->grad_planes;
-                fail |= alloc_act(c, S.gA, C, Ho, true, true, true, gs) != 0;
-                fail |= alloc_act(c, S.gB, C, Ho, true, true, false, gs) != 0;
-                fail |= alloc_act(c, S.gC, C, Ho, true, true, true, gs) != 0;
-                fail |= alloc_act(c, S.gBin, C, Hin, true, true, false, gs) != 0;
+                fail |= alloc_act(c, S.gA, C, Ho) != 0;
+                fail |= alloc_act(c, S.gB, C, Ho) != 0;
+                fail |= alloc_act(c, S.gC, C, Ho) != 0;
+                if (!(s == 0 && c->fuse0)) fail |= alloc_act(c, S.gBin, C, Hin) != 0;
             }
         }
         if (fail) break;
@@ -612,6 +610,10 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             c->cell_scratch = (float*)p;
             if (dev_alloc(c, &p, (size_t)4 * 1024 * 1024 * sizeof(float))) break;
             c->wg_partial = (float*)p;
+            if (dev_alloc(c, &p, 2 * sizeof(float))) break;
+            c->gscale = (float*)p;
+            if (dev_alloc(c, &p, 2 * sizeof(unsigned))) break;
+            c->gs_work = (unsigned*)p;
         }
         ok = true;
     } while (0);
@@ -955,49 +957,44 @@ long long cb_debug_tensor(cb_ctx* c, const char* name, float* host_out, long lon
     Stage& S = c->st[s];
     const char* f = name + 3;
     const Act* a = nullptr;
-    bool want_stream = false;
+    float unscale = 1.f;
     if (name[0] == 's') {
         if (!strcmp(f, "x")) a = &S.x;
         else if (!strcmp(f, "y")) {
-            CB_CHECK(!(s == 0 && c->fuse0) && !(s > 0 && c->fuse12), "tensor s%d.y is not materialised (conv fused with its max-pool)", s);
-            a = &S.y; want_stream = true;
+            CB_CHECK(S.y.pl.hi, "tensor s%d.y is not materialised (conv fused with its max-pool)", s);
+            a = &S.y;
         }
-        else if (!strcmp(f, "p")) { a = &S.p; want_stream = true; }
-        else if (!strcmp(f, "pr")) a = &S.p;
+        else if (!strcmp(f, "p")) a = &S.p;
+        else if (!strcmp(f, "pr")) a = &S.pr;
         else if (!strcmp(f, "a0")) a = &S.a0;
-        else if (!strcmp(f, "b0")) { a = &S.b0; want_stream = true; }
-        else if (!strcmp(f, "b0r")) a = &S.b0;
+        else if (!strcmp(f, "b0")) a = &S.b0;
+        else if (!strcmp(f, "b0r")) a = &S.b0r;
         else if (!strcmp(f, "a1")) a = &S.a1;
         else if (!strcmp(f, "out")) a = &S.out;
     } else {
         if (!strcmp(f, "A")) a = &S.gA;
-        else if (!strcmp(f, "As")) { a = &S.gA; want_stream = true; }
         else if (!strcmp(f, "B")) a = &S.gB;
         else if (!strcmp(f, "C")) a = &S.gC;
         else if (!strcmp(f, "Bin")) a = &S.gBin;
+        float gs[2] = {1.f, 1.f};
+        if (c->gscale) CB_CUDA(cudaMemcpy(gs, c->gscale, sizeof(gs), cudaMemcpyDeviceToHost));
+        unscale = gs[1];                                  // gradient tensors carry the loss scale
     }
-    CB_CHECK(a && (want_stream ? a->s != nullptr : a->pl.hi != nullptr), "tensor %s not available", name);
+    CB_CHECK(a && a->pl.hi != nullptr, "tensor %s not available", name);
     const int H = a->H, C = a->C, Hp = H + 2, P = Hp * Hp, chunks = (C + 7) / 8;
     const long long NP = (long long)n * P;
     const long long cnt = (long long)n * H * H * C;
     CB_CHECK(cnt <= cap, "buffer too small (%lld > %lld)", cnt, cap);
-    std::vector<float> tmp((size_t)chunks * NP * 8);
-    if (want_stream) {
-        CB_CUDA(cudaMemcpy(tmp.data(), a->s, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    } else {
-        std::vector<uint16_t> h((size_t)NP * 8);
+    std::vector<float> tmp((size_t)chunks * NP * 8, 0.f);
+    {
+        std::vector<f16> h((size_t)NP * 8);
         for (int j = 0; j < chunks; ++j) {
-            const bf16* planes[3] = {a->pl.hi, a->pl.mid, a->pl.lo};
-            for (size_t i = 0; i < h.size(); ++i) tmp[(size_t)j * NP * 8 + i] = 0.f;
-            for (int pi = 0; pi < 3; ++pi) {
+            const f16* planes[2] = {a->pl.hi, a->pl.mid};
+            for (int pi = 0; pi < 2; ++pi) {
                 if (!planes[pi]) continue;
-                CB_CUDA(cudaMemcpy(h.data(), planes[pi] + (long long)j * a->pl.plane_px * 8, h.size() * 2, cudaMemcpyDeviceToHost));
-                for (size_t i = 0; i < h.size(); ++i) {
-                    uint32_t u = (uint32_t)h[i] << 16;
-                    float f;
-                    memcpy(&f, &u, 4);
-                    tmp[(size_t)j * NP * 8 + i] += f;
-                }
+                CB_CUDA(cudaMemcpy(h.data(), planes[pi] + (long long)j * a->pl.plane_px * 8, h.size() * sizeof(f16), cudaMemcpyDeviceToHost));
+                const float w = (pi == 0 ? 1.f : MID_INV) * unscale;
+                for (size_t i = 0; i < h.size(); ++i) tmp[(size_t)j * NP * 8 + i] += __half2float(h[i]) * w;
             }
         }
     }

@@ -28,7 +28,7 @@ __device__ __forceinline__ void tile_fma(const float (*As)[LDS_], const float (*
     }
 }
 
-// load 8 channels (one chunk) of sample b, feature pixel `pix` as fp32 (hi + lo)
+// load 8 channels (one chunk) of sample b, feature pixel `pix` as fp32
 __device__ __forceinline__ void load_feat8(const Planes& x, int b, int pix, int chunk, float* f) {
     load_planes8(x, ((long long)chunk * x.plane_px + feat_pixel(b, pix)) * 8, f);
 }
@@ -153,8 +153,9 @@ int launch_dense_bwd_w(const DenseArgs& a, const float* dpre, float* dw, float* 
     return 0;
 }
 
-// ---------------- dX[b][k] = sum_j dpre[b][j] W[k][j], gated by the forward relu (x > 0), written as stream + planes
-__global__ void __launch_bounds__(256) k_dense_bwd_x(DenseArgs a, const float* __restrict__ dpre, float* __restrict__ out_s,
+// ---------------- dX[b][k] = S * sum_j dpre[b][j] W[k][j], gated by the forward relu (x > 0), written as carrier planes
+// (S = *gscale: the loss scale every gradient tensor of the trunk carries)
+__global__ void __launch_bounds__(256) k_dense_bwd_x(DenseArgs a, const float* __restrict__ dpre, const float* __restrict__ gscale,
                                                      Planes out) {
     __shared__ __align__(16) float As[TK][LDS_];   // [j][sample]
     __shared__ __align__(16) float Bs[TK][LDS_];   // [j][k]
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) k_dense_bwd_x(DenseArgs a, const float* _
         __syncthreads();
         tile_fma(As, Bs, ty, tx, acc);
     }
-    const long long NP = (long long)a.n * FP;
+    const float S = *gscale;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int b = m0 + ty * 4 + i;
@@ -183,35 +184,31 @@ __global__ void __launch_bounds__(256) k_dense_bwd_x(DenseArgs a, const float* _
         int pix = k / FC, c = k % FC, chunk = c / 8, e0 = c % 8;   // e0 in {0, 4}
         long long q = feat_pixel(b, pix);
         long long poff = ((long long)chunk * a.x.plane_px + q) * 8 + e0;
-        uint2 m = *reinterpret_cast<const uint2*>(a.x.hi + poff);
-        float mf[4] = {bf16lo_to_f(m.x), bf16hi_to_f(m.x), bf16lo_to_f(m.y), bf16hi_to_f(m.y)};
+        const uint2 m = *reinterpret_cast<const uint2*>(a.x.hi + poff);
         float v[4];
-        bf16 h[4], md[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v[j] = mf[j] > 0.f ? acc[i][j] : 0.f;
-            split_bf16(v[j], h[j], md[j], l[j]);
-        }
-        *reinterpret_cast<float4*>(out_s + ((long long)chunk * NP + q) * 8 + e0) = make_float4(v[0], v[1], v[2], v[3]);
+        v[0] = h_pos(m.x & 0xffffu) ? acc[i][0] * S : 0.f;
+        v[1] = h_pos(m.x >> 16) ? acc[i][1] * S : 0.f;
+        v[2] = h_pos(m.y & 0xffffu) ? acc[i][2] * S : 0.f;
+        v[3] = h_pos(m.y >> 16) ? acc[i][3] * S : 0.f;
+        uint2 h, md;
+        split_f16x2(v[0], v[1], h.x, md.x);
+        split_f16x2(v[2], v[3], h.y, md.y);
         long long ooff = ((long long)chunk * out.plane_px + q) * 8 + e0;
-        *reinterpret_cast<uint2*>(out.hi + ooff) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-        *reinterpret_cast<uint2*>(out.mid + ooff) = make_uint2(pack_bf16x2(md[0], md[1]), pack_bf16x2(md[2], md[3]));
-        if (out.lo) *reinterpret_cast<uint2*>(out.lo + ooff) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+        *reinterpret_cast<uint2*>(out.hi + ooff) = h;
+        *reinterpret_cast<uint2*>(out.mid + ooff) = md;
     }
 }
 
-int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, float* out_s, Planes out, cudaStream_t st) {
+int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, const float* gscale, Planes out, cudaStream_t st) {
     // borders of the gradient tensors must be zero: clear, then fill the interior
     long long NP = (long long)a.n * FP;
-    CB_CUDA(cudaMemsetAsync(out_s, 0, (size_t)NP * FC * sizeof(float), st));
     for (int c = 0; c < FC / 8; ++c) {
         size_t npr = (size_t)((NP + 127) / 128 * 128);   // zero up to the 128-pixel tile boundary (wgrad reads it)
-        CB_CUDA(cudaMemsetAsync(out.hi + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
-        CB_CUDA(cudaMemsetAsync(out.mid + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
-        if (out.lo) CB_CUDA(cudaMemsetAsync(out.lo + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
+        CB_CUDA(cudaMemsetAsync(out.hi + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(f16), st));
+        CB_CUDA(cudaMemsetAsync(out.mid + (long long)c * out.plane_px * 8, 0, npr * 8 * sizeof(f16), st));
     }
     dim3 grid((a.n + TM - 1) / TM, (DK + TN - 1) / TN);
-    k_dense_bwd_x<<<grid, 256, 0, st>>>(a, dpre, out_s, out);
+    k_dense_bwd_x<<<grid, 256, 0, st>>>(a, dpre, gscale, out);
     CB_LAUNCH_CHECK();
     return 0;
 }

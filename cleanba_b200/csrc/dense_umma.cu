@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dx_umma(DenseUmmaArgs a, i
     } else {
         int acc = 0; uint32_t aph = 0;
         const int b = m0 + warp * 32 + lane;
+        const float gS = *a.gscale;                 // loss scale carried by the trunk's gradient tensors
         for (int p = p0; p < p1; ++p) {
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
@@ -252,15 +253,12 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dx_umma(DenseUmmaArgs a, i
                 const long long q = (long long)b * 169 + (h + 1) * 13 + (w + 1);
 #pragma unroll
                 for (int jc = 0; jc < DN_CH; ++jc) {
-                    // relu gate of the forward feature (hi plane of the sample-minor copy), then stream + 2-plane split
+                    // relu gate of the forward feature (hi plane of the sample-minor copy), loss scale, carrier split
                     uint4 m = *reinterpret_cast<const uint4*>(a.ft_hi + (((long long)jc * DN_PIXPAD + p) * a.npad + b) * 8);
                     float mf[8], o[8];
                     unpack8(m, mf);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = mf[e] > 0.f ? v[jc * 8 + e] : 0.f;
-                    float4* so = reinterpret_cast<float4*>(a.out_s + ((long long)jc * a.NP + q) * 8);
-                    so[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    so[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    for (int e = 0; e < 8; ++e) o[e] = mf[e] > 0.f ? v[jc * 8 + e] * gS : 0.f;
                     store_planes8(a.out, ((long long)jc * a.out.plane_px + q) * 8, o);
                 }
             }
@@ -393,9 +391,7 @@ __global__ void k_dpre_transpose(const float* __restrict__ dpre, int n, int npad
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.f;
     }
-    Planes pl;
-    pl.hi = hi; pl.mid = mid; pl.lo = nullptr; pl.plane_px = 0;
-    store_planes8(pl, ((long long)jc * npad + b) * 8, v);
+    store_bf16_split8(hi, mid, nullptr, ((long long)jc * npad + b) * 8, v);
 }
 int launch_dpre_transpose(const float* dpre, int n, int npad, bf16* dp_hi, bf16* dp_mid, cudaStream_t st) {
     int total = npad * (HIDDEN / 8);
@@ -453,11 +449,9 @@ int launch_dense_bwd_umma(const DenseUmmaArgs& a, const float* dpre, float* dw, 
     CB_LAUNCH_CHECK();
     // dX (gradient tensors keep exact zeros on the padding ring and up to the 128-pixel tile boundary)
     const size_t npr = (size_t)((a.NP + 127) / 128 * 128);
-    CB_CUDA(cudaMemsetAsync(a.out_s, 0, (size_t)a.NP * DN_C * sizeof(float), st));
     for (int c = 0; c < DN_CH; ++c) {
-        CB_CUDA(cudaMemsetAsync(a.out.hi + (long long)c * a.out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
-        CB_CUDA(cudaMemsetAsync(a.out.mid + (long long)c * a.out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
-        if (a.out.lo) CB_CUDA(cudaMemsetAsync(a.out.lo + (long long)c * a.out.plane_px * 8, 0, npr * 8 * sizeof(bf16), st));
+        CB_CUDA(cudaMemsetAsync(a.out.hi + (long long)c * a.out.plane_px * 8, 0, npr * 8 * sizeof(f16), st));
+        CB_CUDA(cudaMemsetAsync(a.out.mid + (long long)c * a.out.plane_px * 8, 0, npr * 8 * sizeof(f16), st));
     }
     const int tiles = a.npad / 128;
     int psplit = tiles >= 74 ? 2 : (tiles >= 30 ? 4 : 11);

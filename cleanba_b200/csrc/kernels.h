@@ -14,28 +14,29 @@ struct WgradArgs {
     float* dw;           // [3][3][cin_real][cout] fp32 (HWIO, flax order)
     float* db;           // [cout]
     float scale;         // applied to dW only (1/255 for the first conv, whose forward folds x/255 into the epilogue)
+    const float* inv_scale;   // device scalar 1 / (loss scale carried by gy), applied to dW and db; null = 1
 };
 
 // trunk_simt.cu
-int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr);
+int launch_unpack(const uint8_t* obs, const int* idx, int n, f16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
-int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
+int launch_pool_fwd(Planes in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out, Planes out_relu,
                     uint8_t* amax, cudaStream_t st);
-int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
+int launch_pool_bwd(const uint8_t* amax, Planes dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
                     cudaStream_t st);
 int launch_wgrad_simt(const WgradArgs& a, float* partial, int max_blocks, cudaStream_t st);
 // first ConvSequence: pool backward fused with the frame conv's weight gradient (no 84x84 gradient tensor)
-int launch_pool_bwd_wgrad0(const uint8_t* amax, const float* dpool, const bf16* x_hi, ConvGeom gi, ConvGeom go, float scale,
-                           float* dw, float* db, float* partial, int num_sms, cudaStream_t st);
+int launch_pool_bwd_wgrad0(const uint8_t* amax, Planes dpool, const f16* x_hi, ConvGeom gi, ConvGeom go, float scale,
+                           const float* inv_scale, float* dw, float* db, float* partial, int num_sms, cudaStream_t st);
 
 // conv_umma.cu (tcgen05 + TMA bulk copies)
 int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st);
 int launch_wgrad_umma(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st);
 int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp);
 // frame conv fused with its max-pool (84x84x4 -> pooled 42x42x16: stream, relu'd planes, arg-max bytes)
-int launch_conv0_pool_umma(const ConvArgs& a, float* out_s, Planes out, uint8_t* amax, int num_sms, cudaStream_t st);
+int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t* amax, int num_sms, cudaStream_t st);
 // sequence conv of the second / third ConvSequence fused with its max-pool (same outputs on the pooled grid `go`)
-int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, float* out_s, Planes out, uint8_t* amax, int num_sms,
+int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out, Planes out_r, uint8_t* amax, int num_sms,
                           cudaStream_t st);
 
 // dense.cu
@@ -50,8 +51,8 @@ int dense_fwd_splits(int n);
 int launch_dense_fwd(const DenseArgs& a, float* part, cudaStream_t st);
 // dpre: [n][256] gradient w.r.t. the pre-relu dense output.
 int launch_dense_bwd_w(const DenseArgs& a, const float* dpre, float* dw, float* db, cudaStream_t st);
-// dX -> gradient w.r.t. the (pre-relu) trunk output, masked by the forward relu, as fp32 stream + planes
-int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, float* out_s, Planes out, cudaStream_t st);
+// dX -> gradient w.r.t. the (pre-relu) trunk output, masked by the forward relu, times the loss scale *gscale, as carrier planes
+int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, const float* gscale, Planes out, cudaStream_t st);
 
 // dense_umma.cu (tcgen05 dense layer on the sample-minor copies)
 struct DenseUmmaArgs {
@@ -63,8 +64,8 @@ struct DenseUmmaArgs {
     const float* bias;
     float* hidden;               // forward out [n][256]
     float* part;                 // forward partial sums [psplit][n][256] when the pixels are split over CTAs
-    float* out_s;                // dX stream out
-    Planes out;                  // dX planes out (2 planes)
+    const float* gscale;         // device scalar: loss scale S applied to dX (the trunk's gradient tensors carry it)
+    Planes out;                  // dX planes out (fp16x2 carrier)
 };
 int dense_umma_init();
 int launch_pack_dense(const float* w, bf16* fwd, bf16* dx, cudaStream_t st);
@@ -146,16 +147,18 @@ struct OptArgs {
 constexpr int OPT_MAX_PEERS = 8;
 constexpr int OPT_BLOCKS = 296;
 int launch_optimizer(const OptArgs& a, cudaStream_t st);
+// gscale[0] = S, gscale[1] = 1 / S for this minibatch's gradient tensors (work: 2 zero-initialised words)
+int launch_loss_scale(const float* dpre, long long count, unsigned* work, float* gscale, cudaStream_t st);
 int launch_reduce_peers(const OptArgs& a, float* out, cudaStream_t st);   // needs n, gp, ng only
 
 // pack.cu
 struct PackLayer {
     const float* w;              // HWIO master
     int cin, cout;               // real channel counts
-    bf16* fwd;                   // packed forward image ([hi|mid|lo] stacked along N)
-    bf16* dg;                    // packed dgrad image (null for the first conv)
+    f16* fwd;                    // packed forward image ([hi|mid] stacked along N)
+    f16* dg;                     // packed dgrad image (null for the first conv)
 };
 int launch_pack_conv(const PackLayer* layers_dev, int nlayers, cudaStream_t st);
-long long packed_conv_elems(int cin_chunks, int cout, int wpl);
+long long packed_conv_elems(int cin_chunks, int cout);
 
 }  // namespace cb

@@ -250,6 +250,46 @@ __global__ void __launch_bounds__(256) k_opt_apply(OptArgs a) {
     }
 }
 
+// Loss scale of one minibatch's backward pass: S = 2^k with max |dpre| * S in [32, 64), chosen on the device (no host sync).
+// The trunk's gradient tensors are fp16x2 carriers; S keeps them in fp16's range with >= 2^10 of head room for growth on the
+// way down the trunk and >= 22 significant bits for every element above 2^-19 of the largest (common.cuh).  max is order
+// independent, so the result is deterministic.  work = {max bits, finished-block counter}, both left at zero.
+__global__ void __launch_bounds__(256) k_loss_scale(const float* __restrict__ dpre, long long count, unsigned* __restrict__ work,
+                                                    float* __restrict__ gscale) {
+    __shared__ float red[256];
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < count; i += (long long)gridDim.x * 256) m = fmaxf(m, fabsf(dpre[i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicMax(&work[0], __float_as_uint(red[0]));          // non-negative floats order like their bit patterns
+        __threadfence();
+        if (atomicAdd(&work[1], 1u) == gridDim.x - 1) {
+            const float mx = __uint_as_float(atomicExch(&work[0], 0u));
+            work[1] = 0u;
+            int e = 0;
+            float S = 1.f;
+            if (mx > 0.f && mx < INFINITY) {
+                (void)frexpf(mx, &e);                          // mx = f * 2^e, f in [0.5, 1)
+                int k = 6 - e;
+                k = k < -100 ? -100 : (k > 100 ? 100 : k);
+                S = ldexpf(1.f, k);
+            }
+            gscale[0] = S;
+            gscale[1] = 1.f / S;
+        }
+    }
+}
+int launch_loss_scale(const float* dpre, long long count, unsigned* work, float* gscale, cudaStream_t st) {
+    k_loss_scale<<<64, 256, 0, st>>>(dpre, count, work, gscale);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
 // out[i] = gp[0][i] + gp[1][i] + ... (fixed order, peer memory): the in-process stage of a two-level gradient exchange
 __global__ void __launch_bounds__(256) k_reduce_peers(OptArgs a, float* __restrict__ out) {
     for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < a.n; i += (long long)gridDim.x * 256 * 4) {

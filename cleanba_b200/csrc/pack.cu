@@ -1,9 +1,8 @@
-// Packs the fp32 master conv kernels (HWIO, flax order) into the bf16 hi/lo shared-memory images consumed by the
-// tcgen05 conv kernel (conv_umma.cu): per K=16 step a K-major SWIZZLE_NONE B tile  [kc(2)][n3(3*Cout)][8]  where the
-// N rows are the three bf16 split planes of the weights stacked: rows [0,Cout) = hi, [Cout,2Cout) = mid, [2Cout,3Cout) = lo,
-// so that B(n3,k) sits at n3*16 + (k/8)*3*Cout*16 + (k%8)*2 bytes (LBO = 3*Cout*16, SBO = 128) and an MMA with
-// N = 3*Cout, 2*Cout or Cout uses the hi|mid|lo, hi|mid or hi planes of the same image.  The dgrad image carries the hi and
-// mid planes only (n3 = 2*Cout rows): its A operand (a 2-plane gradient tensor) never meets W_lo.
+// Packs the fp32 master conv kernels (HWIO, flax order) into the fp16 carrier images consumed by the tcgen05 conv kernels
+// (conv_umma.cu): per K=16 step a K-major SWIZZLE_NONE B tile  [kc(2)][n2(2*Cout)][8]  where the N rows are the two carrier
+// planes of the weights stacked: rows [0,Cout) = hi = fp16(w), rows [Cout,2Cout) = mid = fp16((w - hi) * 2^11), so that
+// B(n2,k) sits at n2*16 + (k/8)*2*Cout*16 + (k%8)*2 bytes (LBO = 2*Cout*16, SBO = 128) and an MMA with N = 2*Cout or Cout
+// uses the hi|mid or the hi planes of the same image (forward and dgrad images alike).
 //   forward : step = tap * (Cin/16) + pair,  k -> ci = pair*16 + k,  B[n=co][k] = W[tap][ci][co]
 //   dgrad   : conv of the output gradient with flipped taps and swapped channels:
 //             step = tap' * (Cout/16) + pair, k -> co = pair*16 + k, B[n=ci][k] = W[8 - tap'][ci][co]
@@ -17,14 +16,14 @@ namespace cb {
 __global__ void k_pack_conv(const PackLayer* __restrict__ layers) {
     const PackLayer L = layers[blockIdx.y >> 1];
     const int variant = blockIdx.y & 1;   // 0 forward, 1 dgrad
-    bf16* dst = variant ? L.dg : L.fwd;
+    f16* dst = variant ? L.dg : L.fwd;
     if (!dst) return;
     const int kin = variant ? L.cout : L.cin;     // contraction channels
     const int nout = variant ? L.cin : L.cout;    // output channels of this conv
     const bool frames = (kin < 8);
     const int chunks = frames ? 1 : kin / 8;
     const int steps = frames ? 5 : 9 * (chunks / 2);
-    const int n3tot = (variant ? 2 : 3) * nout;   // dgrad multiplies 2-plane gradients: only W_hi | W_mid are ever used
+    const int n3tot = 2 * nout;                   // [W_hi | W_mid] rows
     const long long total = (long long)steps * 2 * n3tot * 8;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int k8 = (int)(e % 8);
@@ -45,9 +44,9 @@ __global__ void k_pack_conv(const PackLayer* __restrict__ layers) {
             if (!variant) w = L.w[((long long)tap * L.cin + kch) * L.cout + n];
             else w = L.w[((long long)(8 - tap) * L.cin + n) * L.cout + kch];
         }
-        bf16 h, m, l;
-        split_bf16(w, h, m, l);
-        dst[e] = plane == 0 ? h : (plane == 1 ? m : l);
+        f16 h, m;
+        split_f16(w, h, m);
+        dst[e] = plane == 0 ? h : m;
     }
 }
 

@@ -8,13 +8,13 @@
 namespace cb {
 
 // ------------------------------------------------------------------------------------------------
-// uint8 NCHW frame stack -> bf16 chunk plane (8 channels: 4 real + 4 zero), borders zero.
-// cleanba_ppo.py:180-181 (transpose + /255; the 1/255 is folded into the conv epilogue, 0..255 are exact in bf16).
+// uint8 NCHW frame stack -> fp16 chunk plane (8 channels: 4 real + 4 zero), borders zero.
+// cleanba_ppo.py:180-181 (transpose + /255; the 1/255 is folded into the conv epilogue, 0..255 are exact in fp16).
 // One block per (image, group of UNPACK_ROWS padded rows): the channel rows are staged through shared memory with
 // coalesced 4-byte reads, then every thread emits 16-byte pixels (consecutive threads -> consecutive pixels).
 constexpr int UNPACK_ROWS = 8;
 __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, int n,
-                                                       bf16* __restrict__ out_hi, const cb_rollout_cursor* __restrict__ cursor) {
+                                                       f16* __restrict__ out_hi, const cb_rollout_cursor* __restrict__ cursor) {
     griddep_launch();
     griddep_wait();
     if (cursor) obs = reinterpret_cast<const uint8_t*>(cursor->obs) + (long long)cursor->row * cursor->obs_row_stride;
@@ -40,15 +40,16 @@ __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict
             const int x = xp - 1;
             const uint8_t* s = reinterpret_cast<const uint8_t*>(&srow[ry][0][0]);
             const float c0 = s[0 * W + x], c1 = s[1 * W + x], c2 = s[2 * W + x], c3 = s[3 * W + x];
-            o.x = pack_bf16x2(__float2bfloat16_rn(c0), __float2bfloat16_rn(c1));
-            o.y = pack_bf16x2(__float2bfloat16_rn(c2), __float2bfloat16_rn(c3));
+            const __half2 h01 = __floats2half2_rn(c0, c1), h23 = __floats2half2_rn(c2, c3);
+            o.x = *reinterpret_cast<const uint32_t*>(&h01);
+            o.y = *reinterpret_cast<const uint32_t*>(&h23);
         }
         const long long q = (long long)img * (Hp * Wp) + (long long)yp * Wp + xp;
         *reinterpret_cast<uint4*>(out_hi + q * 8) = o;
     }
 }
 
-int launch_unpack(const uint8_t* obs, const int* idx, int n, bf16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor) {
+int launch_unpack(const uint8_t* obs, const int* idx, int n, f16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor) {
     const int groups = (86 + UNPACK_ROWS - 1) / UNPACK_ROWS;
     launch_pdl(k_unpack_frames, dim3(n * groups), dim3(256), 0, st, obs, idx, n, out_hi, cursor);
     CB_LAUNCH_CHECK();
@@ -102,11 +103,11 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------
 // max_pool 3x3 stride 2 SAME, -inf padding, pad_lo = 0 (84->42, 42->21) or 1 (21->11)  (cleanba_ppo.py:168)
-// in : fp32 stream [C/8][n*Pin][8] (conv output)      out: fp32 stream + relu'd bf16 planes on the pooled grid, and
+// in : carrier planes of the conv output      out: raw + rectified carrier planes on the pooled grid, and
 // (training) the arg-max window slot 0..8 of every pooled element as one byte, first maximum in row-major window
 // order (XLA select_and_scatter with a `ge` select), which is all the backward pass needs.
-__global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks,
-                           float* __restrict__ out_s, Planes out_relu, uint8_t* __restrict__ amax) {
+__global__ void k_pool_fwd(Planes in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out, Planes out_relu,
+                           uint8_t* __restrict__ amax) {
     griddep_launch();
     griddep_wait();
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,18 +132,15 @@ __global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom g
                 int x = 2 * j - pad_lo + dx;
                 if (x < 0 || x >= gi.W) continue;
                 long long qi = (long long)img * gi.P + (long long)(y + 1) * gi.Wp + (x + 1);
-                const float4* p = reinterpret_cast<const float4*>(in + ((long long)jc * gi.NP + qi) * 8);
-                float4 a = p[0], b = p[1];
-                float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                float o[8];
+                load_planes8(in, ((long long)jc * in.plane_px + qi) * 8, o);
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
                     if (o[e] > v[e]) { v[e] = o[e]; am[e] = dy * 3 + dx; }
             }
         }
     }
-    float4* o = reinterpret_cast<float4*>(out_s + ((long long)jc * go.NP + q) * 8);
-    o[0] = make_float4(v[0], v[1], v[2], v[3]);
-    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    store_planes8(out, ((long long)jc * out.plane_px + q) * 8, v);
     float rl[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) rl[e] = fmaxf(v[e], 0.f);
@@ -155,10 +153,10 @@ __global__ void k_pool_fwd(const float* __restrict__ in, ConvGeom gi, ConvGeom g
     }
 }
 
-int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, float* out_s, Planes out_relu,
+int launch_pool_fwd(Planes in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out, Planes out_relu,
                     uint8_t* amax, cudaStream_t st) {
     long long total = go.NP * chunks;
-    launch_pdl(k_pool_fwd, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, in, gi, go, pad_lo, chunks, out_s, out_relu, amax);
+    launch_pdl(k_pool_fwd, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, in, gi, go, pad_lo, chunks, out, out_relu, amax);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -167,9 +165,9 @@ int launch_pool_fwd(const float* in, ConvGeom gi, ConvGeom go, int pad_lo, int c
 // slots (0..1, 0..1) of window (i, j); they can only be the arg-max of the four windows (i-1..i, j-1..j), so a thread loads
 // 4 windows (arg-max bytes + gradient) for 4 output pixels (the one-pixel-per-thread form loaded 4 windows per pixel).
 // Contributions are added in window order (i-1,j-1), (i-1,j), (i,j-1), (i,j).
-//   amax: bytes from the forward pass;  dpool: gradient stream on the pooled grid;  out: gradient planes on the input grid
+//   amax: bytes from the forward pass;  dpool: gradient planes on the pooled grid;  out: gradient planes on the input grid
 // grid = (quad blocks of one image, image * chunks); quads cover the whole padded grid so the border ring is zero-filled too.
-__global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ amax, const float* __restrict__ dpool,
+__global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ amax, Planes dpool,
                                                   ConvGeom gi, ConvGeom go, int pad_lo, int chunks, int KQ, Planes out) {
     griddep_launch();
     griddep_wait();
@@ -182,7 +180,6 @@ __global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ am
         for (long long q = gi.NP + threadIdx.x; q < np_pad; q += blockDim.x) {
             *reinterpret_cast<uint4*>(out.hi + (pbase + q) * 8) = z;
             if (out.mid) *reinterpret_cast<uint4*>(out.mid + (pbase + q) * 8) = z;
-            if (out.lo) *reinterpret_cast<uint4*>(out.lo + (pbase + q) * 8) = z;
         }
     }
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +190,8 @@ __global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ am
     // the four windows: w = di * 2 + dj  <->  (i - 1 + di, j - 1 + dj)
     uint2 pk[4];
     float d[4][8];
-    const long long obase = ((long long)jc * go.NP + (long long)img * go.P) * 8;
+    const long long obase = ((long long)jc * go.NP + (long long)img * go.P) * 8;                  // arg-max bytes (no guards)
+    const long long dbase = ((long long)jc * dpool.plane_px + (long long)img * go.P) * 8;       // gradient planes
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         const int wi = i - 1 + (w >> 1), wj = j - 1 + (w & 1);
@@ -201,12 +199,9 @@ __global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ am
 #pragma unroll
         for (int e = 0; e < 8; ++e) d[w][e] = 0.f;
         if (wi >= 0 && wi < go.H && wj >= 0 && wj < go.W) {
-            const long long o = obase + (long long)((wi + 1) * go.Wp + (wj + 1)) * 8;
-            pk[w] = *reinterpret_cast<const uint2*>(amax + o);
-            const float4* p = reinterpret_cast<const float4*>(dpool + o);
-            const float4 a = p[0], b = p[1];
-            d[w][0] = a.x; d[w][1] = a.y; d[w][2] = a.z; d[w][3] = a.w;
-            d[w][4] = b.x; d[w][5] = b.y; d[w][6] = b.z; d[w][7] = b.w;
+            const long long po = (long long)((wi + 1) * go.Wp + (wj + 1)) * 8;
+            pk[w] = *reinterpret_cast<const uint2*>(amax + obase + po);
+            load_planes8(dpool, dbase + po, d[w]);
         }
     }
     // slot of pixel (a, b) of the quad inside window w (di, dj): row slot = a + 2 * (1 - di) (valid if <= 2), same for columns
@@ -239,7 +234,7 @@ __global__ void __launch_bounds__(256) k_pool_bwd(const uint8_t* __restrict__ am
     }
 }
 
-int launch_pool_bwd(const uint8_t* amax, const float* dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
+int launch_pool_bwd(const uint8_t* amax, Planes dpool, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out,
                     cudaStream_t st) {
     const int KQ = (gi.Hp + 2 - pad_lo) / 2;   // quads per image side: padded rows 2k - 1 + pad_lo, 2k + pad_lo
     dim3 grid((KQ * KQ + 255) / 256, gi.n * chunks);
@@ -264,15 +259,17 @@ constexpr int PW0_HP = 86, PW0_P = PW0_HP * PW0_HP, PW0_HO = 42, PW0_WPO = 44, P
 constexpr int PW0_OUT = 37 * 16;      // 36 (tap, ci) x 16 co weight gradients + 16 bias gradients per partial
 constexpr int PW0_SMEM = PW0_P * 8;   // the staged frame; re-used for the 8 x 592 warp partials at the end
 
-__global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_t* __restrict__ amax, const float* __restrict__ dpool,
-                                                                     const bf16* __restrict__ x_hi, int n, long long go_NP,
+__global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_t* __restrict__ amax, Planes dpool,
+                                                                     const f16* __restrict__ x_hi, int n, long long go_NP,
                                                                      float* __restrict__ partial) {
     extern __shared__ __align__(16) uint8_t pw_smem[];
     uint2* sx = reinterpret_cast<uint2*>(pw_smem);
     griddep_launch();
     griddep_wait();
     const int co = threadIdx.x & 15, grp = threadIdx.x >> 4;
-    const long long cbase = (long long)(co >> 3) * go_NP * 8 + (co & 7);
+    const long long cbase = (long long)(co >> 3) * go_NP * 8 + (co & 7);                 // arg-max bytes (no guards)
+    const long long dcbase = (long long)(co >> 3) * dpool.plane_px * 8 + (co & 7);       // gradient planes
+    auto dload = [&](long long off) { return fmaf(__half2float(dpool.mid[off]), MID_INV, __half2float(dpool.hi[off])); };
     float acc[36];
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0.f;
@@ -286,6 +283,7 @@ __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_
         }
         __syncthreads();
         const long long ibase = cbase + (long long)img * PW0_PO * 8;
+        const long long dibase = dcbase + (long long)img * PW0_PO * 8;
         // software pipeline: the arg-max bytes and gradients of the next PF pooled pixels are in flight during the FMAs of
         // the current PF (global latency ~ 800 cycles vs ~90 instructions per pixel)
         constexpr int PF = 4, NPIX = PW0_HO * PW0_HO, PSTEP = PW0_THREADS / 16;
@@ -296,8 +294,8 @@ __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_
             const int p = grp + u * PSTEP;
             am[u] = 0; g[u] = 0.f;
             if (p < NPIX) {
-                const long long off = ibase + (long long)((p / PW0_HO + 1) * PW0_WPO + (p % PW0_HO + 1)) * 8;
-                am[u] = amax[off]; g[u] = dpool[off];
+                const long long po = (long long)((p / PW0_HO + 1) * PW0_WPO + (p % PW0_HO + 1)) * 8;
+                am[u] = amax[ibase + po]; g[u] = dload(dibase + po);
             }
         }
         for (int p0 = grp; p0 < NPIX; p0 += PF * PSTEP) {
@@ -310,8 +308,8 @@ __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_
                 const int p = p0 + (PF + u) * PSTEP;
                 am[u] = 0; g[u] = 0.f;
                 if (p < NPIX) {
-                    const long long off = ibase + (long long)((p / PW0_HO + 1) * PW0_WPO + (p % PW0_HO + 1)) * 8;
-                    am[u] = amax[off]; g[u] = dpool[off];
+                    const long long po = (long long)((p / PW0_HO + 1) * PW0_WPO + (p % PW0_HO + 1)) * 8;
+                    am[u] = amax[ibase + po]; g[u] = dload(dibase + po);
                 }
             }
 #pragma unroll
@@ -330,10 +328,11 @@ __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_
                     for (int kx = 0; kx < 3; ++kx) {
                         const uint2 v = w0[ky * PW0_HP + kx];
                         float* a = acc + (ky * 3 + kx) * 4;
-                        a[0] = fmaf(bf16lo_to_f(v.x), gc, a[0]);
-                        a[1] = fmaf(bf16hi_to_f(v.x), gc, a[1]);
-                        a[2] = fmaf(bf16lo_to_f(v.y), gc, a[2]);
-                        a[3] = fmaf(bf16hi_to_f(v.y), gc, a[3]);
+                        const float2 x01 = h2_to_f2(v.x), x23 = h2_to_f2(v.y);
+                        a[0] = fmaf(x01.x, gc, a[0]);
+                        a[1] = fmaf(x01.y, gc, a[1]);
+                        a[2] = fmaf(x23.x, gc, a[2]);
+                        a[3] = fmaf(x23.y, gc, a[3]);
                     }
             }
         }
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_
 // out[i] = sum_b partial[b][i] in a fixed order: warp w of 32 adds partials w, w + 32, ..., then the 32 warp sums are added in
 // order.  The first nw outputs are scaled and go to dw, the rest to db.
 __global__ void __launch_bounds__(1024) k_partial_reduce(const float* __restrict__ partial, int nparts, int count, int nw, float scale,
-                                                         float* __restrict__ dw, float* __restrict__ db) {
+                                                         const float* __restrict__ inv_scale, float* __restrict__ dw, float* __restrict__ db) {
     __shared__ float sm[32][32];
     griddep_launch();
     griddep_wait();
@@ -379,12 +378,13 @@ __global__ void __launch_bounds__(1024) k_partial_reduce(const float* __restrict
         float t = sm[0][lane];
 #pragma unroll
         for (int k = 1; k < 32; ++k) t += sm[k][lane];
-        if (i < nw) dw[i] = t * scale; else db[i - nw] = t;
+        const float inv = inv_scale ? *inv_scale : 1.f;      // the gradient planes carry the loss scale
+        if (i < nw) dw[i] = t * scale * inv; else db[i - nw] = t * inv;
     }
 }
 
-int launch_pool_bwd_wgrad0(const uint8_t* amax, const float* dpool, const bf16* x_hi, ConvGeom gi, ConvGeom go, float scale,
-                           float* dw, float* db, float* partial, int num_sms, cudaStream_t st) {
+int launch_pool_bwd_wgrad0(const uint8_t* amax, Planes dpool, const f16* x_hi, ConvGeom gi, ConvGeom go, float scale,
+                           const float* inv_scale, float* dw, float* db, float* partial, int num_sms, cudaStream_t st) {
     CB_CHECK(gi.H == 84 && gi.W == 84 && go.H == PW0_HO && go.W == PW0_HO, "pool_bwd_wgrad0: first-stage geometry (84 -> 42) only");
     static std::atomic<unsigned> attr_done{0};
     int dev = 0;
@@ -396,7 +396,7 @@ int launch_pool_bwd_wgrad0(const uint8_t* amax, const float* dpool, const bf16* 
     const int grid = gi.n < 3 * num_sms ? gi.n : 3 * num_sms;
     launch_pdl(k_pool_bwd_wgrad0, dim3(grid), dim3(PW0_THREADS), (size_t)PW0_SMEM, st, amax, dpool, x_hi, gi.n, go.NP, partial);
     CB_LAUNCH_CHECK();
-    launch_pdl(k_partial_reduce, dim3((PW0_OUT + 31) / 32), dim3(1024), 0, st, (const float*)partial, grid, PW0_OUT, 36 * 16, scale, dw, db);
+    launch_pdl(k_partial_reduce, dim3((PW0_OUT + 31) / 32), dim3(1024), 0, st, (const float*)partial, grid, PW0_OUT, 36 * 16, scale, inv_scale, dw, db);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -476,13 +476,14 @@ __global__ void __launch_bounds__(256) k_wgrad_simt(WgradArgs a, float* __restri
 
 // out[i] = sum_b partial[b][i]  (fixed order);  first nw entries -> dW (HWIO), last cout entries -> db
 __global__ void k_wgrad_reduce(const float* __restrict__ partial, int nblocks, int nw, int cout, float scale,
-                               float* __restrict__ dw, float* __restrict__ db) {
+                               const float* __restrict__ inv_scale, float* __restrict__ dw, float* __restrict__ db) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nw + cout) return;
     float s = 0.f;
     for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * (nw + cout) + i];
-    if (i < nw) dw[i] = s * scale;
-    else db[i - nw] = s;
+    const float inv = inv_scale ? *inv_scale : 1.f;
+    if (i < nw) dw[i] = s * scale * inv;
+    else db[i - nw] = s * inv;
 }
 
 int launch_wgrad_simt(const WgradArgs& a, float* partial, int max_blocks, cudaStream_t st) {
@@ -493,7 +494,7 @@ int launch_wgrad_simt(const WgradArgs& a, float* partial, int max_blocks, cudaSt
     k_wgrad_simt<<<nb, 256, smem, st>>>(a, partial);
     CB_LAUNCH_CHECK();
     int nw = 9 * a.cin_real * a.cout;
-    k_wgrad_reduce<<<(nw + a.cout + 255) / 256, 256, 0, st>>>(partial, nb, nw, a.cout, a.scale, a.dw, a.db);
+    k_wgrad_reduce<<<(nw + a.cout + 255) / 256, 256, 0, st>>>(partial, nb, nw, a.cout, a.scale, a.inv_scale, a.dw, a.db);
     CB_LAUNCH_CHECK();
     return 0;
 }

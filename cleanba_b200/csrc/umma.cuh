@@ -116,6 +116,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
            | ((uint32_t)(M >> 4) << 24);   // M / 16
 }
 
+// Instruction descriptor for kind::f16 with fp16 operands (A / B format fields 0) and fp32 accumulation: the trunk carriers.
+// (tcgen05 rejects mixed fp16 x bf16 operands -- tools/mma_mixed_format_probe.cu -- so every trunk tensor is fp16.)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4)                       // D format  = F32
+           | ((uint32_t)a_mn_major << 15)  // A major   (0 = K, 1 = MN)
+           | ((uint32_t)b_mn_major << 16)  // B major
+           | ((uint32_t)(N >> 3) << 17)    // N / 8
+           | ((uint32_t)(M >> 4) << 24);   // M / 16
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

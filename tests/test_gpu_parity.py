@@ -379,8 +379,7 @@ def test_impala_update_every_step_pinned_to_oracle(agent, params, backend):
     L = ImpalaLearner("cuda:0", ImpalaHyper(num_minibatches=2, num_updates=10), T1=T1, Bl=Bl, conv_backend=backend)
     L.ctx.set_params(params)
     diag = []
-    # RMSProp's first steps move a weight by up to lr / (sqrt(1 - decay)) = 10 lr: 1% of that step at lr = 6e-4
-    L.step_hook = _pin_hook(record, diag, "impala", param_bar=6e-5)
+    L.step_hook = _pin_hook(record, diag, "impala")
     dev = L.ctx.device
     tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     stats = L.update(tt(sh.obs), tt(sh.dones), tt(sh.actions), tt(sh.logitss), tt(sh.rewards), tt(sh.firststeps))

@@ -49,9 +49,9 @@ def _run_pinned(args_fn, algo, L=1):
     def make(*a, **k):
         cl = mk_c(*a, **k)
         c_learner[0] = cl
+        shared = {}
         for l, lr in enumerate(cl.learners):
-            lr.step_hook = pin_hook(lambda: records[upd[0]], diag, algo, shard=(l if L > 1 else None),
-                                    param_bar=2e-6 if algo == "ppo" else 6e-5)
+            lr.step_hook = pin_hook(lambda: records[upd[0]], diag, algo, shard=(l if L > 1 else None), nshards=L, shared=shared)
         return cl
 
     cb.make_learner = make
