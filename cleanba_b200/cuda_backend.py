@@ -388,6 +388,7 @@ class CudaBackend:
         if not torch.cuda.is_available():
             raise ag.CleanbaError("CudaBackend needs CUDA devices (sm_100a); there is no CPU fallback")
         self._learner_devices = None
+        self.actors = []            # every CudaActor made (payload bandwidth log, probes)
 
     def first_key(self, seed):
         return _first_key(seed)
@@ -400,4 +401,5 @@ class CudaBackend:
     def make_actor(self, device_id, N, args, key):
         a = CudaActor(device_id, N, args, key)
         a.learner_devices = self._learner_devices
+        self.actors.append(a)
         return a

@@ -331,7 +331,8 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
     learner_policy_version = first_update
     global_step = first_step
     start = time.time()
-    result = SimpleNamespace(learner=learner, stats=None, sps=0.0, updates=0, versions=[])
+    result = SimpleNamespace(learner=learner, stats=None, sps=0.0, updates=0, versions=[], update_seconds=[], queue_get_seconds=[],
+                             update_done_at=[])
     try:
         while True:
             learner_policy_version += 1
@@ -344,6 +345,7 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
                          device_thread_id) = get_payload(rollout_queues[d_idx * args.num_actor_threads + thread_id])
                         payloads.append(sharded)
             rollout_queue_get_time.append(time.time() - t0)
+            result.queue_get_seconds.append(rollout_queue_get_time[-1])
             training_time_start = time.time()
             with tracer.span("multi_device_update", 0, learner_policy_version=learner_policy_version, actor_policy_version=actor_policy_version):
                 stats = learner.update(payloads)      # multi_device_update (cleanba_ppo.py:714-720)
@@ -353,6 +355,8 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
                     for thread_id in range(args.num_actor_threads):
                         params_queues[d_idx * args.num_actor_threads + thread_id].put(device_params)
             result.stats, result.updates = stats, learner_policy_version
+            result.update_seconds.append(time.time() - training_time_start)     # host time of multi_device_update + publish (enqueue)
+            result.update_done_at.append((time.time(), global_step))
             result.versions.append((actor_policy_version, update, learner_policy_version))
             if on_update is not None:
                 on_update(learner_policy_version, global_step, stats)
