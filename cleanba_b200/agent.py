@@ -230,6 +230,14 @@ class Context:
                                                _ptr(norm_out), _stream(self.device)))
 
 
+    def set_grad_milestone(self, event: Optional[torch.cuda.Event]) -> int:
+        """Have every *_grad call record `event` once the tail of the gradient vector (dense layer + heads) is final; returns
+        the tail's first element offset.  See cb_set_grad_milestone."""
+        off = ctypes.c_longlong()
+        handle = None if event is None else ctypes.c_void_p(event.cuda_event)
+        check(self.lib.cb_set_grad_milestone(self.h, handle, ctypes.byref(off)))
+        return int(off.value)
+
     def reduce_peers(self, grads_list, out: torch.Tensor):
         """out = fixed-order sum of the replicas' flat gradient buffers (peer memory); see cb_reduce_peers."""
         arr = (ctypes.c_void_p * len(grads_list))(*[g.data_ptr() for g in grads_list])

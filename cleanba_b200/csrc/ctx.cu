@@ -146,6 +146,7 @@ struct cb_ctx {
     // tcgen05 dense layer (dense_umma.cu)
     bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
     int npad_max = 0;
+    cudaEvent_t milestone = nullptr;        // recorded once the dense + head gradients of a cb_*_grad call are complete
     float* gscale = nullptr;                // device {S, 1 / S}: loss scale of the current minibatch's gradient tensors
     unsigned* gs_work = nullptr;            // scratch of k_loss_scale
     const cb_rollout_cursor* cursor = nullptr;   // set for the duration of a cb_actor_step_cursor call
@@ -379,6 +380,9 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             if (launch_dense_bwd_x(d, c->dpre, c->gscale, c->st[2].gA.pl, st)) return -1;
         }
     }
+    // The flat gradient vector is [conv stages | dense | actor | critic]: its tail (the dense layer: 91% of the parameters) is
+    // final here, before the conv backward starts -- the caller may start exchanging it now (cb_set_grad_milestone).
+    if (c->milestone) CB_CUDA(cudaEventRecord(c->milestone, st));
     for (int s = 2; s >= 0; --s) {
         Stage& S = c->st[s];
         const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
@@ -846,6 +850,13 @@ int cb_memcpy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
     CB_CHECK(width_bytes <= dst_pitch && width_bytes <= src_pitch, "row width %zu exceeds a pitch (%zu, %zu)", width_bytes, dst_pitch, src_pitch);
     if (!width_bytes || !rows) return 0;
     CB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
+int cb_set_grad_milestone(cb_ctx* c, void* cuda_event, long long* tail_offset) {
+    CB_CHECK(c, "null argument");
+    c->milestone = (cudaEvent_t)cuda_event;
+    if (tail_offset) *tail_offset = c->off_dense_b;      // flax order: network Dense_0/bias is the first leaf after the conv stages
     return 0;
 }
 

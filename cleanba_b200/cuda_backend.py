@@ -3,8 +3,8 @@ libcleanba_b200 on CUDA devices.  There is no CPU path here; constructing it wit
 
   actor -> learner payload (prepare_data + device_put_sharded, cleanba_ppo.py:276-278,357-363): each step's observation is
   copied from pinned host memory straight into row t of a pre-allocated [T,N,...] device buffer (no list / stack), the
-  env axis is split into L contiguous slices and each slice is copied to its learner GPU on the actor's side stream
-  (cudaMemcpyAsync / peer copy); an event travels with the payload.
+  env axis is split into L contiguous slices and each slice is copied to its learner GPU as strided block copies on the
+  actor's copy streams (one per learner, cb_memcpy_2d over NVLink); an event travels with the payload.
 """
 import os
 import threading
@@ -60,7 +60,7 @@ class CudaActor:
         self.impala = args.algo == "impala"
         self.ctx = ag.Context(self.dev, max_batch=N, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO)
         self.stream = torch.cuda.Stream(self.dev)
-        self.copy_stream = torch.cuda.Stream(self.dev)      # actor -> learner payload copies (overlap the next rollout)
+        self.copy_streams = []                              # actor -> learner payload copies (overlap the next rollout)
         self._peers, self._payload_log, self._land = set(), [], {}
         self.key = ag.key_tensor(key, self.dev)
         self.act_host = torch.empty(N, dtype=torch.int32).pin_memory()
@@ -109,17 +109,20 @@ class CudaActor:
         rollout's last step: the actor stream is free at once, so the next rollout overlaps the hand-off.  An event recorded
         on the copy stream travels with the payload."""
         N = self.N
-        cs = self.copy_stream
         shards = []
         with torch.cuda.device(self.dev):
             done = torch.cuda.Event()
             done.record(self.stream)                      # the rollout (every step's writes into the storage rows)
-            cs.wait_event(done)
-            t0 = torch.cuda.Event(enable_timing=True); t0.record(cs)
-        nbytes = 0
+            while len(self.copy_streams) < L:             # one copy stream per learner: the L block copies run concurrently
+                self.copy_streams.append(torch.cuda.Stream(self.dev))
+        nbytes, marks = 0, []
         for l in range(L):
             c = slice(l * N // L, (l + 1) * N // L)
             ld = self.learner_devices[l]
+            cs = self.copy_streams[l]
+            with torch.cuda.device(self.dev):
+                cs.wait_event(done)
+                t0 = torch.cuda.Event(enable_timing=True); t0.record(cs)
             local = L == 1 and ld == self.dev              # the only learner is this GPU: hand the storage itself over
             if ld != self.dev and ld not in self._peers:
                 self.ctx.lib.cb_enable_peer_access(self.ctx.h, int(ld.index))    # DMA over NVLink instead of staging through the host
@@ -148,22 +151,24 @@ class CudaActor:
                 no = next_obs if torch.is_tensor(next_obs) else torch.from_numpy(next_obs)
                 sh["next_obs"] = no[c].to(ld, non_blocking=True)
                 sh["next_done"] = torch.from_numpy(np.ascontiguousarray(next_done[c])).to(ld, non_blocking=True)
-            shards.append(sh)
-        with torch.cuda.device(self.dev):
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(cs)
-        for sh in shards:
+            with torch.cuda.device(self.dev):
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(cs)
             sh["event"] = ev
+            marks.append((t0, ev))
+            shards.append(sh)
         if nbytes:
-            self._payload_log.append((t0, ev, nbytes))
+            self._payload_log.append((marks, nbytes))
         return shards
 
     def payload_bandwidth(self):
         """[(GB/s, bytes)] of the finished payload hand-offs (device-timed on the copy stream)."""
         out = []
-        for t0, t1, nb in self._payload_log:
-            if t1.query():
-                out.append((nb / (t0.elapsed_time(t1) * 1e-3) / 1e9, nb))
+        for marks, nb in self._payload_log:
+            if all(t1.query() for _, t1 in marks):     # first start to last end over the per-learner copy streams
+                t_first = marks[0][0]
+                ms = max(t_first.elapsed_time(t1) for _, t1 in marks)
+                out.append((nb / (ms * 1e-3) / 1e9, nb))
         return out
 
 
@@ -236,6 +241,7 @@ class CudaLearner:
                 g.copy_(self.learners[0].grads)
                 torch.cuda.current_stream(g.device).synchronize()
             self.barrier.wait()
+        hook.whole_buffer = len(self.devices) > 1      # the multi-device fallback exchanges whole buffers: not splittable
         return hook
 
     def _make_fused(self, l):

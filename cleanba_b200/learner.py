@@ -17,6 +17,37 @@ from .agent import Context, CB_ALGO_IMPALA, CB_ALGO_PPO, CB_CONV_TCGEN05, Cleanb
 AllReduce = Optional[Callable[[torch.Tensor], None]]
 
 
+class _OverlappedExchange:
+    """lax.pmean(grads) (cleanba_ppo.py:628) as TWO collectives on the flat buffer: the tail [dense | actor | critic] (91% of
+    the bytes) is reduced on a side stream as soon as the backward pass has produced it -- under the whole conv backward -- and
+    only the small conv-stage head after the gradient call.  Every element is reduced exactly once, so replicas stay bit-identical."""
+
+    def __init__(self, ctx: Context, allreduce):
+        self.allreduce = allreduce
+        d = ctx.device
+        with torch.cuda.device(d):
+            self.stream = torch.cuda.Stream(d)
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(d))        # materialises the cudaEvent_t handle
+        self.split = ctx.set_grad_milestone(self.event)
+
+    def __call__(self, grads: torch.Tensor):
+        main = torch.cuda.current_stream(grads.device)
+        self.stream.wait_event(self.event)                          # recorded inside the *_grad call that was just enqueued
+        with torch.cuda.stream(self.stream):
+            self.allreduce(grads[self.split:])
+        self.allreduce(grads[:self.split])
+        main.wait_stream(self.stream)
+
+
+def _wrap_exchange(ctx: Context, allreduce: AllReduce, world_learners: int) -> AllReduce:
+    import os
+    if (allreduce is None or world_learners <= 1 or getattr(allreduce, "whole_buffer", False)
+            or os.environ.get("CLEANBA_OVERLAP_EXCHANGE", "1") == "0"):
+        return allreduce
+    return _OverlappedExchange(ctx, allreduce)
+
+
 def linear_schedule(count: int, base_lr: float, steps_per_update: int, num_updates: int, anneal: bool) -> float:
     """cleanba_ppo.py:475-479 / cleanba_impala.py:515-519, evaluated at the pre-increment optimizer count, in fp32."""
     if not anneal:
@@ -53,9 +84,9 @@ class PPOLearner:
         self.h, self.T, self.Bl = hyper, T, Bl
         self.mb = T * Bl // hyper.num_minibatches
         self.world_learners = world_learners
-        self.allreduce = allreduce
         self.ctx = Context(device, max_batch=max(self.mb, Bl), algo=CB_ALGO_PPO, train=True,
                            num_actions=num_actions, conv_backend=conv_backend)
+        self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners)
         d = self.ctx.device
         self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
         self.stats = torch.zeros(hyper.update_epochs * hyper.num_minibatches, 5, dtype=torch.float32, device=d)
@@ -123,9 +154,9 @@ class ImpalaLearner:
         self.h, self.T1, self.Bl = hyper, T1, Bl
         self.B = Bl // hyper.num_minibatches
         self.world_learners = world_learners
-        self.allreduce = allreduce
         self.ctx = Context(device, max_batch=T1 * self.B, algo=CB_ALGO_IMPALA, train=True, num_actions=num_actions,
                            conv_backend=conv_backend)
+        self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners)
         d = self.ctx.device
         self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
         self.stats = torch.zeros(hyper.num_minibatches, 4, dtype=torch.float32, device=d)

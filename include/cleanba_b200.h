@@ -130,6 +130,13 @@ int cb_optimizer_step(cb_ctx* ctx, const float* grads, float grad_scale, float l
  * 1..8 device pointers; peer devices must have been opened with cb_enable_peer_access. */
 int cb_optimizer_step_peers(cb_ctx* ctx, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
                             float* norm_out, cb_stream stream);
+/* Overlap of the gradient exchange with the backward pass.  The flat gradient vector is ordered [conv stages | dense | actor |
+ * critic] and the backward pass produces it back to front: elements [*tail_offset, num_params) -- the dense layer and the heads,
+ * 91% of the bytes -- are final before the conv backward starts.  With a milestone set, every cb_ppo_grad / cb_impala_grad
+ * records `cuda_event` (a cudaEvent_t; NULL clears it) on its stream at that point, so the caller can run the allreduce of the
+ * tail on a side stream under the conv backward and only the small head of the vector after the call
+ * (`jax.lax.pmean(grads)`, cleanba_ppo.py:628, split in two collectives; every element is still reduced exactly once). */
+int cb_set_grad_milestone(cb_ctx* ctx, void* cuda_event, long long* tail_offset);
 /* out = grads[0] + ... + grads[n-1] (fixed order, read from peer memory): the in-process stage of the gradient exchange when
  * the learner group ALSO spans processes (`--distributed` with several learner devices per process, cleanba_ppo.py:419-423,628):
  * one replica sums its process' replicas into `out`, ONE NCCL allreduce on `out` follows, and every replica then applies

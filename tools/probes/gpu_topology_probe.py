@@ -26,10 +26,24 @@ def main():
     from cleanba_b200 import cleanba_ppo, cuda_backend
     from cleanba_b200.sebulba import Args, impala_defaults
     args = Args(local_num_envs=a.num_envs, actor_device_ids=list(a.actor), learner_device_ids=list(a.learners), distributed=a.distributed,
-                max_updates=a.updates, log_frequency=10 ** 9, total_timesteps=50_000_000)
+                max_updates=a.updates, log_frequency=4, total_timesteps=50_000_000)
     if a.algo == "impala":
         args = impala_defaults(args)
     made = []
+    scalars = {}
+
+    class Writer:                       # keeps the last value of every scalar the rollout / learner loops log
+        def add_scalar(self, k, v, step):
+            scalars[k] = float(v)
+
+        def add_text(self, *a, **k):
+            pass
+
+        def close(self):
+            pass
+    import torch.utils.tensorboard as tb
+    tb.SummaryWriter = lambda *a, **k: Writer()
+    args.log_frequency = 4
     orig = cuda_backend.CudaBackend
     class Probe(orig):
         def __init__(self):
@@ -54,7 +68,9 @@ def main():
                queue_get_ms_mean=round(1e3 * float(np.mean(res.queue_get_seconds[3:])), 2),
                payload_gbs_median=round(float(np.median([b for b, _ in bw])), 1) if bw else None,
                payload_mb_per_handoff=round(bw[0][1] / 1e6, 1) if bw else None, payload_handoffs=len(bw),
-               replicas_identical_in_process=bool(same))
+               replicas_identical_in_process=bool(same),
+               actor_thread0_ms_per_update={k.split("/")[1]: round(1e3 * v, 2) for k, v in scalars.items()
+                                            if k.startswith("stats/") and k.endswith("_time")})
     if a.distributed:
         import torch.distributed as dist
         # cleanba_ppo.main destroyed the process group; a fresh gloo group compares the replicas across processes
