@@ -257,84 +257,87 @@ int launch_pool_bwd(const uint8_t* amax, Planes dpool, ConvGeom gi, ConvGeom go,
 constexpr int PW0_THREADS = 256;
 constexpr int PW0_HP = 86, PW0_P = PW0_HP * PW0_HP, PW0_HO = 42, PW0_WPO = 44, PW0_PO = PW0_WPO * PW0_WPO;
 constexpr int PW0_OUT = 37 * 16;      // 36 (tap, ci) x 16 co weight gradients + 16 bias gradients per partial
-constexpr int PW0_SMEM = PW0_P * 8;   // the staged frame; re-used for the 8 x 592 warp partials at the end
+constexpr int PW0_RB = 3;                                   // pooled rows per staged band
+constexpr int PW0_BANDS = PW0_HO / PW0_RB;                  // 14 bands per image
+constexpr int PW0_BPIX = PW0_RB * PW0_HO;                   // 126 pooled pixels per band
+constexpr int PW0_FRAME = PW0_P * 8;                        // the staged frame (4 fp16 channels per pixel)
+constexpr int PW0_SMEM = PW0_FRAME + PW0_BPIX * 16 * 4 + PW0_BPIX * 16;   // + band gradients (fp32) + band arg-max bytes
+static_assert(PW0_HO % PW0_RB == 0 && PW0_BPIX * 2 <= PW0_THREADS, "one staging item (pixel, chunk) per thread");
 
 __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_t* __restrict__ amax, Planes dpool,
                                                                      const f16* __restrict__ x_hi, int n, long long go_NP,
                                                                      float* __restrict__ partial) {
     extern __shared__ __align__(16) uint8_t pw_smem[];
     uint2* sx = reinterpret_cast<uint2*>(pw_smem);
+    float* sg = reinterpret_cast<float*>(pw_smem + PW0_FRAME);                       // [band pixel][16 channels]
+    uint8_t* sam = pw_smem + PW0_FRAME + PW0_BPIX * 16 * 4;                          // [band pixel][16 channels]
     griddep_launch();
     griddep_wait();
     const int co = threadIdx.x & 15, grp = threadIdx.x >> 4;
-    const long long cbase = (long long)(co >> 3) * go_NP * 8 + (co & 7);                 // arg-max bytes (no guards)
-    const long long dcbase = (long long)(co >> 3) * dpool.plane_px * 8 + (co & 7);       // gradient planes
-    auto dload = [&](long long off) { return fmaf(__half2float(dpool.mid[off]), MID_INV, __half2float(dpool.hi[off])); };
     float acc[36];
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0.f;
     float accb = 0.f;
-    for (int img = blockIdx.x; img < n; img += gridDim.x) {
-        __syncthreads();
-        const uint4* src = reinterpret_cast<const uint4*>(x_hi + (long long)img * PW0_P * 8);
-        for (int q = threadIdx.x; q < PW0_P; q += PW0_THREADS) {
-            const uint4 v = src[q];
-            sx[q] = make_uint2(v.x, v.y);
-        }
-        __syncthreads();
-        const long long ibase = cbase + (long long)img * PW0_PO * 8;
-        const long long dibase = dcbase + (long long)img * PW0_PO * 8;
-        // software pipeline: the arg-max bytes and gradients of the next PF pooled pixels are in flight during the FMAs of
-        // the current PF (global latency ~ 800 cycles vs ~90 instructions per pixel)
-        constexpr int PF = 4, NPIX = PW0_HO * PW0_HO, PSTEP = PW0_THREADS / 16;
-        int am[PF];
-        float g[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const int p = grp + u * PSTEP;
-            am[u] = 0; g[u] = 0.f;
-            if (p < NPIX) {
-                const long long po = (long long)((p / PW0_HO + 1) * PW0_WPO + (p % PW0_HO + 1)) * 8;
-                am[u] = amax[ibase + po]; g[u] = dload(dibase + po);
+    // Staging item of this thread: (band pixel sp, chunk sc).  The pooled gradient planes and the arg-max bytes of a band are
+    // fetched with coalesced 16 / 8-byte loads one band AHEAD (registers), combined to fp32 and parked in shared memory, so the
+    // per-(pixel, channel) reads of the accumulation loop are shared-memory reads (the carrier made them three scalar global
+    // loads per element).
+    const bool stager = threadIdx.x < PW0_BPIX * 2;
+    const int spx = threadIdx.x >> 1, sc = threadIdx.x & 1;
+    uint4 r_hi = make_uint4(0, 0, 0, 0), r_mid = make_uint4(0, 0, 0, 0);
+    uint2 r_am = make_uint2(0, 0);
+    auto fetch = [&](int img, int band) {
+        if (!stager) return;
+        const int row = band * PW0_RB + spx / PW0_HO, col = spx % PW0_HO;
+        const long long q = (long long)img * PW0_PO + (long long)(row + 1) * PW0_WPO + (col + 1);
+        r_hi = *reinterpret_cast<const uint4*>(dpool.hi + ((long long)sc * dpool.plane_px + q) * 8);
+        r_mid = *reinterpret_cast<const uint4*>(dpool.mid + ((long long)sc * dpool.plane_px + q) * 8);
+        r_am = *reinterpret_cast<const uint2*>(amax + ((long long)sc * go_NP + q) * 8);
+    };
+    const int nwork = ((n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * PW0_BANDS;     // (image, band) items of this block
+    if (nwork > 0) fetch(blockIdx.x, 0);
+    for (int w = 0; w < nwork; ++w) {
+        const int img = blockIdx.x + (w / PW0_BANDS) * gridDim.x, band = w % PW0_BANDS;
+        __syncthreads();                                    // the previous band (and frame) is no longer read
+        if (band == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(x_hi + (long long)img * PW0_P * 8);
+            for (int q = threadIdx.x; q < PW0_P; q += PW0_THREADS) {
+                const uint4 v = src[q];
+                sx[q] = make_uint2(v.x, v.y);
             }
         }
-        for (int p0 = grp; p0 < NPIX; p0 += PF * PSTEP) {
-            int am_c[PF];
-            float g_c[PF];
+        if (stager) {
+            float gh[8], gm[8];
+            unpack8h(r_hi, gh);
+            unpack8h(r_mid, gm);
+            float4* d = reinterpret_cast<float4*>(sg + spx * 16 + sc * 8);
+            d[0] = make_float4(fmaf(gm[0], MID_INV, gh[0]), fmaf(gm[1], MID_INV, gh[1]), fmaf(gm[2], MID_INV, gh[2]), fmaf(gm[3], MID_INV, gh[3]));
+            d[1] = make_float4(fmaf(gm[4], MID_INV, gh[4]), fmaf(gm[5], MID_INV, gh[5]), fmaf(gm[6], MID_INV, gh[6]), fmaf(gm[7], MID_INV, gh[7]));
+            *reinterpret_cast<uint2*>(sam + spx * 16 + sc * 8) = r_am;
+        }
+        __syncthreads();
+        if (w + 1 < nwork) fetch(blockIdx.x + ((w + 1) / PW0_BANDS) * gridDim.x, (w + 1) % PW0_BANDS);   // in flight during the FMAs
+        constexpr int PSTEP = PW0_THREADS / 16;
+        for (int p = grp; p < PW0_BPIX; p += PSTEP) {       // uniform trip count per warp (126 = 7 * 16 + 14: the tail is per half-warp)
+            const int i = band * PW0_RB + p / PW0_HO, j = p % PW0_HO;
+            const int am = sam[p * 16 + co];
+            const float gc = sg[p * 16 + co];
+            const int dy = (am * 11) >> 5, dx = am - 3 * dy;   // am = dy * 3 + dx, 0..8
+            // tap (ky, kx) of arg-max pixel (yp, xp) = (2i + dy + 1, 2j + dx + 1) reads padded pixel (yp + ky - 1, xp + kx - 1)
+            const uint2* w0 = sx + (2 * i + dy) * PW0_HP + (2 * j + dx);
+            accb += gc;
 #pragma unroll
-            for (int u = 0; u < PF; ++u) { am_c[u] = am[u]; g_c[u] = g[u]; }
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int p = p0 + (PF + u) * PSTEP;
-                am[u] = 0; g[u] = 0.f;
-                if (p < NPIX) {
-                    const long long po = (long long)((p / PW0_HO + 1) * PW0_WPO + (p % PW0_HO + 1)) * 8;
-                    am[u] = amax[ibase + po]; g[u] = dload(dibase + po);
+                for (int kx = 0; kx < 3; ++kx) {
+                    const uint2 v = w0[ky * PW0_HP + kx];
+                    float* a = acc + (ky * 3 + kx) * 4;
+                    const float2 x01 = h2_to_f2(v.x), x23 = h2_to_f2(v.y);
+                    a[0] = fmaf(x01.x, gc, a[0]);
+                    a[1] = fmaf(x01.y, gc, a[1]);
+                    a[2] = fmaf(x23.x, gc, a[2]);
+                    a[3] = fmaf(x23.y, gc, a[3]);
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int p = p0 + u * PSTEP;
-                if (p >= NPIX) break;            // uniform per warp: both pixel groups of a warp run the same trip count
-                const int i = p / PW0_HO, j = p - i * PW0_HO;
-                const int dy = (am_c[u] * 11) >> 5, dx = am_c[u] - 3 * dy;   // am = dy * 3 + dx, 0..8
-                // tap (ky, kx) of arg-max pixel (yp, xp) = (2i + dy + 1, 2j + dx + 1) reads padded pixel (yp + ky - 1, xp + kx - 1)
-                const uint2* w0 = sx + (2 * i + dy) * PW0_HP + (2 * j + dx);
-                const float gc = g_c[u];
-                accb += gc;
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const uint2 v = w0[ky * PW0_HP + kx];
-                        float* a = acc + (ky * 3 + kx) * 4;
-                        const float2 x01 = h2_to_f2(v.x), x23 = h2_to_f2(v.y);
-                        a[0] = fmaf(x01.x, gc, a[0]);
-                        a[1] = fmaf(x01.y, gc, a[1]);
-                        a[2] = fmaf(x23.x, gc, a[2]);
-                        a[3] = fmaf(x23.y, gc, a[3]);
-                    }
-            }
         }
     }
     // the two pixel groups of a warp, then the 8 warps in a fixed order
