@@ -59,6 +59,15 @@ def main(args: Args):
     derive_sizes(args, world, rank)
     run_name = f"{args.env_id}__{args.exp_name}__{args.seed}__{uuid.uuid4()}"
     writer = None
+    if args.track and rank == 0:
+        # cleanba_ppo.py:447-458: wandb mirrors the TensorBoard scalars (sync_tensorboard) of rank 0
+        try:
+            import wandb
+        except ImportError as e:
+            raise RuntimeError("--track needs the wandb package (not installed in this image); run without --track to log to "
+                               "TensorBoard only") from e
+        wandb.init(project=args.wandb_project_name, entity=args.wandb_entity, sync_tensorboard=True,
+                   config={k: v for k, v in vars(args).items() if not k.startswith("_")}, name=run_name, monitor_gym=True, save_code=True)
     if rank == 0:
         try:
             from torch.utils.tensorboard import SummaryWriter
@@ -67,10 +76,10 @@ def main(args: Args):
         except Exception as e:  # noqa: BLE001
             print(f"warning: TensorBoard logging disabled ({type(e).__name__}: {e})", file=sys.stderr)
             writer = None
-        for flag in ("track", "capture_video", "upload_model"):
+        for flag in ("capture_video", "upload_model"):
             if getattr(args, flag):
                 print(f"warning: --{flag.replace('_', '-')} is accepted for CLI compatibility but not implemented "
-                      "(wandb / video capture / HF upload are outside the hot path, DESIGN.md section 7)", file=sys.stderr)
+                      "(video capture / HF upload are outside the hot path, DESIGN.md section 7)", file=sys.stderr)
     backend = CudaBackend()
     t0 = time.time()
     res = train(args, backend, make_env, writer=writer, allreduce=allreduce)

@@ -210,3 +210,27 @@ def test_header_is_plain_c_and_a_c_program_can_drive_the_abi(tmp_path):
         assert r.returncode == 0 and "actions:" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 2 and "cb_create failed" in r.stdout and "cuda" in r.stdout.lower(), r.stdout + r.stderr
+
+
+def test_benchmark_fanout_launcher(tmp_path, monkeypatch, capsys):
+    """cleanba_b200.benchmark (the reference's cleanrl_utils/benchmark.py:12-137): seed-major expansion, local workers, SLURM script."""
+    from cleanba_b200 import benchmark as bm
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.delenv("WANDB_TAGS", raising=False)
+    cmds = bm.expand("run", ["A", "B"], 2, 5)
+    assert cmds == ["run --env-id A --seed 5", "run --env-id B --seed 5", "run --env-id A --seed 6", "run --env-id B --seed 6"]
+    marker = tmp_path / "out"
+    marker.mkdir()
+    script = tmp_path / "job.py"
+    script.write_text("import sys, pathlib\na = sys.argv\npathlib.Path(r'%s', a[a.index('--env-id') + 1] + '_' + a[a.index('--seed') + 1]).write_text('ok')\n" % marker)
+    res = bm.main(["--env-ids", "X", "Y", "--num-seeds", "2", "--workers", "2", "--auto-tag", "False", "--command", f"{sys.executable} {script}"])
+    assert len(res) == 4 and all(rc == 0 for rc in res.values())
+    assert sorted(p.name for p in marker.iterdir()) == ["X_1", "X_2", "Y_1", "Y_2"]
+    tpl = tmp_path / "tpl.slurm"
+    tpl.write_text("#SBATCH --array={{array}}\n{{nodes}}\nenvs={{env_ids}} seeds={{seeds}} n={{len_seeds}} cpg={{cpus_per_gpu}} g={{gpus_per_task}} t={{ntasks}}\n{{command}}\n")
+    bm.main(["--env-ids", "X", "--num-seeds", "3", "--workers", "0", "--auto-tag", "False", "--command", "cmd", "--slurm-template-path", str(tpl),
+             "--slurm-total-cpus", "10", "--slurm-gpus-per-task", "2", "--slurm-ntasks", "2", "--slurm-nodes", "1"])
+    out = next((tmp_path / "slurm").glob("*.slurm")).read_text()
+    assert "--array=0-2%0" in out and "#SBATCH --nodes=1" in out and "envs=(X) seeds=(1 2 3) n=3 cpg=3 g=2 t=2" in out and out.strip().endswith("cmd")
+    with pytest.raises(SystemExit):
+        bm.main(["--env-ids", "X", "--num-seeds", "1", "--workers", "1", "--auto-tag", "False", "--command", f"{sys.executable} -c \"raise SystemExit(3)\""])
