@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from . import lib as _lib
-from .lib import CB_ALGO_IMPALA, CB_ALGO_PPO, CB_CONV_SIMT, CB_CONV_TCGEN05, CleanbaError, cb_config, check
+from .lib import (CB_ALGO_IMPALA, CB_ALGO_PPO, CB_CONV_SIMT, CB_CONV_TCGEN05, CB_MODEL_IMPALA_RESNET, CB_MODEL_NATURE_CNN, CleanbaError,
+                  cb_config, check)
 
 NUM_ACTIONS = 18
 
@@ -39,7 +40,7 @@ class Context:
     """One model replica on one GPU (an actor copy or a learner replica)."""
 
     def __init__(self, device, max_batch: int, algo: int = CB_ALGO_PPO, train: bool = False,
-                 num_actions: int = NUM_ACTIONS, conv_backend: int = CB_CONV_TCGEN05):
+                 num_actions: int = NUM_ACTIONS, conv_backend: int = CB_CONV_TCGEN05, model: int = CB_MODEL_IMPALA_RESNET):
         if not torch.cuda.is_available():
             raise CleanbaError("cleanba_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.lib = _lib.load()
@@ -52,11 +53,13 @@ class Context:
         self.algo = algo
         self.train = train
         self.max_batch = max_batch
-        cfg = cb_config(self.device.index, algo, max_batch, int(train), num_actions, conv_backend)
+        self.model = model
+        cfg = cb_config(self.device.index, algo, max_batch, int(train), num_actions, conv_backend, model)
         h = ctypes.c_void_p()
         check(self.lib.cb_create(ctypes.byref(cfg), ctypes.byref(h)))
         self.h = h
-        self.num_params = int(self.lib.cb_num_params(num_actions))
+        self.num_params = int(self.lib.cb_num_params_model(model, num_actions))
+        self.hidden_width = int(self.lib.cb_hidden_width(h))
 
     def close(self):
         if getattr(self, "h", None):

@@ -11,9 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/cleanba_b200.h"
-#include "common.cuh"
-#include "kernels.h"
+#include "ctx.h"
 
 namespace cb {
 
@@ -41,18 +39,6 @@ static const int kStageHin[3] = {84, 42, 21};
 static const int kStageHout[3] = {42, 21, 11};
 static const int kStagePadLo[3] = {0, 0, 1};
 constexpr int kFlat = 11 * 11 * 32;
-
-struct Leaf {
-    std::string name;
-    long long offset;
-    int ndim;
-    int shape[4];
-    long long size() const {
-        long long s = 1;
-        for (int i = 0; i < ndim; ++i) s *= shape[i];
-        return s;
-    }
-};
 
 static std::vector<Leaf> build_leaves(int A) {
     std::vector<Leaf> L;
@@ -86,77 +72,13 @@ static std::vector<Leaf> build_leaves(int A) {
     return L;
 }
 
-struct ConvLayer {
-    int cin, cout;          // real channels
-    long long off_b, off_w; // offsets in the flat parameter vector
-    f16 *fwd, *dg;          // packed [hi|mid] weight images (forward / dgrad)
-};
-
-struct Act {                // one activation / gradient tensor: fp16x2 carrier planes (common.cuh)
-    Planes pl = {nullptr, nullptr, 0};
-    int C = 0, H = 0;
-};
-
-struct Stage {
-    Act x;                  // input of the sequence conv (stage 0: frames, hi only; else the previous stage's raw output)
-    Act y;                  // conv output before the pool (only when the conv is not fused with its pool)
-    Act p, pr;              // pooled: raw (residual input of block 0) and rectified (operand of its first conv)
-    uint8_t* amax = nullptr; // arg-max slots of the pool (learner contexts)
-    Act a0;                 // relu(conv1(relu(p)))
-    Act b0, b0r;            // p + conv2(a0): raw and rectified
-    Act a1;                 // relu(conv3(relu(b0)))
-    Act out;                // b0 + conv4(a1): raw for stages 0 / 1 (the next ConvSequence is fed un-rectified), rectified for stage 2
-    Act gA, gB, gC, gBin;   // gradients (learner contexts), all scaled by the minibatch's loss scale
-};
-
 }  // namespace cb
 
 using namespace cb;
 
-// bytes  = what the kernel moves in THIS library's storage formats (carrier planes, padded grids);
-// abytes = SURVEY 8(d) algorithmic bytes: every operand tensor of the operator read / written once as unpadded fp32.
-struct ProfAgg { long long launches = 0, records = 0; double ms = 0, flops = 0, bytes = 0, abytes = 0; };
-struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes, abytes; int launches; };
-
-struct cb_ctx {
-    cb_config cfg;
-    bool prof_on = false;
-    std::vector<ProfRec> prof_recs;
-    std::vector<cudaEvent_t> prof_pool;
-    int num_sms = 148;
-    int A = 18;
-    std::vector<Leaf> leaves;
-    long long nparam = 0;
-    std::vector<void*> allocs;
-    float *params = nullptr, *m = nullptr, *v = nullptr;
-    long long opt_count = 0;
-    ConvLayer conv[15];
-    PackLayer* pack_dev = nullptr;
-    long long off_dense_b, off_dense_w, off_actor_b, off_actor_w, off_critic_b, off_critic_w;
-    Stage st[3];
-    float *hidden = nullptr, *dense_part = nullptr, *dpre = nullptr, *dlogits = nullptr, *terms = nullptr;
-    float *logits_scratch = nullptr, *cell_scratch = nullptr, *wg_partial = nullptr, *opt_partials = nullptr;
-    uint32_t* subkey = nullptr;
-    uint32_t* key_tmp = nullptr;
-    int* perm_tmp = nullptr;
-    int* perm_rank = nullptr;
-    uint32_t* sort_keys = nullptr;
-    int perm_cap = 0;
-    int last_n = 0;
-    // tcgen05 dense layer (dense_umma.cu)
-    bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
-    int npad_max = 0;
-    cudaEvent_t milestone = nullptr;        // recorded once the dense + head gradients of a cb_*_grad call are complete
-    float* gscale = nullptr;                // device {S, 1 / S}: loss scale of the current minibatch's gradient tensors
-    unsigned* gs_work = nullptr;            // scratch of k_loss_scale
-    const cb_rollout_cursor* cursor = nullptr;   // set for the duration of a cb_actor_step_cursor call
-    bool fuse0 = false;
-    bool fuse12 = false;                    // second / third ConvSequence: conv + pool (forward) fused                     // first ConvSequence: conv + pool (forward) and pool + wgrad (backward) fused
-};
-
 namespace cb {
 
-static int dev_alloc(cb_ctx* c, void** p, size_t bytes, bool zero = true) {
+int dev_alloc(cb_ctx* c, void** p, size_t bytes, bool zero) {
     CB_CUDA(cudaMalloc(p, bytes));
     c->allocs.push_back(*p);
     if (zero) CB_CUDA(cudaMemset(*p, 0, bytes));
@@ -185,31 +107,12 @@ static int alloc_act(cb_ctx* c, Act& a, int C, int H, bool two = true) {
     return 0;
 }
 
-// CUDA-event bracket around one launcher call (only when profiling is enabled): per-kernel device time measured on the
-// launching stream, with the kernel's algorithmic flops / bytes, for bench.py's roofline.
-struct ProfScope {
-    cb_ctx* c; cudaStream_t st; ProfRec r; bool on; long long l0;
-    ProfScope(cb_ctx* c_, const std::string& name, double flops, double bytes, cudaStream_t st_, double abytes = -1.0)
-        : c(c_), st(st_), on(c_->prof_on) {
-        if (!on) return;
-        r.abytes = abytes >= 0 ? abytes : bytes;
-        auto get = [&]() { cudaEvent_t e; if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(&e); return e; };
-        r.name = name; r.flops = flops; r.bytes = bytes; r.a = get(); r.b = get();
-        l0 = g_launches.load();
-        cudaEventRecord(r.a, st);
-    }
-    ~ProfScope() {
-        if (!on) return;
-        cudaEventRecord(r.b, st);
-        r.launches = (int)(g_launches.load() - l0);
-        c->prof_recs.push_back(r);
-    }
-};
 static double f32_once(const ConvGeom& g, int channels) { return 4.0 * g.n * g.H * g.W * channels; }   // unpadded fp32 tensor
 static double planes_bytes(const ConvGeom& g, int chunks, bool two = true) { return (double)g.NP * chunks * 8 * (two ? 4 : 2); }
 static double planes_bytes(const ConvGeom& g, int chunks, const Planes& p) { return p.hi ? planes_bytes(g, chunks, p.mid != nullptr) : 0.0; }
 
 static int refresh_weights(cb_ctx* c, cudaStream_t st) {
+    if (c->nat) return nature_refresh_weights(c, st);
     ProfScope ps(c, "pack_weights", 0, 1089232.0 * (4 + 8), st);
     if (launch_pack_conv(c->pack_dev, 15, st)) return -1;
     if (c->wd_fwd) return launch_pack_dense(c->params + c->off_dense_w, c->wd_fwd, c->wd_dx, st);
@@ -278,6 +181,11 @@ static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, cons
 static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStream_t st) {
     CB_CHECK(n > 0 && n <= c->cfg.max_batch, "batch %d outside (0, max_batch=%d]", n, c->cfg.max_batch);
     c->last_n = n;
+    if (c->nat) {
+        static const int nat_pdl_max = [] { const char* e = getenv("CLEANBA_PDL_MAX_BATCH"); return e ? atoi(e) : 1024; }();
+        g_pdl_scope = n <= nat_pdl_max;
+        return nature_forward(c, obs, idx, n, st);
+    }
     static const int pdl_max = [] { const char* e = getenv("CLEANBA_PDL_MAX_BATCH"); return e ? atoi(e) : 1024; }();
     g_pdl_scope = n <= pdl_max;
     {
@@ -359,8 +267,9 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
 
 // Backward of the trunk given c->dpre (gradient w.r.t. the pre-relu dense output); writes all trunk gradients.
 static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
+    if (c->nat) return nature_backward(c, n, grads, st);
     // per-minibatch power-of-two loss scale of the fp16 gradient carriers (device side, no host sync)
-    if (launch_loss_scale(c->dpre, (long long)n * HIDDEN, c->gs_work, c->gscale, st)) return -1;
+    if (launch_loss_scale(c->dpre, (long long)n * c->HID, c->gs_work, c->gscale, st)) return -1;
     DenseArgs d;
     d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
     if (c->wd_fwd) {
@@ -455,13 +364,19 @@ extern "C" {
 const char* cb_last_error(void) { return g_err; }
 int cb_version(void) { return 1; }
 
-long long cb_num_params(int num_actions) {
-    auto L = build_leaves(num_actions);
+static std::vector<Leaf> model_leaves(int model, int A) { return model == CB_MODEL_NATURE_CNN ? nature_leaves(A) : build_leaves(A); }
+long long cb_num_params_model(int model, int num_actions) {
+    auto L = model_leaves(model, num_actions);
     return L.back().offset + L.back().size();
 }
+int cb_num_leaves_model(int model) { return (int)model_leaves(model, 18).size(); }
+long long cb_num_params(int num_actions) { return cb_num_params_model(CB_MODEL_IMPALA_RESNET, num_actions); }
 int cb_num_leaves(void) { return 36; }
 int cb_leaf_info(int index, int num_actions, char* name, int name_cap, long long* offset, int* ndim, int* shape) {
-    auto L = build_leaves(num_actions);
+    return cb_leaf_info_model(CB_MODEL_IMPALA_RESNET, index, num_actions, name, name_cap, offset, ndim, shape);
+}
+int cb_leaf_info_model(int model, int index, int num_actions, char* name, int name_cap, long long* offset, int* ndim, int* shape) {
+    auto L = model_leaves(model, num_actions);
     CB_CHECK(index >= 0 && index < (int)L.size(), "leaf index %d out of range", index);
     if (name && name_cap > 0) snprintf(name, name_cap, "%s", L[index].name.c_str());
     if (offset) *offset = L[index].offset;
@@ -474,6 +389,7 @@ void cb_destroy(cb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     for (void* p : c->allocs) cudaFree(p);
+    if (c->nat) nature_destroy(c);
     delete c;
 }
 
@@ -494,7 +410,11 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
     c->A = cfg->num_actions;
     c->fuse0 = cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_NO_FUSE0");
     c->fuse12 = cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_NO_FUSE12");
-    c->leaves = build_leaves(c->A);
+    const bool nature = cfg->model == CB_MODEL_NATURE_CNN;
+    if (cfg->model != CB_MODEL_IMPALA_RESNET && !nature) { set_error("unknown model %d", cfg->model); delete c; return -1; }
+    if (nature && cfg->conv_backend != CB_CONV_TCGEN05) { set_error("the Nature-CNN trunk has no CUDA-core cross-check backend"); delete c; return -1; }
+    c->HID = nature ? 512 : HIDDEN;
+    c->leaves = model_leaves(cfg->model, c->A);
     c->nparam = c->leaves.back().offset + c->leaves.back().size();
     bool ok = false;
     do {
@@ -509,10 +429,11 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             if (dev_alloc(c, &p, OPT_BLOCKS * sizeof(float))) break;
             c->opt_partials = (float*)p;
         }
+        bool fail = false;
+        if (nature && nature_create(c)) break;
         // conv layer table + packed weights
         std::vector<PackLayer> pl(15);
-        bool fail = false;
-        for (int s = 0; s < 3 && !fail; ++s)
+        for (int s = 0; s < 3 && !fail && !nature; ++s)
             for (int k = 0; k < 5 && !fail; ++k) {
                 int li = s * 5 + k;
                 ConvLayer& L = c->conv[li];
@@ -533,17 +454,19 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
                 pl[li].fwd = L.fwd; pl[li].dg = L.dg;
             }
         if (fail) break;
-        if (dev_alloc(c, &p, 15 * sizeof(PackLayer))) break;
-        c->pack_dev = (PackLayer*)p;
-        if (cudaMemcpy(c->pack_dev, pl.data(), 15 * sizeof(PackLayer), cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error("cudaMemcpy(pack table) failed");
-            break;
+        if (!nature) {
+            if (dev_alloc(c, &p, 15 * sizeof(PackLayer))) break;
+            c->pack_dev = (PackLayer*)p;
+            if (cudaMemcpy(c->pack_dev, pl.data(), 15 * sizeof(PackLayer), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("cudaMemcpy(pack table) failed");
+                break;
+            }
+            c->off_dense_b = c->leaves[30].offset; c->off_dense_w = c->leaves[31].offset;
+            c->off_actor_b = c->leaves[32].offset; c->off_actor_w = c->leaves[33].offset;
+            c->off_critic_b = c->leaves[34].offset; c->off_critic_w = c->leaves[35].offset;
         }
-        c->off_dense_b = c->leaves[30].offset; c->off_dense_w = c->leaves[31].offset;
-        c->off_actor_b = c->leaves[32].offset; c->off_actor_w = c->leaves[33].offset;
-        c->off_critic_b = c->leaves[34].offset; c->off_critic_w = c->leaves[35].offset;
         // activations
-        for (int s = 0; s < 3 && !fail; ++s) {
+        for (int s = 0; s < 3 && !fail && !nature; ++s) {
             Stage& S = c->st[s];
             const int C = kStageC[s], Hin = kStageHin[s], Ho = kStageHout[s];
             const bool fused = (s == 0) ? c->fuse0 : c->fuse12;
@@ -569,7 +492,7 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
         }
         if (fail) break;
         const size_t mb = (size_t)cfg->max_batch;
-        if (cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_DENSE_SIMT")) {
+        if (!nature && cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_DENSE_SIMT")) {
             c->npad_max = (cfg->max_batch + 127) / 128 * 128;
             bool bad = false;
             for (int i = 0; i < 3 && !bad; ++i) {
@@ -590,7 +513,7 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             }
             if (dense_umma_init()) break;
         }
-        if (dev_alloc(c, &p, mb * HIDDEN * sizeof(float))) break;
+        if (dev_alloc(c, &p, mb * c->HID * sizeof(float))) break;
         c->hidden = (float*)p;
         size_t part = mb * HIDDEN;
         if (part < (size_t)11 * 256 * HIDDEN) part = (size_t)11 * 256 * HIDDEN;
@@ -602,7 +525,7 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
         if (dev_alloc(c, &p, 2 * sizeof(uint32_t))) break;
         c->key_tmp = (uint32_t*)p;
         if (cfg->train) {
-            if (dev_alloc(c, &p, mb * HIDDEN * sizeof(float))) break;
+            if (dev_alloc(c, &p, mb * c->HID * sizeof(float))) break;
             c->dpre = (float*)p;
             if (dev_alloc(c, &p, mb * (MAX_ACTIONS + 1) * sizeof(float))) break;
             c->dlogits = (float*)p;
@@ -682,10 +605,10 @@ int cb_actor_step(cb_ctx* c, const uint8_t* obs, int n, uint32_t* key, int32_t* 
     cudaStream_t st = (cudaStream_t)stream;
     if (trunk_forward(c, obs, nullptr, n, st)) return -1;
     if (launch_split_key(key, c->subkey, st)) return -1;   // key, subkey = jax.random.split(key)
-    ProfScope ps(c, "actor_head", 2.0 * n * HIDDEN * (c->A + 1), (double)n * (HIDDEN * 4 + 12), st);
+    ProfScope ps(c, "actor_head", 2.0 * n * c->HID * (c->A + 1), (double)n * (c->HID * 4 + 12), st);
     return launch_actor_head(c->hidden, n, c->A, c->params + c->off_actor_w, c->params + c->off_actor_b,
                              c->params + c->off_critic_w, c->params + c->off_critic_b, c->subkey, logits, value, action,
-                             logprob, st);
+                             logprob, st, nullptr, c->HID);
 }
 
 int cb_actor_step_cursor(cb_ctx* c, cb_rollout_cursor* cursor, int n, uint32_t* key, cb_stream stream) {
@@ -698,10 +621,10 @@ int cb_actor_step_cursor(cb_ctx* c, cb_rollout_cursor* cursor, int n, uint32_t* 
     const int rc = trunk_forward(c, nullptr, nullptr, n, st);
     c->cursor = nullptr;
     if (rc) return -1;
-    ProfScope ps(c, "actor_head", 2.0 * n * HIDDEN * (c->A + 1), (double)n * (HIDDEN * 4 + 12), st);
+    ProfScope ps(c, "actor_head", 2.0 * n * c->HID * (c->A + 1), (double)n * (c->HID * 4 + 12), st);
     return launch_actor_head(c->hidden, n, c->A, c->params + c->off_actor_w, c->params + c->off_actor_b,
                              c->params + c->off_critic_w, c->params + c->off_critic_b, c->subkey, nullptr, nullptr,
-                             reinterpret_cast<int*>(c->dense_part), nullptr, st, cursor);
+                             reinterpret_cast<int*>(c->dense_part), nullptr, st, cursor, c->HID);
 }
 
 // forward-only heads (no sampling): reuse the actor head kernel with a scratch action buffer
@@ -714,7 +637,7 @@ int cb_policy_value(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int n, fl
     int* scratch_act = reinterpret_cast<int*>(c->dense_part);
     return launch_actor_head(c->hidden, n, c->A, c->params + c->off_actor_w, c->params + c->off_actor_b,
                              c->params + c->off_critic_w, c->params + c->off_critic_b, c->subkey, logits, value,
-                             scratch_act, nullptr, st);
+                             scratch_act, nullptr, st, nullptr, c->HID);
 }
 
 int cb_gae(cb_ctx* c, const float* rewards, const float* values, const uint8_t* dones, const float* next_value,
@@ -775,7 +698,7 @@ int cb_ppo_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int mb, const
     cudaStream_t st = (cudaStream_t)stream;
     if (trunk_forward(c, obs, idx, mb, st)) return -1;
     PpoHeadArgs h;
-    h.n = mb; h.num_actions = c->A; h.hidden = c->hidden;
+    h.n = mb; h.num_actions = c->A; h.hid = c->HID; h.hidden = c->hidden;
     h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
     h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
     h.idx = idx; h.actions = actions; h.old_logprobs = logprobs; h.advantages = advantages; h.returns = returns;
@@ -800,7 +723,7 @@ int cb_impala_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int T1, in
     const int n = T1 * B;
     if (trunk_forward(c, obs, idx, n, st)) return -1;
     ImpalaHeadArgs h;
-    h.T1 = T1; h.B = B; h.num_actions = c->A; h.hidden = c->hidden;
+    h.T1 = T1; h.B = B; h.num_actions = c->A; h.hid = c->HID; h.hidden = c->hidden;
     h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
     h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
     h.idx = idx; h.actions = actions; h.behaviour_logits = behaviour_logits; h.rewards = rewards; h.dones = dones;
@@ -852,6 +775,8 @@ int cb_memcpy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
     CB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream));
     return 0;
 }
+
+int cb_hidden_width(cb_ctx* c) { return c ? c->HID : 0; }
 
 int cb_set_grad_milestone(cb_ctx* c, void* cuda_event, long long* tail_offset) {
     CB_CHECK(c, "null argument");
@@ -957,11 +882,12 @@ long long cb_debug_tensor(cb_ctx* c, const char* name, float* host_out, long lon
     if (!strcmp(name, "hidden") || !strcmp(name, "dpre")) {
         const float* src = !strcmp(name, "hidden") ? c->hidden : c->dpre;
         CB_CHECK(src, "tensor %s not allocated", name);
-        long long cnt = (long long)n * HIDDEN;
+        long long cnt = (long long)n * c->HID;
         CB_CHECK(cnt <= cap, "buffer too small");
         CB_CUDA(cudaMemcpy(host_out, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
         return cnt;
     }
+    CB_CHECK(!c->nat, "only \"hidden\" and \"dpre\" are exposed for the Nature-CNN trunk");
     CB_CHECK(strlen(name) >= 4 && (name[0] == 's' || name[0] == 'g') && name[2] == '.', "bad tensor name %s", name);
     int s = name[1] - '0';
     CB_CHECK(s >= 0 && s < 3, "bad stage in %s", name);

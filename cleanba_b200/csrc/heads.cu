@@ -27,36 +27,38 @@ struct HeadSmem {
     float bc;
 };
 
+template <int HID>
 __device__ __forceinline__ HeadSmem load_head_smem(float* sm, const float* wa, const float* ba, const float* wc,
                                                    const float* bc, int A) {
     HeadSmem h;
-    h.wa = sm; h.wc = sm + HIDDEN * A; h.ba = h.wc + HIDDEN;
-    for (int t = threadIdx.x; t < HIDDEN * A; t += blockDim.x) h.wa[t] = wa[t];
-    for (int t = threadIdx.x; t < HIDDEN; t += blockDim.x) h.wc[t] = wc[t];
+    h.wa = sm; h.wc = sm + HID * A; h.ba = h.wc + HID;
+    for (int t = threadIdx.x; t < HID * A; t += blockDim.x) h.wa[t] = wa[t];
+    for (int t = threadIdx.x; t < HID; t += blockDim.x) h.wc[t] = wc[t];
     for (int t = threadIdx.x; t < A; t += blockDim.x) h.ba[t] = ba[t];
     h.bc = bc[0];
     __syncthreads();
     return h;
 }
-static inline size_t head_smem_bytes(int A) { return (size_t)(HIDDEN * A + HIDDEN + A) * sizeof(float); }
+static inline size_t head_smem_bytes(int HID, int A) { return (size_t)(HID * A + HID + A) * sizeof(float); }
 
 // One warp computes the A logits and the value of one sample.  Lane a (< A) returns logit a; every lane returns value.
 // The summation order is fixed, so the actor and the learner see bit-identical logits for identical hidden rows.
+template <int HID>
 __device__ __forceinline__ void head_forward(const HeadSmem& h, const float* hid /*[256]*/, int A, int lane,
-                                             float hreg[8], float& mylogit, float& value) {
+                                             float hreg[HID / 32], float& mylogit, float& value) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hreg[i] = hid[lane + 32 * i];
+    for (int i = 0; i < HID / 32; ++i) hreg[i] = hid[lane + 32 * i];
     mylogit = -INFINITY;
     for (int a = 0; a < A; ++a) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(hreg[i], h.wa[(lane + 32 * i) * A + a], s);
+        for (int i = 0; i < HID / 32; ++i) s = fmaf(hreg[i], h.wa[(lane + 32 * i) * A + a], s);
         s = warp_sum(s);
         if (lane == a) mylogit = s + h.ba[a];
     }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(hreg[i], h.wc[lane + 32 * i], s);
+    for (int i = 0; i < HID / 32; ++i) s = fmaf(hreg[i], h.wc[lane + 32 * i], s);
     value = warp_sum(s) + h.bc;
 }
 
@@ -79,6 +81,7 @@ int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st,
 
 // Sampling head: u = uniform(subkey, (n, A)); action = argmax(logits - log(-log u)) (first index on ties);
 // logprob = log_softmax(logits)[action]; value.  One warp per sample.
+template <int HID>
 __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hidden, int n, int A, const float* wa,
                                                     const float* ba, const float* wc, const float* bc,
                                                     const uint32_t* __restrict__ subkey, float* logits_out,
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hi
                                                     const cb_rollout_cursor* __restrict__ cursor) {
     extern __shared__ float sm[];
     griddep_launch();
-    HeadSmem h = load_head_smem(sm, wa, ba, wc, bc, A);   // master parameters: not written by the preceding kernels
+    HeadSmem h = load_head_smem<HID>(sm, wa, ba, wc, bc, A);   // master parameters: not written by the preceding kernels
     griddep_wait();
     if (cursor) {   // outputs go to row cursor->row of the rollout storages
         const long long r = (long long)cursor->row * cursor->out_row_stride;
@@ -99,8 +102,8 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hi
     const uint32_t k0 = subkey[0], k1 = subkey[1];
     const uint32_t total = (uint32_t)n * (uint32_t)A;
     for (int b = blockIdx.x * nwarp + warp; b < n; b += gridDim.x * nwarp) {
-        float hreg[8], logit, value;
-        head_forward(h, hidden + (long long)b * HIDDEN, A, lane, hreg, logit, value);
+        float hreg[HID / 32], logit, value;
+        head_forward<HID>(h, hidden + (long long)b * HID, A, lane, hreg, logit, value);
         float pert = -INFINITY;
         if (lane < A) {
             uint32_t bits = jax_random_bits_elem(k0, k1, (uint32_t)b * A + lane, total);
@@ -131,41 +134,48 @@ __global__ void __launch_bounds__(256) k_actor_head(const float* __restrict__ hi
 
 int launch_actor_head(const float* hidden, int n, int A, const float* wa, const float* ba, const float* wc,
                       const float* bc, const uint32_t* subkey, float* logits_out, float* value_out, int* action_out,
-                      float* logprob_out, cudaStream_t st, const cb_rollout_cursor* cursor) {
+                      float* logprob_out, cudaStream_t st, const cb_rollout_cursor* cursor, int hid) {
     int blocks = (n + 7) / 8;
     if (blocks > 296) blocks = 296;
-    launch_pdl(k_actor_head, dim3(blocks), dim3(256), (size_t)head_smem_bytes(A), st, hidden, n, A, wa, ba, wc, bc, subkey, logits_out,
-               value_out, action_out, logprob_out, cursor);
+    CB_CHECK(hid == 256 || hid == 512, "heads: hidden width %d not built (256 | 512)", hid);
+    if (hid == 256)
+        launch_pdl(k_actor_head<256>, dim3(blocks), dim3(256), (size_t)head_smem_bytes(256, A), st, hidden, n, A, wa, ba, wc, bc, subkey,
+                   logits_out, value_out, action_out, logprob_out, cursor);
+    else
+        launch_pdl(k_actor_head<512>, dim3(blocks), dim3(256), (size_t)head_smem_bytes(512, A), st, hidden, n, A, wa, ba, wc, bc, subkey,
+                   logits_out, value_out, action_out, logprob_out, cursor);
     CB_LAUNCH_CHECK();
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // dpre[k] = (sum_a dl[a] Wa[k][a] + dv Wc[k]) * (hidden[k] > 0)   for the 8 k's of this lane
-__device__ __forceinline__ void head_backward_hidden(const HeadSmem& h, int A, int lane, const float hreg[8], float dl,
+template <int HID>
+__device__ __forceinline__ void head_backward_hidden(const HeadSmem& h, int A, int lane, const float hreg[HID / 32], float dl,
                                                      float dv, float* dpre_row) {
-    float acc[8];
+    float acc[HID / 32];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = dv * h.wc[lane + 32 * i];
+    for (int i = 0; i < HID / 32; ++i) acc[i] = dv * h.wc[lane + 32 * i];
     for (int a = 0; a < A; ++a) {
         float d = __shfl_sync(0xffffffffu, dl, a);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(d, h.wa[(lane + 32 * i) * A + a], acc[i]);
+        for (int i = 0; i < HID / 32; ++i) acc[i] = fmaf(d, h.wa[(lane + 32 * i) * A + a], acc[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dpre_row[lane + 32 * i] = hreg[i] > 0.f ? acc[i] : 0.f;
+    for (int i = 0; i < HID / 32; ++i) dpre_row[lane + 32 * i] = hreg[i] > 0.f ? acc[i] : 0.f;
 }
 
 // PPO loss head, forward + backward, one warp per minibatch sample.
+template <int HID>
 __global__ void __launch_bounds__(256) k_ppo_head(PpoHeadArgs a) {
     extern __shared__ float sm[];
     const int A = a.num_actions;
-    HeadSmem h = load_head_smem(sm, a.wa, a.ba, a.wc, a.bc, A);
+    HeadSmem h = load_head_smem<HID>(sm, a.wa, a.ba, a.wc, a.bc, A);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const float inv_n = 1.f / (float)a.n;
     for (int b = blockIdx.x * nwarp + warp; b < a.n; b += gridDim.x * nwarp) {
-        float hreg[8], logit, value;
-        head_forward(h, a.hidden + (long long)b * HIDDEN, A, lane, hreg, logit, value);
+        float hreg[HID / 32], logit, value;
+        head_forward<HID>(h, a.hidden + (long long)b * HID, A, lane, hreg, logit, value);
         const int src = a.idx ? a.idx[b] : b;
         const int act = min(max(a.actions[src], 0), A - 1);   // defensive: never index with a corrupt action
         const float oldlp = a.old_logprobs[src], adv = a.advantages[src], ret = a.returns[src];
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(256) k_ppo_head(PpoHeadArgs a) {
         float dl = 0.f;
         if (lane < A) dl = c_lp * ((lane == act ? 1.f : 0.f) - p) + a.ent_coef * inv_n * p * (logp + ent);
         float dv = a.vf_coef * verr * inv_n;
-        head_backward_hidden(h, A, lane, hreg, dl, dv, a.dpre + (long long)b * HIDDEN);
+        head_backward_hidden<HID>(h, A, lane, hreg, dl, dv, a.dpre + (long long)b * HID);
         if (lane < A) a.dlogits[(long long)b * (A + 1) + lane] = dl;
         if (lane == 0) {
             a.dlogits[(long long)b * (A + 1) + A] = dv;
@@ -226,17 +236,18 @@ __global__ void __launch_bounds__(256) k_ppo_stats(const float* __restrict__ ter
 // Head weight gradients: dWa[k][a] = sum_b hidden[b][k] dl[b][a]; column A of dl is dvalue (critic); k == 256 is the bias.
 // Two deterministic stages: every block reduces a slice of HW_SLICE samples (hidden tile staged in shared memory, one
 // thread per hidden unit), then a second kernel adds the slices in a fixed order.
-constexpr int HW_SLICE = 32;
-__global__ void __launch_bounds__(HIDDEN) k_head_wgrad_partial(const float* __restrict__ hidden, const float* __restrict__ dl,
+constexpr int HW_SLICE = 16;      // samples per slice: sh[16][512] floats = 32 KB of static shared memory at the widest trunk
+template <int HID>
+__global__ void __launch_bounds__(HID) k_head_wgrad_partial(const float* __restrict__ hidden, const float* __restrict__ dl,
                                                                int n, int A, float* __restrict__ partial) {
-    __shared__ float sh[HW_SLICE][HIDDEN];
+    __shared__ float sh[HW_SLICE][HID];
     __shared__ float sd[HW_SLICE][MAX_ACTIONS + 1];
     const int b0 = blockIdx.x * HW_SLICE, k = threadIdx.x;
     const int nb = min(HW_SLICE, n - b0);
-    for (int b = 0; b < nb; ++b) sh[b][k] = hidden[(long long)(b0 + b) * HIDDEN + k];
-    for (int t = threadIdx.x; t < nb * (A + 1); t += HIDDEN) sd[t / (A + 1)][t % (A + 1)] = dl[(long long)b0 * (A + 1) + t];
+    for (int b = 0; b < nb; ++b) sh[b][k] = hidden[(long long)(b0 + b) * HID + k];
+    for (int t = threadIdx.x; t < nb * (A + 1); t += HID) sd[t / (A + 1)][t % (A + 1)] = dl[(long long)b0 * (A + 1) + t];
     __syncthreads();
-    float* out = partial + (long long)blockIdx.x * (HIDDEN + 1) * (A + 1);
+    float* out = partial + (long long)blockIdx.x * (HID + 1) * (A + 1);
     for (int a = 0; a <= A; ++a) {
         float s = 0.f;
         for (int b = 0; b < nb; ++b) s = fmaf(sh[b][k], sd[b][a], s);
@@ -245,38 +256,45 @@ __global__ void __launch_bounds__(HIDDEN) k_head_wgrad_partial(const float* __re
     if (k <= A) {   // bias row
         float s = 0.f;
         for (int b = 0; b < nb; ++b) s += sd[b][k];
-        out[HIDDEN * (A + 1) + k] = s;
+        out[HID * (A + 1) + k] = s;
     }
 }
+template <int HID>
 __global__ void __launch_bounds__(128) k_head_wgrad_reduce(const float* __restrict__ partial, int nslices, int A, float* dwa,
                                                            float* dba, float* dwc, float* dbc) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (HIDDEN + 1) * (A + 1)) return;
+    if (t >= (HID + 1) * (A + 1)) return;
     int k = t / (A + 1), a = t % (A + 1);
     float s = 0.f;
-    for (int i = 0; i < nslices; ++i) s += partial[(long long)i * (HIDDEN + 1) * (A + 1) + t];
-    if (k < HIDDEN) { if (a < A) dwa[k * A + a] = s; else dwc[k] = s; }
+    for (int i = 0; i < nslices; ++i) s += partial[(long long)i * (HID + 1) * (A + 1) + t];
+    if (k < HID) { if (a < A) dwa[k * A + a] = s; else dwc[k] = s; }
     else { if (a < A) dba[a] = s; else dbc[0] = s; }
 }
+template <int HID>
 static int launch_head_wgrad(const float* hidden, const float* dl, int n, int A, float* scratch, float* dwa, float* dba,
                              float* dwc, float* dbc, cudaStream_t st) {
     int nslices = (n + HW_SLICE - 1) / HW_SLICE;
-    k_head_wgrad_partial<<<nslices, HIDDEN, 0, st>>>(hidden, dl, n, A, scratch);
+    k_head_wgrad_partial<HID><<<nslices, HID, 0, st>>>(hidden, dl, n, A, scratch);
     CB_LAUNCH_CHECK();
-    int total = (HIDDEN + 1) * (A + 1);
-    k_head_wgrad_reduce<<<(total + 127) / 128, 128, 0, st>>>(scratch, nslices, A, dwa, dba, dwc, dbc);
+    int total = (HID + 1) * (A + 1);
+    k_head_wgrad_reduce<HID><<<(total + 127) / 128, 128, 0, st>>>(scratch, nslices, A, dwa, dba, dwc, dbc);
     CB_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
+template <int HID>
+static int launch_ppo_head_t(const PpoHeadArgs& a, cudaStream_t st) {
     int blocks = (a.n + 7) / 8;
     if (blocks > 592) blocks = 592;
-    k_ppo_head<<<blocks, 256, head_smem_bytes(a.num_actions), st>>>(a);
+    k_ppo_head<HID><<<blocks, 256, head_smem_bytes(HID, a.num_actions), st>>>(a);
     CB_LAUNCH_CHECK();
     k_ppo_stats<<<1, 256, 0, st>>>(a.terms, a.n, a.ent_coef, a.vf_coef, a.stats);
     CB_LAUNCH_CHECK();
-    return launch_head_wgrad(a.hidden, a.dlogits, a.n, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
+    return launch_head_wgrad<HID>(a.hidden, a.dlogits, a.n, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
+}
+int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
+    CB_CHECK(a.hid == 256 || a.hid == 512, "heads: hidden width %d not built (256 | 512)", a.hid);
+    return a.hid == 256 ? launch_ppo_head_t<256>(a, st) : launch_ppo_head_t<512>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -285,18 +303,19 @@ int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
 //   phases = 2: per-cell terms, the V-trace scan along T, loss scalars, d/dlogits, d/dvalue   (ONE block: the scan is a
 //               sequential recurrence per column and the whole minibatch is <= a few thousand cells)
 //   phases = 4: gradient w.r.t. the pre-relu dense output (one warp per frame, all SMs)
+template <int HID>
 __global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a, int phases) {
     extern __shared__ float sm[];
     const int A = a.num_actions, T1 = a.T1, B = a.B, T = T1 - 1;
-    HeadSmem h = load_head_smem(sm, a.wa, a.ba, a.wc, a.bc, A);
+    HeadSmem h = load_head_smem<HID>(sm, a.wa, a.ba, a.wc, a.bc, A);
     float* red = h.ba + A + 1;   // [3][1024]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int nf = T1 * B, nc = T * B;
     if (phases & 1) {
         // phase 0: logits + value of every frame
         for (int f = blockIdx.x * nwarp + warp; f < nf; f += gridDim.x * nwarp) {
-            float hreg[8], logit, value;
-            head_forward(h, a.hidden + (long long)f * HIDDEN, A, lane, hreg, logit, value);
+            float hreg[HID / 32], logit, value;
+            head_forward<HID>(h, a.hidden + (long long)f * HID, A, lane, hreg, logit, value);
             if (lane < A) a.logits_scratch[(long long)f * (A + 1) + lane] = logit;
             if (lane == 0) a.logits_scratch[(long long)f * (A + 1) + A] = value;
         }
@@ -304,12 +323,12 @@ __global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a, int phas
     if (phases & 4) {
         // phase 4: gradient w.r.t. the pre-relu dense output
         for (int f = blockIdx.x * nwarp + warp; f < nf; f += gridDim.x * nwarp) {
-            float hreg[8];
+            float hreg[HID / 32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) hreg[i] = a.hidden[(long long)f * HIDDEN + lane + 32 * i];
+            for (int i = 0; i < HID / 32; ++i) hreg[i] = a.hidden[(long long)f * HID + lane + 32 * i];
             float dl = lane < A ? a.dlogits[(long long)f * (A + 1) + lane] : 0.f;
             float dv = a.dlogits[(long long)f * (A + 1) + A];
-            head_backward_hidden(h, A, lane, hreg, dl, dv, a.dpre + (long long)f * HIDDEN);
+            head_backward_hidden<HID>(h, A, lane, hreg, dl, dv, a.dpre + (long long)f * HID);
         }
     }
     if (!(phases & 2) || blockIdx.x != 0) return;
@@ -398,18 +417,32 @@ __global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a, int phas
     }
 }
 
-int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st) {
-    size_t smem = head_smem_bytes(a.num_actions) + (1 + 3 * 1024) * sizeof(float);
+template <int HID>
+static int launch_impala_head_t(const ImpalaHeadArgs& a, cudaStream_t st) {
+    size_t smem = head_smem_bytes(HID, a.num_actions) + (1 + 3 * 1024) * sizeof(float);
+    if (smem > 48 * 1024) {      // the 512-wide trunk needs the opt-in limit (once per device, outside graph capture)
+        static std::atomic<unsigned> attr_done{0};
+        int dev = 0;
+        CB_CUDA(cudaGetDevice(&dev));
+        if (!(attr_done.load() & (1u << dev))) {
+            CB_CUDA(cudaFuncSetAttribute(k_impala_head<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_done.fetch_or(1u << dev);
+        }
+    }
     const int nf = a.T1 * a.B;
     int blocks = (nf + 7) / 8;                       // 8 warps (frames) per block
     if (blocks > 592) blocks = 592;
-    k_impala_head<<<blocks, 256, smem, st>>>(a, 1);
+    k_impala_head<HID><<<blocks, 256, smem, st>>>(a, 1);
     CB_LAUNCH_CHECK();
-    k_impala_head<<<1, 1024, smem, st>>>(a, 2);
+    k_impala_head<HID><<<1, 1024, smem, st>>>(a, 2);
     CB_LAUNCH_CHECK();
-    k_impala_head<<<blocks, 256, smem, st>>>(a, 4);
+    k_impala_head<HID><<<blocks, 256, smem, st>>>(a, 4);
     CB_LAUNCH_CHECK();
-    return launch_head_wgrad(a.hidden, a.dlogits, a.T1 * a.B, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
+    return launch_head_wgrad<HID>(a.hidden, a.dlogits, a.T1 * a.B, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
+}
+int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st) {
+    CB_CHECK(a.hid == 256 || a.hid == 512, "heads: hidden width %d not built (256 | 512)", a.hid);
+    return a.hid == 256 ? launch_impala_head_t<256>(a, st) : launch_impala_head_t<512>(a, st);
 }
 
 }  // namespace cb

@@ -77,14 +77,48 @@ int launch_dense_fwd_umma(const DenseUmmaArgs& a, cudaStream_t st);
 int launch_dense_bwd_umma(const DenseUmmaArgs& a, const float* dpre, float* dw, float* db, float* scratch, cudaStream_t st);
 int launch_dpre_transpose(const float* dpre, int n, int npad, bf16* dp_hi, bf16* dp_mid, cudaStream_t st);
 
+// gemm_umma.cu (generic tcgen05 GEMMs on carrier "row planes": the Nature-CNN trunk)
+struct RowPlanes {               // X[R, K] as plane[K / 8][rpad][8], hi / mid carrier planes (mid null: exact single plane)
+    const f16* hi;
+    const f16* mid;
+    long long rpad;
+};
+struct GemmArgs {                // C[R, N] = A[R, K] * W[K, N]
+    RowPlanes a;
+    int K;                       // multiple of 64
+    long long R, Rpad;           // valid rows; rows padded to 128 (outputs of padded rows are written as zeros)
+    const f16* wp;               // packed weights (launch_pack_gemm) for the N block size used
+    int N;                       // output columns (multiple of the N block)
+    const float* bias;           // [N] or null
+    float acc_scale;
+    int relu;
+    f16 *out_hi, *out_mid;       // carrier planes out [N / 8][out_rpad][8], or null
+    long long out_rpad;
+    float* out_f32;              // row-major fp32 out [R][out_ld], or null
+    int out_ld;
+};
+struct GemmWgradArgs {           // dW[K, N] = scale * inv_scale * A[R, K]^T * G[R, N]
+    RowPlanes a, g;
+    int K, N;
+    long long Rpad;
+    float scale;
+    const float* inv_scale;      // device scalar or null
+    float* dw;                   // [K][N]
+};
+int launch_gemm_umma(const GemmArgs& a, int NB, int num_sms, cudaStream_t st);
+int launch_gemm_wgrad_umma(const GemmWgradArgs& a, float* partial, long long partial_cap, int num_sms, cudaStream_t st);
+long long gemm_pack_elems(int Kl, int Nl, int transpose, int NB);
+int launch_pack_gemm(const float* w, int Kl, int Nl, int transpose, int NB, f16* out, cudaStream_t st);
+
 // heads.cu
 int launch_split_key(uint32_t* key_inout, uint32_t* subkey_out, cudaStream_t st, cb_rollout_cursor* cursor = nullptr);
 int launch_actor_head(const float* hidden, int n, int num_actions, const float* wa, const float* ba, const float* wc,
                       const float* bc, const uint32_t* subkey, float* logits_out, float* value_out, int* action_out,
-                      float* logprob_out, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr);
+                      float* logprob_out, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr, int hid = HIDDEN);
 struct PpoHeadArgs {
     int n, num_actions;
-    const float* hidden;         // [n][256]
+    int hid;                     // width of `hidden` (256 | 512)
+    const float* hidden;         // [n][hid]
     const float *wa, *ba, *wc, *bc;
     const int* idx;              // minibatch sample indices into the flat [T*B] fields (null = identity)
     const int* actions;          // flat fields of the whole update
@@ -102,6 +136,7 @@ struct PpoHeadArgs {
 int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st);
 struct ImpalaHeadArgs {
     int T1, B, num_actions;      // T1 = T + 1 rows; frames are ordered f = t * B + b
+    int hid;                     // width of `hidden` (256 | 512)
     const float* hidden;
     const float *wa, *ba, *wc, *bc;
     const int* idx;              // [T1*B] indices into the flat [T1*Bl] fields (null = identity)

@@ -20,6 +20,11 @@ from .params import init_params
 from .prng import first_key as _first_key
 
 
+def _model_of(args) -> int:
+    from .lib import MODELS
+    return MODELS[getattr(args, "network", "impala_resnet")]
+
+
 class _Storage:
     def __init__(self, actor, rows):
         d, N, A = actor.dev, actor.N, actor.ctx.num_actions
@@ -58,7 +63,8 @@ class CudaActor:
         self.dev = torch.device("cuda", device_id)
         self.N = N
         self.impala = args.algo == "impala"
-        self.ctx = ag.Context(self.dev, max_batch=N, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO)
+        self.ctx = ag.Context(self.dev, max_batch=N, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO,
+                              model=_model_of(args))
         self.stream = torch.cuda.Stream(self.dev)
         self.copy_streams = []                              # actor -> learner payload copies (overlap the next rollout)
         self._peers, self._payload_log, self._land = set(), [], {}
@@ -188,14 +194,16 @@ class CudaLearner:
             h = ImpalaHyper(learning_rate=args.learning_rate, anneal_lr=args.anneal_lr, gamma=args.gamma,
                             num_minibatches=args.num_minibatches, ent_coef=args.ent_coef, vf_coef=args.vf_coef,
                             max_grad_norm=args.max_grad_norm, num_updates=max(args.num_updates, 1))
-            self.learners = [ImpalaLearner(d, h, args.num_steps + 1, Bl, world_learners, hooks[l]) for l, d in enumerate(self.devices)]
+            self.learners = [ImpalaLearner(d, h, args.num_steps + 1, Bl, world_learners, hooks[l], model=_model_of(args))
+                             for l, d in enumerate(self.devices)]
         else:
             h = PPOHyper(learning_rate=args.learning_rate, anneal_lr=args.anneal_lr, gamma=args.gamma, gae_lambda=args.gae_lambda,
                          num_minibatches=args.num_minibatches, update_epochs=args.update_epochs, norm_adv=args.norm_adv,
                          clip_coef=args.clip_coef, ent_coef=args.ent_coef, vf_coef=args.vf_coef, max_grad_norm=args.max_grad_norm,
                          num_updates=max(args.num_updates, 1))
-            self.learners = [PPOLearner(d, h, args.num_steps, Bl, world_learners, hooks[l]) for l, d in enumerate(self.devices)]
-        params = init_params(args.seed)
+            self.learners = [PPOLearner(d, h, args.num_steps, Bl, world_learners, hooks[l], model=_model_of(args))
+                             for l, d in enumerate(self.devices)]
+        params = init_params(args.seed, model=_model_of(args))
         for lr in self.learners:
             lr.ctx.set_params(params)
         self.keys = [ag.key_tensor(key, d) for d in self.devices]    # learner_keys = device_put_replicated(key) (cleanba_ppo.py:470)

@@ -11,7 +11,7 @@ from typing import Callable, Optional
 import numpy as np
 import torch
 
-from .agent import Context, CB_ALGO_IMPALA, CB_ALGO_PPO, CB_CONV_TCGEN05, CleanbaError
+from .agent import Context, CB_ALGO_IMPALA, CB_ALGO_PPO, CB_CONV_TCGEN05, CB_MODEL_IMPALA_RESNET, CleanbaError
 
 # allreduce hook: f(flat_grad_tensor) -> None, sums in place over all learner devices of all processes
 AllReduce = Optional[Callable[[torch.Tensor], None]]
@@ -76,7 +76,7 @@ class PPOHyper:
 
 class PPOLearner:
     def __init__(self, device, hyper: PPOHyper, T: int, Bl: int, world_learners: int = 1, allreduce: AllReduce = None,
-                 conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18):
+                 conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18, model: int = CB_MODEL_IMPALA_RESNET):
         if (T * Bl) % hyper.num_minibatches:
             raise CleanbaError("T*Bl must be divisible by num_minibatches")
         if Bl % hyper.num_minibatches and hyper.norm_adv:
@@ -85,7 +85,7 @@ class PPOLearner:
         self.mb = T * Bl // hyper.num_minibatches
         self.world_learners = world_learners
         self.ctx = Context(device, max_batch=max(self.mb, Bl), algo=CB_ALGO_PPO, train=True,
-                           num_actions=num_actions, conv_backend=conv_backend)
+                           num_actions=num_actions, conv_backend=conv_backend, model=model)
         self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners)
         d = self.ctx.device
         self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
@@ -148,14 +148,14 @@ class ImpalaHyper:
 
 class ImpalaLearner:
     def __init__(self, device, hyper: ImpalaHyper, T1: int, Bl: int, world_learners: int = 1, allreduce: AllReduce = None,
-                 conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18):
+                 conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18, model: int = CB_MODEL_IMPALA_RESNET):
         if Bl % hyper.num_minibatches:
             raise CleanbaError("Bl must be divisible by num_minibatches (cleanba_impala.py:456-458)")
         self.h, self.T1, self.Bl = hyper, T1, Bl
         self.B = Bl // hyper.num_minibatches
         self.world_learners = world_learners
         self.ctx = Context(device, max_batch=T1 * self.B, algo=CB_ALGO_IMPALA, train=True, num_actions=num_actions,
-                           conv_backend=conv_backend)
+                           conv_backend=conv_backend, model=model)
         self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners)
         d = self.ctx.device
         self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)

@@ -9,6 +9,8 @@ LIB_PATH = os.path.join(_HERE, "libcleanba_b200.so")
 
 CB_ALGO_PPO, CB_ALGO_IMPALA = 0, 1
 CB_CONV_TCGEN05, CB_CONV_SIMT = 0, 1
+CB_MODEL_IMPALA_RESNET, CB_MODEL_NATURE_CNN = 0, 1
+MODELS = {"impala_resnet": CB_MODEL_IMPALA_RESNET, "nature_cnn": CB_MODEL_NATURE_CNN}
 
 
 class CleanbaError(RuntimeError):
@@ -17,7 +19,7 @@ class CleanbaError(RuntimeError):
 
 class cb_config(ctypes.Structure):
     _fields_ = [("device", c_int), ("algo", c_int), ("max_batch", c_int), ("train", c_int),
-                ("num_actions", c_int), ("conv_backend", c_int)]
+                ("num_actions", c_int), ("conv_backend", c_int), ("model", c_int)]
 
 
 # every symbol declared in include/cleanba_b200.h: (restype, argtypes)
@@ -30,6 +32,10 @@ SIGNATURES = {
     "cb_num_params": (c_longlong, [c_int]),
     "cb_num_leaves": (c_int, []),
     "cb_leaf_info": (c_int, [c_int, c_int, c_char_p, c_int, POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),
+    "cb_num_params_model": (c_longlong, [c_int, c_int]),
+    "cb_num_leaves_model": (c_int, [c_int]),
+    "cb_leaf_info_model": (c_int, [c_int, c_int, c_int, c_char_p, c_int, POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),
+    "cb_hidden_width": (c_int, [_P]),
     "cb_set_params": (c_int, [_P, _P, _P]),
     "cb_get_params": (c_int, [_P, _P, _P]),
     "cb_params_ptr": (_P, [_P]),
@@ -83,14 +89,14 @@ def check(rc):
         raise CleanbaError(load().cb_last_error().decode("utf-8", "replace"))
 
 
-def leaves(num_actions=18):
-    """[(flax path, offset, shape)] of the flat parameter vector."""
+def leaves(num_actions=18, model=CB_MODEL_IMPALA_RESNET):
+    """[(flax path, offset, shape)] of the flat parameter vector of the given trunk."""
     lib = load()
     out = []
-    for i in range(lib.cb_num_leaves()):
+    for i in range(lib.cb_num_leaves_model(model)):
         name = ctypes.create_string_buffer(256)
         off, nd = c_longlong(), c_int()
         shape = (c_int * 4)()
-        check(lib.cb_leaf_info(i, num_actions, name, 256, ctypes.byref(off), ctypes.byref(nd), shape))
+        check(lib.cb_leaf_info_model(model, i, num_actions, name, 256, ctypes.byref(off), ctypes.byref(nd), shape))
         out.append((name.value.decode(), off.value, tuple(shape[: nd.value])))
     return out

@@ -9,8 +9,8 @@ import numpy as np
 from . import lib as _lib
 
 
-def leaves(num_actions: int = 18):
-    return _lib.leaves(num_actions)
+def leaves(num_actions: int = 18, model: int = 0):
+    return _lib.leaves(num_actions, model)
 
 
 def _orthogonal(rng, rows, cols, scale):
@@ -22,12 +22,16 @@ def _orthogonal(rng, rows, cols, scale):
     return (scale * q[:rows, :cols]).astype(np.float32)
 
 
-def init_params(seed: int = 1, num_actions: int = 18) -> np.ndarray:
+def init_params(seed: int = 1, num_actions: int = 18, model: int = 0) -> np.ndarray:
+    """model = lib.CB_MODEL_IMPALA_RESNET | lib.CB_MODEL_NATURE_CNN.  The Nature-CNN convs are orthogonal(sqrt 2) like its dense
+    layer (cleanba/legacy_scripts/cleanba_ppo_envpool_impala_atari_wrapper_naturecnn.py:152,160,168)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     out = []
-    for name, _, shape in leaves(num_actions):
+    for name, _, shape in leaves(num_actions, model):
         if name.endswith("bias"):
             out.append(np.zeros(shape, np.float32))
+        elif len(shape) == 4 and model == _lib.CB_MODEL_NATURE_CNN:
+            out.append(_orthogonal(rng, shape[0] * shape[1] * shape[2], shape[3], np.sqrt(2.0)).reshape(shape))
         elif len(shape) == 4:
             fan_in = shape[0] * shape[1] * shape[2]
             std = np.sqrt(1.0 / fan_in) / 0.87962566103423978   # truncated-normal variance correction (lecun_normal)

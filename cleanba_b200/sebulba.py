@@ -66,6 +66,7 @@ class Args:
 
     # B200 build additions (not in the reference): which algorithm this Args drives and how many updates to run at most
     algo: str = "ppo"
+    network: str = "impala_resnet"  # trunk: "impala_resnet" (cleanba_ppo.py:149-189) or "nature_cnn" (legacy_scripts/..._naturecnn.py:143-178)
     max_updates: int = 0          # 0 = run to total_timesteps
     synthetic_env: bool = True    # envpool is not installable here; frames come from cleanba_b200.envs.SyntheticAtari
     eval_max_steps: int = 27000   # step cap of one evaluation episode after --save-model (envpool's max_episode_steps)
@@ -96,8 +97,11 @@ def impala_defaults(args: Args) -> Args:
 
 def derive_sizes(args: Args, world_size: int = 1, local_rank: int = 0) -> Args:
     """cleanba_ppo.py:411-430: batch sizes, divisibility asserts, num_updates."""
-    if args.channels != [16, 32, 32] or args.hiddens != [256]:
-        raise ValueError("libcleanba_b200 implements the reference's default IMPALA-ResNet (channels 16,32,32; hiddens 256)")
+    if args.network not in ("impala_resnet", "nature_cnn"):
+        raise ValueError("--network must be impala_resnet or nature_cnn")
+    if args.network == "impala_resnet" and (args.channels != [16, 32, 32] or args.hiddens != [256]):
+        raise ValueError("libcleanba_b200 implements the reference's default IMPALA-ResNet (channels 16,32,32; hiddens 256) "
+                         "and the legacy Nature-CNN (--network nature_cnn)")
     if args.gradient_accumulation_steps != 1:
         # cleanba_ppo.py:492-500 wraps the optimizer in optax.MultiSteps(every_k_schedule=k); only k = 1 (its default) is built
         raise ValueError("gradient_accumulation_steps != 1 is not supported (reference default: 1)")

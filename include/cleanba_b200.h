@@ -29,6 +29,10 @@ typedef void* cb_stream; /* cudaStream_t */
 
 enum { CB_ALGO_PPO = 0, CB_ALGO_IMPALA = 1 };        /* Adam (eps 1e-5) vs PyTorch-style RMSProp (eps .01, decay .99) */
 enum { CB_CONV_TCGEN05 = 0, CB_CONV_SIMT = 1 };      /* tensor-core kernels (product) or the fp32 CUDA-core cross-check */
+/* Trunk: the IMPALA-ResNet of cleanba_ppo.py:149-189 (channels 16,32,32; hidden 256) or the Nature-CNN of
+ * legacy_scripts/cleanba_ppo_envpool_impala_atari_wrapper_naturecnn.py:143-178 (8x8 s4 / 4x4 s2 / 3x3 s1 VALID convs, hidden 512;
+ * tcgen05 only).  The parameter vector follows the flax tree of the selected trunk (cb_leaf_info_model). */
+enum { CB_MODEL_IMPALA_RESNET = 0, CB_MODEL_NATURE_CNN = 1 };
 
 typedef struct cb_config {
     int device;       /* CUDA device ordinal */
@@ -37,12 +41,14 @@ typedef struct cb_config {
     int train;        /* 0: actor / inference context, 1: learner (allocates backward workspace + optimizer state) */
     int num_actions;  /* 18 for full_action_space Atari (cleanba_ppo.py:135) */
     int conv_backend; /* CB_CONV_* */
+    int model;        /* CB_MODEL_* */
 } cb_config;
 
 /* ---- lifecycle / errors ------------------------------------------------------------------------------------ */
 const char* cb_last_error(void);
 int cb_version(void);
 int cb_create(const cb_config* cfg, cb_ctx** out);
+int cb_hidden_width(cb_ctx* ctx);   /* width of the trunk's dense output: 256 (IMPALA-ResNet) or 512 (Nature-CNN) */
 void cb_destroy(cb_ctx* ctx);
 
 /* ---- parameters (AgentParams / TrainState, cleanba_ppo.py:206-210,485-502) ---------------------------------- */
@@ -50,6 +56,10 @@ long long cb_num_params(int num_actions);
 int cb_num_leaves(void);
 /* name_cap bytes of `name` receive the flax path; shape has up to 4 entries. */
 int cb_leaf_info(int index, int num_actions, char* name, int name_cap, long long* offset, int* ndim, int* shape);
+/* The same three queries for a given trunk (CB_MODEL_*); the functions above answer for CB_MODEL_IMPALA_RESNET. */
+long long cb_num_params_model(int model, int num_actions);
+int cb_num_leaves_model(int model);
+int cb_leaf_info_model(int model, int index, int num_actions, char* name, int name_cap, long long* offset, int* ndim, int* shape);
 /* src / dst may be host or device memory (cudaMemcpyDefault). cb_set_params also refreshes the packed bf16 weights. */
 int cb_set_params(cb_ctx* ctx, const float* src, cb_stream stream);
 int cb_get_params(cb_ctx* ctx, float* dst, cb_stream stream);

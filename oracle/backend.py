@@ -71,7 +71,7 @@ class OracleActor:
 class OracleLearner:
     def __init__(self, args, key, allreduce):
         self.args, self.impala = args, args.algo == "impala"
-        params = net.init_params(args.seed)
+        params = net.init_params(args.seed, net.nature_param_spec() if getattr(args, "network", "impala_resnet") == "nature_cnn" else None)
         self.L = len(args.learner_device_ids)
         self.key = np.asarray(key).copy()
         self.allreduce = allreduce

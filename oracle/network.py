@@ -55,6 +55,26 @@ def param_spec(channels: Sequence[int] = CHANNELS, hidden: int = HIDDEN, num_act
     return spec
 
 
+def nature_param_spec(num_actions: int = NUM_ACTIONS) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Leaves of the Nature-CNN agent in flax tree order
+    (cleanba/legacy_scripts/cleanba_ppo_envpool_impala_atari_wrapper_naturecnn.py:143-193: Conv_0..2, Dense_0, actor, critic)."""
+    p = "network_params/params"
+    return [(f"{p}/Conv_0/bias", (32,)), (f"{p}/Conv_0/kernel", (8, 8, 4, 32)),
+            (f"{p}/Conv_1/bias", (64,)), (f"{p}/Conv_1/kernel", (4, 4, 32, 64)),
+            (f"{p}/Conv_2/bias", (64,)), (f"{p}/Conv_2/kernel", (3, 3, 64, 64)),
+            (f"{p}/Dense_0/bias", (512,)), (f"{p}/Dense_0/kernel", (3136, 512)),
+            ("actor_params/params/Dense_0/bias", (num_actions,)), ("actor_params/params/Dense_0/kernel", (512, num_actions)),
+            ("critic_params/params/Dense_0/bias", (1,)), ("critic_params/params/Dense_0/kernel", (512, 1))]
+
+
+def spec_for_size(n: int):
+    """The two trunks have different parameter counts: pick the spec a flat vector belongs to."""
+    for spec in (param_spec(), nature_param_spec()):
+        if num_params(spec) == n:
+            return spec
+    raise ValueError(f"no known model has {n} parameters")
+
+
 def num_params(spec=None) -> int:
     spec = spec or param_spec()
     return int(sum(int(np.prod(s)) for _, s in spec))
@@ -78,11 +98,15 @@ def init_params(seed: int = 1, spec=None) -> np.ndarray:
     explicit seeded INPUT shared by the oracle and the CUDA path (SURVEY.md section 7 hard part 6).
     """
     spec = spec or param_spec()
+    nature = any(name.endswith("/Conv_2/kernel") and "ConvSequence" not in name for name, _ in spec)
     rng = np.random.Generator(np.random.PCG64(seed))
     leaves = []
     for name, shape in spec:
         if name.endswith("bias"):
             leaves.append(np.zeros(shape, np.float32))
+        elif len(shape) == 4 and nature:
+            # Nature-CNN convs: orthogonal(sqrt 2) on the [kh*kw*cin, cout] matrix (naturecnn.py:152,160,168)
+            leaves.append(_orthogonal(rng, shape[0] * shape[1] * shape[2], shape[3], np.sqrt(2.0)).reshape(shape))
         elif len(shape) == 4:
             fan_in = shape[0] * shape[1] * shape[2]
             # lecun_normal = truncated normal(+-2 sigma) with variance 1/fan_in
@@ -101,7 +125,7 @@ def init_params(seed: int = 1, spec=None) -> np.ndarray:
 
 def unflatten(flat, spec=None) -> Dict[str, torch.Tensor]:
     """Views of the flat vector as named leaves (works for numpy arrays and torch tensors)."""
-    spec = spec or param_spec()
+    spec = spec or spec_for_size(int(flat.shape[0]))
     out, off = {}, 0
     for name, shape in spec:
         n = int(np.prod(shape))
@@ -131,6 +155,8 @@ def trunk_forward(p: Dict[str, torch.Tensor], obs_u8: torch.Tensor, channels=CHA
     The reference transposes to NHWC; torch computes in NCHW, which is the same arithmetic.  Only the
     flatten order (h,w,c) (cleanba_ppo.py:185) needs an explicit permute."""
     dt = p["network_params/params/Dense_0/kernel"].dtype
+    if "network_params/params/Conv_0/kernel" in p:
+        return nature_trunk_forward(p, obs_u8, record)
 
     def rec(name, t):
         # test hook: keep intermediates (NCHW) and, when differentiating, their gradients
@@ -154,6 +180,22 @@ def trunk_forward(p: Dict[str, torch.Tensor], obs_u8: torch.Tensor, channels=CHA
             x = rec(f"s{s}.b{r}", x + inputs)
     x = torch.relu(x)
     x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # NHWC flatten
+    x = x @ p["network_params/params/Dense_0/kernel"] + p["network_params/params/Dense_0/bias"]
+    return torch.relu(x)
+
+
+def nature_trunk_forward(p: Dict[str, torch.Tensor], obs_u8: torch.Tensor, record: dict = None) -> torch.Tensor:
+    """Nature-CNN Network.__call__ (cleanba/legacy_scripts/cleanba_ppo_envpool_impala_atari_wrapper_naturecnn.py:143-178):
+    x/255 -> Conv(32, 8x8, s4, VALID) -> relu -> Conv(64, 4x4, s2, VALID) -> relu -> Conv(64, 3x3, s1, VALID) -> relu -> NHWC flatten
+    -> Dense(512) -> relu.  obs_u8 [b,4,84,84] -> hidden [b,512]."""
+    dt = p["network_params/params/Dense_0/kernel"].dtype
+    x = obs_u8.to(dt) / 255.0
+    for l, stride in enumerate((4, 2, 1)):
+        w = p[f"network_params/params/Conv_{l}/kernel"].permute(3, 2, 0, 1)      # HWIO -> OIHW
+        x = torch.relu(F.conv2d(x, w, p[f"network_params/params/Conv_{l}/bias"], stride=stride, padding=0))
+        if record is not None:
+            record[f"c{l}"] = x
+    x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
     x = x @ p["network_params/params/Dense_0/kernel"] + p["network_params/params/Dense_0/bias"]
     return torch.relu(x)
 

@@ -8,7 +8,7 @@ from oracle import optim as ooptim
 def pin_hook(record, diag, algo, grad_bar=1e-3, param_bar=2e-7, shard=None, nshards=1, shared=None, max_norm=None, on_last=None):
     """BEFORE minibatch step k the replica is put into the oracle's recorded pre-step state (parameters, optimizer moments,
     count), so every step of the update is a SINGLE-step comparison held to the single-step bars:
-      * loss scalars: 1e-4 relative to the oracle's;
+      * loss scalars: 1e-4 relative to the oracle's (scalars below 1% of the largest one are compared at that floor);
       * gradient: `grad_bar` (1e-3) in relative L2 norm against the oracle's fp32 autograd gradient;
       * optimizer: the parameters after the step against the ORACLE's optimizer (optax chain restated in oracle/optim.py)
         applied to the recorded pre-step state and the replicas' OWN gradients: `param_bar` = 2e-7 absolute.  (Feeding the
@@ -36,7 +36,9 @@ def pin_hook(record, diag, algo, grad_bar=1e-3, param_bar=2e-7, shard=None, nsha
             want_s = r["stats"] if shard is None else r["shard_stats"][shard]
             want_g = r["raw_grad"] if shard is None else r["shard_grads"][shard]
             st = L.stats[k].detach().cpu().numpy().astype(np.float64)
-            serr = np.abs(st[:4] - want_s[:4]) / np.maximum(np.abs(want_s[:4]), 1e-6)
+            # relative to each scalar's own magnitude, floored at 1% of the largest of the four: the policy loss of normalised
+            # advantages is a mean of +-O(1) terms that cancels to ~1e-3, where its own magnitude is no scale for a 1e-4 bar
+            serr = np.abs(st[:4] - want_s[:4]) / np.maximum(np.abs(want_s[:4]), 1e-2 * np.abs(want_s[:4]).max())
             g32 = L.grads.detach().cpu().numpy()
             shared[(id(rec), k, shard or 0)] = g32
             g = g32.astype(np.float64)
