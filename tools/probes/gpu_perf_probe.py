@@ -7,7 +7,8 @@ from cleanba_b200 import agent as ag
 
 mb = int(sys.argv[1]) if len(sys.argv) > 1 else 3840
 backends = [int(b) for b in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
-params = net.init_params(1)
+model = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # 0 IMPALA-ResNet, 1 Nature-CNN
+params = net.init_params(1, net.nature_param_spec() if model else None)
 rng = np.random.default_rng(0)
 N = mb
 obs = torch.from_numpy(rng.integers(0, 256, (N, 4, 84, 84), dtype=np.uint8)).cuda()
@@ -16,7 +17,7 @@ oldlp = torch.full((N,), float(np.log(1 / 18)), dtype=torch.float32).cuda()
 adv = torch.randn(N, device="cuda"); ret = torch.randn(N, device="cuda")
 idx = torch.from_numpy(rng.permutation(N).astype(np.int32)).cuda()
 for backend in backends:
-    ctx = ag.Context("cuda:0", max_batch=mb, train=True, conv_backend=backend)
+    ctx = ag.Context("cuda:0", max_batch=mb, train=True, conv_backend=backend, model=model)
     ctx.set_params(params)
     grads = torch.zeros(ctx.num_params, device="cuda"); stats = torch.zeros(5, device="cuda")
     def step():
@@ -30,7 +31,7 @@ for backend in backends:
     for _ in range(iters): step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    print(f"== backend={'simt' if backend else 'tcgen05'} mb={mb}: {ms:.3f} ms per minibatch grad+opt step  ({mb/ms*1e3:.0f} samples/s)")
+    print(f"== model={'nature_cnn' if model else 'impala_resnet'} backend={'simt' if backend else 'tcgen05'} mb={mb}: {ms:.3f} ms per minibatch grad+opt step  ({mb/ms*1e3:.0f} samples/s)")
     ctx.profile(True); step(); rep = ctx.profile_report(); ctx.profile(False)
     tot = sum(r["ms"] for r in rep)
     for r in sorted(rep, key=lambda r: -r["ms"]):
@@ -41,7 +42,7 @@ for backend in backends:
     ctx.close()
 # actor step latency
 for backend in backends:
-    ctx = ag.Context("cuda:0", max_batch=60, conv_backend=backend)
+    ctx = ag.Context("cuda:0", max_batch=60, conv_backend=backend, model=model)
     ctx.set_params(params)
     key = ag.key_tensor(np.array([1, 2], np.uint32), ctx.device)
     o = obs[:60].contiguous()
