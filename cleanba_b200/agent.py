@@ -217,6 +217,10 @@ class Context:
                                          _ptr(norm_out), _stream(self.device)))
 
 
+    def grad_accumulate(self, acc: torch.Tensor, grads: torch.Tensor, mini_step: int):
+        """optax.MultiSteps running mean: acc += (grads - acc) / (mini_step + 1)."""
+        check(self.lib.cb_grad_accumulate(self.h, _ptr(acc), _ptr(grads), int(mini_step), _stream(self.device)))
+
     def set_sm_budget(self, num_sms: int):
         """Size this context's persistent grids for an SM partition (see cleanba_b200.partition)."""
         check(self.lib.cb_set_sm_budget(self.h, int(num_sms)))

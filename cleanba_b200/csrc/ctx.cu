@@ -768,6 +768,12 @@ int cb_reduce_peers(cb_ctx* c, const float* const* grads, int num_grads, float* 
     return launch_reduce_peers(o, out, (cudaStream_t)stream);
 }
 
+int cb_grad_accumulate(cb_ctx* c, float* acc, const float* grads, int mini_step, cb_stream stream) {
+    CB_CHECK(c && acc && grads && mini_step >= 0, "bad argument");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    return launch_grad_accumulate(acc, grads, c->nparam, mini_step, (cudaStream_t)stream);
+}
+
 int cb_memcpy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, cb_stream stream) {
     CB_CHECK(dst && src, "null argument");
     CB_CHECK(width_bytes <= dst_pitch && width_bytes <= src_pitch, "row width %zu exceeds a pitch (%zu, %zu)", width_bytes, dst_pitch, src_pitch);

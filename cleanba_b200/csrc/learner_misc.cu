@@ -290,6 +290,19 @@ int launch_loss_scale(const float* dpre, long long count, unsigned* work, float*
     return 0;
 }
 
+// optax.MultiSteps accumulation (cleanba_ppo.py:492-500 with gradient_accumulation_steps > 1): acc <- acc + (g - acc) / (mini_step + 1)
+__global__ void __launch_bounds__(256) k_grad_accumulate(float* __restrict__ acc, const float* __restrict__ g, long long n, float inv) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float a = acc[i];
+        acc[i] = a + (g[i] - a) * inv;
+    }
+}
+int launch_grad_accumulate(float* acc, const float* g, long long n, int mini_step, cudaStream_t st) {
+    k_grad_accumulate<<<OPT_BLOCKS, 256, 0, st>>>(acc, g, n, 1.0f / (float)(mini_step + 1));
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
 // out[i] = gp[0][i] + gp[1][i] + ... (fixed order, peer memory): the in-process stage of a two-level gradient exchange
 __global__ void __launch_bounds__(256) k_reduce_peers(OptArgs a, float* __restrict__ out) {
     for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < a.n; i += (long long)gridDim.x * 256 * 4) {

@@ -193,14 +193,15 @@ class CudaLearner:
         if self.impala:
             h = ImpalaHyper(learning_rate=args.learning_rate, anneal_lr=args.anneal_lr, gamma=args.gamma,
                             num_minibatches=args.num_minibatches, ent_coef=args.ent_coef, vf_coef=args.vf_coef,
-                            max_grad_norm=args.max_grad_norm, num_updates=max(args.num_updates, 1))
+                            max_grad_norm=args.max_grad_norm, num_updates=max(args.num_updates, 1),
+                            gradient_accumulation_steps=args.gradient_accumulation_steps)
             self.learners = [ImpalaLearner(d, h, args.num_steps + 1, Bl, world_learners, hooks[l], model=_model_of(args))
                              for l, d in enumerate(self.devices)]
         else:
             h = PPOHyper(learning_rate=args.learning_rate, anneal_lr=args.anneal_lr, gamma=args.gamma, gae_lambda=args.gae_lambda,
                          num_minibatches=args.num_minibatches, update_epochs=args.update_epochs, norm_adv=args.norm_adv,
                          clip_coef=args.clip_coef, ent_coef=args.ent_coef, vf_coef=args.vf_coef, max_grad_norm=args.max_grad_norm,
-                         num_updates=max(args.num_updates, 1))
+                         num_updates=max(args.num_updates, 1), gradient_accumulation_steps=args.gradient_accumulation_steps)
             self.learners = [PPOLearner(d, h, args.num_steps, Bl, world_learners, hooks[l], model=_model_of(args))
                              for l, d in enumerate(self.devices)]
         params = init_params(args.seed, model=_model_of(args))
@@ -238,15 +239,15 @@ class CudaLearner:
             torch.cuda.current_stream(g.device).synchronize()
             self.barrier.wait()
             if l == 0:
-                g0 = self.learners[0].grads
+                g0 = self.learners[0].exchange_buffer
                 for k in range(1, L):
-                    g0.add_(self.learners[k].grads.to(g0.device))
+                    g0.add_(self.learners[k].exchange_buffer.to(g0.device))
                 if self.cross is not None:
                     self.cross(g0)
                 torch.cuda.current_stream(g0.device).synchronize()
             self.barrier.wait()
             if l != 0:
-                g.copy_(self.learners[0].grads)
+                g.copy_(self.learners[0].exchange_buffer)
                 torch.cuda.current_stream(g.device).synchronize()
             self.barrier.wait()
         hook.whole_buffer = len(self.devices) > 1      # the multi-device fallback exchanges whole buffers: not splittable
@@ -264,7 +265,7 @@ class CudaLearner:
             for k in range(L):
                 if k != l:
                     st.wait_event(self.ev_done[k])
-            lr.ctx.optimizer_step_peers([x.grads for x in self.learners], grad_scale, lrate, max_norm)
+            lr.ctx.optimizer_step_peers([x.exchange_buffer for x in self.learners], grad_scale, lrate, max_norm)
             ev = torch.cuda.Event()
             ev.record(st)                                   # this replica has read every peer buffer
             self.ev_read[l] = ev
@@ -288,7 +289,7 @@ class CudaLearner:
             if l == 0:
                 for k in range(1, L):
                     st.wait_event(self.ev_done[k])
-                lr.ctx.reduce_peers([x.grads for x in self.learners], self.gsum)
+                lr.ctx.reduce_peers([x.exchange_buffer for x in self.learners], self.gsum)
                 self.cross(self.gsum)                       # ONE NCCL allreduce per minibatch on the flat gradient buffer
                 ev = torch.cuda.Event()
                 ev.record(st)

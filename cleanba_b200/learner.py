@@ -72,24 +72,29 @@ class PPOHyper:
     vf_coef: float = 0.5
     max_grad_norm: float = 0.5
     num_updates: int = 3255
+    gradient_accumulation_steps: int = 1    # optax.MultiSteps(every_k_schedule) (cleanba_ppo.py:78, 492-500)
 
 
 class PPOLearner:
     def __init__(self, device, hyper: PPOHyper, T: int, Bl: int, world_learners: int = 1, allreduce: AllReduce = None,
                  conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18, model: int = CB_MODEL_IMPALA_RESNET):
-        if (T * Bl) % hyper.num_minibatches:
-            raise CleanbaError("T*Bl must be divisible by num_minibatches")
+        self.k = max(int(hyper.gradient_accumulation_steps), 1)
+        if (T * Bl) % (hyper.num_minibatches * self.k):
+            raise CleanbaError("T*Bl must be divisible by num_minibatches * gradient_accumulation_steps")
         if Bl % hyper.num_minibatches and hyper.norm_adv:
             raise CleanbaError("Bl must be divisible by num_minibatches (cleanba_ppo.py:416-418)")
         self.h, self.T, self.Bl = hyper, T, Bl
-        self.mb = T * Bl // hyper.num_minibatches
+        self.mb = T * Bl // (hyper.num_minibatches * self.k)      # the shuffled batch is cut into num_minibatches * k mini-steps (:607)
         self.world_learners = world_learners
         self.ctx = Context(device, max_batch=max(self.mb, Bl), algo=CB_ALGO_PPO, train=True,
                            num_actions=num_actions, conv_backend=conv_backend, model=model)
-        self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners)
+        # with accumulation the exchanged buffer is complete only after the last mini-step's accumulate kernel: no overlap
+        self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners) if self.k == 1 else allreduce
         d = self.ctx.device
         self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
-        self.stats = torch.zeros(hyper.update_epochs * hyper.num_minibatches, 5, dtype=torch.float32, device=d)
+        self.acc = torch.zeros_like(self.grads) if self.k > 1 else None
+        self.exchange_buffer = self.acc if self.k > 1 else self.grads     # what the (fused) gradient exchange reads
+        self.stats = torch.zeros(hyper.update_epochs * hyper.num_minibatches * self.k, 5, dtype=torch.float32, device=d)
         self.opt_count = 0
         self.fused_step = None      # f(learner, grad_scale, lr, max_norm): gradient exchange fused into the optimizer step
         self.step_hook = None       # f(phase, k, learner), phase in "pre" | "grad" | "post" of minibatch step k: lets the parity
@@ -110,7 +115,7 @@ class PPOLearner:
         for _ in range(h.update_epochs):
             sub = c.split_key(key)                                    # key, subkey = split(key) (cleanba_ppo.py:599)
             perm = c.permutation(sub, T * Bl)                         # jax.random.permutation(subkey, .) (:606)
-            for j in range(h.num_minibatches):
+            for j in range(h.num_minibatches * self.k):
                 idx = perm[j * self.mb:(j + 1) * self.mb]
                 if self.step_hook is not None:
                     self.step_hook("pre", k, self)
@@ -118,18 +123,24 @@ class PPOLearner:
                            self.grads, self.stats[k])
                 if self.step_hook is not None:
                     self.step_hook("grad", k, self)
+                k += 1
+                g = self.grads
+                if self.k > 1:                                        # optax.MultiSteps: running mean over the k mini-steps
+                    c.grad_accumulate(self.acc, self.grads, (j % self.k))
+                    if (j + 1) % self.k:
+                        continue
+                    g = self.acc
                 lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches * h.update_epochs,
                                      h.num_updates, h.anneal_lr)
                 if self.fused_step is not None:                       # pmean + apply_gradients in one pass over peer memory
                     self.fused_step(self, 1.0 / self.world_learners, lr, h.max_grad_norm)
                 else:
                     if self.allreduce is not None and self.world_learners > 1:
-                        self.allreduce(self.grads)                    # lax.pmean(grads) (cleanba_ppo.py:628)
-                    c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
+                        self.allreduce(g)                             # lax.pmean(grads) (cleanba_ppo.py:628)
+                    c.optimizer_step(g, 1.0 / self.world_learners, lr, h.max_grad_norm)
                 self.opt_count += 1
                 if self.step_hook is not None:
-                    self.step_hook("post", k, self)
-                k += 1
+                    self.step_hook("post", k - 1, self)
         return self.stats.mean(0)
 
 
@@ -144,28 +155,32 @@ class ImpalaHyper:
     vf_coef: float = 0.5
     max_grad_norm: float = 40.0
     num_updates: int = 20833
+    gradient_accumulation_steps: int = 1    # optax.MultiSteps(every_k_schedule) (cleanba_impala.py:76, 532-540, 626-633)
 
 
 class ImpalaLearner:
     def __init__(self, device, hyper: ImpalaHyper, T1: int, Bl: int, world_learners: int = 1, allreduce: AllReduce = None,
                  conv_backend: int = CB_CONV_TCGEN05, num_actions: int = 18, model: int = CB_MODEL_IMPALA_RESNET):
-        if Bl % hyper.num_minibatches:
-            raise CleanbaError("Bl must be divisible by num_minibatches (cleanba_impala.py:456-458)")
+        self.k = max(int(hyper.gradient_accumulation_steps), 1)
+        if Bl % (hyper.num_minibatches * self.k):
+            raise CleanbaError("Bl must be divisible by num_minibatches * gradient_accumulation_steps (cleanba_impala.py:456-458, 626-633)")
         self.h, self.T1, self.Bl = hyper, T1, Bl
-        self.B = Bl // hyper.num_minibatches
+        self.B = Bl // (hyper.num_minibatches * self.k)           # env columns per mini-step
         self.world_learners = world_learners
         self.ctx = Context(device, max_batch=T1 * self.B, algo=CB_ALGO_IMPALA, train=True, num_actions=num_actions,
                            conv_backend=conv_backend, model=model)
-        self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners)
+        self.allreduce = _wrap_exchange(self.ctx, allreduce, world_learners) if self.k == 1 else allreduce
         d = self.ctx.device
         self.grads = torch.zeros(self.ctx.num_params, dtype=torch.float32, device=d)
-        self.stats = torch.zeros(hyper.num_minibatches, 4, dtype=torch.float32, device=d)
+        self.acc = torch.zeros_like(self.grads) if self.k > 1 else None
+        self.exchange_buffer = self.acc if self.k > 1 else self.grads
+        self.stats = torch.zeros(hyper.num_minibatches * self.k, 4, dtype=torch.float32, device=d)
         # contiguous env-column blocks, never shuffled (cleanba_impala.py:626-633): idx[j][t*B+b] = t*Bl + j*B + b
         t = torch.arange(T1, device=d, dtype=torch.int32)[:, None] * Bl
         self.fused_step = None
         self.step_hook = None       # see PPOLearner
         self.idx = [(t + (j * self.B + torch.arange(self.B, device=d, dtype=torch.int32))[None, :]).reshape(-1).contiguous()
-                    for j in range(hyper.num_minibatches)]
+                    for j in range(hyper.num_minibatches * self.k)]
         self.opt_count = 0
 
     def update(self, obs, dones, actions, logitss, rewards, firststeps) -> torch.Tensor:
@@ -175,20 +190,26 @@ class ImpalaLearner:
         T1, Bl = self.T1, self.Bl
         obs_f = obs.reshape(T1 * Bl, 4, 84, 84)
         A = c.num_actions
-        for j in range(h.num_minibatches):
+        for j in range(h.num_minibatches * self.k):
             if self.step_hook is not None:
                 self.step_hook("pre", j, self)
             c.impala_grad(obs_f, self.idx[j], T1, self.B, actions.reshape(-1), logitss.reshape(-1, A), rewards.reshape(-1),
                           dones.reshape(-1), firststeps.reshape(-1), h.gamma, h.vf_coef, h.ent_coef, self.grads, self.stats[j])
             if self.step_hook is not None:
                 self.step_hook("grad", j, self)
+            g = self.grads
+            if self.k > 1:                                            # optax.MultiSteps: running mean over the k mini-steps
+                c.grad_accumulate(self.acc, self.grads, j % self.k)
+                if (j + 1) % self.k:
+                    continue
+                g = self.acc
             lr = linear_schedule(self.opt_count, h.learning_rate, h.num_minibatches, h.num_updates, h.anneal_lr)
             if self.fused_step is not None:                           # pmean + apply_gradients in one pass over peer memory
                 self.fused_step(self, 1.0 / self.world_learners, lr, h.max_grad_norm)
             else:
                 if self.allreduce is not None and self.world_learners > 1:
-                    self.allreduce(self.grads)                        # lax.pmean(grads) (cleanba_impala.py:619)
-                c.optimizer_step(self.grads, 1.0 / self.world_learners, lr, h.max_grad_norm)
+                    self.allreduce(g)                                 # lax.pmean(grads) (cleanba_impala.py:619)
+                c.optimizer_step(g, 1.0 / self.world_learners, lr, h.max_grad_norm)
             self.opt_count += 1
             if self.step_hook is not None:
                 self.step_hook("post", j, self)

@@ -52,6 +52,7 @@ SIGNATURES = {
     "cb_ppo_grad": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, c_float, c_float, c_float, _P, _P, _P]),
     "cb_impala_grad": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, _P, _P, _P]),
     "cb_optimizer_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P]),
+    "cb_grad_accumulate": (c_int, [_P, _P, _P, c_int, _P]),
     "cb_optimizer_step_peers": (c_int, [_P, POINTER(_P), c_int, c_float, c_float, c_float, _P, _P]),
     "cb_enable_peer_access": (c_int, [_P, c_int]),
     "cb_set_grad_milestone": (c_int, [_P, _P, POINTER(c_longlong)]),

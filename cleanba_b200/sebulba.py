@@ -102,9 +102,8 @@ def derive_sizes(args: Args, world_size: int = 1, local_rank: int = 0) -> Args:
     if args.network == "impala_resnet" and (args.channels != [16, 32, 32] or args.hiddens != [256]):
         raise ValueError("libcleanba_b200 implements the reference's default IMPALA-ResNet (channels 16,32,32; hiddens 256) "
                          "and the legacy Nature-CNN (--network nature_cnn)")
-    if args.gradient_accumulation_steps != 1:
-        # cleanba_ppo.py:492-500 wraps the optimizer in optax.MultiSteps(every_k_schedule=k); only k = 1 (its default) is built
-        raise ValueError("gradient_accumulation_steps != 1 is not supported (reference default: 1)")
+    if args.gradient_accumulation_steps < 1:
+        raise ValueError("gradient_accumulation_steps must be >= 1")
     args.local_batch_size = int(args.local_num_envs * args.num_steps * args.num_actor_threads * len(args.actor_device_ids))
     args.local_minibatch_size = int(args.local_batch_size // args.num_minibatches)
     assert args.local_num_envs % len(args.learner_device_ids) == 0, \

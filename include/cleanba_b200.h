@@ -131,6 +131,10 @@ int cb_impala_grad(cb_ctx* ctx, const uint8_t* obs, const int32_t* idx, int T1, 
  * may be NULL) receives the pre-clip global norm.  Refreshes the packed bf16 weights. */
 int cb_optimizer_step(cb_ctx* ctx, const float* grads, float grad_scale, float lr, float max_norm, float* norm_out,
                       cb_stream stream);
+/* optax.MultiSteps(every_k_schedule = gradient_accumulation_steps) (cleanba_ppo.py:492-500): running mean of the gradients of the k
+ * mini-steps that make up one optimizer step, acc <- acc + (grads - acc) / (mini_step + 1), mini_step = 0 .. k-1 (mini_step 0
+ * overwrites acc).  The optimizer step is then taken on acc. */
+int cb_grad_accumulate(cb_ctx* ctx, float* acc, const float* grads, int mini_step, cb_stream stream);
 /* The same step with the gradient exchange FUSED in: the gradient is the fixed-order sum grads[0] + ... + grads[n-1] of the
  * flat gradient buffers of all learner replicas of this process, read directly from peer memory over NVLink / NVSwitch inside
  * the norm and the update kernels -- `jax.lax.pmean(grads, "local_devices")` (cleanba_ppo.py:628) without a separate

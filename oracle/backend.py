@@ -78,13 +78,15 @@ class OracleLearner:
         if self.impala:
             cfg = oimpala.ImpalaConfig(num_minibatches=args.num_minibatches, gamma=args.gamma, ent_coef=args.ent_coef,
                                        vf_coef=args.vf_coef, max_grad_norm=args.max_grad_norm, learning_rate=args.learning_rate,
-                                       anneal_lr=args.anneal_lr, num_updates=max(args.num_updates, 1))
+                                       anneal_lr=args.anneal_lr, num_updates=max(args.num_updates, 1),
+                                       gradient_accumulation_steps=getattr(args, "gradient_accumulation_steps", 1))
             self.learner = oimpala.ImpalaLearner(params, cfg)
         else:
             cfg = oppo.PPOConfig(num_minibatches=args.num_minibatches, update_epochs=args.update_epochs, gamma=args.gamma,
                                  gae_lambda=args.gae_lambda, clip_coef=args.clip_coef, ent_coef=args.ent_coef, vf_coef=args.vf_coef,
                                  max_grad_norm=args.max_grad_norm, learning_rate=args.learning_rate, anneal_lr=args.anneal_lr,
-                                 norm_adv=args.norm_adv, num_updates=max(args.num_updates, 1))
+                                 norm_adv=args.norm_adv, num_updates=max(args.num_updates, 1),
+                                 gradient_accumulation_steps=getattr(args, "gradient_accumulation_steps", 1))
             self.learner = oppo.PPOLearner(params, cfg)
         self.learner.cross_allreduce = allreduce
         self.world = max(args.world_size, 1)

@@ -114,6 +114,7 @@ class ImpalaConfig:
     learning_rate: float = 6e-4
     anneal_lr: bool = True
     num_updates: int = 20833  # 50_000_000 // 2_400
+    gradient_accumulation_steps: int = 1   # optax.MultiSteps(every_k_schedule) (cleanba_impala.py:76,532-540,626-633)
 
 
 @dataclass
@@ -139,8 +140,9 @@ class ImpalaLearner:
         cfg = self.cfg
         stats_all = []
         Bl = shards[0].rewards.shape[1]
-        cols = np.split(np.arange(Bl), cfg.num_minibatches)  # contiguous column blocks (cleanba_impala.py:626-633)
-        for j in range(cfg.num_minibatches):
+        kacc = max(cfg.gradient_accumulation_steps, 1)
+        cols = np.split(np.arange(Bl), cfg.num_minibatches * kacc)  # contiguous column blocks (cleanba_impala.py:626-633)
+        for j in range(cfg.num_minibatches * kacc):
             grads, stats = [], []
             for s in shards:
                 c = cols[j]
@@ -152,6 +154,15 @@ class ImpalaLearner:
             g = np.mean(np.stack(grads), axis=0, dtype=F32)  # lax.pmean of summed-loss grads (quirk D.7)
             if getattr(self, "cross_allreduce", None) is not None:
                 g = self.cross_allreduce(g)
+            if kacc > 1:   # optax.MultiSteps (0.1.4): running mean of the mini-step gradients, inner update on the k-th
+                ms = j % kacc
+                self._acc = g.copy() if ms == 0 else (self._acc + (g - self._acc) / F32(ms + 1)).astype(F32)
+                if ms != kacc - 1:
+                    stats_all.append(np.mean(np.stack(stats), axis=0))
+                    if record is not None:
+                        record.append(dict(mini_step=ms, raw_grad=g.copy(), stats=stats_all[-1].copy(), cols=cols[j].copy(), params_before=self.params.copy()))
+                    continue
+                g = self._acc
             lr = optim.linear_schedule(self.opt.count, cfg.learning_rate, cfg.num_minibatches, cfg.num_updates, cfg.anneal_lr)
             if record is not None:   # the complete pre-step state: lets a test replay THIS step alone (no chained drift)
                 pre = dict(params_before=self.params.copy(), nu_before=self.opt.nu.copy(), count_before=int(self.opt.count),

@@ -159,6 +159,7 @@ class PPOConfig:
     anneal_lr: bool = True
     norm_adv: bool = True
     num_updates: int = 3255  # 50_000_000 // 15_360
+    gradient_accumulation_steps: int = 1   # optax.MultiSteps(every_k_schedule) (cleanba_ppo.py:78,492-500,607)
 
 
 @dataclass
@@ -187,7 +188,7 @@ class PPOLearner:
         """update_epoch's shuffle (cleanba_ppo.py:599-615): returns (new_key, idx[num_minibatches, mb])."""
         key, subkey = threefry.split(key)
         perm = threefry.permutation(subkey, n)
-        return key, perm.reshape(self.cfg.num_minibatches, -1)
+        return key, perm.reshape(self.cfg.num_minibatches * max(self.cfg.gradient_accumulation_steps, 1), -1)
 
     def prepare(self, shard: Shard):
         with torch.no_grad():
@@ -206,7 +207,8 @@ class PPOLearner:
         for _ in range(cfg.update_epochs):
             T, Bl = shards[0].rewards.shape
             key, idx = self.minibatch_indices(key, T * Bl)
-            for j in range(cfg.num_minibatches):
+            kacc = max(cfg.gradient_accumulation_steps, 1)
+            for j in range(cfg.num_minibatches * kacc):
                 grads, stats = [], []
                 for s, (adv, ret) in zip(shards, prepared):
                     ii = idx[j]
@@ -219,6 +221,18 @@ class PPOLearner:
                 g = np.mean(np.stack(grads), axis=0, dtype=F32)  # lax.pmean (cleanba_ppo.py:628)
                 if getattr(self, "cross_allreduce", None) is not None:   # pmean also spans processes when --distributed
                     g = self.cross_allreduce(g)
+                if kacc > 1:   # optax.MultiSteps (0.1.4): running mean of the mini-step gradients, inner update on the k-th
+                    ms = j % kacc
+                    self._acc = g.copy() if ms == 0 else (self._acc + (g - self._acc) / F32(ms + 1)).astype(F32)
+                    stats_all.append(np.mean(np.stack(stats), axis=0))
+                    if record is not None:
+                        record.append(dict(mini_step=ms, raw_grad=g.copy(), stats=stats_all[-1].copy(), idx=idx[j].copy(), params_before=self.params.copy()))
+                    if ms != kacc - 1:
+                        continue
+                    g = self._acc
+                    stats_all.pop()
+                    if record is not None:
+                        record.pop()
                 lr = optim.linear_schedule(self.opt.count, cfg.learning_rate, cfg.num_minibatches * cfg.update_epochs,
                                            cfg.num_updates, cfg.anneal_lr)
                 if record is not None:   # the complete pre-step state: lets a test replay THIS step alone (no chained drift)

@@ -585,3 +585,62 @@ def test_rollout_actor_rows_match_plain_actor_steps(agent, params):
     with pytest.raises(agent.CleanbaError):
         ra.step(frames[0], 0)                            # rows must be stepped in order
     ref.close(); ctx.close()
+
+
+# --------------------------------------------------------------------------------------------- gradient accumulation
+def test_gradient_accumulation_matches_optax_multisteps(agent, params):
+    """gradient_accumulation_steps = 2 (optax.MultiSteps(every_k_schedule), cleanba_ppo.py:78,492-500,607): the shuffled batch is cut into
+    num_minibatches * k mini-steps, the optimizer steps on the running mean of k mini-step gradients.  Every mini-step starts from
+    the oracle's recorded parameters; the accumulated gradient is compared with the oracle's (1e-3), the parameters after each
+    optimizer step with the oracle's optimizer applied to the replica's own accumulated gradient (2e-7)."""
+    from cleanba_b200.learner import PPOHyper, PPOLearner
+    rng = np.random.default_rng(51)
+    T, B = 4, 8
+    shard = oppo.Shard(obs=rng.integers(0, 256, (T, B, 4, 84, 84), dtype=np.uint8), dones=rng.random((T, B)) < 0.1,
+                       actions=rng.integers(0, 18, (T, B)).astype(np.int32),
+                       logprobs=(np.log(1 / 18) + rng.standard_normal((T, B)) * 0.01).astype(np.float32),
+                       values=(rng.standard_normal((T, B)) * 0.1).astype(np.float32),
+                       rewards=rng.choice([-1.0, 0.0, 1.0], size=(T, B)).astype(np.float32),
+                       next_obs=rng.integers(0, 256, (B, 4, 84, 84), dtype=np.uint8), next_done=rng.random(B) < 0.1)
+    key = tf.split(tf.PRNGKey(1), 4)[0]
+    ol = oppo.PPOLearner(params, oppo.PPOConfig(update_epochs=1, num_minibatches=2, gradient_accumulation_steps=2, num_updates=10))
+    rec = []
+    ostats, okey = ol.update([shard], key, record=rec)
+    assert [r.get("mini_step") for r in rec] == [0, None, 0, None]      # (mini-step, optimizer step) x 2
+    L = PPOLearner("cuda:0", PPOHyper(update_epochs=1, num_minibatches=2, gradient_accumulation_steps=2, num_updates=10), T=T, Bl=B)
+    L.ctx.set_params(params)
+    assert L.mb == T * B // 4
+    seen = []
+
+    def hook(phase, k, LL):
+        step = rec[k | 1]                                   # the optimizer step this mini-step belongs to
+        if phase == "pre":
+            LL.ctx.set_params(step["params_before"])
+            LL.ctx.set_opt_state(step["m_before"], step["v_before"], step["count_before"])
+            LL.opt_count = step["count_before"]
+        elif phase == "grad" and "mini_step" in rec[k]:
+            g = LL.grads.cpu().numpy().astype(np.float64)
+            err = float(np.linalg.norm(g - rec[k]["raw_grad"]) / np.linalg.norm(rec[k]["raw_grad"]))
+            seen.append(("mini", k, err))
+            assert err < 1e-3, (k, err)
+        elif phase == "post":
+            acc = LL.acc.cpu().numpy()
+            err = float(np.linalg.norm(acc.astype(np.float64) - step["raw_grad"]) / np.linalg.norm(step["raw_grad"]))
+            opt = ooptim.Adam(acc.size)
+            opt.m, opt.v, opt.count = step["m_before"].copy(), step["v_before"].copy(), step["count_before"]
+            want = opt.step(step["params_before"], ooptim.clip_by_global_norm(acc, 0.5), step["lr"])
+            perr = float(np.abs(LL.ctx.get_params().cpu().numpy() - want).max())
+            seen.append(("step", k, err, perr))
+            assert err < 1e-3 and perr < 2e-7, (k, err, perr)
+
+    L.step_hook = hook
+    dev = L.ctx.device
+    tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    kt = agent.key_tensor(key, dev)
+    stats = L.update(tt(shard.obs), tt(shard.dones), tt(shard.actions), tt(shard.logprobs), tt(shard.values), tt(shard.rewards),
+                     tt(shard.next_obs), tt(shard.next_done), kt)
+    assert agent.key_numpy(kt).tolist() == okey.tolist() and L.opt_count == 2
+    assert [s[0] for s in seen] == ["mini", "step", "mini", "step"], seen
+    serr = [abs(float(stats[i]) - ostats[i]) / max(abs(ostats[i]), 1e-2 * np.abs(ostats[:4]).max()) for i in range(4)]
+    _diag("ppo_gradient_accumulation_k2", seen=[list(map(float, s[1:])) for s in seen], mean_stats_relerr=serr)
+    assert max(serr) < 1e-4, (stats, ostats)
