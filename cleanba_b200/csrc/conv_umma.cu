@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
     uint8_t* wsm = smem + 1024;
     uint8_t* stages = wsm + L.w_bytes;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(CIN_CHUNKS);
     constexpr int ACC_COLS = 2 * COUT;                           // column block 0: hi*hi, block 1: (hi*mid + mid*hi) * 2^11
     constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : ((2 * ACC_COLS <= 128) ? 128 : 256);
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
         // ===================== MMA issuer =====================
         constexpr uint32_t IDESC2 = make_idesc_f16(TILE_M, 2 * COUT, 0, 0);
         constexpr uint32_t IDESC1 = make_idesc_f16(TILE_M, COUT, 0, 0);
+        const uint32_t leader = elect_one();
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         int acc = 0; uint32_t aph = 0;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
             mbar_wait(&tempty[acc], aph ^ 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            if (lane == 0) {
+            {   // the whole warp runs the issue code converged (uniform datapath); only the elected lane issues (umma.cuh)
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 const uint32_t st16 = (smem_u32(stages + s * L.stage_bytes) >> 4);   // stage base (hi planes), 16-byte units
                 const uint32_t mid16 = CIN_CHUNKS * win16;
@@ -162,11 +163,11 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
                 for (int step = 0; step < STEPS; ++step) {
                     const uint32_t a_lo = st16 + a_rel[step];
                     const uint32_t b_lo = b_lo0 + step * (2 * WPL * COUT);
-                    mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0);                 // A_hi * [W_hi | W_mid]
-                    if (APL == 2) mma_bf16_parts(d_tmem + COUT, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1);   // block 1 += A_mid * W_hi
+                    mma_f16_elect(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0, leader);                 // A_hi * [W_hi | W_mid]
+                    if (APL == 2) mma_f16_elect(d_tmem + COUT, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1, leader);   // block 1 += A_mid * W_hi
                 }
-                mma_commit(&empty[s]);      // smem stage reusable once these MMAs have read it
-                mma_commit(&tfull[acc]);    // accumulator complete
+                mma_commit_elect(&empty[s], leader);      // smem stage reusable once these MMAs have read it
+                mma_commit_elect(&tfull[acc], leader);    // accumulator complete
             }
             __syncwarp();
             if (++s == NSTAGES) { s = 0; ph ^= 1; }
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
     uint8_t* stages = wsm + C0_W_BYTES;
     uint8_t* band = stages + C0_STAGES * C0_STAGE_BYTES;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(1);
     constexpr int ACC_COLS = 2 * C0_COUT;
     constexpr uint32_t TMEM_COLS = 256;                          // 5 accumulators x 32 columns: the MMAs of the NEXT band run
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
     } else if (warp == 9) {
         // ===================== MMA issuer (frames: one exact fp16 plane, two taps per K = 16 step) =====================
         constexpr uint32_t IDESC2 = make_idesc_f16(TILE_M, 2 * C0_COUT, 0, 0);
+        const uint32_t leader = elect_one();
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         uint32_t aph = 0;                                        // accumulator phase: flips once per band
@@ -355,14 +357,14 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
                 mbar_wait(&tempty[t], aph ^ 1);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                {   // warp-uniform issue (umma.cuh)
                     const uint32_t d_tmem = tmem_base + t * ACC_COLS;
                     const uint32_t st16 = (smem_u32(stages + s * C0_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int step = 0; step < STEPS; ++step)
-                        mma_bf16_parts(d_tmem, st16 + a_rel[step], a_hi, b_lo0 + step * (2 * 2 * C0_COUT), b_hi, IDESC2, step > 0);
-                    mma_commit(&empty[s]);
-                    mma_commit(&tfull[t]);
+                        mma_f16_elect(d_tmem, st16 + a_rel[step], a_hi, b_lo0 + step * (2 * 2 * C0_COUT), b_hi, IDESC2, step > 0, leader);
+                    mma_commit_elect(&empty[s], leader);
+                    mma_commit_elect(&tfull[t], leader);
                 }
                 __syncwarp();
                 if (++s == C0_STAGES) { s = 0; ph ^= 1; }
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
     uint8_t* stages = wsm + L.w_bytes;
     uint8_t* band = stages + NSTAGES * L.stage_bytes;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr int STEPS = conv_steps(CIN_CHUNKS);
     constexpr uint32_t TMEM_COLS = CP_MAXT * CP_ACC_COLS <= 128 ? 128 : (CP_MAXT * CP_ACC_COLS <= 256 ? 256 : 512);   // CP_MAXT accumulators x 64 columns
     constexpr int NPLANES = 2 * CIN_CHUNKS;
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
         // ===================== MMA issuer: two MMAs per K step (see k_conv_umma) =====================
         constexpr uint32_t IDESC2 = make_idesc_f16(TILE_M, 2 * CP_COUT, 0, 0);
         constexpr uint32_t IDESC1 = make_idesc_f16(TILE_M, CP_COUT, 0, 0);
+        const uint32_t leader = elect_one();
         mbar_wait(wbar, 0);
         int s = 0; uint32_t ph = 0;
         uint32_t accph = 0;                                      // bit t: phase of accumulator t (flips each time it is used)
@@ -621,18 +624,18 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
                 mbar_wait(&tempty[t], ((accph >> t) & 1) ^ 1);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                {   // warp-uniform issue (umma.cuh)
                     const uint32_t d_tmem = tmem_base + t * CP_ACC_COLS;
                     const uint32_t st16 = (smem_u32(stages + s * L.stage_bytes) >> 4);
 #pragma unroll
                     for (int step = 0; step < STEPS; ++step) {
                         const uint32_t a_lo = st16 + a_rel[step];
                         const uint32_t b_lo = b_lo0 + step * (2 * 2 * CP_COUT);
-                        mma_bf16_parts(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0);
-                        mma_bf16_parts(d_tmem + CP_COUT, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1);
+                        mma_f16_elect(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC2, step > 0, leader);
+                        mma_f16_elect(d_tmem + CP_COUT, a_lo + mid16, a_hi, b_lo, b_hi, IDESC1, 1, leader);
                     }
-                    mma_commit(&empty[s]);
-                    mma_commit(&tfull[t]);
+                    mma_commit_elect(&empty[s], leader);
+                    mma_commit_elect(&tfull[t], leader);
                 }
                 __syncwarp();
                 accph ^= 1u << t;
@@ -846,7 +849,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
     uint64_t* done = empty + WG_MAXST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     uint8_t* stages = smem + 1024;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr int XPL = S::XPL, GROUPS = S::GROUPS, NCH = COUT / 8;
     constexpr int ACC0 = 2 * COUT;                             // columns of one kx accumulator: [G_hi | G_mid]
     constexpr int ACC1 = S::DUAL ? COUT : 0;                   // second issuer: X_mid * G_hi
@@ -907,12 +910,13 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
         const uint32_t idesc = make_idesc_f16(S::MMA_M, who == 0 ? 2 * COUT : COUT, 1, 1);
         const uint32_t d0 = tmem_base + (who == 0 ? 0 : 3 * ACC0);
         const uint32_t dstep = who == 0 ? ACC0 : ACC1;
+        const uint32_t leader = elect_one();
         int s = 0; uint32_t ph = 0;
         uint32_t accum = 0;
         for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            if (lane == 0) {
+            {   // warp-uniform issue (umma.cuh)
                 const uint32_t st_base = smem_u32(stages + s * L.stage_bytes);
                 // K step = 16 pixels = 2 core-matrix groups of 8 pixels (128 bytes each, LBO); M groups WG_PLANE apart,
                 // N groups (8 channels of one G plane chunk) WG_BCHUNK apart (SBO)
@@ -922,16 +926,16 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_umma(WgradArgs a, int nblo
                 for (int ks = 0; ks < WG_BLOCK / 16; ++ks) {
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
-                        mma_bf16_parts(d0 + kx * dstep, a_lo0 + ks * 16 + kx, a_hi_w, b_lo0 + ks * 16, b_hi_w, idesc,
-                                       ks == 0 ? accum : 1u);
+                        mma_f16_elect(d0 + kx * dstep, a_lo0 + ks * 16 + kx, a_hi_w, b_lo0 + ks * 16, b_hi_w, idesc,
+                                      ks == 0 ? accum : 1u, leader);
                 }
                 accum = 1;
-                mma_commit(&empty[s]);
+                mma_commit_elect(&empty[s], leader);
             }
             __syncwarp();
             if (++s == NSTAGES) { s = 0; ph ^= 1; }
         }
-        if (lane == 0) mma_commit(done);
+        mma_commit_elect(done, leader);
         __syncwarp();
     } else if (warp < 4) {
         mbar_wait(done, 0);

@@ -156,7 +156,8 @@ static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
     double bytes = planes_bytes(a.g, a.cin_chunks, a.in) + planes_bytes(a.g, a.cout / 8, a.ep.out) + planes_bytes(a.g, a.cout / 8, a.ep.out_r) +
                    planes_bytes(a.g, a.cout / 8, a.ep.res);
     if (a.ep.mask_hi) bytes += planes_bytes(a.g, a.cout / 8, false);
-    const double abytes = f32_once(a.g, a.cin_real) + f32_once(a.g, a.cout) * (1 + (a.ep.res.hi ? 1 : 0) + (a.ep.mask_hi ? 1 : 0));
+    // algorithmic: input, output and residual tensors once as unpadded fp32 (the relu gate of dgrad is one BIT per element: not counted)
+    const double abytes = f32_once(a.g, a.cin_real) + f32_once(a.g, a.cout) * (1 + (a.ep.res.hi ? 1 : 0));
     ProfScope ps(c, name, flops, bytes, st, abytes);
     if (c->cfg.conv_backend == CB_CONV_SIMT) return launch_conv_simt(a, st);
     return launch_conv_umma(a, c->num_sms, st);

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_fwd_umma(DenseUmmaArgs a) 
     uint64_t* done = empty + DF_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     uint8_t* stages = smem + 1024;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128, ns = blockIdx.y;
     // small batches (the actor's N = 60) split the 121 pixels over gridDim.z CTAs; partial sums are added by k_dense_finish
     const int ppc = (DN_PIX + gridDim.z - 1) / gridDim.z;
@@ -103,26 +103,27 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_fwd_umma(DenseUmmaArgs a) 
     } else if (warp == 5) {
         constexpr uint32_t ID3 = make_idesc_bf16(128, 192, 0, 0), ID2 = make_idesc_bf16(128, 128, 0, 0), ID1 = make_idesc_bf16(128, 64, 0, 0);
         const uint32_t a_hi_w = desc_hi(128), b_hi_w = desc_hi(128);
+        const uint32_t leader = elect_one();
         int s = 0; uint32_t ph = 0;
         for (int p = p0; p < p1; ++p) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            if (lane == 0) {
+            {   // warp-uniform issue (umma.cuh)
                 const uint32_t sa = smem_u32(stages + s * DF_STAGE);
                 const uint32_t a_lo0 = desc_lo(sa, 2048), b_lo0 = desc_lo(sa + DF_A_BYTES, 192 * 16);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint32_t al = a_lo0 + ks * (2 * 2048 / 16), bl = b_lo0 + ks * (2 * 192 * 16 / 16);
-                    mma_bf16_parts(tmem_base, al, a_hi_w, bl, b_hi_w, ID3, (p != p0) || (ks != 0));
-                    mma_bf16_parts(tmem_base, al + (DN_CH * 2048 / 16), a_hi_w, bl, b_hi_w, ID2, 1);
-                    mma_bf16_parts(tmem_base, al + (2 * DN_CH * 2048 / 16), a_hi_w, bl, b_hi_w, ID1, 1);
+                    mma_f16_elect(tmem_base, al, a_hi_w, bl, b_hi_w, ID3, (p != p0) || (ks != 0), leader);
+                    mma_f16_elect(tmem_base, al + (DN_CH * 2048 / 16), a_hi_w, bl, b_hi_w, ID2, 1, leader);
+                    mma_f16_elect(tmem_base, al + (2 * DN_CH * 2048 / 16), a_hi_w, bl, b_hi_w, ID1, 1, leader);
                 }
-                mma_commit(&empty[s]);
+                mma_commit_elect(&empty[s], leader);
             }
             __syncwarp();
             if (++s == DF_STAGES) { s = 0; ph ^= 1; }
         }
-        if (lane == 0) mma_commit(done);
+        mma_commit_elect(done, leader);
         __syncwarp();
     } else {
         mbar_wait(done, 0);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dx_umma(DenseUmmaArgs a, i
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(abar + 1);
     uint8_t* sa = smem + 1024;
     uint8_t* sb = sa + DX_A_BYTES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128;
     const int p0 = blockIdx.y * pix_per_cta, p1 = min(DN_PIX, p0 + pix_per_cta);
     if (threadIdx.x == 0) {
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dx_umma(DenseUmmaArgs a, i
     } else if (warp == 5) {
         constexpr uint32_t ID2 = make_idesc_bf16(128, 64, 0, 0), ID1 = make_idesc_bf16(128, 32, 0, 0);
         const uint32_t hw = desc_hi(128);
+        const uint32_t leader = elect_one();
         mbar_wait(abar, 0);
         const uint32_t a_lo0 = desc_lo(smem_u32(sa), 2048);
         int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
@@ -213,17 +215,17 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dx_umma(DenseUmmaArgs a, i
             mbar_wait(&tempty[acc], aph ^ 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            if (lane == 0) {
+            {   // warp-uniform issue (umma.cuh)
                 const uint32_t b_lo0 = desc_lo(smem_u32(sb + s * DX_B_BYTES), 64 * 16);
                 const uint32_t d = tmem_base + acc * 64;
 #pragma unroll
                 for (int ks = 0; ks < 16; ++ks) {
                     const uint32_t al = a_lo0 + ks * (2 * 2048 / 16), bl = b_lo0 + ks * (2 * 64 * 16 / 16);
-                    mma_bf16_parts(d, al, hw, bl, hw, ID2, ks != 0);
-                    mma_bf16_parts(d, al + (32 * 2048 / 16), hw, bl, hw, ID1, 1);
+                    mma_f16_elect(d, al, hw, bl, hw, ID2, ks != 0, leader);
+                    mma_f16_elect(d, al + (32 * 2048 / 16), hw, bl, hw, ID1, 1, leader);
                 }
-                mma_commit(&empty[s]);
-                mma_commit(&tfull[acc]);
+                mma_commit_elect(&empty[s], leader);
+                mma_commit_elect(&tfull[acc], leader);
             }
             __syncwarp();
             if (++s == 2) { s = 0; ph ^= 1; }
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dw_umma(DenseUmmaArgs a, f
     uint64_t* done = empty + DW_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     uint8_t* stages = smem + 1024;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int pg = blockIdx.x * 4, j0 = blockIdx.y * 64;
     const int nblk = a.npad / DW_BLOCK;
     if (threadIdx.x == 0) {
@@ -319,25 +321,26 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dw_umma(DenseUmmaArgs a, f
     } else if (warp == 5) {
         constexpr uint32_t ID2 = make_idesc_bf16(128, 128, 1, 1), ID1 = make_idesc_bf16(128, 64, 1, 1);
         const uint32_t hw = desc_hi(1024);         // M / N groups (8 channels / 8 outputs) are 1 KB apart
+        const uint32_t leader = elect_one();
         int s = 0; uint32_t ph = 0;
         for (int blk = 0; blk < nblk; ++blk) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            if (lane == 0) {
+            {   // warp-uniform issue (umma.cuh)
                 const uint32_t base = smem_u32(stages + s * DW_STAGE);
                 const uint32_t a_lo0 = desc_lo(base, 128), b_lo0 = desc_lo(base + DW_A_BYTES, 128);
 #pragma unroll
                 for (int ks = 0; ks < DW_BLOCK / 16; ++ks) {
                     const uint32_t al = a_lo0 + ks * 16, bl = b_lo0 + ks * 16;
-                    mma_bf16_parts(tmem_base, al, hw, bl, hw, ID2, (blk | ks) != 0);
-                    mma_bf16_parts(tmem_base, al + (16 * 1024 / 16), hw, bl, hw, ID1, 1);
+                    mma_f16_elect(tmem_base, al, hw, bl, hw, ID2, (blk | ks) != 0, leader);
+                    mma_f16_elect(tmem_base, al + (16 * 1024 / 16), hw, bl, hw, ID1, 1, leader);
                 }
-                mma_commit(&empty[s]);
+                mma_commit_elect(&empty[s], leader);
             }
             __syncwarp();
             if (++s == DW_STAGES) { s = 0; ph ^= 1; }
         }
-        if (lane == 0) mma_commit(done);
+        mma_commit_elect(done, leader);
         __syncwarp();
     } else {
         mbar_wait(done, 0);

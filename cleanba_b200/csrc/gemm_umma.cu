@@ -38,11 +38,10 @@ __host__ __device__ inline GemmSmem gemm_smem(int apl, int NB) {
     return L;
 }
 
-template <int NB>
+template <int NB, int APL>
 __global__ void __launch_bounds__(GM_THREADS) k_gemm_umma(GemmArgs a, int ntiles, int nblocks) {
     extern __shared__ __align__(1024) uint8_t smem[];
     griddep_launch();
-    const int APL = a.a.mid ? 2 : 1;
     const GemmSmem L = gemm_smem(APL, NB);
     const int NSTAGES = L.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [GM_MAXST]
@@ -51,7 +50,7 @@ __global__ void __launch_bounds__(GM_THREADS) k_gemm_umma(GemmArgs a, int ntiles
     uint64_t* tempty = tfull + 2;                                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     uint8_t* stages = smem + 1024;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr int ACC_COLS = 2 * NB;                             // block 0: hi*hi, block 1: (hi*mid + mid*hi) * 2^11
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
     const int nkb = a.K / GM_KB;
@@ -95,6 +94,7 @@ __global__ void __launch_bounds__(GM_THREADS) k_gemm_umma(GemmArgs a, int ntiles
         constexpr uint32_t IDESC2 = make_idesc_f16(GM_TILE, 2 * NB, 0, 0);
         constexpr uint32_t IDESC1 = make_idesc_f16(GM_TILE, NB, 0, 0);
         const uint32_t hw = desc_hi(128);
+        const uint32_t leader = elect_one();
         int s = 0; uint32_t ph = 0;
         int acc = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -103,18 +103,18 @@ __global__ void __launch_bounds__(GM_THREADS) k_gemm_umma(GemmArgs a, int ntiles
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                {   // warp-uniform issue (umma.cuh)
                     const uint32_t sa = smem_u32(stages + s * L.stage_bytes);
                     const uint32_t a_lo0 = desc_lo(sa, GM_SLOT);                      // K chunks GM_SLOT apart (LBO), 8-row groups 128 B (SBO)
                     const uint32_t b_lo0 = desc_lo(sa + L.a_bytes, 2 * NB * 16);
 #pragma unroll
                     for (int ks = 0; ks < GM_KB / 16; ++ks) {
                         const uint32_t al = a_lo0 + ks * (2 * GM_SLOT / 16), bl = b_lo0 + ks * (2 * 2 * NB);
-                        mma_bf16_parts(d_tmem, al, hw, bl, hw, IDESC2, (kb | ks) != 0);
-                        if (APL == 2) mma_bf16_parts(d_tmem + NB, al + ((GM_KB / 8) * GM_SLOT / 16), hw, bl, hw, IDESC1, 1);
+                        mma_f16_elect(d_tmem, al, hw, bl, hw, IDESC2, (kb | ks) != 0, leader);
+                        if (APL == 2) mma_f16_elect(d_tmem + NB, al + ((GM_KB / 8) * GM_SLOT / 16), hw, bl, hw, IDESC1, 1, leader);
                     }
-                    mma_commit(&empty[s]);
-                    if (kb == nkb - 1) mma_commit(&tfull[acc]);
+                    mma_commit_elect(&empty[s], leader);
+                    if (kb == nkb - 1) mma_commit_elect(&tfull[acc], leader);
                 }
                 __syncwarp();
                 if (++s == NSTAGES) { s = 0; ph ^= 1; }
@@ -169,21 +169,21 @@ __global__ void __launch_bounds__(GM_THREADS) k_gemm_umma(GemmArgs a, int ntiles
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int NB>
+template <int NB, int APL>
 static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
-    const GemmSmem L = gemm_smem(a.a.mid ? 2 : 1, NB);
+    const GemmSmem L = gemm_smem(APL, NB);
     CB_CHECK(L.stages >= 2, "gemm_umma<%d>: stage of %d bytes does not fit twice", NB, L.stage_bytes);
     static std::atomic<unsigned> attr_done{0};
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     if (!(attr_done.load() & (1u << dev))) {
-        CB_CUDA(cudaFuncSetAttribute(k_gemm_umma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CB_CUDA(cudaFuncSetAttribute(k_gemm_umma<NB, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done.fetch_or(1u << dev);
     }
     const int nblocks = (a.N + NB - 1) / NB;
     const long long ntiles = (a.Rpad / GM_TILE) * nblocks;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-    launch_pdl(k_gemm_umma<NB>, dim3(grid), dim3(GM_THREADS), (size_t)L.total, st, a, (int)ntiles, nblocks);
+    launch_pdl(k_gemm_umma<NB, APL>, dim3(grid), dim3(GM_THREADS), (size_t)L.total, st, a, (int)ntiles, nblocks);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -191,9 +191,10 @@ static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
 int launch_gemm_umma(const GemmArgs& a, int NB, int num_sms, cudaStream_t st) {
     CB_CHECK(a.K % GM_KB == 0 && a.Rpad % GM_TILE == 0 && a.a.rpad >= a.Rpad, "gemm_umma: K=%d must be a multiple of %d, rows padded to %d", a.K, GM_KB, GM_TILE);
     CB_CHECK(a.N % 16 == 0 || a.N % 8 == 0, "gemm_umma: N=%d must be a multiple of 8", a.N);
-    if (NB == 32) return launch_gemm_t<32>(a, num_sms, st);
-    if (NB == 64) return launch_gemm_t<64>(a, num_sms, st);
-    if (NB == 128) return launch_gemm_t<128>(a, num_sms, st);
+    if (NB == 32 && !a.a.mid) return launch_gemm_t<32, 1>(a, num_sms, st);
+    if (NB == 32) return launch_gemm_t<32, 2>(a, num_sms, st);
+    if (NB == 64 && a.a.mid) return launch_gemm_t<64, 2>(a, num_sms, st);
+    if (NB == 128 && a.a.mid) return launch_gemm_t<128, 2>(a, num_sms, st);
     CB_CHECK(false, "gemm_umma: unsupported N block %d", NB);
 }
 
@@ -244,11 +245,10 @@ __host__ __device__ inline GwSmem gw_smem(int apl, int NB) {
     return L;
 }
 
-template <int NB>
+template <int NB, int APL>
 __global__ void __launch_bounds__(GW_THREADS) k_gemm_wgrad_umma(GemmWgradArgs a, int nmt, int nnb, int nsplit, float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
     griddep_launch();
-    const int APL = a.a.mid ? 2 : 1;
     const GwSmem L = gw_smem(APL, NB);
     const int NSTAGES = L.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(GW_THREADS) k_gemm_wgrad_umma(GemmWgradArgs a,
     uint64_t* done = empty + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     uint8_t* stages = smem + 1024;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr int COLS = 3 * NB;                                 // D1 = A_hi * [G_hi | G_mid] (2 NB), D2 = A_mid * G_hi (NB)
     constexpr uint32_t TMEM_COLS = COLS <= 128 ? 128 : 256;
     const int item = blockIdx.x;                                 // (mt, nb, sp), sp fastest
@@ -312,27 +312,28 @@ __global__ void __launch_bounds__(GW_THREADS) k_gemm_wgrad_umma(GemmWgradArgs a,
     } else if (warp == 5) {
         constexpr uint32_t ID2 = make_idesc_f16(GM_TILE, 2 * NB, 1, 1), ID1 = make_idesc_f16(GM_TILE, NB, 1, 1);
         const uint32_t hw = desc_hi(GM_SLOT);                    // M / N groups (8 channels) are one slot apart
+        const uint32_t leader = elect_one();
         int s = 0; uint32_t ph = 0;
         uint32_t accum = 0;
         for (int rb = sp; rb < nrb; rb += nsplit) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            if (lane == 0) {
+            {   // warp-uniform issue (umma.cuh)
                 const uint32_t base = smem_u32(stages + s * L.stage_bytes);
                 const uint32_t a_lo0 = desc_lo(base, 128), b_lo0 = desc_lo(base + L.a_bytes, 128);   // K step of 8 rows = 128 B (LBO)
 #pragma unroll
                 for (int ks = 0; ks < GM_TILE / 16; ++ks) {
-                    mma_bf16_parts(tmem_base, a_lo0 + ks * 16, hw, b_lo0 + ks * 16, hw, ID2, ks == 0 ? accum : 1u);
+                    mma_f16_elect(tmem_base, a_lo0 + ks * 16, hw, b_lo0 + ks * 16, hw, ID2, ks == 0 ? accum : 1u, leader);
                     if (APL == 2)
-                        mma_bf16_parts(tmem_base + 2 * NB, a_lo0 + (GW_MCH * GM_SLOT / 16) + ks * 16, hw, b_lo0 + ks * 16, hw, ID1, ks == 0 ? accum : 1u);
+                        mma_f16_elect(tmem_base + 2 * NB, a_lo0 + (GW_MCH * GM_SLOT / 16) + ks * 16, hw, b_lo0 + ks * 16, hw, ID1, ks == 0 ? accum : 1u, leader);
                 }
                 accum = 1;
-                mma_commit(&empty[s]);
+                mma_commit_elect(&empty[s], leader);
             }
             __syncwarp();
             if (++s == NSTAGES) { s = 0; ph ^= 1; }
         }
-        if (lane == 0) mma_commit(done);
+        mma_commit_elect(done, leader);
         __syncwarp();
     } else if (warp < 4) {
         mbar_wait(done, 0);
@@ -385,15 +386,15 @@ __global__ void k_gemm_wgrad_reduce(const float* __restrict__ partial, int nspli
     *reinterpret_cast<float4*>(dw + i) = make_float4(s.x * f, s.y * f, s.z * f, s.w * f);
 }
 
-template <int NB>
+template <int NB, int APL>
 static int launch_gemm_wgrad_t(const GemmWgradArgs& a, float* partial, long long partial_cap, int num_sms, cudaStream_t st) {
-    const GwSmem L = gw_smem(a.a.mid ? 2 : 1, NB);
+    const GwSmem L = gw_smem(APL, NB);
     CB_CHECK(L.stages >= 2, "gemm_wgrad_umma<%d>: stage of %d bytes does not fit twice", NB, L.stage_bytes);
     static std::atomic<unsigned> attr_done{0};
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     if (!(attr_done.load() & (1u << dev))) {
-        CB_CUDA(cudaFuncSetAttribute(k_gemm_wgrad_umma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CB_CUDA(cudaFuncSetAttribute(k_gemm_wgrad_umma<NB, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done.fetch_or(1u << dev);
     }
     const int nmt = (a.K / 8 + GW_MCH - 1) / GW_MCH, nnb = a.N / NB;
@@ -404,7 +405,7 @@ static int launch_gemm_wgrad_t(const GemmWgradArgs& a, float* partial, long long
     const long long count = (long long)a.K * a.N;
     while (nsplit > 1 && (long long)nsplit * count > partial_cap) --nsplit;
     CB_CHECK((long long)nsplit * count <= partial_cap, "gemm_wgrad: partial buffer too small (%lld floats needed)", (long long)nsplit * count);
-    launch_pdl(k_gemm_wgrad_umma<NB>, dim3(nmt * nnb * nsplit), dim3(GW_THREADS), (size_t)L.total, st, a, nmt, nnb, nsplit, partial);
+    launch_pdl(k_gemm_wgrad_umma<NB, APL>, dim3(nmt * nnb * nsplit), dim3(GW_THREADS), (size_t)L.total, st, a, nmt, nnb, nsplit, partial);
     CB_LAUNCH_CHECK();
     launch_pdl(k_gemm_wgrad_reduce, dim3((unsigned)((count / 4 + 255) / 256)), dim3(256), 0, st, (const float*)partial, nsplit, count, a.scale,
                a.inv_scale, a.dw);
@@ -414,8 +415,9 @@ static int launch_gemm_wgrad_t(const GemmWgradArgs& a, float* partial, long long
 
 int launch_gemm_wgrad_umma(const GemmWgradArgs& a, float* partial, long long partial_cap, int num_sms, cudaStream_t st) {
     CB_CHECK(a.K % 8 == 0 && a.Rpad % GM_TILE == 0 && a.g.mid, "gemm_wgrad_umma: bad shapes (K=%d, Rpad=%lld)", a.K, a.Rpad);
-    if (a.N % 64 == 0) return launch_gemm_wgrad_t<64>(a, partial, partial_cap, num_sms, st);
-    if (a.N % 32 == 0) return launch_gemm_wgrad_t<32>(a, partial, partial_cap, num_sms, st);
+    if (a.N % 64 == 0 && a.a.mid) return launch_gemm_wgrad_t<64, 2>(a, partial, partial_cap, num_sms, st);
+    if (a.N % 32 == 0 && !a.a.mid) return launch_gemm_wgrad_t<32, 1>(a, partial, partial_cap, num_sms, st);
+    if (a.N % 32 == 0) return launch_gemm_wgrad_t<32, 2>(a, partial, partial_cap, num_sms, st);
     CB_CHECK(false, "gemm_wgrad_umma: N=%d must be a multiple of 32", a.N);
 }
 

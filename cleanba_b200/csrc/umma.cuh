@@ -154,6 +154,36 @@ __device__ __forceinline__ void mma_bf16_parts(uint32_t d_tmem, uint32_t a_lo, u
         ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Warp-uniform issue.  tcgen05.mma / tcgen05.commit take their descriptors from UNIFORM registers.  Issued from inside an
+// `if (lane == 0)` branch the operands live in per-thread registers the compiler cannot prove uniform, and every MMA becomes a
+// "waterfall" (R2UR + ELECT + BRA.U.ANY per operand): ~170 cycles per MMA on one thread -- measured as THE limiter of the
+// 32-channel conv kernels (ncu source page, profiles/r02_v2_ncu_full_conv_4_32_raw.csv: the issuing warp never waits).  Instead
+// the whole warp runs the issue loop converged (warp index made provably uniform with a shuffle, all descriptor arithmetic on
+// warp-uniform values -> uniform datapath) and only the instruction itself is predicated on an elected lane.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(leader)
+        : "memory");
+}
 // mbarrier arrives when all tcgen05.mma previously issued by this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
