@@ -644,3 +644,44 @@ def test_gradient_accumulation_matches_optax_multisteps(agent, params):
     serr = [abs(float(stats[i]) - ostats[i]) / max(abs(ostats[i]), 1e-2 * np.abs(ostats[:4]).max()) for i in range(4)]
     _diag("ppo_gradient_accumulation_k2", seen=[list(map(float, s[1:])) for s in seen], mean_stats_relerr=serr)
     assert max(serr) < 1e-4, (stats, ostats)
+
+
+# --------------------------------------------------------------------------------------------- exchange / hand-off primitives
+def test_reduce_peers_copy_columns_and_milestone(agent, params):
+    """The small ABI pieces around the hot path: cb_reduce_peers (fixed-order sum of replica buffers), cb_memcpy_2d through
+    agent.copy_columns (column block of a [T, N, ...] storage, no contiguous temporary) and cb_set_grad_milestone (the event fires
+    inside the gradient call and the tail offset is the dense layer's first leaf)."""
+    from cleanba_b200 import lib
+    ctx = agent.Context("cuda:0", max_batch=8, train=True)
+    ctx.set_params(params)
+    dev = ctx.device
+    g = [torch.randn(ctx.num_params, device=dev) for _ in range(3)]
+    out = torch.empty(ctx.num_params, device=dev)
+    ctx.reduce_peers(g, out)
+    assert torch.equal(out, (g[0] + g[1]) + g[2])                      # the kernel's order: ((g0 + g1) + g2)
+    T, N = 5, 12
+    storage = torch.randint(0, 255, (T, N, 4, 84, 84), dtype=torch.uint8, device=dev)
+    vals = torch.randn(T, N, device=dev)
+    st = torch.cuda.Stream(dev)
+    st.wait_stream(torch.cuda.current_stream(dev))
+    for c in (slice(0, 4), slice(4, 12)):
+        d1 = torch.empty((T, c.stop - c.start, 4, 84, 84), dtype=torch.uint8, device=dev)
+        d2 = torch.empty((T, c.stop - c.start), device=dev)
+        agent.copy_columns(d1, storage[:, c], st)
+        agent.copy_columns(d2, vals[:, c], st)
+        st.synchronize()
+        assert torch.equal(d1, storage[:, c]) and torch.equal(d2, vals[:, c])
+    ev = torch.cuda.Event()
+    ev.record()
+    tail = ctx.set_grad_milestone(ev)
+    assert tail == dict((n, o) for n, o, _ in lib.leaves())["network_params/params/Dense_0/bias"]
+    rng = np.random.default_rng(3)
+    obs = torch.from_numpy(_frames(rng, 8)).to(dev)
+    grads = torch.zeros(ctx.num_params, device=dev); stats = torch.zeros(5, device=dev)
+    z = torch.zeros(8, device=dev)
+    ctx.ppo_grad(obs, None, 8, torch.zeros(8, dtype=torch.int32, device=dev), z, z + 1, z, 0.1, 0.01, 0.5, grads, stats)
+    ev.synchronize()                                                    # recorded by the call: completes without a device sync
+    torch.cuda.synchronize()
+    assert float(grads[tail:].abs().sum()) > 0
+    ctx.set_grad_milestone(None)
+    ctx.close()
