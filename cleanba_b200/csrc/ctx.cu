@@ -779,6 +779,17 @@ int cb_memcpy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
     CB_CHECK(dst && src, "null argument");
     CB_CHECK(width_bytes <= dst_pitch && width_bytes <= src_pitch, "row width %zu exceeds a pitch (%zu, %zu)", width_bytes, dst_pitch, src_pitch);
     if (!width_bytes || !rows) return 0;
+    // device -> (peer) device with 16-byte granularity: copy with the SMs of the source GPU (stores over NVLink); anything else
+    // (host memory, odd sizes) goes through the DMA engines
+    cudaPointerAttributes sa, da;
+    const bool okq = cudaPointerGetAttributes(&sa, src) == cudaSuccess && cudaPointerGetAttributes(&da, dst) == cudaSuccess;
+    if (!okq) (void)cudaGetLastError();
+    const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | dst_pitch | src_pitch | width_bytes) & 15) == 0;
+    static const bool use_kernel = [] { const char* e = getenv("CLEANBA_COPY_KERNEL"); return !e || atoi(e) != 0; }();
+    if (use_kernel && okq && vec && sa.type == cudaMemoryTypeDevice && da.type == cudaMemoryTypeDevice) {
+        CB_CUDA(cudaSetDevice(sa.device));      // the stream must belong to the source device (the actor's copy streams do)
+        return launch_copy_2d(dst, dst_pitch, src, src_pitch, width_bytes, rows, (cudaStream_t)stream);
+    }
     CB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream));
     return 0;
 }

@@ -184,6 +184,7 @@ constexpr int OPT_BLOCKS = 296;
 int launch_optimizer(const OptArgs& a, cudaStream_t st);
 // gscale[0] = S, gscale[1] = 1 / S for this minibatch's gradient tensors (work: 2 zero-initialised words)
 int launch_loss_scale(const float* dpre, long long count, unsigned* work, float* gscale, cudaStream_t st);
+int launch_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
 int launch_grad_accumulate(float* acc, const float* g, long long n, int mini_step, cudaStream_t st);
 int launch_reduce_peers(const OptArgs& a, float* out, cudaStream_t st);   // needs n, gp, ng only
 

@@ -290,6 +290,28 @@ int launch_loss_scale(const float* dpre, long long count, unsigned* work, float*
     return 0;
 }
 
+// Strided block copy by the SMs: `rows` rows of width16 16-byte words, src row pitch spitch16, dst row pitch dpitch16 (in words).
+// dst may live on a PEER GPU: the stores go out over NVLink at several hundred GB/s, where cudaMemcpy2DAsync's DMA path
+// measured 107 GB/s for the payload's 0.5 MB rows (profiles/r02_v2_config4_*).
+__global__ void __launch_bounds__(256) k_copy_2d(uint4* __restrict__ dst, long long dpitch16, const uint4* __restrict__ src, long long spitch16,
+                                                 long long width16, long long rows) {
+    const long long total = width16 * rows;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long r = i / width16, c = i - r * width16;
+        dst[r * dpitch16 + c] = src[r * spitch16 + c];
+    }
+}
+int launch_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t st) {
+    const long long total = (long long)(width / 16) * (long long)rows;
+    long long blocks = (total + 255) / 256 / 8;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_copy_2d<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(dst), (long long)(dpitch / 16), reinterpret_cast<const uint4*>(src),
+                                                (long long)(spitch / 16), (long long)(width / 16), (long long)rows);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
 // optax.MultiSteps accumulation (cleanba_ppo.py:492-500 with gradient_accumulation_steps > 1): acc <- acc + (g - acc) / (mini_step + 1)
 __global__ void __launch_bounds__(256) k_grad_accumulate(float* __restrict__ acc, const float* __restrict__ g, long long n, float inv) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {

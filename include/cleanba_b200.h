@@ -156,8 +156,9 @@ int cb_set_grad_milestone(cb_ctx* ctx, void* cuda_event, long long* tail_offset)
  * one replica sums its process' replicas into `out`, ONE NCCL allreduce on `out` follows, and every replica then applies
  * cb_optimizer_step_peers on that single buffer.  Same stream-ordering rules as cb_optimizer_step_peers. */
 int cb_reduce_peers(cb_ctx* ctx, const float* const* grads, int num_grads, float* out, cb_stream stream);
-/* Strided block copy (cudaMemcpy2DAsync, cudaMemcpyDefault): `rows` rows of `width_bytes` from src (row pitch src_pitch) to
- * dst (row pitch dst_pitch) on `stream`, between any two of host-pinned / device / peer-device memory.  The actor -> learner
+/* Strided block copy: `rows` rows of `width_bytes` from src (row pitch src_pitch) to dst (row pitch dst_pitch) on `stream`,
+ * between any two of host-pinned / device / peer-device memory.  Device -> (peer) device copies with 16-byte granularity are done
+ * by a copy kernel on the source GPU (`stream` must belong to it; stores over NVLink), everything else by cudaMemcpy2DAsync.  The actor -> learner
  * payload hand-off (`jax.device_put_sharded`, cleanba_ppo.py:357-363) uses it to move one learner's env-column block of the
  * [T, N, ...] rollout storage straight to that learner's GPU on the actor's copy stream, without a contiguous temporary. */
 int cb_memcpy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, cb_stream stream);
