@@ -163,7 +163,25 @@ static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
     return launch_conv_umma(a, c->num_sms, st);
 }
 
-static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, const Act& gy, float* grads, cudaStream_t st) {
+// Weight gradients feed nothing but the optimizer, so they run on the context's side stream beside the dgrad chain (the caller's
+// stream): fork = "the gradient tensor gy is complete on `main`".  The one buffer hazard (the dgrad of the block's second conv
+// re-writes gB while the wgrad of its first conv may still read it) is closed by wgrad_done_before().
+static int fork_side(cb_ctx* c, cudaStream_t main_st) {
+    if (!c->side) return 0;
+    CB_CUDA(cudaEventRecord(c->ev_fork, main_st));
+    CB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    return 0;
+}
+static int wgrad_done_before(cb_ctx* c, cudaStream_t main_st) {    // main waits for everything queued on the side stream so far
+    if (!c->side) return 0;
+    CB_CUDA(cudaEventRecord(c->ev_join, c->side));
+    CB_CUDA(cudaStreamWaitEvent(main_st, c->ev_join, 0));
+    return 0;
+}
+
+static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, const Act& gy, float* grads, cudaStream_t main_st) {
+    if (fork_side(c, main_st)) return -1;
+    cudaStream_t st = c->side ? c->side : main_st;
     const ConvLayer& L = c->conv[layer];
     WgradArgs w;
     w.g = g; w.x = x.pl; w.cin_chunks = (L.cin + 7) / 8; w.cin_real = L.cin; w.gy = gy.pl; w.cout = L.cout;
@@ -315,6 +333,7 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         }
         // ---- ResidualBlock 0: b0 = p + conv2(relu(conv1(relu(p))))
         if (run_wgrad(c, base + 2, go, S.a0, S.gC, grads, st)) return -1;
+        if (wgrad_done_before(c, st)) return -1;      // the next dgrad re-writes gB, which the wgrad of base + 3 reads
         {
             ConvArgs a = conv_args(c, base + 2, go, S.gC, true);
             a.ep.mask_hi = S.a0.pl.hi; a.ep.mask_plane_px = S.a0.pl.plane_px; a.ep.out = S.gB.pl;
@@ -330,10 +349,12 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         // ---- max-pool backward, then the sequence conv
         if (s == 0 && c->fuse0) {
             // frames need no dX: the pooled gradient goes straight into the frame conv's weight gradient (trunk_simt.cu)
-            ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), st,
+            if (fork_side(c, st)) return -1;
+            cudaStream_t ws = c->side ? c->side : st;
+            ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), ws,
                          f32_once(go, 16) + (double)n * 28224.0);
             if (launch_pool_bwd_wgrad0(S.amax, S.gA.pl, S.x.pl.hi, gi, go, 1.0f / 255.0f, c->gscale + 1, grads + c->conv[0].off_w,
-                                       grads + c->conv[0].off_b, c->wg_partial, c->num_sms, st)) return -1;
+                                       grads + c->conv[0].off_b, c->wg_partial, c->num_sms, ws)) return -1;
             continue;
         }
         {
@@ -348,7 +369,7 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             if (run_conv(c, a, st)) return -1;
         }
     }
-    return 0;
+    return wgrad_done_before(c, st);      // every weight gradient is complete on the caller's stream
 }
 
 static int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t st) {
@@ -390,6 +411,9 @@ void cb_destroy(cb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     for (void* p : c->allocs) cudaFree(p);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->nat) nature_destroy(c);
     delete c;
 }
@@ -516,9 +540,12 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
         }
         if (dev_alloc(c, &p, mb * c->HID * sizeof(float))) break;
         c->hidden = (float*)p;
+        // split-K partial sums of the dense forward (dense_umma.cu: 11 splits up to 384 samples, 4 up to 1920, else none) and of
+        // the SIMT path (dense.cu: 11 up to 256, 4 up to 1024): size for the worst batch <= max_batch
         size_t part = mb * HIDDEN;
-        if (part < (size_t)11 * 256 * HIDDEN) part = (size_t)11 * 256 * HIDDEN;
-        if (part < (size_t)4 * 1024 * HIDDEN) part = (size_t)4 * 1024 * HIDDEN;
+        if (part < (size_t)11 * (mb < 384 ? mb : 384) * HIDDEN) part = (size_t)11 * (mb < 384 ? mb : 384) * HIDDEN;
+        if (part < (size_t)4 * (mb < 1920 ? mb : 1920) * HIDDEN) part = (size_t)4 * (mb < 1920 ? mb : 1920) * HIDDEN;
+        if (part < (size_t)64 * HIDDEN) part = (size_t)64 * HIDDEN;       // column-sum partials of the dense bias gradient
         if (dev_alloc(c, &p, part * sizeof(float))) break;
         c->dense_part = (float*)p;
         if (dev_alloc(c, &p, 2 * sizeof(uint32_t))) break;
@@ -542,6 +569,15 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             c->gscale = (float*)p;
             if (dev_alloc(c, &p, 2 * sizeof(unsigned))) break;
             c->gs_work = (unsigned*)p;
+            static const bool side_on = [] { const char* e = getenv("CLEANBA_WGRAD_SIDE"); return !e || atoi(e) != 0; }();
+            if (side_on && !nature && cfg->conv_backend == CB_CONV_TCGEN05) {
+                if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+                    set_error("cannot create the weight-gradient side stream");
+                    break;
+                }
+            }
         }
         ok = true;
     } while (0);

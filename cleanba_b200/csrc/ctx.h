@@ -82,6 +82,8 @@ struct cb_ctx {
     // tcgen05 dense layer (dense_umma.cu)
     cb::bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
     int npad_max = 0;
+    cudaStream_t side = nullptr;            // weight-gradient kernels run here, beside the dgrad chain on the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t milestone = nullptr;        // recorded once the dense + head gradients of a cb_*_grad call are complete
     float* gscale = nullptr;                // device {S, 1 / S}: loss scale of the current minibatch's gradient tensors
     unsigned* gs_work = nullptr;            // scratch of k_loss_scale

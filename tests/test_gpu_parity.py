@@ -685,3 +685,28 @@ def test_reduce_peers_copy_columns_and_milestone(agent, params):
     assert float(grads[tail:].abs().sum()) > 0
     ctx.set_grad_milestone(None)
     ctx.close()
+
+
+@pytest.mark.slow
+def test_forward_config4_minibatch_size(agent, params):
+    """mb = 1280 (BASELINE config 4: 3 learner GPUs, 5,120 samples each) and its neighbours sit in the 4-way split-K range of the
+    dense forward (1024 < n <= 1920): regression test for the partial-sum buffer, which round 1 sized for n <= 1024."""
+    rng = np.random.default_rng(61)
+    n = 1300
+    obs = _frames(rng, n)
+    ctx = agent.Context("cuda:0", max_batch=n, train=True)
+    ctx.set_params(params)
+    guard = torch.full((1 << 20,), 7.0, device=ctx.device)        # whatever the allocator placed nearby must stay intact
+    logits, value = ctx.policy_value(torch.from_numpy(obs).to(ctx.device))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ol, ov, _ = net.forward(params, obs)
+    e1, e2 = _relerr(logits.cpu().numpy(), ol.numpy()), _relerr(value.cpu().numpy(), ov.numpy())
+    _diag("forward_n1300", logits=e1, value=e2)
+    assert e1 < 1e-4 and e2 < 1e-4 and bool((guard == 7.0).all())
+    grads = torch.zeros(ctx.num_params, device=ctx.device); stats = torch.zeros(5, device=ctx.device)
+    z = torch.zeros(n, device=ctx.device)
+    ctx.ppo_grad(torch.from_numpy(obs).to(ctx.device), None, 1280, torch.zeros(n, dtype=torch.int32, device=ctx.device), z, z + 1, z, 0.1, 0.01, 0.5, grads, stats)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(grads).all()) and bool(torch.isfinite(stats).all())
+    ctx.close()

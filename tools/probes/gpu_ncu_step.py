@@ -8,7 +8,8 @@ from cleanba_b200 import agent as ag
 
 mb = int(sys.argv[1]) if len(sys.argv) > 1 else 3840
 what = sys.argv[2] if len(sys.argv) > 2 else "learner"
-params = net.init_params(1)
+model = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # 0 IMPALA-ResNet, 1 Nature-CNN
+params = net.init_params(1, net.nature_param_spec() if model else None)
 rng = np.random.default_rng(0)
 obs = torch.from_numpy(rng.integers(0, 256, (mb, 4, 84, 84), dtype=np.uint8)).cuda()
 cudart = torch.cuda.cudart()
@@ -17,7 +18,7 @@ if what == "learner":
     oldlp = torch.full((mb,), float(np.log(1 / 18)), dtype=torch.float32).cuda()
     adv = torch.randn(mb, device="cuda"); ret = torch.randn(mb, device="cuda")
     idx = torch.from_numpy(rng.permutation(mb).astype(np.int32)).cuda()
-    ctx = ag.Context("cuda:0", max_batch=mb, train=True)
+    ctx = ag.Context("cuda:0", max_batch=mb, train=True, model=model)
     ctx.set_params(params)
     grads = torch.zeros(ctx.num_params, device="cuda"); stats = torch.zeros(5, device="cuda")
     # the once-per-update kernels too: bootstrap value is skipped, GAE scan + advantage normalisation at [T=128, Bl=120] and one
@@ -33,7 +34,7 @@ if what == "learner":
         ctx.ppo_grad(obs, idx, mb, actions, oldlp, adv, ret, 0.1, 0.01, 0.5, grads, stats)
         ctx.optimizer_step(grads, 1.0, 2.5e-4, 0.5)
 else:
-    ctx = ag.Context("cuda:0", max_batch=mb)
+    ctx = ag.Context("cuda:0", max_batch=mb, model=model)
     ctx.set_params(params)
     key = ag.key_tensor(np.array([1, 2], np.uint32), ctx.device)
     def step():
