@@ -563,7 +563,12 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             c->logits_scratch = (float*)p;
             if (dev_alloc(c, &p, mb * 8 * sizeof(float))) break;
             c->cell_scratch = (float*)p;
-            if (dev_alloc(c, &p, (size_t)4 * 1024 * 1024 * sizeof(float))) break;
+            // partial sums of the weight-gradient kernels (<= 3.2 M floats for the conv shapes) and of the head weight gradients
+            // (one slice of (HID + 1) x (A + 1) floats per 16 samples: grows with max_batch)
+            c->wg_cap = 4LL * 1024 * 1024;
+            const long long head_need = ((long long)mb / 16 + 1) * (c->HID + 1) * (c->A + 1);
+            if (c->wg_cap < head_need) c->wg_cap = head_need;
+            if (dev_alloc(c, &p, (size_t)c->wg_cap * sizeof(float))) break;
             c->wg_partial = (float*)p;
             if (dev_alloc(c, &p, 2 * sizeof(float))) break;
             c->gscale = (float*)p;

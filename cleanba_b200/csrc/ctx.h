@@ -78,6 +78,7 @@ struct cb_ctx {
     int* perm_rank = nullptr;
     uint32_t* sort_keys = nullptr;
     int perm_cap = 0;
+    long long wg_cap = 0;                   // floats in wg_partial
     int last_n = 0;
     // tcgen05 dense layer (dense_umma.cu)
     cb::bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;

@@ -352,7 +352,7 @@ int nature_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         k_nat_dpre_planes<<<blocks_for(Rp * 64), 256, 0, st>>>(c->dpre, n, N->rpad[3], Rp, c->gscale, N->dp_hi, N->dp_mid);
         CB_LAUNCH_CHECK();
     }
-    const long long wg_cap = 4LL * 1024 * 1024;      // floats in c->wg_partial
+    const long long wg_cap = c->wg_cap;              // floats in c->wg_partial
     for (int l = 3; l >= 0; --l) {
         NatLayer& L = N->L[l];
         const long long R = (long long)n * L.Hout * L.Hout, Rp = pad128(R), rp = N->rpad[l];
