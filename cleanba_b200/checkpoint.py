@@ -77,9 +77,18 @@ def msgpack_restore(data: bytes) -> Any:
 
 
 # ------------------------------------------------------------------------------------------------ parameter tree
-def _leaves(num_actions: int):
+def _leaves(num_actions: int, model: int = 0):
     from . import lib
-    return lib.leaves(num_actions)
+    return lib.leaves(num_actions, model)
+
+
+def _model_of_size(n: int, num_actions: int) -> int:
+    """The two trunks have different parameter counts: the flat vector's length identifies its model."""
+    from . import lib
+    for m in (lib.CB_MODEL_IMPALA_RESNET, lib.CB_MODEL_NATURE_CNN):
+        if int(lib.load().cb_num_params_model(m, num_actions)) == n:
+            return m
+    raise ValueError(f"no built model has {n} parameters")
 
 
 def flat_to_tree(flat: np.ndarray, num_actions: int = 18) -> Dict[str, Any]:
@@ -87,7 +96,7 @@ def flat_to_tree(flat: np.ndarray, num_actions: int = 18) -> Dict[str, Any]:
     flat = np.asarray(flat, dtype=np.float32).ravel()
     tree: Dict[str, Any] = {}
     end = 0
-    for name, offset, shape in _leaves(num_actions):
+    for name, offset, shape in _leaves(num_actions, _model_of_size(flat.size, num_actions)):
         size = int(np.prod(shape))
         node = tree
         parts = name.split("/")
@@ -101,7 +110,9 @@ def flat_to_tree(flat: np.ndarray, num_actions: int = 18) -> Dict[str, Any]:
 
 
 def tree_to_flat(tree: Mapping[str, Any], num_actions: int = 18) -> np.ndarray:
-    leaves = _leaves(num_actions)
+    from . import lib
+    nature = "Conv_0" in tree.get("network_params", {}).get("params", {})       # flax names of the Nature-CNN trunk
+    leaves = _leaves(num_actions, lib.CB_MODEL_NATURE_CNN if nature else lib.CB_MODEL_IMPALA_RESNET)
     total = max(off + int(np.prod(shape)) for _, off, shape in leaves)
     flat = np.empty(total, np.float32)
     for name, offset, shape in leaves:

@@ -84,3 +84,44 @@ class SyntheticAtari:
 
     def close(self):
         pass
+
+
+class SignalAtari(SyntheticAtari):
+    """A learnable stand-in with the same call surface: every env shows a frame whose brightness encodes a target action
+    (18 levels + pixel noise) and pays reward 1 when the agent picks it, else 0; a new target is drawn every step and episodes
+    last `horizon` steps.  Random policy: 1/18 per step.  Used by the end-to-end "does the whole actor-learner system learn" test
+    (the i.i.d.-noise SyntheticAtari has nothing to learn)."""
+
+    def __init__(self, num_envs: int, seed: int = 1, horizon: int = 64, num_actions: int = 18, **kw):
+        super().__init__(num_envs, seed=seed, pool_batches=1, pin=kw.get("pin", True), num_actions=num_actions)
+        self.horizon, self.num_actions = horizon, num_actions
+        self.target = self.rng.integers(0, num_actions, num_envs)
+        self.frame = torch.empty((num_envs, 4, 84, 84), dtype=torch.uint8)
+        if torch.cuda.is_available() and kw.get("pin", True):
+            self.frame = self.frame.pin_memory()
+        self.mean_reward = 0.0
+
+    def _obs(self) -> torch.Tensor:
+        level = (self.target * (255 // self.num_actions) + 7).astype(np.int16)[:, None, None, None]
+        noise = self.rng.integers(-6, 7, size=(self.num_envs, 4, 84, 84), dtype=np.int16)
+        self.frame.numpy()[...] = np.clip(level + noise, 0, 255).astype(np.uint8)
+        return self.frame
+
+    def _transition_signal(self, action):
+        n = self.num_envs
+        reward = (np.asarray(action).reshape(-1)[:n] == self.target).astype(np.float32)
+        self.mean_reward = 0.98 * self.mean_reward + 0.02 * float(reward.mean())
+        self.elapsed += 1
+        terminated = self.elapsed >= self.horizon
+        self.elapsed[terminated] = 0
+        self.target = self.rng.integers(0, self.num_actions, n)
+        info = {"env_id": np.arange(n, dtype=np.int32), "elapsed_step": self.elapsed.copy(), "terminated": terminated.astype(np.int32),
+                "reward": reward.copy(), "TimeLimit.truncated": np.zeros(n, bool)}
+        return reward, terminated.copy(), info
+
+    def step(self, action):
+        reward, done, info = self._transition_signal(action)
+        return self._obs(), reward, done, info
+
+    def send(self, action, env_id=None):
+        self._pending = self._transition_signal(action)

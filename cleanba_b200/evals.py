@@ -17,7 +17,8 @@ def evaluate(model_path: str, make_env: Callable, env_id: str, eval_episodes: in
              capture_video: bool = False, seed: int = 1, device="cuda:0", max_episode_steps: int = 27000) -> List[float]:
     envs = make_env(env_id, seed, num_envs=1)()
     _, flat = load_cleanrl_model(model_path)
-    ctx = ag.Context(device, max_batch=1, train=False)
+    from .checkpoint import _model_of_size
+    ctx = ag.Context(device, max_batch=1, train=False, model=_model_of_size(flat.size, ag.NUM_ACTIONS))
     ctx.set_params(flat)
     key = ag.key_tensor(first_key(seed), ctx.device)      # key, *_ = jax.random.split(PRNGKey(seed), 4)
     limit = getattr(getattr(getattr(envs, "spec", None), "config", None), "max_episode_steps", max_episode_steps)
