@@ -60,6 +60,11 @@ struct ConvEpilogue {
     float acc_scale;          // 1/255 for the first conv (cleanba_ppo.py:181), else 1
     const f16* mask_hi;       // hi plane of the (rectified) forward activation whose sign gates the gradient, or null
     long long mask_plane_px;
+    // relu gates as BITS (tcgen05 path): one byte per (flat pixel, 8-channel chunk), bit e = (value of channel chunk*8+e > 0),
+    // written by the producer of a rectified tensor (bits_out) and read by the dgrad that is gated by it (bits_in): Cout / 8
+    // bytes per pixel instead of the 2-byte-per-element hi plane
+    uint8_t* bits_out;
+    const uint8_t* bits_in;
     Planes res;               // tensor added after the mask (residual input / residual gradient); res.hi null = none
     Planes out;               // raw output planes (hi may be null)
     Planes out_r;             // rectified output planes (hi may be null)
@@ -236,6 +241,7 @@ template <int COUT>
 struct EpiPrefetch {
     uint4 res_hi[COUT / 8], res_mid[COUT / 8];
     uint4 mask[COUT / 8];
+    uint32_t mbits;
     bool in, tail;
 };
 
@@ -244,9 +250,13 @@ __device__ __forceinline__ void epi_prefetch(const ConvEpilogue& ep, const ConvG
     p.tail = q >= g.NP;
     p.in = !p.tail && interior(g, q);
     if (!p.in) return;
+    if (ep.bits_in) {
+        if (COUT == 16) p.mbits = *reinterpret_cast<const uint16_t*>(ep.bits_in + q * 2);
+        else p.mbits = *reinterpret_cast<const uint32_t*>(ep.bits_in + q * (COUT / 8));
+    }
 #pragma unroll
     for (int oc = 0; oc < COUT / 8; ++oc) {
-        if (ep.mask_hi) p.mask[oc] = *reinterpret_cast<const uint4*>(ep.mask_hi + ((long long)oc * ep.mask_plane_px + q) * 8);
+        if (ep.mask_hi && !ep.bits_in) p.mask[oc] = *reinterpret_cast<const uint4*>(ep.mask_hi + ((long long)oc * ep.mask_plane_px + q) * 8);
         if (ep.res.hi) {
             const long long off = ((long long)oc * ep.res.plane_px + q) * 8;
             p.res_hi[oc] = *reinterpret_cast<const uint4*>(ep.res.hi + off);
@@ -258,6 +268,7 @@ __device__ __forceinline__ void epi_prefetch(const ConvEpilogue& ep, const ConvG
 template <int COUT>
 __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeom& g, long long q, const float* acc,
                                            const EpiPrefetch<COUT>& p) {
+    uint32_t obits = 0;
 #pragma unroll
     for (int oc = 0; oc < COUT / 8; ++oc) {
         float v[8];
@@ -269,7 +280,13 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeo
                 float b = ep.bias ? ep.bias[oc * 8 + e] : 0.f;
                 v[e] = acc[oc * 8 + e] * ep.acc_scale + b;
             }
-            if (ep.mask_hi) gate8h(p.mask[oc], v);
+            if (ep.bits_in) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (!((p.mbits >> (oc * 8 + e)) & 1u)) v[e] = 0.f;
+            } else if (ep.mask_hi) {
+                gate8h(p.mask[oc], v);
+            }
             if (ep.res.hi) {
                 float rh[8], rm[8];
                 unpack8h(p.res_hi[oc], rh);
@@ -278,7 +295,15 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeo
                 for (int e = 0; e < 8; ++e) v[e] += fmaf(rm[e], MID_INV, rh[e]);
             }
         }
+        if (ep.bits_out) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) obits |= (v[e] > 0.f ? 1u : 0u) << (oc * 8 + e);
+        }
         epi_store8(ep, g, q, oc, v, p.in);
+    }
+    if (ep.bits_out) {      // rows up to the 128-pixel tile boundary exist (zero bits for border / tail pixels)
+        if (COUT == 16) *reinterpret_cast<uint16_t*>(ep.bits_out + q * 2) = (uint16_t)obits;
+        else *reinterpret_cast<uint32_t*>(ep.bits_out + q * (COUT / 8)) = obits;
     }
 }
 

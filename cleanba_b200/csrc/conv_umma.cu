@@ -273,6 +273,7 @@ struct Conv0PoolArgs {
     Planes out;               // pooled planes (raw: the residual input of the first block)
     Planes out_r;             // rectified pooled planes (the first block's conv operand)
     uint8_t* amax;            // arg-max bytes [2][n * 44 * 44][8] or null (actor contexts)
+    uint8_t* bits;            // relu gate bits of out_r [n * 44 * 44][2] or null (common.cuh ConvEpilogue::bits_out)
 };
 
 // 16-byte chunk c (0..3) of band pixel pb.  A pixel PAIR is one 128-byte row (all 32 banks); the 3-bit index (pixel parity, c)
@@ -394,6 +395,12 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
                 pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
                 *reinterpret_cast<uint2*>(a.amax + so) = pk;
             }
+            if (a.bits) {
+                uint32_t bb = 0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bb |= (v[e] > 0.f ? 1u : 0u) << e;
+                a.bits[qo * 2 + jc] = (uint8_t)bb;
+            }
         };
         auto emit_zero = [&](int img, int ypo, int xp, int jc) {
             float v[8];
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t* amax, int num_sms, cudaStream_t st) {
+int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t* amax, uint8_t* bits, int num_sms, cudaStream_t st) {
     CB_CHECK(a.g.H == 84 && a.g.W == 84 && a.cin_chunks == 1 && a.cout == C0_COUT && !a.transpose,
              "conv0_pool_umma: frame conv (84x84, 4 -> 16 channels) only");
     CB_CHECK(C0_HP + 1 <= GUARD && TILE_M + C0_HP + 2 + TILE_M <= GUARD + 128, "conv0_pool_umma: guard too small");
@@ -475,7 +482,7 @@ int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t*
     }
     Conv0PoolArgs p;
     p.n = a.g.n; p.x_hi = a.in.hi; p.wp = a.wp; p.bias = a.ep.bias; p.acc_scale = a.ep.acc_scale;
-    p.out = out; p.out_r = out_r; p.amax = amax;
+    p.out = out; p.out_r = out_r; p.amax = amax; p.bits = bits;
     const int nbands = a.g.n * C0_BANDS;
     const int grid = nbands < 2 * num_sms ? nbands : 2 * num_sms;
     launch_pdl(k_conv0_pool_umma, dim3(grid), dim3(CONV_THREADS), (size_t)C0_SMEM, st, p);
@@ -507,6 +514,7 @@ struct ConvPoolArgs {
     Planes out;               // pooled planes (raw)
     Planes out_r;             // rectified pooled planes
     uint8_t* amax;            // arg-max bytes or null
+    uint8_t* bits;            // relu gate bits of out_r [go.NP][4] or null
 };
 
 struct ConvPoolSmem { int win, plane_bytes, stage_bytes, w_bytes, stages, band_bytes, total, ctas_per_sm; };
@@ -666,6 +674,12 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
                 pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
                 *reinterpret_cast<uint2*>(a.amax + so) = pk;
             }
+            if (a.bits) {
+                uint32_t bb = 0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bb |= (v[e] > 0.f ? 1u : 0u) << e;
+                a.bits[qo * NCH + jc] = (uint8_t)bb;
+            }
         };
         auto emit_zero = [&](int img, int ypo, int xp, int jc) {
             float v[8];
@@ -769,14 +783,14 @@ static int launch_conv_pool_umma_t(ConvPoolArgs p, int num_sms, cudaStream_t st)
     return 0;
 }
 
-int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out, Planes out_r, uint8_t* amax, int num_sms,
+int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out, Planes out_r, uint8_t* amax, uint8_t* bits, int num_sms,
                           cudaStream_t st) {
     CB_CHECK(a.cout == CP_COUT && !a.transpose && a.in.mid && (a.cin_chunks == 2 || a.cin_chunks == 4),
              "conv_pool_umma: 16|32 -> 32 channel sequence convs only");
     CB_CHECK(a.g.Wp + 1 <= GUARD && 2 * TILE_M + a.g.Wp + 2 <= GUARD + 128, "conv_pool_umma: guard too small for Wp=%d", a.g.Wp);
     ConvPoolArgs p;
     p.gi = a.g; p.go = go; p.pad_lo = pad_lo; p.bands_per_img = 0;
-    p.in = a.in; p.wp = a.wp; p.bias = a.ep.bias; p.out = out; p.out_r = out_r; p.amax = amax;
+    p.in = a.in; p.wp = a.wp; p.bias = a.ep.bias; p.out = out; p.out_r = out_r; p.amax = amax; p.bits = bits;
     if (a.cin_chunks == 2) return launch_conv_pool_umma_t<2, 2, 2>(p, num_sms, st);
     return launch_conv_pool_umma_t<4, 5, 2>(p, num_sms, st);
 }

@@ -155,7 +155,9 @@ static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
     const double flops = 2.0 * a.g.n * a.g.H * a.g.W * 9.0 * a.cin_real * a.cout;
     double bytes = planes_bytes(a.g, a.cin_chunks, a.in) + planes_bytes(a.g, a.cout / 8, a.ep.out) + planes_bytes(a.g, a.cout / 8, a.ep.out_r) +
                    planes_bytes(a.g, a.cout / 8, a.ep.res);
-    if (a.ep.mask_hi) bytes += planes_bytes(a.g, a.cout / 8, false);
+    if (a.ep.bits_in) bytes += (double)a.g.NP * (a.cout / 8);
+    else if (a.ep.mask_hi) bytes += planes_bytes(a.g, a.cout / 8, false);
+    if (a.ep.bits_out) bytes += (double)a.g.NP * (a.cout / 8);
     // algorithmic: input, output and residual tensors once as unpadded fp32 (the relu gate of dgrad is one BIT per element: not counted)
     const double abytes = f32_once(a.g, a.cin_real) + f32_once(a.g, a.cout) * (1 + (a.ep.res.hi ? 1 : 0));
     ProfScope ps(c, name, flops, bytes, st, abytes);
@@ -226,7 +228,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             ProfScope ps(c, "conv0_pool_fwd@84", 2.0 * n * 84 * 84 * 9.0 * 4 * 16,
                          planes_bytes(gi, 1, false) + 2 * planes_bytes(go, 2) + (S.amax ? (double)go.NP * 16 : 0.0), st,
                          (double)n * 28224.0 + f32_once(go, 16));      // uint8 frames in, pooled fp32 out
-            if (launch_conv0_pool_umma(a, S.p.pl, S.pr.pl, S.amax, c->num_sms, st)) return -1;
+            if (launch_conv0_pool_umma(a, S.p.pl, S.pr.pl, S.amax, S.bits_pr, c->num_sms, st)) return -1;
         } else if (fused) {
             // sequence conv + max-pool in one kernel (conv_umma.cu: k_conv_pool_umma)
             ConvArgs a = conv_args(c, base, gi, S.x, false);
@@ -236,7 +238,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             ProfScope ps(c, name, 2.0 * n * gi.H * gi.W * 9.0 * a.cin_real * a.cout,
                          planes_bytes(gi, a.cin_chunks, a.in) + 2 * planes_bytes(go, a.cout / 8) + (S.amax ? (double)go.NP * a.cout : 0.0), st,
                          f32_once(gi, a.cin_real) + f32_once(go, a.cout));
-            if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.pl, S.pr.pl, S.amax, c->num_sms, st)) return -1;
+            if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.pl, S.pr.pl, S.amax, S.bits_pr, c->num_sms, st)) return -1;
         } else {
             // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
             ConvArgs a = conv_args(c, base + 0, gi, S.x, false);
@@ -253,17 +255,17 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
         {   // ResidualBlock 0: x + Conv(relu(Conv(relu(x))))                    (cleanba_ppo.py:153-159)
             ConvArgs a = conv_args(c, base + 1, go, S.pr, false);
             a.ep.bias = c->params + c->conv[base + 1].off_b;
-            a.ep.out_r = S.a0.pl;
+            a.ep.out_r = S.a0.pl; a.ep.bits_out = S.bits_a0;
             if (run_conv(c, a, st)) return -1;
             ConvArgs b = conv_args(c, base + 2, go, S.a0, false);
             b.ep.bias = c->params + c->conv[base + 2].off_b;
-            b.ep.res = S.p.pl; b.ep.out = S.b0.pl; b.ep.out_r = S.b0r.pl;
+            b.ep.res = S.p.pl; b.ep.out = S.b0.pl; b.ep.out_r = S.b0r.pl; b.ep.bits_out = S.bits_b0r;
             if (run_conv(c, b, st)) return -1;
         }
         {   // ResidualBlock 1; its output feeds the next ConvSequence un-rectified, or the final nn.relu (cleanba_ppo.py:184)
             ConvArgs a = conv_args(c, base + 3, go, S.b0r, false);
             a.ep.bias = c->params + c->conv[base + 3].off_b;
-            a.ep.out_r = S.a1.pl;
+            a.ep.out_r = S.a1.pl; a.ep.bits_out = S.bits_a1;
             if (run_conv(c, a, st)) return -1;
             ConvArgs b = conv_args(c, base + 4, go, S.a1, false);
             b.ep.bias = c->params + c->conv[base + 4].off_b;
@@ -321,13 +323,13 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         if (run_wgrad(c, base + 4, go, S.a1, S.gA, grads, st)) return -1;
         {
             ConvArgs a = conv_args(c, base + 4, go, S.gA, true);
-            a.ep.mask_hi = S.a1.pl.hi; a.ep.mask_plane_px = S.a1.pl.plane_px; a.ep.out = S.gB.pl;
+            a.ep.mask_hi = S.a1.pl.hi; a.ep.mask_plane_px = S.a1.pl.plane_px; a.ep.bits_in = S.bits_a1; a.ep.out = S.gB.pl;
             if (run_conv(c, a, st)) return -1;
         }
         if (run_wgrad(c, base + 3, go, S.b0r, S.gB, grads, st)) return -1;
         {
             ConvArgs a = conv_args(c, base + 3, go, S.gB, true);
-            a.ep.mask_hi = S.b0r.pl.hi; a.ep.mask_plane_px = S.b0r.pl.plane_px; a.ep.res = S.gA.pl;
+            a.ep.mask_hi = S.b0r.pl.hi; a.ep.mask_plane_px = S.b0r.pl.plane_px; a.ep.bits_in = S.bits_b0r; a.ep.res = S.gA.pl;
             a.ep.out = S.gC.pl;
             if (run_conv(c, a, st)) return -1;
         }
@@ -336,13 +338,13 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         if (wgrad_done_before(c, st)) return -1;      // the next dgrad re-writes gB, which the wgrad of base + 3 reads
         {
             ConvArgs a = conv_args(c, base + 2, go, S.gC, true);
-            a.ep.mask_hi = S.a0.pl.hi; a.ep.mask_plane_px = S.a0.pl.plane_px; a.ep.out = S.gB.pl;
+            a.ep.mask_hi = S.a0.pl.hi; a.ep.mask_plane_px = S.a0.pl.plane_px; a.ep.bits_in = S.bits_a0; a.ep.out = S.gB.pl;
             if (run_conv(c, a, st)) return -1;
         }
         if (run_wgrad(c, base + 1, go, S.pr, S.gB, grads, st)) return -1;
         {
             ConvArgs a = conv_args(c, base + 1, go, S.gB, true);
-            a.ep.mask_hi = S.pr.pl.hi; a.ep.mask_plane_px = S.pr.pl.plane_px; a.ep.res = S.gC.pl;
+            a.ep.mask_hi = S.pr.pl.hi; a.ep.mask_plane_px = S.pr.pl.plane_px; a.ep.bits_in = S.bits_pr; a.ep.res = S.gC.pl;
             a.ep.out = S.gA.pl;    // gradient w.r.t. the pooled tensor (gA is free again)
             if (run_conv(c, a, st)) return -1;
         }
@@ -509,6 +511,16 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
                 void* ap;
                 if (dev_alloc(c, &ap, (size_t)cfg->max_batch * (Ho + 2) * (Ho + 2) * C)) { fail = true; break; }
                 S.amax = (uint8_t*)ap;
+                static const bool bits_on = [] { const char* e = getenv("CLEANBA_GATE_BITS"); return !e || atoi(e) != 0; }();
+                if (bits_on && cfg->conv_backend == CB_CONV_TCGEN05) {      // relu gates as bits: [pixels to the tile boundary][C / 8] bytes
+                    const size_t nb = (size_t)((((long long)cfg->max_batch * (Ho + 2) * (Ho + 2) + 127) / 128) * 128) * (C / 8);
+                    uint8_t** dst[4] = {&S.bits_a0, &S.bits_b0r, &S.bits_a1, fused ? &S.bits_pr : nullptr};
+                    for (auto d : dst) {
+                        if (!d) continue;
+                        if (dev_alloc(c, &ap, nb)) { fail = true; break; }
+                        *d = (uint8_t*)ap;
+                    }
+                }
                 fail |= alloc_act(c, S.gA, C, Ho) != 0;
                 fail |= alloc_act(c, S.gB, C, Ho) != 0;
                 fail |= alloc_act(c, S.gC, C, Ho) != 0;

@@ -38,6 +38,7 @@ struct Stage {
     Act y;                  // conv output before the pool (only when the conv is not fused with its pool)
     Act p, pr;              // pooled: raw (residual input of block 0) and rectified (operand of its first conv)
     uint8_t* amax = nullptr; // arg-max slots of the pool (learner contexts)
+    uint8_t *bits_pr = nullptr, *bits_a0 = nullptr, *bits_b0r = nullptr, *bits_a1 = nullptr;   // relu gate bits (learner, tcgen05)
     Act a0;                 // relu(conv1(relu(p)))
     Act b0, b0r;            // p + conv2(a0): raw and rectified
     Act a1;                 // relu(conv3(relu(b0)))

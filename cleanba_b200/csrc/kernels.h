@@ -34,9 +34,9 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st);
 int launch_wgrad_umma(const WgradArgs& a, float* partial, int num_sms, cudaStream_t st);
 int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp);
 // frame conv fused with its max-pool (84x84x4 -> pooled 42x42x16: stream, relu'd planes, arg-max bytes)
-int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t* amax, int num_sms, cudaStream_t st);
+int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t* amax, uint8_t* bits, int num_sms, cudaStream_t st);
 // sequence conv of the second / third ConvSequence fused with its max-pool (same outputs on the pooled grid `go`)
-int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out, Planes out_r, uint8_t* amax, int num_sms,
+int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out, Planes out_r, uint8_t* amax, uint8_t* bits, int num_sms,
                           cudaStream_t st);
 
 // dense.cu

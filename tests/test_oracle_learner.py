@@ -153,3 +153,32 @@ def test_multi_shard_update_matches_manual_mean():
     assert len(rec) == 4 and np.isfinite(stats).all() and (k2 != key).any()
     assert optim.global_norm(rec[0]["grad"]) <= 0.5 + 1e-6
     assert not np.array_equal(rec[-1]["params"], fp)
+
+
+def test_gradient_accumulation_is_optax_multisteps():
+    """gradient_accumulation_steps = k (cleanba_ppo.py:78,492-500,607): the shuffled batch is cut into num_minibatches * k mini-steps;
+    optax.MultiSteps keeps the running mean of the k mini-step gradients and applies clip + Adam to it on the k-th.  Checked against an
+    explicit computation with the primitives (one update epoch, 1 minibatch, k = 2)."""
+    import numpy as np
+    from oracle import network as net, optim, ppo as oppo, threefry as tf
+    rng = np.random.default_rng(5)
+    T, B = 2, 4
+    shard = oppo.Shard(obs=rng.integers(0, 256, (T, B, 4, 84, 84), dtype=np.uint8), dones=np.zeros((T, B), bool),
+                       actions=rng.integers(0, 18, (T, B)).astype(np.int32), logprobs=np.full((T, B), np.log(1 / 18), np.float32),
+                       values=(rng.standard_normal((T, B)) * 0.1).astype(np.float32), rewards=rng.choice([-1.0, 0.0, 1.0], size=(T, B)).astype(np.float32),
+                       next_obs=rng.integers(0, 256, (B, 4, 84, 84), dtype=np.uint8), next_done=np.zeros(B, bool))
+    p0 = net.init_params(1)
+    key = tf.split(tf.PRNGKey(3), 4)[0]
+    cfg = oppo.PPOConfig(update_epochs=1, num_minibatches=1, gradient_accumulation_steps=2, num_updates=10, norm_adv=False)
+    L = oppo.PPOLearner(p0, cfg)
+    stats, _ = L.update([shard], key)
+    assert L.opt.count == 1
+    adv, ret = oppo.PPOLearner(p0, cfg).prepare(shard)
+    _, sub = tf.split(key)
+    idx = tf.permutation(sub, T * B).reshape(2, -1)
+    flat = lambda x: x.reshape((-1,) + x.shape[2:])
+    gs = [oppo.ppo_loss_and_grad(p0, flat(shard.obs)[ii], flat(shard.actions)[ii], flat(shard.logprobs)[ii], adv.reshape(-1)[ii], ret.reshape(-1)[ii])[1]
+          for ii in idx]
+    acc = gs[0] + (gs[1] - gs[0]) / np.float32(2)
+    want = optim.Adam(p0.size).step(p0, optim.clip_by_global_norm(acc.astype(np.float32), 0.5), optim.linear_schedule(0, 2.5e-4, 1, 10))
+    assert np.abs(L.params - want).max() < 1e-7
