@@ -166,12 +166,14 @@ class Cycle:
     topology of BASELINE configs[1] (PPO) / configs[2] (IMPALA).  One step() = rollout of T steps + single_device_update +
     parameter publish."""
 
-    def __init__(self, device, world, allreduce, workload="ppo", seed=1):
+    def __init__(self, device, world, allreduce, workload="ppo", seed=1, network="impala_resnet"):
         import torch
         from cleanba_b200 import agent as ag
         from cleanba_b200.learner import ImpalaHyper, ImpalaLearner, PPOHyper, PPOLearner
         from cleanba_b200.params import init_params
         from cleanba_b200.prng import first_key
+        from cleanba_b200.lib import MODELS
+        model = MODELS[network]
         self.torch, self.ag = torch, ag
         self.dev = d = torch.device(device)
         self.impala = workload == "impala"
@@ -179,15 +181,15 @@ class Cycle:
         self.rows = rows = T + 1 if self.impala else T          # IMPALA: row 0 is carried over from the previous rollout
         Bl = self.Bl = N_ENVS * N_THREADS
         if self.impala:
-            self.learner = ImpalaLearner(d, ImpalaHyper(), T1=rows, Bl=Bl, world_learners=world, allreduce=allreduce)
+            self.learner = ImpalaLearner(d, ImpalaHyper(), T1=rows, Bl=Bl, world_learners=world, allreduce=allreduce, model=model)
         else:
-            self.learner = PPOLearner(d, PPOHyper(), T=T, Bl=Bl, world_learners=world, allreduce=allreduce)
-        self.learner.ctx.set_params(init_params(seed))
+            self.learner = PPOLearner(d, PPOHyper(), T=T, Bl=Bl, world_learners=world, allreduce=allreduce, model=model)
+        self.learner.ctx.set_params(init_params(seed, model=model))
         # one actor context + CUDA-graphed step per actor thread, each on its own stream (the reference runs
         # num_actor_threads = 2 Python threads per actor device, cleanba_ppo.py:670-686)
         self.actors, self.graphed = [], []
         for th in range(N_THREADS):
-            a = ag.Context(d, max_batch=N_ENVS, train=False, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO)
+            a = ag.Context(d, max_batch=N_ENVS, train=False, algo=ag.CB_ALGO_IMPALA if self.impala else ag.CB_ALGO_PPO, model=model)
             self.learner.ctx.publish_to(a)
             torch.cuda.synchronize()
             key = ag.key_tensor(first_key(seed), d)
@@ -276,7 +278,7 @@ def run_our_arm(args):
     from cleanba_b200 import lib
     wl = args.workload
     T_STEPS = WORKLOADS[wl]["T"]
-    cyc = Cycle(f"cuda:{local_rank}", world, allreduce, workload=wl)
+    cyc = Cycle(f"cuda:{local_rank}", world, allreduce, workload=wl, network=args.network)
     if world > 1:   # identical initial parameters on every learner (the reference relies on equal seeds, cleanba_ppo.py:468)
         pv = cyc.learner.ctx.params_view(); dist.broadcast(pv, 0); cyc.learner.ctx.refresh_weights()
         for a in cyc.actors:
@@ -367,7 +369,8 @@ def run_our_arm(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": workload_name(wl, T_STEPS), "env_steps_per_bench_step": env_steps, "topology": f"a0-l0-d{world}",
+        "config": {"workload": workload_name(wl, T_STEPS) + ("" if args.network == "impala_resnet" else f", network={args.network}"),
+                   "env_steps_per_bench_step": env_steps, "topology": f"a0-l0-d{world}",
                    "cache": "inputs larger than L2: 433 MB device frame pool cycled, 433 MB rollout storage per update",
                    "tensor_roof_frac_end_to_end": value * WORKLOADS[wl]["flop_per_env_step"] / (peaks["tf"] * 1e12 * world)},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": cyc.h2d // args.steps,
@@ -401,6 +404,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="ppo", choices=sorted(WORKLOADS), help="ppo = BASELINE configs[1] (default), impala = configs[2]")
+    ap.add_argument("--network", default="impala_resnet", choices=["impala_resnet", "nature_cnn"],
+                    help="trunk: the reference's IMPALA-ResNet (default, the configuration the metric is quoted on) or its legacy Nature-CNN")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -60,7 +60,11 @@ def main():
     bw = [x for act in be.actors for x in act.payload_bandwidth()]
     learners = res.learner.learners
     same = all(torch.equal(learners[0].ctx.get_params().cpu(), l.ctx.get_params().cpu()) for l in learners[1:])
-    out = dict(rank=int(os.environ.get("RANK", 0)), world=int(os.environ.get("WORLD_SIZE", 1)), algo=a.algo,
+    free_b, total_b = torch.cuda.mem_get_info(learners[0].ctx.device)
+    final_stats = res.learner.stats_to_host(res.stats)
+    out = dict(final_stats={k: round(v, 6) for k, v in final_stats.items()}, stats_finite=bool(all(np.isfinite(v) for v in final_stats.values())),
+               learner_gpu_used_gb=round((total_b - free_b) / 1e9, 2),
+               rank=int(os.environ.get("RANK", 0)), world=int(os.environ.get("WORLD_SIZE", 1)), algo=a.algo,
                topology=f"a{','.join(map(str, a.actor))}-l{','.join(map(str, a.learners))}-d{int(os.environ.get('WORLD_SIZE', 1))}",
                updates=res.updates, global_step=res.global_step, wall_s=round(wall, 2),
                steady_env_steps_per_s=round((sb - sa) / (tb - ta), 1),
