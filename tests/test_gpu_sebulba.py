@@ -260,15 +260,15 @@ def test_sm_partition_actor_step_is_bit_identical():
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("network", ["impala_resnet", "nature_cnn"])
-def test_the_system_learns_a_signal_task(network):
+@pytest.mark.parametrize("algo,network", [("ppo", "impala_resnet"), ("ppo", "nature_cnn"), ("impala", "impala_resnet")])
+def test_the_system_learns_a_signal_task(algo, network):
     """End to end, free running (no pinning): actor threads + queues + PPO learner on the CUDA backend learn envs.SignalAtari
     (frame brightness encodes the rewarded action; a random policy earns 1/18 = 0.056 per step) to > 0.3 reward per step (5x the random policy) within
     120 updates, with finite losses throughout -- kernels, loss scale, optimizer, parameter publish and the plumbing all have to be
     right for that."""
     from cleanba_b200.cuda_backend import CudaBackend
     from cleanba_b200.envs import SignalAtari
-    from cleanba_b200.sebulba import Args, derive_sizes, train
+    from cleanba_b200.sebulba import Args, derive_sizes, impala_defaults, train
     envs = []
 
     def make_env(env_id, seed, num_envs):
@@ -280,9 +280,17 @@ def test_the_system_learns_a_signal_task(network):
 
     a = Args(local_num_envs=32, num_actor_threads=2, num_steps=16, num_minibatches=2, update_epochs=2, total_timesteps=10 ** 7, log_frequency=10 ** 6,
              max_updates=120, learning_rate=1e-3, anneal_lr=False, ent_coef=0.0, gamma=0.0, gae_lambda=0.0, network=network)
-    a.concurrency = False
+    if algo == "impala":          # V-trace learner, RMSProp, async env interface, actors one policy version behind (concurrency)
+        a = impala_defaults(a)
+        # The reference pairs transition t -> t+1 with the reward that ARRIVED with obs[t], i.e. the reward of action t-1
+        # (cleanba_impala.py:352,375-379,580-582; SURVEY appendix D.8, replicated).  With gamma = 0 action t would never see its own
+        # reward; with gamma > 0 it does through the bootstrapped V-trace target gamma * vs[t+1].
+        a.num_steps, a.learning_rate, a.max_updates, a.gamma = 16, 1e-3, 800, 0.9
+    else:
+        a.concurrency = False
     losses = []
     res = train(derive_sizes(a, 1), CudaBackend(), make_env, on_update=lambda v, gs, st: losses.append(st.detach().cpu().numpy()))
-    assert res.updates == 120 and np.isfinite(np.stack(losses)).all()
+    assert res.updates == a.max_updates and np.isfinite(np.stack(losses)).all()
     got = float(np.mean([e.mean_reward for e in envs]))
-    assert got > 0.3, f"mean reward per step {got:.3f} after 120 updates (random policy: 0.056)"
+    bar = 0.3 if algo == "ppo" else 0.15      # IMPALA's credit reaches the action only through the bootstrapped target (see above)
+    assert got > bar, f"mean reward per step {got:.3f} after {a.max_updates} updates (random policy: 0.056)"
