@@ -245,6 +245,15 @@ class Context:
         check(self.lib.cb_set_grad_milestone(self.h, handle, ctypes.byref(off)))
         return int(off.value)
 
+    def graph_steps(self, enable: bool = True):
+        """Replay ppo_grad / impala_grad as a captured CUDA graph (one small launch + one graph launch per call instead of ~70
+        launches); see cb_graph_steps."""
+        check(self.lib.cb_graph_steps(self.h, int(bool(enable))))
+
+    @property
+    def graph_replays(self) -> int:
+        return int(self.lib.cb_graph_replays(self.h))
+
     def reduce_peers(self, grads_list, out: torch.Tensor):
         """out = fixed-order sum of the replicas' flat gradient buffers (peer memory); see cb_reduce_peers."""
         arr = (ctypes.c_void_p * len(grads_list))(*[g.data_ptr() for g in grads_list])

@@ -168,14 +168,16 @@ static int run_conv(cb_ctx* c, const ConvArgs& a, cudaStream_t st) {
 // Weight gradients feed nothing but the optimizer, so they run on the context's side stream beside the dgrad chain (the caller's
 // stream): fork = "the gradient tensor gy is complete on `main`".  The one buffer hazard (the dgrad of the block's second conv
 // re-writes gB while the wgrad of its first conv may still read it) is closed by wgrad_done_before().
+// While profiling (cb_profile) everything runs on the caller's stream, so that the event brackets time each kernel ALONE.
+static bool side_active(const cb_ctx* c) { return c->side && !c->prof_on; }
 static int fork_side(cb_ctx* c, cudaStream_t main_st) {
-    if (!c->side) return 0;
+    if (!side_active(c)) return 0;
     CB_CUDA(cudaEventRecord(c->ev_fork, main_st));
     CB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     return 0;
 }
 static int wgrad_done_before(cb_ctx* c, cudaStream_t main_st) {    // main waits for everything queued on the side stream so far
-    if (!c->side) return 0;
+    if (!side_active(c)) return 0;
     CB_CUDA(cudaEventRecord(c->ev_join, c->side));
     CB_CUDA(cudaStreamWaitEvent(main_st, c->ev_join, 0));
     return 0;
@@ -183,7 +185,7 @@ static int wgrad_done_before(cb_ctx* c, cudaStream_t main_st) {    // main waits
 
 static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, const Act& gy, float* grads, cudaStream_t main_st) {
     if (fork_side(c, main_st)) return -1;
-    cudaStream_t st = c->side ? c->side : main_st;
+    cudaStream_t st = side_active(c) ? c->side : main_st;
     const ConvLayer& L = c->conv[layer];
     WgradArgs w;
     w.g = g; w.x = x.pl; w.cin_chunks = (L.cin + 7) / 8; w.cin_real = L.cin; w.gy = gy.pl; w.cout = L.cout;
@@ -211,7 +213,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
     g_pdl_scope = n <= pdl_max;
     {
         ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 86.0 * 86 * 16), st);
-        if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st, c->cursor)) return -1;
+        if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st, c->cursor, c->ind)) return -1;
     }
     for (int s = 0; s < 3; ++s) {
         Stage& S = c->st[s];
@@ -312,7 +314,8 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
     }
     // The flat gradient vector is [conv stages | dense | actor | critic]: its tail (the dense layer: 91% of the parameters) is
     // final here, before the conv backward starts -- the caller may start exchanging it now (cb_set_grad_milestone).
-    if (c->milestone) CB_CUDA(cudaEventRecord(c->milestone, st));
+    // (inside a captured step the record is an EXTERNAL event node: every replay records the caller's event again)
+    if (c->milestone) CB_CUDA(cudaEventRecordWithFlags(c->milestone, st, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
     for (int s = 2; s >= 0; --s) {
         Stage& S = c->st[s];
         const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
@@ -352,7 +355,7 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         if (s == 0 && c->fuse0) {
             // frames need no dX: the pooled gradient goes straight into the frame conv's weight gradient (trunk_simt.cu)
             if (fork_side(c, st)) return -1;
-            cudaStream_t ws = c->side ? c->side : st;
+            cudaStream_t ws = side_active(c) ? c->side : st;
             ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), ws,
                          f32_once(go, 16) + (double)n * 28224.0);
             if (launch_pool_bwd_wgrad0(S.amax, S.gA.pl, S.x.pl.hi, gi, go, 1.0f / 255.0f, c->gscale + 1, grads + c->conv[0].off_w,
@@ -372,6 +375,91 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
         }
     }
     return wgrad_done_before(c, st);      // every weight gradient is complete on the caller's stream
+}
+
+// ---- graphed gradient steps (cb_graph_steps) --------------------------------------------------------------------------------
+// A cb_*_grad call is ~70 launches on two streams.  With graph mode on, the launches of a (shape, gradient buffer, coefficients)
+// combination are captured ONCE -- the second time the combination is seen, so that every lazily created resource exists -- and
+// replayed afterwards: per step the host enqueues one tiny launch (the step's pointers -> cb_ctx::step_dev, which the frame
+// unpack and the loss head read instead of their frozen arguments) and one cudaGraphLaunch.
+template <class Body>
+static int graphed_step(cb_ctx* c, const StepGraph& key, const StepPtrs& ptrs, cudaStream_t st, Body body) {
+    StepGraph* g = nullptr;
+    for (auto& e : c->graphs)
+        if (e.kind == key.kind && e.n == key.n && e.T1 == key.T1 && e.B == key.B && e.grads == key.grads && e.c0 == key.c0 &&
+            e.c1 == key.c1 && e.c2 == key.c2 && e.milestone == key.milestone) { g = &e; break; }
+    if (!g) {                                   // first sight: run eagerly (warms every launcher), remember the key
+        if (c->graphs.size() >= 64) {           // a caller that keeps changing shapes: drop the oldest entries
+            for (int i = 0; i < 32; ++i) if (c->graphs[i].exec) cudaGraphExecDestroy(c->graphs[i].exec);
+            c->graphs.erase(c->graphs.begin(), c->graphs.begin() + 32);
+        }
+        c->graphs.push_back(key);
+        return body(st);
+    }
+    if (launch_set_step_ptrs(c->step_dev, ptrs, st)) return -1;
+    if (!g->exec) {
+        // captured on a private stream (the caller's may be the legacy default stream, which cannot capture); replayed on `st`
+        CB_CUDA(cudaStreamBeginCapture(c->cap, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true; c->ind = c->step_dev;
+        const long long l0 = g_launches.load();
+        const int rc = body(c->cap);
+        c->capturing = false; c->ind = nullptr;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->cap, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return -1; }   // body() set the error text
+        CB_CUDA(e);
+        g->launches = g_launches.load() - l0;
+        g_launches.fetch_sub(g->launches);      // captured, not launched yet
+        const cudaError_t ei = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CB_CUDA(ei);
+    }
+    CB_CUDA(cudaGraphLaunch(g->exec, st));
+    g_launches.fetch_add(g->launches);
+    c->graph_replays += 1;
+    return 0;
+}
+
+static int ppo_grad_body(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int mb, const int32_t* actions, const float* logprobs,
+                         const float* advantages, const float* returns, float clip_coef, float ent_coef, float vf_coef,
+                         float* grads, float* stats, cudaStream_t st) {
+    if (trunk_forward(c, obs, idx, mb, st)) return -1;
+    PpoHeadArgs h;
+    h.n = mb; h.num_actions = c->A; h.hid = c->HID; h.hidden = c->hidden;
+    h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
+    h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
+    h.idx = idx; h.actions = actions; h.old_logprobs = logprobs; h.advantages = advantages; h.returns = returns;
+    h.clip_coef = clip_coef; h.ent_coef = ent_coef; h.vf_coef = vf_coef;
+    h.dpre = c->dpre; h.dlogits = c->dlogits; h.terms = c->terms; h.stats = stats; h.wgrad_scratch = c->wg_partial;
+    h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
+    h.ind = c->ind;
+    {
+        ProfScope ps(c, "ppo_loss_head", 6.0 * mb * HIDDEN * (c->A + 1), (double)mb * (2 * HIDDEN * 4 + 92 + 76), st);
+        if (launch_ppo_head(h, st)) return -1;
+    }
+    return trunk_backward(c, mb, grads, st);
+}
+
+static int impala_grad_body(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int T1, int B, const int32_t* actions,
+                            const float* behaviour_logits, const float* rewards, const uint8_t* dones, const uint8_t* firststeps,
+                            float gamma, float vf_coef, float ent_coef, float* grads, float* stats, cudaStream_t st) {
+    const int n = T1 * B;
+    if (trunk_forward(c, obs, idx, n, st)) return -1;
+    ImpalaHeadArgs h;
+    h.T1 = T1; h.B = B; h.num_actions = c->A; h.hid = c->HID; h.hidden = c->hidden;
+    h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
+    h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
+    h.idx = idx; h.actions = actions; h.behaviour_logits = behaviour_logits; h.rewards = rewards; h.dones = dones;
+    h.firststeps = firststeps; h.gamma = gamma; h.vf_coef = vf_coef; h.ent_coef = ent_coef;
+    h.logits_scratch = c->logits_scratch; h.cell_scratch = c->cell_scratch; h.dpre = c->dpre; h.dlogits = c->dlogits;
+    h.stats = stats; h.wgrad_scratch = c->wg_partial;
+    h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
+    h.ind = c->ind;
+    {
+        ProfScope ps(c, "vtrace_loss_head", 6.0 * n * HIDDEN * (c->A + 1), (double)n * (2 * HIDDEN * 4 + 157 + 76), st);
+        if (launch_impala_head(h, st)) return -1;
+    }
+    return trunk_backward(c, n, grads, st);
 }
 
 static int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t st) {
@@ -412,8 +500,10 @@ int cb_leaf_info_model(int model, int index, int num_actions, char* name, int na
 void cb_destroy(cb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
+    for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : c->allocs) cudaFree(p);
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->cap) cudaStreamDestroy(c->cap);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->nat) nature_destroy(c);
@@ -586,6 +676,8 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             c->gscale = (float*)p;
             if (dev_alloc(c, &p, 2 * sizeof(unsigned))) break;
             c->gs_work = (unsigned*)p;
+            if (dev_alloc(c, &p, sizeof(StepPtrs))) break;
+            c->step_dev = (StepPtrs*)p;
             static const bool side_on = [] { const char* e = getenv("CLEANBA_WGRAD_SIDE"); return !e || atoi(e) != 0; }();
             if (side_on && !nature && cfg->conv_backend == CB_CONV_TCGEN05) {
                 if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -748,22 +840,18 @@ int cb_ppo_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int mb, const
                 float* stats, cb_stream stream) {
     CB_CHECK(c && obs && actions && logprobs && advantages && returns && grads && stats, "null argument");
     CB_CHECK(c->cfg.train, "cb_ppo_grad needs a learner context (train=1)");
+    CB_CHECK(mb > 0 && mb <= c->cfg.max_batch, "batch %d outside (0, max_batch=%d]", mb, c->cfg.max_batch);
     CB_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (trunk_forward(c, obs, idx, mb, st)) return -1;
-    PpoHeadArgs h;
-    h.n = mb; h.num_actions = c->A; h.hid = c->HID; h.hidden = c->hidden;
-    h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
-    h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
-    h.idx = idx; h.actions = actions; h.old_logprobs = logprobs; h.advantages = advantages; h.returns = returns;
-    h.clip_coef = clip_coef; h.ent_coef = ent_coef; h.vf_coef = vf_coef;
-    h.dpre = c->dpre; h.dlogits = c->dlogits; h.terms = c->terms; h.stats = stats; h.wgrad_scratch = c->wg_partial;
-    h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
-    {
-        ProfScope ps(c, "ppo_loss_head", 6.0 * mb * HIDDEN * (c->A + 1), (double)mb * (2 * HIDDEN * 4 + 92 + 76), st);
-        if (launch_ppo_head(h, st)) return -1;
-    }
-    return trunk_backward(c, mb, grads, st);
+    auto body = [&](cudaStream_t s) {
+        return ppo_grad_body(c, obs, idx, mb, actions, logprobs, advantages, returns, clip_coef, ent_coef, vf_coef, grads, stats, s);
+    };
+    if (!c->graph_on || c->prof_on) return body(st);
+    StepGraph key;
+    key.kind = 0; key.n = mb; key.T1 = key.B = 0; key.grads = grads; key.c0 = clip_coef; key.c1 = ent_coef; key.c2 = vf_coef;
+    key.milestone = c->milestone;
+    StepPtrs p = {{obs, idx, actions, logprobs, advantages, returns, stats, nullptr}};
+    return graphed_step(c, key, p, st, body);
 }
 
 int cb_impala_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int T1, int B, const int32_t* actions,
@@ -772,24 +860,19 @@ int cb_impala_grad(cb_ctx* c, const uint8_t* obs, const int32_t* idx, int T1, in
     CB_CHECK(c && obs && actions && behaviour_logits && rewards && dones && firststeps && grads && stats, "null argument");
     CB_CHECK(c->cfg.train, "cb_impala_grad needs a learner context (train=1)");
     CB_CHECK(T1 >= 2 && B >= 1, "need T+1 >= 2 rows and B >= 1 columns");
+    CB_CHECK((long long)T1 * B <= c->cfg.max_batch, "batch %lld outside (0, max_batch=%d]", (long long)T1 * B, c->cfg.max_batch);
     CB_CUDA(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int n = T1 * B;
-    if (trunk_forward(c, obs, idx, n, st)) return -1;
-    ImpalaHeadArgs h;
-    h.T1 = T1; h.B = B; h.num_actions = c->A; h.hid = c->HID; h.hidden = c->hidden;
-    h.wa = c->params + c->off_actor_w; h.ba = c->params + c->off_actor_b;
-    h.wc = c->params + c->off_critic_w; h.bc = c->params + c->off_critic_b;
-    h.idx = idx; h.actions = actions; h.behaviour_logits = behaviour_logits; h.rewards = rewards; h.dones = dones;
-    h.firststeps = firststeps; h.gamma = gamma; h.vf_coef = vf_coef; h.ent_coef = ent_coef;
-    h.logits_scratch = c->logits_scratch; h.cell_scratch = c->cell_scratch; h.dpre = c->dpre; h.dlogits = c->dlogits;
-    h.stats = stats; h.wgrad_scratch = c->wg_partial;
-    h.dwa = grads + c->off_actor_w; h.dba = grads + c->off_actor_b; h.dwc = grads + c->off_critic_w; h.dbc = grads + c->off_critic_b;
-    {
-        ProfScope ps(c, "vtrace_loss_head", 6.0 * n * HIDDEN * (c->A + 1), (double)n * (2 * HIDDEN * 4 + 157 + 76), st);
-        if (launch_impala_head(h, st)) return -1;
-    }
-    return trunk_backward(c, n, grads, st);
+    auto body = [&](cudaStream_t s) {
+        return impala_grad_body(c, obs, idx, T1, B, actions, behaviour_logits, rewards, dones, firststeps, gamma, vf_coef, ent_coef,
+                                grads, stats, s);
+    };
+    if (!c->graph_on || c->prof_on) return body(st);
+    StepGraph key;
+    key.kind = 1; key.n = T1 * B; key.T1 = T1; key.B = B; key.grads = grads; key.c0 = gamma; key.c1 = vf_coef; key.c2 = ent_coef;
+    key.milestone = c->milestone;
+    StepPtrs p = {{obs, idx, actions, behaviour_logits, rewards, dones, stats, firststeps}};
+    return graphed_step(c, key, p, st, body);
 }
 
 static int optimizer_step(cb_ctx* c, const float* const* grads, int num_grads, float grad_scale, float lr, float max_norm,
@@ -855,6 +938,17 @@ int cb_set_grad_milestone(cb_ctx* c, void* cuda_event, long long* tail_offset) {
     if (tail_offset) *tail_offset = c->off_dense_b;      // flax order: network Dense_0/bias is the first leaf after the conv stages
     return 0;
 }
+
+int cb_graph_steps(cb_ctx* c, int enable) {
+    CB_CHECK(c, "null argument");
+    CB_CHECK(!enable || c->cfg.train, "cb_graph_steps needs a learner context (train=1)");
+    CB_CUDA(cudaSetDevice(c->cfg.device));
+    if (enable && !c->cap) CB_CUDA(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
+    c->graph_on = enable != 0;
+    return 0;
+}
+
+long long cb_graph_replays(cb_ctx* c) { return c ? c->graph_replays : 0; }
 
 int cb_set_sm_budget(cb_ctx* c, int num_sms) {
     CB_CHECK(c, "null argument");

@@ -55,6 +55,17 @@ struct NatureNet;           // nature.cu
 struct ProfAgg { long long launches = 0, records = 0; double ms = 0, flops = 0, bytes = 0, abytes = 0; };
 struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes, abytes; int launches; };
 
+// One captured gradient step (cb_graph_steps): everything that is baked into the graph is in the key; the per-step pointers
+// are read through cb_ctx::step_dev.
+struct StepGraph {
+    int kind, n, T1, B;                     // 0 = cb_ppo_grad, 1 = cb_impala_grad
+    const float* grads;
+    float c0, c1, c2;
+    void* milestone;
+    cudaGraphExec_t exec = nullptr;         // null: seen once (ran eagerly, warm), captured on the next call
+    long long launches = 0;
+};
+
 struct cb_ctx {
     cb_config cfg;
     bool prof_on = false;
@@ -92,6 +103,13 @@ struct cb_ctx {
     const cb_rollout_cursor* cursor = nullptr;   // set for the duration of a cb_actor_step_cursor call
     cb::NatureNet* nat = nullptr;           // Nature-CNN trunk (cfg.model == CB_MODEL_NATURE)
     int HID = 256;                          // width of the trunk's dense output (256 IMPALA-ResNet, 512 Nature-CNN)
+    bool graph_on = false;                  // cb_graph_steps: cb_*_grad replays a captured CUDA graph
+    bool capturing = false;
+    const cb::StepPtrs* ind = nullptr;      // non-null while a gradient step is being captured (= step_dev)
+    cb::StepPtrs* step_dev = nullptr;
+    cudaStream_t cap = nullptr;             // capture stream of the graphed steps
+    std::vector<StepGraph> graphs;
+    long long graph_replays = 0;
     bool fuse0 = false;
     bool fuse12 = false;                    // second / third ConvSequence: conv + pool (forward) fused                     // first ConvSequence: conv + pool (forward) and pool + wgrad (backward) fused
 };

@@ -170,6 +170,11 @@ template <int HID>
 __global__ void __launch_bounds__(256) k_ppo_head(PpoHeadArgs a) {
     extern __shared__ float sm[];
     const int A = a.num_actions;
+    if (a.ind) {
+        a.idx = static_cast<const int*>(a.ind->p[1]); a.actions = static_cast<const int*>(a.ind->p[2]);
+        a.old_logprobs = static_cast<const float*>(a.ind->p[3]); a.advantages = static_cast<const float*>(a.ind->p[4]);
+        a.returns = static_cast<const float*>(a.ind->p[5]);
+    }
     HeadSmem h = load_head_smem<HID>(sm, a.wa, a.ba, a.wc, a.bc, A);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const float inv_n = 1.f / (float)a.n;
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(256) k_ppo_head(PpoHeadArgs a) {
 
 // stats = mean over samples of the per-sample terms (fixed summation order)
 __global__ void __launch_bounds__(256) k_ppo_stats(const float* __restrict__ terms, int n, float ent_coef, float vf_coef,
-                                                   float* __restrict__ stats) {
+                                                   float* __restrict__ stats, const StepPtrs* __restrict__ ind) {
+    if (ind) stats = static_cast<float*>(const_cast<void*>(ind->p[6]));
     __shared__ float red[4][256];
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int b = threadIdx.x; b < n; b += 256)
@@ -288,7 +294,7 @@ static int launch_ppo_head_t(const PpoHeadArgs& a, cudaStream_t st) {
     if (blocks > 592) blocks = 592;
     k_ppo_head<HID><<<blocks, 256, head_smem_bytes(HID, a.num_actions), st>>>(a);
     CB_LAUNCH_CHECK();
-    k_ppo_stats<<<1, 256, 0, st>>>(a.terms, a.n, a.ent_coef, a.vf_coef, a.stats);
+    k_ppo_stats<<<1, 256, 0, st>>>(a.terms, a.n, a.ent_coef, a.vf_coef, a.stats, a.ind);
     CB_LAUNCH_CHECK();
     return launch_head_wgrad<HID>(a.hidden, a.dlogits, a.n, a.num_actions, a.wgrad_scratch, a.dwa, a.dba, a.dwc, a.dbc, st);
 }
@@ -306,6 +312,12 @@ int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st) {
 template <int HID>
 __global__ void __launch_bounds__(1024) k_impala_head(ImpalaHeadArgs a, int phases) {
     extern __shared__ float sm[];
+    if (a.ind) {
+        a.idx = static_cast<const int*>(a.ind->p[1]); a.actions = static_cast<const int*>(a.ind->p[2]);
+        a.behaviour_logits = static_cast<const float*>(a.ind->p[3]); a.rewards = static_cast<const float*>(a.ind->p[4]);
+        a.dones = static_cast<const uint8_t*>(a.ind->p[5]); a.stats = static_cast<float*>(const_cast<void*>(a.ind->p[6]));
+        a.firststeps = static_cast<const uint8_t*>(a.ind->p[7]);
+    }
     const int A = a.num_actions, T1 = a.T1, B = a.B, T = T1 - 1;
     HeadSmem h = load_head_smem<HID>(sm, a.wa, a.ba, a.wc, a.bc, A);
     float* red = h.ba + A + 1;   // [3][1024]

@@ -5,6 +5,12 @@
 
 namespace cb {
 
+// Per-step pointers of a GRAPHED learner step (cb_graph_steps): the captured kernels read them from this device-side table,
+// which one tiny launch rewrites before every replay, instead of from their (frozen) launch arguments.
+//   p[0] obs  p[1] idx  p[2] actions  p[3] old logprobs | behaviour logits  p[4] advantages | rewards  p[5] returns | dones
+//   p[6] stats  p[7] firststeps
+struct StepPtrs { const void* p[8]; };
+
 struct WgradArgs {
     ConvGeom g;
     Planes x;            // forward input planes of the conv
@@ -18,7 +24,8 @@ struct WgradArgs {
 };
 
 // trunk_simt.cu
-int launch_unpack(const uint8_t* obs, const int* idx, int n, f16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr);
+int launch_unpack(const uint8_t* obs, const int* idx, int n, f16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor = nullptr,
+                  const StepPtrs* ind = nullptr);
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_pool_fwd(Planes in, ConvGeom gi, ConvGeom go, int pad_lo, int chunks, Planes out, Planes out_relu,
                     uint8_t* amax, cudaStream_t st);
@@ -132,6 +139,7 @@ struct PpoHeadArgs {
     float* stats;                // [5] loss, pg_loss, v_loss, entropy, approx_kl
     float* wgrad_scratch;        // [ceil(n/32)][257][A+1] partial head weight gradients
     float *dwa, *dba, *dwc, *dbc;
+    const StepPtrs* ind;         // graphed step: idx / actions / old_logprobs / advantages / returns / stats come from here
 };
 int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st);
 struct ImpalaHeadArgs {
@@ -153,6 +161,7 @@ struct ImpalaHeadArgs {
     float* stats;                // [4] total, pg, baseline, entropy
     float* wgrad_scratch;
     float *dwa, *dba, *dwc, *dbc;
+    const StepPtrs* ind;         // graphed step: the per-step pointers come from here
 };
 int launch_impala_head(const ImpalaHeadArgs& a, cudaStream_t st);
 
@@ -186,6 +195,7 @@ int launch_optimizer(const OptArgs& a, cudaStream_t st);
 int launch_loss_scale(const float* dpre, long long count, unsigned* work, float* gscale, cudaStream_t st);
 int launch_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
 int launch_grad_accumulate(float* acc, const float* g, long long n, int mini_step, cudaStream_t st);
+int launch_set_step_ptrs(StepPtrs* dst, const StepPtrs& v, cudaStream_t st);
 int launch_reduce_peers(const OptArgs& a, float* out, cudaStream_t st);   // needs n, gp, ng only
 
 // pack.cu

@@ -325,6 +325,17 @@ int launch_grad_accumulate(float* acc, const float* g, long long n, int mini_ste
     return 0;
 }
 
+// graphed learner step: publish this step's pointers to the table the captured kernels read (launch arguments are copied at launch
+// time, so the host may reuse `v` at once)
+__global__ void k_set_step_ptrs(StepPtrs* __restrict__ dst, StepPtrs v) {
+    if (threadIdx.x < 8) dst->p[threadIdx.x] = v.p[threadIdx.x];
+}
+int launch_set_step_ptrs(StepPtrs* dst, const StepPtrs& v, cudaStream_t st) {
+    k_set_step_ptrs<<<1, 32, 0, st>>>(dst, v);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
 // out[i] = gp[0][i] + gp[1][i] + ... (fixed order, peer memory): the in-process stage of a two-level gradient exchange
 __global__ void __launch_bounds__(256) k_reduce_peers(OptArgs a, float* __restrict__ out) {
     for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < a.n; i += (long long)gridDim.x * 256 * 4) {

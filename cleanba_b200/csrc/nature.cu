@@ -67,9 +67,11 @@ std::vector<Leaf> nature_leaves(int A) {
 // 8 x-positions of the 4 channels are 4 aligned 8-byte reads; the thread writes the 4 chunks (2 pixels x 4 channels each).
 __global__ void __launch_bounds__(256) k_nat_im2col_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, long long R,
                                                            long long rpad, long long rows_used, f16* __restrict__ out,
-                                                           const cb_rollout_cursor* __restrict__ cursor) {
+                                                           const cb_rollout_cursor* __restrict__ cursor,
+                                                           const StepPtrs* __restrict__ ind) {
     griddep_launch();
     griddep_wait();
+    if (ind) { obs = static_cast<const uint8_t*>(ind->p[0]); idx = static_cast<const int*>(ind->p[1]); }
     if (cursor) obs = reinterpret_cast<const uint8_t*>(cursor->obs) + (long long)cursor->row * cursor->obs_row_stride;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows_used * 8) return;
@@ -312,7 +314,7 @@ int nature_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStr
             const double moved = l == 0 ? (double)n * 28224.0 + (double)Rp * L.K * 2 : (double)Rp * L.K * 4 * 2;
             ProfScope ps(c, name, 0, moved, st, l == 0 ? (double)n * 28224.0 : 4.0 * n * L.Hin * L.Hin * L.Cin);
             if (l == 0) {
-                launch_pdl(k_nat_im2col_frames, dim3(blocks_for(Rp * 8)), dim3(256), 0, st, obs, idx, R, rp, Rp, N->A_hi[0], c->cursor);
+                launch_pdl(k_nat_im2col_frames, dim3(blocks_for(Rp * 8)), dim3(256), 0, st, obs, idx, R, rp, Rp, N->A_hi[0], c->cursor, c->ind);
             } else {
                 launch_pdl(k_nat_im2col, dim3(blocks_for(Rp * (L.K / 8))), dim3(256), 0, st, (const f16*)N->act_hi[l - 1], (const f16*)N->act_mid[l - 1],
                            N->rpad[l - 1], N->A_hi[l], N->A_mid[l], rp, Rp, R, L.KH, L.stride, L.Cin / 8, L.Hin, L.Hout);
@@ -372,7 +374,7 @@ int nature_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             if (launch_gemm_wgrad_umma(w, c->wg_partial, wg_cap, c->num_sms, st)) return -1;
             if (nat_colsum(c, ghi, gmid, rp, R, L.Cout, grads + L.off_b, st)) return -1;
         }
-        if (l == 3 && c->milestone) CB_CUDA(cudaEventRecord(c->milestone, st));   // dense + head gradients are final (the tail of the flat vector)
+        if (l == 3 && c->milestone) CB_CUDA(cudaEventRecordWithFlags(c->milestone, st, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));   // dense + head gradients are final (the tail of the flat vector)
         if (l == 0) break;
         {   // dA = G W^T (im2col space), then col2im + relu gate -> gradient w.r.t. the previous layer's pre-relu output
             GemmArgs g;

@@ -14,9 +14,11 @@ namespace cb {
 // coalesced 4-byte reads, then every thread emits 16-byte pixels (consecutive threads -> consecutive pixels).
 constexpr int UNPACK_ROWS = 8;
 __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict__ obs, const int* __restrict__ idx, int n,
-                                                       f16* __restrict__ out_hi, const cb_rollout_cursor* __restrict__ cursor) {
+                                                       f16* __restrict__ out_hi, const cb_rollout_cursor* __restrict__ cursor,
+                                                       const StepPtrs* __restrict__ ind) {
     griddep_launch();
     griddep_wait();
+    if (ind) { obs = static_cast<const uint8_t*>(ind->p[0]); idx = static_cast<const int*>(ind->p[1]); }
     if (cursor) obs = reinterpret_cast<const uint8_t*>(cursor->obs) + (long long)cursor->row * cursor->obs_row_stride;
     constexpr int H = 84, W = 84, Wp = 86, Hp = 86, GROUPS = (Hp + UNPACK_ROWS - 1) / UNPACK_ROWS;
     const int img = blockIdx.x / GROUPS;
@@ -49,9 +51,10 @@ __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict
     }
 }
 
-int launch_unpack(const uint8_t* obs, const int* idx, int n, f16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor) {
+int launch_unpack(const uint8_t* obs, const int* idx, int n, f16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor,
+                  const StepPtrs* ind) {
     const int groups = (86 + UNPACK_ROWS - 1) / UNPACK_ROWS;
-    launch_pdl(k_unpack_frames, dim3(n * groups), dim3(256), 0, st, obs, idx, n, out_hi, cursor);
+    launch_pdl(k_unpack_frames, dim3(n * groups), dim3(256), 0, st, obs, idx, n, out_hi, cursor, ind);
     CB_LAUNCH_CHECK();
     return 0;
 }

@@ -151,6 +151,15 @@ int cb_optimizer_step_peers(cb_ctx* ctx, const float* const* grads, int num_grad
  * tail on a side stream under the conv backward and only the small head of the vector after the call
  * (`jax.lax.pmean(grads)`, cleanba_ppo.py:628, split in two collectives; every element is still reduced exactly once). */
 int cb_set_grad_milestone(cb_ctx* ctx, void* cuda_event, long long* tail_offset);
+/* CUDA-graph replay of the gradient step.  A cb_ppo_grad / cb_impala_grad call is ~70 kernel launches on two streams; with
+ * graph mode on, the launches of one (shape, `grads` buffer, loss coefficients, milestone) combination are captured into a CUDA
+ * graph the second time the combination is seen and replayed from then on: per call the host enqueues one small launch that
+ * publishes the call's obs / idx / field / stats pointers to a device-side table (the captured frame-unpack and loss-head
+ * kernels read them from there) plus one cudaGraphLaunch.  Results are identical to the un-graphed call.  The reference's
+ * equivalent is the jit/pmap-compiled `update_minibatch` executable (cleanba_ppo.py:621-633, 656-660).  Profiling
+ * (cb_profile) temporarily falls back to plain launches.  cb_graph_replays counts the replays (tests, bench). */
+int cb_graph_steps(cb_ctx* ctx, int enable);
+long long cb_graph_replays(cb_ctx* ctx);
 /* out = grads[0] + ... + grads[n-1] (fixed order, read from peer memory): the in-process stage of the gradient exchange when
  * the learner group ALSO spans processes (`--distributed` with several learner devices per process, cleanba_ppo.py:419-423,628):
  * one replica sums its process' replicas into `out`, ONE NCCL allreduce on `out` follows, and every replica then applies

@@ -710,3 +710,64 @@ def test_forward_config4_minibatch_size(agent, params):
     torch.cuda.synchronize()
     assert bool(torch.isfinite(grads).all()) and bool(torch.isfinite(stats).all())
     ctx.close()
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_graphed_gradient_step_equals_plain_launches(agent, params, model):
+    """cb_graph_steps: the gradient step replayed as a captured CUDA graph (pointers read through the device-side table) gives
+    BIT-identical gradients and loss scalars to the plain launches, with different obs / idx / field / stats pointers on every
+    call, for both algorithms and both trunks; an external milestone event is recorded by every replay."""
+    from oracle import network as onet
+    p = params if model == 0 else onet.init_params(3, onet.nature_param_spec())
+    rng = np.random.default_rng(77)
+    mb, N = 24, 96
+    dev = torch.device("cuda:0")
+    tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    plain = agent.Context("cuda:0", max_batch=mb, train=True, model=model)
+    graphed = agent.Context("cuda:0", max_batch=mb, train=True, model=model)
+    ev = torch.cuda.Event(); ev.record()
+    for c in (plain, graphed):
+        c.set_params(p)
+    graphed.graph_steps(True)
+    graphed.set_grad_milestone(ev)
+    gp, gg = (torch.zeros(plain.num_params, device=dev) for _ in range(2))
+    sp, sg = torch.zeros(6, 5, device=dev), torch.zeros(6, 5, device=dev)
+    l0 = None
+    for k in range(6):
+        obs = tt(_frames(rng, N)); idx = tt(rng.permutation(N)[:mb].astype(np.int32))
+        f = [tt(rng.integers(0, 18, N).astype(np.int32)), tt((np.log(1 / 18) + rng.standard_normal(N) * 0.05).astype(np.float32)),
+             tt(rng.standard_normal(N).astype(np.float32)), tt(rng.standard_normal(N).astype(np.float32))]
+        plain.ppo_grad(obs, idx, mb, *f, 0.1, 0.01, 0.5, gp, sp[k])
+        graphed.ppo_grad(obs, idx, mb, *f, 0.1, 0.01, 0.5, gg, sg[k])
+        torch.cuda.synchronize()
+        assert ev.query()
+        assert torch.equal(gp, gg), (k, float((gp - gg).abs().max()))
+        assert torch.equal(sp[k], sg[k])
+    assert graphed.graph_replays == 5 and plain.graph_replays == 0      # call 0 ran eagerly, call 1 captured + replayed
+    plain.close(); graphed.close()
+    # IMPALA head: the [T1, B] column block moves between calls
+    T1, Bl, B = 5, 8, 4
+    plain = agent.Context("cuda:0", max_batch=T1 * B, algo=1, train=True, model=model)
+    graphed = agent.Context("cuda:0", max_batch=T1 * B, algo=1, train=True, model=model)
+    for c in (plain, graphed):
+        c.set_params(p)
+    graphed.graph_steps(True)
+    sp, sg = torch.zeros(4, 4, device=dev), torch.zeros(4, 4, device=dev)
+    for k in range(4):
+        obs = tt(rng.integers(0, 256, (T1 * Bl, 4, 84, 84), dtype=np.uint8))
+        cols = np.arange(4) + 4 * (k % 2)
+        idx = tt((np.arange(T1)[:, None] * Bl + cols[None, :]).astype(np.int32).ravel())
+        f = [tt(rng.integers(0, 18, T1 * Bl).astype(np.int32)), tt((rng.standard_normal((T1 * Bl, 18)) * 0.3).astype(np.float32)),
+             tt(rng.choice([-1.0, 0.0, 1.0], size=T1 * Bl).astype(np.float32)), tt(rng.random(T1 * Bl) < 0.15), tt(rng.random(T1 * Bl) < 0.15)]
+        plain.impala_grad(obs, idx, T1, B, *f, 0.99, 0.5, 0.01, gp, sp[k])
+        graphed.impala_grad(obs, idx, T1, B, *f, 0.99, 0.5, 0.01, gg, sg[k])
+        torch.cuda.synchronize()
+        assert torch.equal(gp, gg), (k, float((gp - gg).abs().max()))
+        assert torch.equal(sp[k], sg[k])
+    assert graphed.graph_replays == 3
+    # profiling falls back to plain launches and still reports kernels
+    graphed.profile(True)
+    graphed.impala_grad(obs, idx, T1, B, *f, 0.99, 0.5, 0.01, gg, sg[0])
+    assert len(graphed.profile_report()) > 3 and graphed.graph_replays == 3
+    graphed.profile(False)
+    plain.close(); graphed.close()
