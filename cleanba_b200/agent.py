@@ -245,6 +245,10 @@ class Context:
         check(self.lib.cb_set_grad_milestone(self.h, handle, ctypes.byref(off)))
         return int(off.value)
 
+    def set_actor_tail(self, cluster_size: int):
+        """Opt in to the persistent ConvSequence 1+2 kernel (cluster_size 1 | 2; 0 = off); see cb_set_actor_tail."""
+        check(self.lib.cb_set_actor_tail(self.h, int(cluster_size)))
+
     def graph_steps(self, enable: bool = True):
         """Replay ppo_grad / impala_grad as a captured CUDA graph (one small launch + one graph launch per call instead of ~70
         launches); see cb_graph_steps."""

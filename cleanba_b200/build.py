@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcleanba_b200.so")
 SOURCES = ["ctx.cu", "trunk_simt.cu", "conv_umma.cu", "dense.cu", "dense_umma.cu", "heads.cu", "learner_misc.cu", "pack.cu", "gemm_umma.cu",
-           "nature.cu"]
+           "nature.cu", "actor_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

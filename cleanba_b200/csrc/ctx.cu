@@ -215,6 +215,12 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
         ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 86.0 * 86 * 16), st);
         if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st, c->cursor, c->ind)) return -1;
     }
+    // Opt-in (cb_set_actor_tail): ConvSequence 1 and 2 as ONE persistent kernel, one thread-block cluster per frame
+    // (actor_fused.cu).  Bit-identical to the per-layer launches; measured SLOWER at the rollout batch, so off by default.
+    const int tail_cluster = c->actor_tail;
+    const bool tail = tail_cluster > 0 && c->fuse12 && c->cfg.conv_backend == CB_CONV_TCGEN05 && n <= 128 && !c->prof_on;
+    ActorTailHost th;
+    th.n = n;
     for (int s = 0; s < 3; ++s) {
         Stage& S = c->st[s];
         const ConvGeom gi = make_geom(n, kStageHin[s], kStageHin[s]);
@@ -222,6 +228,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
         const int base = s * 5;
         const int C = kStageC[s];
         const bool fused = (s == 0) ? c->fuse0 : c->fuse12;       // sequence conv + max-pool in ONE tcgen05 kernel
+        const bool in_tail = tail && s >= 1;
         if (fused && s == 0) {
             // frame conv + max-pool in one kernel: the 84x84x16 conv output never reaches HBM (conv_umma.cu)
             ConvArgs a = conv_args(c, 0, gi, S.x, false);
@@ -240,7 +247,10 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             ProfScope ps(c, name, 2.0 * n * gi.H * gi.W * 9.0 * a.cin_real * a.cout,
                          planes_bytes(gi, a.cin_chunks, a.in) + 2 * planes_bytes(go, a.cout / 8) + (S.amax ? (double)go.NP * a.cout : 0.0), st,
                          f32_once(gi, a.cin_real) + f32_once(go, a.cout));
-            if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.pl, S.pr.pl, S.amax, S.bits_pr, c->num_sms, st)) return -1;
+            if (in_tail) {
+                th.pool[s - 1] = a; th.pool_go[s - 1] = go; th.pad_lo[s - 1] = kStagePadLo[s];
+                th.pool_out[s - 1] = S.p.pl; th.pool_out_r[s - 1] = S.pr.pl;
+            } else if (launch_conv_pool_umma(a, go, kStagePadLo[s], S.p.pl, S.pr.pl, S.amax, S.bits_pr, c->num_sms, st)) return -1;
         } else {
             // x = nn.Conv(channels)(x)                                          (cleanba_ppo.py:167)
             ConvArgs a = conv_args(c, base + 0, gi, S.x, false);
@@ -258,17 +268,20 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
             ConvArgs a = conv_args(c, base + 1, go, S.pr, false);
             a.ep.bias = c->params + c->conv[base + 1].off_b;
             a.ep.out_r = S.a0.pl; a.ep.bits_out = S.bits_a0;
-            if (run_conv(c, a, st)) return -1;
+            if (in_tail) th.conv[(s - 1) * 4 + 0] = a;
+            else if (run_conv(c, a, st)) return -1;
             ConvArgs b = conv_args(c, base + 2, go, S.a0, false);
             b.ep.bias = c->params + c->conv[base + 2].off_b;
             b.ep.res = S.p.pl; b.ep.out = S.b0.pl; b.ep.out_r = S.b0r.pl; b.ep.bits_out = S.bits_b0r;
-            if (run_conv(c, b, st)) return -1;
+            if (in_tail) th.conv[(s - 1) * 4 + 1] = b;
+            else if (run_conv(c, b, st)) return -1;
         }
         {   // ResidualBlock 1; its output feeds the next ConvSequence un-rectified, or the final nn.relu (cleanba_ppo.py:184)
             ConvArgs a = conv_args(c, base + 3, go, S.b0r, false);
             a.ep.bias = c->params + c->conv[base + 3].off_b;
             a.ep.out_r = S.a1.pl; a.ep.bits_out = S.bits_a1;
-            if (run_conv(c, a, st)) return -1;
+            if (in_tail) th.conv[(s - 1) * 4 + 2] = a;
+            else if (run_conv(c, a, st)) return -1;
             ConvArgs b = conv_args(c, base + 4, go, S.a1, false);
             b.ep.bias = c->params + c->conv[base + 4].off_b;
             b.ep.res = S.b0.pl;
@@ -277,9 +290,11 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
                 b.ep.ft_hi = c->ft[0]; b.ep.ft_mid = c->ft[1]; b.ep.ft_lo = c->ft[2];
                 b.ep.ft_npad = (n + 127) / 128 * 128; b.ep.ft_pixpad = 124;
             }
-            if (run_conv(c, b, st)) return -1;
+            if (in_tail) th.conv[(s - 1) * 4 + 3] = b;
+            else if (run_conv(c, b, st)) return -1;
         }
     }
+    if (tail && launch_actor_tail(th, tail_cluster, c->num_sms, st)) return -1;
     DenseArgs d;
     d.n = n; d.x = c->st[2].out.pl; d.w = c->params + c->off_dense_w; d.b = c->params + c->off_dense_b; d.hidden = c->hidden;
     ProfScope ps(c, "dense_fwd", 2.0 * n * kFlat * HIDDEN, (double)n * kFlat * 6 + (double)kFlat * HIDDEN * 6, st,
@@ -936,6 +951,14 @@ int cb_set_grad_milestone(cb_ctx* c, void* cuda_event, long long* tail_offset) {
     CB_CHECK(c, "null argument");
     c->milestone = (cudaEvent_t)cuda_event;
     if (tail_offset) *tail_offset = c->off_dense_b;      // flax order: network Dense_0/bias is the first leaf after the conv stages
+    return 0;
+}
+
+int cb_set_actor_tail(cb_ctx* c, int cluster_size) {
+    CB_CHECK(c, "null argument");
+    CB_CHECK(cluster_size >= 0 && cluster_size <= 2, "cluster_size must be 0 (off), 1 or 2");
+    CB_CHECK(!cluster_size || (!c->nat && c->cfg.conv_backend == CB_CONV_TCGEN05), "the persistent tail exists for the tcgen05 IMPALA-ResNet trunk only");
+    c->actor_tail = cluster_size;
     return 0;
 }
 

@@ -103,6 +103,7 @@ struct cb_ctx {
     const cb_rollout_cursor* cursor = nullptr;   // set for the duration of a cb_actor_step_cursor call
     cb::NatureNet* nat = nullptr;           // Nature-CNN trunk (cfg.model == CB_MODEL_NATURE)
     int HID = 256;                          // width of the trunk's dense output (256 IMPALA-ResNet, 512 Nature-CNN)
+    int actor_tail = 0;                     // cb_set_actor_tail: cluster size of the persistent ConvSequence 1+2 kernel (0 = per-layer launches)
     bool graph_on = false;                  // cb_graph_steps: cb_*_grad replays a captured CUDA graph
     bool capturing = false;
     const cb::StepPtrs* ind = nullptr;      // non-null while a gradient step is being captured (= step_dev)

@@ -196,6 +196,18 @@ int launch_loss_scale(const float* dpre, long long count, unsigned* work, float*
 int launch_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
 int launch_grad_accumulate(float* acc, const float* g, long long n, int mini_step, cudaStream_t st);
 int launch_set_step_ptrs(StepPtrs* dst, const StepPtrs& v, cudaStream_t st);
+
+// actor_fused.cu: ConvSequence 1 and 2 of the actor's forward pass (ten convs, two pools) in one persistent kernel, one
+// thread-block cluster per frame.  The ConvArgs are exactly what the per-layer launches would get.
+struct ActorTailHost {
+    int n;
+    ConvArgs pool[2];          // the sequence convs (fused with their pools): 16 -> 32 at 42x42, 32 -> 32 at 21x21
+    ConvGeom pool_go[2];       // pooled grids
+    int pad_lo[2];
+    Planes pool_out[2], pool_out_r[2];
+    ConvArgs conv[8];          // residual-block convs, in execution order
+};
+int launch_actor_tail(const ActorTailHost& h, int csize, int num_sms, cudaStream_t st);
 int launch_reduce_peers(const OptArgs& a, float* out, cudaStream_t st);   // needs n, gp, ng only
 
 // pack.cu

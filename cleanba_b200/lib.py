@@ -57,6 +57,7 @@ SIGNATURES = {
     "cb_enable_peer_access": (c_int, [_P, c_int]),
     "cb_set_grad_milestone": (c_int, [_P, _P, POINTER(c_longlong)]),
     "cb_graph_steps": (c_int, [_P, c_int]),
+    "cb_set_actor_tail": (c_int, [_P, c_int]),
     "cb_graph_replays": (c_longlong, [_P]),
     "cb_reduce_peers": (c_int, [_P, POINTER(_P), c_int, _P, _P]),
     "cb_memcpy_2d": (c_int, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _P]),

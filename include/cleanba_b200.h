@@ -159,6 +159,11 @@ int cb_set_grad_milestone(cb_ctx* ctx, void* cuda_event, long long* tail_offset)
  * equivalent is the jit/pmap-compiled `update_minibatch` executable (cleanba_ppo.py:621-633, 656-660).  Profiling
  * (cb_profile) temporarily falls back to plain launches.  cb_graph_replays counts the replays (tests, bench). */
 int cb_graph_steps(cb_ctx* ctx, int enable);
+/* Experimental forward path for small batches (n <= 128): ConvSequence 1 and 2 of Network.__call__ (cleanba_ppo.py:178-189) --
+ * ten convolutions and two max-pools -- run as ONE persistent kernel with one thread-block cluster of `cluster_size` CTAs
+ * (1 | 2) per frame instead of ten launches; 0 restores the per-layer launches.  Results are bit-identical either way.  Off by
+ * default: on B200 the per-layer launches are faster at the rollout batch. */
+int cb_set_actor_tail(cb_ctx* ctx, int cluster_size);
 long long cb_graph_replays(cb_ctx* ctx);
 /* out = grads[0] + ... + grads[n-1] (fixed order, read from peer memory): the in-process stage of the gradient exchange when
  * the learner group ALSO spans processes (`--distributed` with several learner devices per process, cleanba_ppo.py:419-423,628):

@@ -771,3 +771,26 @@ def test_graphed_gradient_step_equals_plain_launches(agent, params, model):
     assert len(graphed.profile_report()) > 3 and graphed.graph_replays == 3
     graphed.profile(False)
     plain.close(); graphed.close()
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("n", [1, 7, 60, 128])
+def test_actor_persistent_tail_equals_per_layer_kernels(agent, params, n, cluster):
+    """cb_set_actor_tail: ConvSequence 1 and 2 as ONE persistent kernel, one thread-block cluster (1 or 2 CTAs) per frame
+    (actor_fused.cu), against the same ten layers as ten launches.  Same packed weights, same MMAs, same epilogues: logits and
+    values must be BIT-identical, for a single frame, a ragged batch, the rollout batch and the largest fused batch."""
+    rng = np.random.default_rng(300 + n)
+    obs = torch.from_numpy(_frames(rng, n)).cuda()
+    actor = agent.Context("cuda:0", max_batch=n, train=False)
+    learner = agent.Context("cuda:0", max_batch=n, train=False)
+    actor.set_actor_tail(cluster)
+    for c in (actor, learner):
+        c.set_params(params)
+    for rep in range(3):                                        # repeated calls: barrier re-initialisation, buffer reuse
+        la, va = actor.policy_value(obs)
+        ll, vl = learner.policy_value(obs)
+        torch.cuda.synchronize()
+        assert torch.equal(la, ll), (rep, float((la - ll).abs().max()))
+        assert torch.equal(va, vl)
+        obs = torch.from_numpy(_frames(rng, n)).cuda()
+    actor.close(); learner.close()

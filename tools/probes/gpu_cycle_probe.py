@@ -30,7 +30,7 @@ def rollout(nthreads=2, e2e=False):
         g.stream.wait_stream(main)
         c = slice(th * bench.N_ENVS, (th + 1) * bench.N_ENVS)
         g.begin(cyc.obs[:, c], cyc.actions[:, c], cyc.logprobs[:, c], cyc.values[:, c])
-    for t in range(bench.T_STEPS):
+    for t in range(bench.WORKLOADS["ppo"]["T"]):
         for th, g in enumerate(gs):
             c = slice(th * bench.N_ENVS, (th + 1) * bench.N_ENVS)
             g.step(pool[cyc.cursor % 256], t)
@@ -71,7 +71,7 @@ def gae_part():
     c.gae(cyc.rew_pool[0], cyc.values, cyc.done_pool[0], nv, cyc.next_done, 0.99, 0.95, 4)
     for _ in range(4):
         sub = c.split_key(cyc.lkey)
-        c.permutation(sub, bench.T_STEPS * cyc.Bl)
+        c.permutation(sub, bench.WORKLOADS["ppo"]["T"] * cyc.Bl)
 
 
 for name, fn in [("rollout 2 threads (256 steps into storage rows)", rollout),

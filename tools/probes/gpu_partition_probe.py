@@ -31,7 +31,7 @@ if use_part:
 else:
     s_learn = torch.cuda.Stream(dev)
     a_streams = [torch.cuda.Stream(dev, priority=-1) for _ in range(bench.N_THREADS)]
-N, T, Bl = bench.N_ENVS, bench.T_STEPS, cyc.Bl
+N, T, Bl = bench.N_ENVS, bench.WORKLOADS["ppo"]["T"], cyc.Bl
 actors, graphed = [], []
 for th in range(bench.N_THREADS):
     a = ag.Context(dev, max_batch=N, train=False)
