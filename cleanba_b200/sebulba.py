@@ -303,6 +303,8 @@ def train(args: Args, backend, make_env: Callable, writer=None, allreduce=None, 
         if first_update >= args.num_updates:
             raise ValueError(f"--resume-from: the saved run already finished {first_update} of {args.num_updates} updates "
                              "(raise --total-timesteps to continue it)")
+        # the actor threads continue from the saved (advanced) key instead of replaying the first run's random stream
+        key = np.asarray(st["key"], dtype=np.uint32).reshape(2).copy()
     args._resume = (first_update, first_step)
     params_queues, rollout_queues, threads = [], [], []
     stop = threading.Event()
