@@ -35,10 +35,10 @@ constexpr uint32_t AT_TMEM_COLS = 128;           // two accumulators of 64 colum
 __host__ __device__ constexpr int at_steps(int cin_chunks) { return 9 * (cin_chunks / 2); }
 __host__ __device__ constexpr int at_wbytes(int cin_chunks) { return at_steps(cin_chunks) * 2 * 2 * AT_COUT * 16; }
 constexpr int AT_WSLOT = at_wbytes(4);                                   // 36,864 bytes: one packed 32 -> 32 weight image
-constexpr int AT_STAGE_SLOT = 8 * (AT_TILE_M + 2 * 23 + 2) * 16;         // 22,528 bytes: 8 planes of a 21x21 window (the largest)
+constexpr int AT_STAGE_SLOT = 8 * (AT_TILE_M + 2 * 22 + 2) * 16;         // 22,272 bytes: 8 planes of a 21x21 window (the largest)
 constexpr int AT_BAND = 2 * AT_TILE_M * AT_COUT * 4;                     // 32,768 bytes: two tiles of fp32 conv outputs
 constexpr int AT_SMEM = 1024 + 2 * AT_WSLOT + AT_NST * AT_STAGE_SLOT + AT_BAND;
-static_assert(4 * (AT_TILE_M + 2 * 44 + 2) * 16 <= AT_STAGE_SLOT, "the 42x42 window (4 planes) fits a stage slot");
+static_assert(4 * (AT_TILE_M + 2 * 43 + 2) * 16 <= AT_STAGE_SLOT, "the 42x42 window (4 planes) fits a stage slot");
 static_assert(AT_SMEM <= 227 * 1024, "shared memory");
 
 struct AtBars {                      // first 1 KB of shared memory
@@ -310,17 +310,15 @@ __device__ __forceinline__ void tail_conv_pool(const TailPool& a, int img, uint3
                 }
                 emit(b * CP_K + r + 1, j + 1, jc, v);
             }
-            const int nside = kb * 2 * NCH;
-            const int ntop = (b == 0) ? Wpo * NCH : 0, nbot = (b == a.bands_per_img - 1) ? Wpo * NCH : 0;
-            for (int it = etid; it < nside + ntop + nbot; it += 256) {
+            // shared borders (common.cuh): the zero pixel that starts each of this band's rows, plus the row above the image
+            const int nside = kb * NCH;
+            const int ntop = (b == 0) ? Wpo * NCH : 0;
+            for (int it = etid; it < nside + ntop; it += 256) {
                 if (it < nside) {
-                    emit_zero(b * CP_K + it / (2 * NCH) + 1, ((it / NCH) & 1) ? Wpo - 1 : 0, it % NCH);
-                } else if (it < nside + ntop) {
+                    emit_zero(b * CP_K + it / NCH + 1, 0, it % NCH);
+                } else {
                     const int k = it - nside;
                     emit_zero(0, k % Wpo, k / Wpo);
-                } else {
-                    const int k = it - nside - ntop;
-                    emit_zero(Ho + 1, k % Wpo, k / Wpo);
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");       // band buffer free for the next band

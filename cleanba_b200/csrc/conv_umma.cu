@@ -249,14 +249,14 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
 // write what the separate pool kernel wrote: the fp32 stream, the relu'd 3-way split planes and the arg-max bytes of the
 // pooled 44x44 padded grid (borders zero).  The TMA producer and the MMA issuer run ahead of the pooling by the two
 // TMEM accumulators.  HBM traffic per frame: 118 KB in + 340 KB out instead of 1.4 MB through the two kernels.
-constexpr int C0_HP = 86, C0_P = C0_HP * C0_HP, C0_HO = 42, C0_WPO = 44, C0_PO = C0_WPO * C0_WPO;
+constexpr int C0_HP = 85, C0_P = C0_HP * C0_HP, C0_HO = 42, C0_WPO = 43, C0_PO = C0_WPO * C0_WPO;   // shared borders (common.cuh)
 constexpr int C0_BAND_K = 3;                                   // pooled rows per band
 constexpr int C0_BANDS = C0_HO / C0_BAND_K;                    // 14 bands per frame
-constexpr int C0_BAND_TILES = 5;                               // ceil(7 * 86 / 128)
+constexpr int C0_BAND_TILES = 5;                               // ceil(7 * 85 / 128)
 constexpr int C0_BAND_PX = C0_BAND_TILES * TILE_M;             // 640 pixels in the band buffer
 constexpr int C0_COUT = 16;
 constexpr int C0_STAGES = 8;
-constexpr int C0_WIN = TILE_M + 2 * C0_HP + 3;                 // 303 pixels per input window (see conv_smem_layout)
+constexpr int C0_WIN = TILE_M + 2 * C0_HP + 3;                 // 301 pixels per input window (see conv_smem_layout)
 constexpr int C0_STAGE_BYTES = C0_WIN * 16;
 constexpr int C0_W_BYTES = conv_wbytes(1, C0_COUT);
 constexpr int C0_BAND_BYTES = C0_BAND_PX * C0_COUT * 4;
@@ -456,11 +456,12 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv0_pool_umma(Conv0PoolArgs 
                 }
                 emit(img, C0_BAND_K * b + r + 1, j + 1, jc, v, am);
             } else {
-                for (int k = etid - C0_BAND_K * C0_HO * 2; k < C0_BAND_K * 4; k += 4)      // (row, left | right, chunk)
-                    emit_zero(img, C0_BAND_K * b + (k >> 2) + 1, (k & 2) ? C0_WPO - 1 : 0, k & 1);
+                // shared borders: the zero pixel that starts each of these rows (= the right border of the row above) ...
+                for (int k = etid - C0_BAND_K * C0_HO * 2; k < C0_BAND_K * 2; k += 4)      // (row, chunk)
+                    emit_zero(img, C0_BAND_K * b + (k >> 1) + 1, 0, k & 1);
             }
-            if ((b == 0 || b == C0_BANDS - 1) && etid < 2 * C0_WPO)
-                emit_zero(img, b == 0 ? 0 : C0_WPO - 1, etid % C0_WPO, etid / C0_WPO);
+            if (b == 0 && etid < 2 * C0_WPO)                                               // ... and the zero row above the image
+                emit_zero(img, 0, etid % C0_WPO, etid / C0_WPO);
             asm volatile("bar.sync 1, 256;" ::: "memory");       // band buffer free for the next band
         }
     }
@@ -739,18 +740,16 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
                 }
                 emit(img, b * CP_K + r + 1, j + 1, jc, v, am);
             }
-            // zero border of the pooled grid: left / right pixels of this band's rows, plus the top / bottom row of the image
-            const int nside = kb * 2 * NCH;
-            const int ntop = (b == 0) ? Wpo * NCH : 0, nbot = (b == a.bands_per_img - 1) ? Wpo * NCH : 0;
-            for (int it = etid; it < nside + ntop + nbot; it += 256) {
+            // zero border of the pooled grid (shared borders, common.cuh): the pixel that starts each of this band's rows, plus
+            // the row above the image
+            const int nside = kb * NCH;
+            const int ntop = (b == 0) ? Wpo * NCH : 0;
+            for (int it = etid; it < nside + ntop; it += 256) {
                 if (it < nside) {
-                    emit_zero(img, b * CP_K + it / (2 * NCH) + 1, ((it / NCH) & 1) ? Wpo - 1 : 0, it % NCH);
-                } else if (it < nside + ntop) {
+                    emit_zero(img, b * CP_K + it / NCH + 1, 0, it % NCH);
+                } else {
                     const int k = it - nside;
                     emit_zero(img, 0, k % Wpo, k / Wpo);
-                } else {
-                    const int k = it - nside - ntop;
-                    emit_zero(img, Ho + 1, k % Wpo, k / Wpo);
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");       // band buffer free for the next band

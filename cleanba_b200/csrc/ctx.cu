@@ -86,7 +86,7 @@ int dev_alloc(cb_ctx* c, void** p, size_t bytes, bool zero) {
 }
 
 static long long plane_px_for(int max_batch, int H) {
-    long long np = (long long)max_batch * (H + 2) * (H + 2);
+    long long np = (long long)max_batch * (H + 1) * (H + 1) + (H + 3);      // + the zero row after the last image
     np = (np + 127) / 128 * 128;
     return GUARD + np + GUARD;
 }
@@ -121,7 +121,7 @@ static int refresh_weights(cb_ctx* c, cudaStream_t st) {
 static DenseUmmaArgs dense_umma_args(cb_ctx* c, int n) {
     DenseUmmaArgs u;
     memset(&u, 0, sizeof(u));
-    u.n = n; u.npad = (n + 127) / 128 * 128; u.NP = (long long)n * 169;
+    u.n = n; u.npad = (n + 127) / 128 * 128; u.NP = (long long)n * 144;
     u.ft_hi = c->ft[0]; u.ft_mid = c->ft[1]; u.ft_lo = c->ft[2];
     u.dp_hi = c->dpT[0]; u.dp_mid = c->dpT[1];
     u.w_fwd = c->wd_fwd; u.w_dx = c->wd_dx;
@@ -200,10 +200,20 @@ static int run_wgrad(cb_ctx* c, int layer, const ConvGeom& g, const Act& x, cons
     return launch_wgrad_umma(w, c->wg_partial, c->num_sms, st);
 }
 
+// The zero row after the last image of a batch of n (common.cuh) is dirty whenever a larger batch went through the context's
+// buffers since the last batch of n: clear it before any kernel of a batch of a different size reads it.
+static int clear_trailing_rows(cb_ctx* c, int n, cudaStream_t st) {
+    if (c->clean_n == n || !c->trail_count) return 0;
+    if (launch_clear_trailing_rows(c->trail_dev, c->trail_count, n, st)) return -1;
+    c->clean_n = n;
+    return 0;
+}
+
 // Network.__call__ (cleanba_ppo.py:178-189) on n frames -> c->hidden [n,256]
 static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, cudaStream_t st) {
     CB_CHECK(n > 0 && n <= c->cfg.max_batch, "batch %d outside (0, max_batch=%d]", n, c->cfg.max_batch);
     c->last_n = n;
+    if (!c->capturing && clear_trailing_rows(c, n, st)) return -1;
     if (c->nat) {
         static const int nat_pdl_max = [] { const char* e = getenv("CLEANBA_PDL_MAX_BATCH"); return e ? atoi(e) : 1024; }();
         g_pdl_scope = n <= nat_pdl_max;
@@ -212,7 +222,7 @@ static int trunk_forward(cb_ctx* c, const uint8_t* obs, const int* idx, int n, c
     static const int pdl_max = [] { const char* e = getenv("CLEANBA_PDL_MAX_BATCH"); return e ? atoi(e) : 1024; }();
     g_pdl_scope = n <= pdl_max;
     {
-        ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 86.0 * 86 * 16), st);
+        ProfScope ps(c, "unpack_frames", 0, (double)n * (28224.0 + 85.0 * 85 * 16), st);
         if (launch_unpack(obs, idx, n, c->st[0].x.pl.hi, st, c->cursor, c->ind)) return -1;
     }
     // Opt-in (cb_set_actor_tail): ConvSequence 1 and 2 as ONE persistent kernel, one thread-block cluster per frame
@@ -371,7 +381,7 @@ static int trunk_backward(cb_ctx* c, int n, float* grads, cudaStream_t st) {
             // frames need no dX: the pooled gradient goes straight into the frame conv's weight gradient (trunk_simt.cu)
             if (fork_side(c, st)) return -1;
             cudaStream_t ws = side_active(c) ? c->side : st;
-            ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1936.0 * (16 + 64) + 7396.0 * 16), ws,
+            ProfScope ps(c, "pool_bwd_wgrad0@84", 2.0 * n * 42 * 42 * 16 * 36, (double)n * (1849.0 * (16 + 64) + 7225.0 * 16), ws,
                          f32_once(go, 16) + (double)n * 28224.0);
             if (launch_pool_bwd_wgrad0(S.amax, S.gA.pl, S.x.pl.hi, gi, go, 1.0f / 255.0f, c->gscale + 1, grads + c->conv[0].off_w,
                                        grads + c->conv[0].off_b, c->wg_partial, c->num_sms, ws)) return -1;
@@ -412,6 +422,7 @@ static int graphed_step(cb_ctx* c, const StepGraph& key, const StepPtrs& ptrs, c
         return body(st);
     }
     if (launch_set_step_ptrs(c->step_dev, ptrs, st)) return -1;
+    if (clear_trailing_rows(c, key.n, st)) return -1;      // the replayed trunk_forward cannot do it
     if (!g->exec) {
         // captured on a private stream (the caller's may be the legacy default stream, which cannot capture); replayed on `st`
         CB_CUDA(cudaStreamBeginCapture(c->cap, cudaStreamCaptureModeThreadLocal));
@@ -614,11 +625,11 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             if (s < 2 && !fail) c->st[s + 1].x = S.out;
             if (cfg->train) {
                 void* ap;
-                if (dev_alloc(c, &ap, (size_t)cfg->max_batch * (Ho + 2) * (Ho + 2) * C)) { fail = true; break; }
+                if (dev_alloc(c, &ap, (size_t)cfg->max_batch * (Ho + 1) * (Ho + 1) * C)) { fail = true; break; }
                 S.amax = (uint8_t*)ap;
                 static const bool bits_on = [] { const char* e = getenv("CLEANBA_GATE_BITS"); return !e || atoi(e) != 0; }();
                 if (bits_on && cfg->conv_backend == CB_CONV_TCGEN05) {      // relu gates as bits: [pixels to the tile boundary][C / 8] bytes
-                    const size_t nb = (size_t)((((long long)cfg->max_batch * (Ho + 2) * (Ho + 2) + 127) / 128) * 128) * (C / 8);
+                    const size_t nb = (size_t)((((long long)cfg->max_batch * (Ho + 1) * (Ho + 1) + 127) / 128) * 128) * (C / 8);
                     uint8_t** dst[4] = {&S.bits_a0, &S.bits_b0r, &S.bits_a1, fused ? &S.bits_pr : nullptr};
                     for (auto d : dst) {
                         if (!d) continue;
@@ -633,6 +644,27 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
             }
         }
         if (fail) break;
+        if (!nature) {      // table of every activation / gradient plane for clear_trailing_rows
+            std::vector<TrailRow> rows;
+            for (int s = 0; s < 3; ++s) {
+                Stage& S = c->st[s];
+                const Act* acts[] = {s == 0 ? &S.x : nullptr, &S.y, &S.p, &S.pr, &S.a0, &S.b0, &S.b0r, &S.a1, &S.out, &S.gA, &S.gB, &S.gC, &S.gBin};
+                for (const Act* a : acts) {
+                    if (!a || !a->pl.hi) continue;
+                    const ConvGeom g = make_geom(1, a->H, a->H);
+                    for (int j = 0; j < (a->C + 7) / 8; ++j)
+                        for (f16* base : {a->pl.hi, a->pl.mid})
+                            if (base) rows.push_back(TrailRow{base + (long long)j * a->pl.plane_px * 8, g.P, g.Wp});
+                }
+            }
+            if (dev_alloc(c, &p, rows.size() * sizeof(TrailRow))) break;
+            c->trail_dev = (TrailRow*)p;
+            c->trail_count = (int)rows.size();
+            if (cudaMemcpy(c->trail_dev, rows.data(), rows.size() * sizeof(TrailRow), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("cudaMemcpy(trailing-row table) failed");
+                break;
+            }
+        }
         const size_t mb = (size_t)cfg->max_batch;
         if (!nature && cfg->conv_backend == CB_CONV_TCGEN05 && !getenv("CLEANBA_DENSE_SIMT")) {
             c->npad_max = (cfg->max_batch + 127) / 128 * 128;
@@ -1106,7 +1138,7 @@ long long cb_debug_tensor(cb_ctx* c, const char* name, float* host_out, long lon
         unscale = gs[1];                                  // gradient tensors carry the loss scale
     }
     CB_CHECK(a && a->pl.hi != nullptr, "tensor %s not available", name);
-    const int H = a->H, C = a->C, Hp = H + 2, P = Hp * Hp, chunks = (C + 7) / 8;
+    const int H = a->H, C = a->C, Hp = H + 1, P = Hp * Hp, chunks = (C + 7) / 8;
     const long long NP = (long long)n * P;
     const long long cnt = (long long)n * H * H * C;
     CB_CHECK(cnt <= cap, "buffer too small (%lld > %lld)", cnt, cap);

@@ -92,6 +92,9 @@ struct cb_ctx {
     int perm_cap = 0;
     long long wg_cap = 0;                   // floats in wg_partial
     int last_n = 0;
+    int clean_n = -1;                       // batch size whose trailing zero row is known to be clear (shared-border layout)
+    cb::TrailRow* trail_dev = nullptr;      // every plane of every activation / gradient tensor
+    int trail_count = 0;
     // tcgen05 dense layer (dense_umma.cu)
     cb::bf16 *ft[3] = {nullptr, nullptr, nullptr}, *dpT[2] = {nullptr, nullptr}, *wd_fwd = nullptr, *wd_dx = nullptr;
     int npad_max = 0;

@@ -6,7 +6,7 @@
 
 namespace cb {
 
-constexpr int FH = 11, FW = 11, FC = 32, FP = 13 * 13, FWp = 13;   // final feature map
+constexpr int FH = 11, FW = 11, FC = 32, FP = 12 * 12, FWp = 12;   // final feature map (shared borders, common.cuh)
 constexpr int DK = FH * FW * FC;                                    // 3872
 constexpr int TM = 64, TN = 64, TK = 32, LDS_ = 68;
 

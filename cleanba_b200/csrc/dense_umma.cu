@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(DN_THREADS) k_dense_dx_umma(DenseUmmaArgs a, i
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (b < a.n) {
                 const int h = p / 11, w = p - h * 11;
-                const long long q = (long long)b * 169 + (h + 1) * 13 + (w + 1);
+                const long long q = (long long)b * 144 + (h + 1) * 12 + (w + 1);      // 11x11 map, shared borders (common.cuh)
 #pragma unroll
                 for (int jc = 0; jc < DN_CH; ++jc) {
                     // relu gate of the forward feature (hi plane of the sample-minor copy), loss scale, carrier split

@@ -49,7 +49,7 @@ int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out
 // dense.cu
 struct DenseArgs {
     int n;                       // samples
-    Planes x;                    // final feature planes (relu'd), 4 chunks on the 13x13 padded grid
+    Planes x;                    // final feature planes (relu'd), 4 chunks on the 12x12 padded grid (shared borders)
     const float* w;              // [3872][256] fp32 master (k = (h*11+w)*32 + c)
     const float* b;              // [256]
     float* hidden;               // [n][256]  relu(x W + b)
@@ -64,7 +64,7 @@ int launch_dense_bwd_x(const DenseArgs& a, const float* dpre, const float* gscal
 // dense_umma.cu (tcgen05 dense layer on the sample-minor copies)
 struct DenseUmmaArgs {
     int n, npad;                 // samples, samples rounded up to 128
-    long long NP;                // n * 169 (flat pixels of the 11x11 grid with its padding ring)
+    long long NP;                // n * 144 (flat pixels of the 11x11 grid with its shared zero borders)
     const bf16 *ft_hi, *ft_mid, *ft_lo;   // featT[chunk 4][pixel 124][npad][8]
     const bf16 *dp_hi, *dp_mid;           // dpreT[256/8][npad][8]
     const bf16 *w_fwd, *w_dx;             // packed weights (k_pack_dense)
@@ -196,6 +196,8 @@ int launch_loss_scale(const float* dpre, long long count, unsigned* work, float*
 int launch_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
 int launch_grad_accumulate(float* acc, const float* g, long long n, int mini_step, cudaStream_t st);
 int launch_set_step_ptrs(StepPtrs* dst, const StepPtrs& v, cudaStream_t st);
+struct TrailRow { f16* base; int P, Wp; };      // one 8-channel plane (flat pixel 0), pixels per image, row length
+int launch_clear_trailing_rows(const TrailRow* rows, int count, int n, cudaStream_t st);
 
 // actor_fused.cu: ConvSequence 1 and 2 of the actor's forward pass (ten convs, two pools) in one persistent kernel, one
 // thread-block cluster per frame.  The ConvArgs are exactly what the per-layer launches would get.

@@ -325,6 +325,20 @@ int launch_grad_accumulate(float* acc, const float* g, long long n, int mini_ste
     return 0;
 }
 
+// Shared-border layout (common.cuh): the zero row AFTER the last image of a batch of n is the first row of image n in a
+// larger batch, so it holds stale data whenever the context has seen a larger batch.  One block per plane clears it.
+__global__ void __launch_bounds__(128) k_clear_trailing_rows(const TrailRow* __restrict__ rows, int n) {
+    const TrailRow r = rows[blockIdx.x];
+    uint4* dst = reinterpret_cast<uint4*>(r.base + ((long long)n * r.P) * 8);
+    for (int i = threadIdx.x; i < r.Wp + 1; i += blockDim.x) dst[i] = make_uint4(0, 0, 0, 0);
+}
+int launch_clear_trailing_rows(const TrailRow* rows, int count, int n, cudaStream_t st) {
+    if (count <= 0) return 0;
+    k_clear_trailing_rows<<<count, 128, 0, st>>>(rows, n);
+    CB_LAUNCH_CHECK();
+    return 0;
+}
+
 // graphed learner step: publish this step's pointers to the table the captured kernels read (launch arguments are copied at launch
 // time, so the host may reuse `v` at once)
 __global__ void k_set_step_ptrs(StepPtrs* __restrict__ dst, StepPtrs v) {

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict
     griddep_wait();
     if (ind) { obs = static_cast<const uint8_t*>(ind->p[0]); idx = static_cast<const int*>(ind->p[1]); }
     if (cursor) obs = reinterpret_cast<const uint8_t*>(cursor->obs) + (long long)cursor->row * cursor->obs_row_stride;
-    constexpr int H = 84, W = 84, Wp = 86, Hp = 86, GROUPS = (Hp + UNPACK_ROWS - 1) / UNPACK_ROWS;
+    constexpr int H = 84, W = 84, Wp = 85, Hp = 85, GROUPS = (Hp + UNPACK_ROWS - 1) / UNPACK_ROWS;   // shared borders (common.cuh)
     const int img = blockIdx.x / GROUPS;
     const int yp0 = (blockIdx.x % GROUPS) * UNPACK_ROWS;
     __shared__ uint32_t srow[UNPACK_ROWS][4][W / 4];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_unpack_frames(const uint8_t* __restrict
 
 int launch_unpack(const uint8_t* obs, const int* idx, int n, f16* out_hi, cudaStream_t st, const cb_rollout_cursor* cursor,
                   const StepPtrs* ind) {
-    const int groups = (86 + UNPACK_ROWS - 1) / UNPACK_ROWS;
+    const int groups = (85 + UNPACK_ROWS - 1) / UNPACK_ROWS;
     launch_pdl(k_unpack_frames, dim3(n * groups), dim3(256), 0, st, obs, idx, n, out_hi, cursor, ind);
     CB_LAUNCH_CHECK();
     return 0;
@@ -258,12 +258,13 @@ int launch_pool_bwd(const uint8_t* amax, Planes dpool, ConvGeom gi, ConvGeom go,
 // (8 bytes per pixel); a half-warp of 16 threads owns one pooled pixel (thread = output channel, 36 + 1 accumulators that
 // live across all images of the block).  One partial per block, reduced in a fixed order by k_partial_reduce.
 constexpr int PW0_THREADS = 256;
-constexpr int PW0_HP = 86, PW0_P = PW0_HP * PW0_HP, PW0_HO = 42, PW0_WPO = 44, PW0_PO = PW0_WPO * PW0_WPO;
+constexpr int PW0_HP = 85, PW0_P = PW0_HP * PW0_HP, PW0_HO = 42, PW0_WPO = 43, PW0_PO = PW0_WPO * PW0_WPO;   // shared borders (common.cuh)
 constexpr int PW0_OUT = 37 * 16;      // 36 (tap, ci) x 16 co weight gradients + 16 bias gradients per partial
 constexpr int PW0_RB = 3;                                   // pooled rows per staged band
 constexpr int PW0_BANDS = PW0_HO / PW0_RB;                  // 14 bands per image
 constexpr int PW0_BPIX = PW0_RB * PW0_HO;                   // 126 pooled pixels per band
-constexpr int PW0_FRAME = PW0_P * 8;                        // the staged frame (4 fp16 channels per pixel)
+constexpr int PW0_STAGED = PW0_P + PW0_HP + 1;               // the frame plus the zero row / pixel that follow it (taps of the last row)
+constexpr int PW0_FRAME = (PW0_STAGED + 1) / 2 * 2 * 8;       // the staged frame (4 fp16 channels per pixel), 16-byte multiple
 constexpr int PW0_SMEM = PW0_FRAME + PW0_BPIX * 16 * 4 + PW0_BPIX * 16;   // + band gradients (fp32) + band arg-max bytes
 static_assert(PW0_HO % PW0_RB == 0 && PW0_BPIX * 2 <= PW0_THREADS, "one staging item (pixel, chunk) per thread");
 
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(PW0_THREADS, 3) k_pool_bwd_wgrad0(const uint8_
         __syncthreads();                                    // the previous band (and frame) is no longer read
         if (band == 0) {
             const uint4* src = reinterpret_cast<const uint4*>(x_hi + (long long)img * PW0_P * 8);
-            for (int q = threadIdx.x; q < PW0_P; q += PW0_THREADS) {
+            for (int q = threadIdx.x; q < PW0_STAGED; q += PW0_THREADS) {
                 const uint4 v = src[q];
                 sx[q] = make_uint2(v.x, v.y);
             }

@@ -794,3 +794,47 @@ def test_actor_persistent_tail_equals_per_layer_kernels(agent, params, n, cluste
         assert torch.equal(va, vl)
         obs = torch.from_numpy(_frames(rng, n)).cuda()
     actor.close(); learner.close()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_shared_border_layout_survives_batch_size_changes(agent, params, graph):
+    """Shared-border plane layout (csrc/common.cuh): the zero row after the last image of a batch of n is the first row of
+    image n of a larger batch, so a context that alternates batch sizes must clear it (ctx.cu clear_trailing_rows) -- also
+    when the larger batch ran as a graph replay.  Small batches computed in a context that keeps running larger ones must be
+    BIT-identical to the same batches in a fresh context: logits / values and the full PPO gradient."""
+    rng = np.random.default_rng(91)
+    dev = torch.device("cuda:0")
+    tt = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    big, small = 40, 7
+    used = agent.Context("cuda:0", max_batch=big, train=True)
+    used.set_params(params)
+    if graph:
+        used.graph_steps(True)
+
+    def batch(n):
+        return dict(obs=tt(_frames(rng, n)), idx=tt(rng.permutation(n).astype(np.int32)), act=tt(rng.integers(0, 18, n).astype(np.int32)),
+                    lp=tt(np.full(n, np.log(1 / 18), np.float32)), adv=tt(rng.standard_normal(n).astype(np.float32)),
+                    ret=tt(rng.standard_normal(n).astype(np.float32)))
+
+    def grad(c, b, n):
+        g = torch.zeros(c.num_params, device=dev); s = torch.zeros(5, device=dev)
+        c.ppo_grad(b["obs"], b["idx"], n, b["act"], b["lp"], b["adv"], b["ret"], 0.1, 0.01, 0.5, g, s)
+        return g, s
+
+    gbuf = torch.zeros(used.num_params, device=dev); sbuf = torch.zeros(5, device=dev)
+    for rep in range(3):
+        for _ in range(3):                                  # larger batches fill every plane (the third one replays a graph)
+            b = batch(big)
+            used.ppo_grad(b["obs"], b["idx"], big, b["act"], b["lp"], b["adv"], b["ret"], 0.1, 0.01, 0.5, gbuf, sbuf)
+        b = batch(small)
+        fresh = agent.Context("cuda:0", max_batch=small, train=True)
+        fresh.set_params(params)
+        lu, vu = used.policy_value(b["obs"]); lf, vf = fresh.policy_value(b["obs"])
+        assert torch.equal(lu, lf) and torch.equal(vu, vf), rep
+        gu, su = grad(used, b, small); gf, sf = grad(fresh, b, small)
+        assert torch.equal(gu, gf), (rep, float((gu - gf).abs().max()))
+        assert torch.equal(su, sf)
+        fresh.close()
+    if graph:
+        assert used.graph_replays >= 4
+    used.close()
