@@ -498,10 +498,11 @@ int launch_conv0_pool_umma(const ConvArgs& a, Planes out, Planes out_r, uint8_t*
 // the MMAs of the next band overlap the pooling of this one.  The last band of an image may be shorter (21 = 4*5 + 1,
 // 11 = 2*5 + 1).  pad_lo = 0 (42 -> 21: windows 2i .. 2i+2) or 1 (21 -> 11: windows 2i-1 .. 2i+1), clipped to the image.
 // Band shapes (template parameters K = pooled rows per band, MAXT = tiles per band):
-//   42x42 (Wp = 44): K = 2 -> 5 conv rows = 220 px = 2 tiles; 2 accumulators = 256 TMEM columns and ~100 KB of shared memory,
-//                    so TWO CTAs (16 epilogue warps, two MMA issuers) share an SM -- with K = 5 (4 tiles, 512 columns, one CTA per
-//                    SM) the 8 epilogue warps were the bottleneck (0.78 ms vs 0.83 ms unfused);
-//   21x21 (Wp = 23): K = 5 -> 11 conv rows = 253 px = 2 tiles, one CTA per SM (the 55 KB weight image leaves no room for two).
+//   42x42 (Wp = 43): K = 3 -> 7 conv rows = 301 px = 3 tiles; 3 accumulators = 256 TMEM columns and ~95 KB of shared memory, so
+//                    TWO CTAs (16 epilogue warps, two MMA issuers) share an SM; 7 bands x 7 rows = 49 conv rows per image for 43
+//                    needed (K = 2: 11 x 5 = 55; measured 0.516 -> 0.428 ms per 3840 frames).  With K = 5 (4 tiles, 512 columns,
+//                    one CTA per SM) the 8 epilogue warps were the bottleneck;
+//   21x21 (Wp = 22): K = 5 -> 11 conv rows = 242 px = 2 tiles, one CTA per SM (the 37 KB weight image + 8-plane stages leave no room for two).
 constexpr int CP_COUT = 32;
 constexpr int CP_ACC_COLS = 2 * CP_COUT;
 
@@ -767,6 +768,12 @@ static int launch_conv_pool_umma_t(ConvPoolArgs p, int num_sms, cudaStream_t st)
     CB_CHECK(((2 * CP_K + 1) * p.gi.Wp + TILE_M - 1) / TILE_M <= CP_MAXT, "conv_pool_umma: band of %d rows x %d does not fit %d tiles",
              2 * CP_K + 1, p.gi.Wp, CP_MAXT);
     p.bands_per_img = (p.go.H + CP_K - 1) / CP_K;
+    {   // the last band's windows may run past the last image: they must stay inside the back guard
+        const int bl = p.bands_per_img - 1, kbl = p.go.H - bl * CP_K;
+        const int ntl = ((2 * kbl + 1) * p.gi.Wp + TILE_M - 1) / TILE_M;
+        const int over = (2 * bl * CP_K - p.pad_lo + 1) * p.gi.Wp + ntl * TILE_M + p.gi.Wp + 1 - p.gi.P;
+        CB_CHECK(over <= GUARD, "conv_pool_umma: the last band reads %d pixels past the image (guard %d)", over, GUARD);
+    }
     static std::atomic<unsigned> attr_done{0};
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
@@ -786,11 +793,13 @@ int launch_conv_pool_umma(const ConvArgs& a, ConvGeom go, int pad_lo, Planes out
                           cudaStream_t st) {
     CB_CHECK(a.cout == CP_COUT && !a.transpose && a.in.mid && (a.cin_chunks == 2 || a.cin_chunks == 4),
              "conv_pool_umma: 16|32 -> 32 channel sequence convs only");
-    CB_CHECK(a.g.Wp + 1 <= GUARD && 2 * TILE_M + a.g.Wp + 2 <= GUARD + 128, "conv_pool_umma: guard too small for Wp=%d", a.g.Wp);
+    CB_CHECK(a.g.Wp + 1 <= GUARD, "conv_pool_umma: guard too small for Wp=%d", a.g.Wp);
     ConvPoolArgs p;
     p.gi = a.g; p.go = go; p.pad_lo = pad_lo; p.bands_per_img = 0;
     p.in = a.in; p.wp = a.wp; p.bias = a.ep.bias; p.out = out; p.out_r = out_r; p.amax = amax; p.bits = bits;
-    if (a.cin_chunks == 2) return launch_conv_pool_umma_t<2, 2, 2>(p, num_sms, st);
+    static const int k42 = [] { const char* e = getenv("CLEANBA_CP42_K"); return e ? atoi(e) : 3; }();      // A/B knob (2 | 3)
+    if (a.cin_chunks == 2 && k42 == 2) return launch_conv_pool_umma_t<2, 2, 2>(p, num_sms, st);
+    if (a.cin_chunks == 2) return launch_conv_pool_umma_t<2, 3, 3>(p, num_sms, st);
     return launch_conv_pool_umma_t<4, 5, 2>(p, num_sms, st);
 }
 
