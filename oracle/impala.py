@@ -168,6 +168,14 @@ class ImpalaLearner:
                 pre = dict(params_before=self.params.copy(), nu_before=self.opt.nu.copy(), count_before=int(self.opt.count),
                            raw_grad=g.copy(), cols=cols[j].copy(), shard_grads=[x.copy() for x in grads],
                            shard_stats=[x.copy() for x in stats])
+                if kacc == 1:
+                    # the same gradient in float64 on demand (shard index, or None = pmean); see oracle/ppo.py
+                    def grad64(si=None, p0=pre["params_before"], c=cols[j].copy()):
+                        gs = [impala_loss_and_grad(p0, s.obs[:, c], s.actions[:, c], s.logitss[:, c], s.rewards[:, c], s.dones[:, c],
+                                                   s.firststeps[:, c], cfg.gamma, cfg.vf_coef, cfg.ent_coef, dtype=torch.float64)[1]
+                              for k, s in enumerate(shards) if si is None or k == si]
+                        return np.mean(np.stack(gs), axis=0)
+                    pre["grad64"] = grad64
             g = optim.clip_by_global_norm(g, cfg.max_grad_norm)
             self.params = self.opt.step(self.params, g, lr)
             stats_all.append(np.mean(np.stack(stats), axis=0))

@@ -239,6 +239,16 @@ class PPOLearner:
                     pre = dict(params_before=self.params.copy(), m_before=self.opt.m.copy(), v_before=self.opt.v.copy(),
                                count_before=int(self.opt.count), raw_grad=g.copy(), idx=idx[j].copy(),
                                shard_grads=[x.copy() for x in grads], shard_stats=[x.copy() for x in stats])
+                    if kacc == 1:
+                        # the same gradient in float64 on demand (shard index, or None = pmean): the tie-breaker when THIS fp32
+                        # evaluation rounds a relu / max-pool gate the other way than the kernels under test (tests/_pin.py)
+                        def grad64(si=None, p0=pre["params_before"], ii=idx[j].copy(), prep=prepared):
+                            gs = [ppo_loss_and_grad(p0, s.obs.reshape((-1,) + s.obs.shape[2:])[ii], s.actions.reshape(-1)[ii],
+                                                    s.logprobs.reshape(-1)[ii], adv.reshape(-1)[ii], ret.reshape(-1)[ii], cfg.clip_coef,
+                                                    cfg.ent_coef, cfg.vf_coef, dtype=torch.float64)[1]
+                                  for k, (s, (adv, ret)) in enumerate(zip(shards, prep)) if si is None or k == si]
+                            return np.mean(np.stack(gs), axis=0)
+                        pre["grad64"] = grad64
                 g = optim.clip_by_global_norm(g, cfg.max_grad_norm)
                 self.params = self.opt.step(self.params, g, lr)
                 stats_all.append(np.mean(np.stack(stats), axis=0))

