@@ -12,7 +12,17 @@ PARITY PINNING STATUS
 * `oracle.threefry` (JAX 0.4.8 threefry2x32 PRNG: PRNGKey/split/random_bits/uniform/permutation) is
   PINNED: it reproduces the three Random123 threefry2x32-20 known-answer vectors and the public JAX
   documentation constants for `split(PRNGKey(0))` and `uniform(PRNGKey(0))` (tests/test_oracle_prng.py).
-* Everything else is "PARITY UNPINNED": the reference ships no tests, golden vectors or fixtures
+* The reference's OWN LINES of the path are PINNED BY EXECUTION: tests/golden/make_reference_exec.py lifts the hot-path
+  functions out of cleanba/cleanba_ppo.py and cleanba/cleanba_impala.py with `ast` (get_action_and_value, get_action,
+  compute_gae_once / compute_gae, the advantage normalisation block, get_logprob_entropy_value, ppo_loss, impala_loss and its
+  two loss wrappers, scale_by_rms_pytorch_style, both linear_schedules, BOTH whole single_device_update functions, `class Args`
+  and the size derivation of `__main__`) and executes those bodies unchanged over PyTorch-CPU stand-ins for the third-party
+  names they call.  tests/test_reference_exec.py holds the oracle to the resulting vectors (GAE bit-exact; fp64 loss values
+  1e-12 and gradients 1e-9; whole PPO / IMPALA updates: key, optimizer count, scalars 2e-5, parameters) and, under `-m gpu`,
+  the CUDA actor step / GAE / PPO update directly.  The stand-ins are restatements (threefry: pinned below; flax modules:
+  oracle.network; optax: oracle.optim; rlax: restated a second time in the generator), so the third-party arithmetic itself
+  stays in the next category.
+* The third-party arithmetic is "PARITY UNPINNED": the reference ships no tests, golden vectors or fixtures
   (SURVEY.md section 4), and its third-party arithmetic (jax 0.4.8, flax 0.6.8, optax 0.1.4, rlax 0.1.5 --
   poetry.lock) is neither vendored under /root/reference nor installable in this image, so the
   reference cannot be run to generate fixtures.  Those parts restate the published semantics of the

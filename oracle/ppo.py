@@ -80,16 +80,22 @@ def normalize_advantages(adv: np.ndarray, num_minibatches: int) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------- loss
-def logprob_entropy_value(p, obs_u8: torch.Tensor, actions: torch.Tensor):
-    """get_logprob_entropy_value (cleanba_ppo.py:516-530)."""
-    hidden = net.trunk_forward(p, obs_u8)
-    logits, value = net.heads(p, hidden)
+def logprob_entropy_from_logits(logits: torch.Tensor, actions: torch.Tensor):
+    """The part of get_logprob_entropy_value after the network (cleanba_ppo.py:524-528)."""
     logp_all = torch.log_softmax(logits, dim=-1)
     logprob = logp_all.gather(1, actions.long()[:, None]).squeeze(1)
     nl = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
     nl = nl.clamp(min=torch.finfo(nl.dtype).min)
     p_log_p = nl * torch.softmax(nl, dim=-1)
     entropy = -p_log_p.sum(-1)
+    return logprob, entropy
+
+
+def logprob_entropy_value(p, obs_u8: torch.Tensor, actions: torch.Tensor):
+    """get_logprob_entropy_value (cleanba_ppo.py:516-530)."""
+    hidden = net.trunk_forward(p, obs_u8)
+    logits, value = net.heads(p, hidden)
+    logprob, entropy = logprob_entropy_from_logits(logits, actions)
     return logprob, entropy, value
 
 
