@@ -179,7 +179,8 @@ def _jnp_array(x, dtype=None):
 jnp = NS(
     array=_jnp_array, asarray=_jnp_array, zeros_like=lambda x: torch.zeros_like(x).as_subclass(JT),
     concatenate=lambda xs, axis=0: torch.cat(list(xs), dim=axis), hstack=lambda xs: torch.hstack(list(xs)),
-    stack=lambda xs, axis=0: torch.stack(list(xs), dim=axis), split=_split,
+    stack=lambda xs, axis=0: torch.stack([torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x for x in xs], dim=axis).as_subclass(JT),
+    split=_split, zeros=lambda n, dtype=None: torch.zeros(n, dtype=dtype).as_subclass(JT),
     exp=torch.exp, log=torch.log, clip=lambda x, a, b: torch.clamp(x, a, b), maximum=torch.maximum, minimum=torch.minimum,
     arange=lambda n: torch.arange(int(n)), finfo=torch.finfo, sum=torch.sum, square=torch.square,
     reshape=lambda x, shape: x.reshape(tuple(shape)), argmax=lambda x, axis=None: torch.argmax(x, dim=axis),
@@ -223,6 +224,16 @@ jax = NS(
 
 
 # flax modules (cleanba_ppo.py:140-203): restated by oracle.network; here only the .apply call shape of the reference
+class _Tree(dict):
+    """Leaves by flat flax path; `p["params"]["Dense_0"]["kernel"].block_until_ready()` (cleanba_ppo.py:299-301) is a no-op."""
+
+    def __missing__(self, key):
+        return self
+
+    def block_until_ready(self):
+        return self
+
+
 class Params:
     """AgentParams(network_params, actor_params, critic_params) over one flat vector."""
 
@@ -232,7 +243,7 @@ class Params:
 
     def _tree(self):
         if self._p is None:
-            self._p = net.unflatten(self.flat)
+            self._p = _Tree(net.unflatten(self.flat))
         return self._p
 
     network_params = actor_params = critic_params = property(_tree)
@@ -527,6 +538,8 @@ def build():
     # ---- the whole single_device_update of both scripts (cleanba_ppo.py:579-654, cleanba_impala.py:599-639), fp32, tiny shapes
     out.update(run_ppo_update(ppo, rng))
     out.update(run_impala_update(imp, rng))
+    out.update(run_rollout(ppo, "ppo", rng))
+    out.update(run_rollout(imp, "impala", rng))
     out["meta_json"] = np.array(json.dumps(meta))
     return out
 
@@ -602,6 +615,57 @@ def run_impala_update(imp, rng):
     out.update(upd_imp_cfg=np.array([T1, Bl, nmb, 1000], np.int64), upd_imp_params_seed=np.int64(12),
                upd_imp_scalars=np.array([float(loss), float(pg), float(vl), float(el)]), **digest("upd_imp", flat, t2n(state.flat).astype(np.float32)),
                upd_imp_opt_count=np.int64(state.opt.count))
+    return out
+
+
+def run_rollout(tree, algo, rng):
+    """The reference's whole rollout() thread function (cleanba_ppo.py:226-406 / cleanba_impala.py:268-447) for three updates on
+    tests/golden/tiny_env.py, two learner devices: storage order, done / truncation / first-step flags, the IMPALA carried row,
+    prepare_data's split of the env axis, global_step and policy-version accounting, episodic-return bookkeeping, scalar names."""
+    import queue
+    import time
+    from collections import deque
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import tiny_env
+    N, T, L, updates = 4, 3, 2, 3
+    a = ref_args(tree, local_num_envs=N, num_steps=T, num_actor_threads=2, learner_device_ids=[0, 1], log_frequency=1, seed=3)
+    a.num_updates, a.world_size = updates - 1, 1          # the loop runs range(1, num_updates + 2)
+    scalars = []
+    writer = NS(add_scalar=lambda name, value, step: scalars.append((name, float(value), int(step))))
+    jx = NS(**{**jax.__dict__, "process_index": lambda: 0, "device_put_sharded": lambda xs, devices=None: list(xs)})
+    ns = base_ns(args=a, jax=jx, make_env=tiny_env.make_env, time=time, deque=deque, queue=queue, print=lambda *x, **k: None)
+    run(lift(tree, "Transition"), ns)
+    run(lift(tree, "rollout"), ns)
+    flat = [net.init_params(21), net.init_params(22), net.init_params(23)]
+    pq, rq = queue.Queue(), queue.Queue()
+    for f in flat:
+        pq.put(Params(J(f)))
+    key = tf.split(tf.PRNGKey(3), 4)[0]
+    with torch.no_grad():
+        ns["rollout"](key, a, rq, pq, writer, [0, 1], 1, 0)          # device_thread_id = 1 (seed offset), actor device 0
+    out = {f"ro_{algo}_cfg": np.array([N, T, L, updates], np.int64), f"ro_{algo}_param_seeds": np.array([21, 22, 23], np.int64), f"ro_{algo}_key": key}
+    u = 0
+    while not rq.empty():
+        payload = rq.get()
+        if algo == "ppo":
+            gs, ver, upd, st, nobs, ndone, _, dtid = payload
+            for l in range(L):
+                out[f"ro_ppo_u{u}_l{l}_next_obs_sum"] = np.int64(np.asarray(nobs[l]).astype(np.int64).sum())
+                out[f"ro_ppo_u{u}_l{l}_next_done"] = np.asarray(ndone[l])
+        else:
+            gs, ver, upd, st, _, dtid = payload
+        out[f"ro_{algo}_u{u}_meta"] = np.array([gs, ver, upd, dtid], np.int64)
+        for field in st._fields:
+            for l in range(L):
+                x = t2n(getattr(st, field)[l])
+                if field == "obs":                       # frames: row-wise checksums instead of the bytes
+                    x = x.reshape(x.shape[0], x.shape[1], -1).astype(np.int64).sum(-1)
+                out[f"ro_{algo}_u{u}_l{l}_{field}"] = x
+        u += 1
+    assert u == updates
+    out[f"ro_{algo}_scalar_names"] = np.array(json.dumps([n for n, _, _ in scalars]))
+    keep = ("charts/avg_episodic_return", "charts/avg_episodic_length")
+    out[f"ro_{algo}_scalars"] = np.array([[v, s] for n, v, s in scalars if n in keep], np.float64)
     return out
 
 

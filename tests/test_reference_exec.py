@@ -234,3 +234,53 @@ def test_fixture_regenerates_from_the_reference_sources():
             np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9, err_msg=k)
         else:
             assert np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("algo", ["ppo", "impala"])
+def test_rollout_thread_against_the_reference_rollout(algo):
+    """cleanba_b200.sebulba._rollout (the product's actor thread, here over the CPU oracle backend) against the reference's whole
+    rollout() function executed on the same deterministic env for three updates with two learner devices: every payload field of
+    every learner shard (frames as checksums), next_obs / next_done, global_step, policy version (one behind under IMPALA's
+    concurrency), update index, thread id, the scalar names in order and the episodic-return scalars."""
+    import queue
+    import sys
+    import threading
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tiny_env
+    from cleanba_b200 import sebulba
+    from oracle.backend import OracleBackend
+    N, T, L, updates = (int(x) for x in G[f"ro_{algo}_cfg"])
+    a = sebulba.Args() if algo == "ppo" else sebulba.impala_defaults(sebulba.Args())
+    a.local_num_envs, a.num_steps, a.num_actor_threads, a.learner_device_ids, a.log_frequency, a.seed = N, T, 2, [0, 1], 1, 3
+    a.num_updates, a.world_size, a.local_rank = updates - 1, 1, 0
+    scalars = []
+
+    class W:
+        def add_scalar(self, name, value, step):
+            scalars.append((name, float(value), int(step)))
+    pq, rq = queue.Queue(), queue.Queue()
+    for s in G[f"ro_{algo}_param_seeds"]:
+        pq.put(net.init_params(int(s)))
+    sebulba._rollout(a, OracleBackend(), tiny_env.make_env, rq, pq, W(), 1, 0, threading.Event(), G[f"ro_{algo}_key"])
+    for u in range(updates):
+        gs, ver, upd, sharded, _, dtid = rq.get_nowait()
+        assert [gs, ver, upd, dtid] == G[f"ro_{algo}_u{u}_meta"].tolist()
+        for l in range(L):
+            sh = sharded[l]
+            fields = ("obs", "dones", "actions", "rewards", "firststeps") + (("logprobs", "values") if algo == "ppo" else ("logitss",))
+            for f in fields:
+                want = G[f"ro_{algo}_u{u}_l{l}_{f}"]
+                got = np.asarray(sh[f])
+                if f == "obs":
+                    got = got.reshape(got.shape[0], got.shape[1], -1).astype(np.int64).sum(-1)
+                if got.dtype.kind == "f":
+                    assert got.shape == want.shape and relerr(got, want) < 1e-6, (u, l, f)
+                else:
+                    assert np.array_equal(got, want), (u, l, f)
+            if algo == "ppo":
+                assert np.asarray(sh["next_obs"]).astype(np.int64).sum() == int(G[f"ro_ppo_u{u}_l{l}_next_obs_sum"])
+                assert np.array_equal(np.asarray(sh["next_done"]), G[f"ro_ppo_u{u}_l{l}_next_done"])
+    assert rq.empty()
+    assert [n for n, _, _ in scalars] == json.loads(str(G[f"ro_{algo}_scalar_names"]))
+    keep = ("charts/avg_episodic_return", "charts/avg_episodic_length")
+    np.testing.assert_allclose(np.array([[v, s] for n, v, s in scalars if n in keep]), G[f"ro_{algo}_scalars"], rtol=1e-6)
