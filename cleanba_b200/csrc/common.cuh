@@ -250,10 +250,12 @@ struct EpiPrefetch {
     bool in, tail;
 };
 
+// `in` / `tail` known to the caller (the persistent tcgen05 kernels carry the pixel's position from tile to tile instead of
+// dividing the flat index again: the divisions were 16 % of the epilogue's instructions, profiles/r02_v9_*)
 template <int COUT>
-__device__ __forceinline__ void epi_prefetch(const ConvEpilogue& ep, const ConvGeom& g, long long q, EpiPrefetch<COUT>& p) {
-    p.tail = q >= g.NP;
-    p.in = !p.tail && interior(g, q);
+__device__ __forceinline__ void epi_prefetch_known(const ConvEpilogue& ep, long long q, bool in, bool tail, EpiPrefetch<COUT>& p) {
+    p.tail = tail;
+    p.in = in;
     if (!p.in) return;
     if (ep.bits_in) {
         if (COUT == 16) p.mbits = *reinterpret_cast<const uint16_t*>(ep.bits_in + q * 2);
@@ -271,8 +273,15 @@ __device__ __forceinline__ void epi_prefetch(const ConvEpilogue& ep, const ConvG
 }
 
 template <int COUT>
+__device__ __forceinline__ void epi_prefetch(const ConvEpilogue& ep, const ConvGeom& g, long long q, EpiPrefetch<COUT>& p) {
+    const bool tail = q >= g.NP;
+    epi_prefetch_known<COUT>(ep, q, !tail && interior(g, q), tail, p);
+}
+
+// STAGED_BIAS: `bias` = COUT floats (zeros when the layer has none) staged once per CTA, e.g. in shared memory; else ep.bias
+template <int COUT, bool STAGED_BIAS = false>
 __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeom& g, long long q, const float* acc,
-                                           const EpiPrefetch<COUT>& p) {
+                                           const EpiPrefetch<COUT>& p, const float* bias = nullptr) {
     uint32_t obits = 0;
 #pragma unroll
     for (int oc = 0; oc < COUT / 8; ++oc) {
@@ -280,10 +289,17 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const ConvGeo
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.f;
         if (p.in) {
+            if (STAGED_BIAS) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + oc * 8), b1 = *reinterpret_cast<const float4*>(bias + oc * 8 + 4);
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float b = ep.bias ? ep.bias[oc * 8 + e] : 0.f;
-                v[e] = acc[oc * 8 + e] * ep.acc_scale + b;
+                for (int e = 0; e < 8; ++e) v[e] = acc[oc * 8 + e] * ep.acc_scale + b[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float b = ep.bias ? ep.bias[oc * 8 + e] : 0.f;
+                    v[e] = acc[oc * 8 + e] * ep.acc_scale + b;
+                }
             }
             if (ep.bits_in) {
 #pragma unroll

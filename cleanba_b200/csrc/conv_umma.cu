@@ -66,6 +66,10 @@ int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_la
 
 // One kernel for the forward conv and for dgrad (activations and gradients use the same carrier); CIN_CHUNKS == 1 is the
 // frame stack (one exact plane, ONE MMA per step: A_hi * [W_hi | W_mid]).
+// Registers: the 32-channel instantiations need ~130 registers per thread, so only ONE of the two CTAs per SM that the shared-
+// memory layout provides for is resident at a time (2 x 320 x 130 > 65,536; the grid of 2 x SMs runs as two waves).  Capping them
+// at 96 (__launch_bounds__(320, 2), 88 bytes of spills) makes both resident and was measured SLOWER at 21x21 (forward 0.160 vs
+// 0.150 ms, dgrad 0.144 vs 0.140 per 3840 frames) and mixed at 11x11: profiles/r02_v9_conv_epilogue_ab.txt.  Not kept.
 template <int CIN_CHUNKS, int COUT>
 __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntiles) {
     constexpr int APL = CIN_CHUNKS == 1 ? 1 : 2;
@@ -176,11 +180,26 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
     } else {
         // ===================== epilogue: group g = warp / 4 owns accumulator g (every second tile of this CTA) ==========
         const int grp = warp >> 2, quad = warp & 3;
+        // the layer's bias once per CTA in shared memory (the 1 KB header has room) instead of COUT global loads per tile
+        float* bias_sm = reinterpret_cast<float*>(smem + 512);
+        if (threadIdx.x < COUT) bias_sm[threadIdx.x] = a.ep.bias ? a.ep.bias[threadIdx.x] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps only
+        // Position of this thread's pixel inside its image, carried from tile to tile: r = q mod P advances by a constant, and
+        // the row is one float multiply (exact: (r + 0.5) / Wp is at least 0.5 / Wp away from an integer and r < 2^20).
+        const uint32_t P = (uint32_t)a.g.P, Wp = (uint32_t)a.g.Wp;
+        const float inv_wp = 1.f / (float)a.g.Wp;
+        uint32_t r = (uint32_t)(((long long)(blockIdx.x + grp * gridDim.x) * TILE_M + quad * 32 + lane) % a.g.P);
+        const uint32_t dr = (uint32_t)(((long long)2 * gridDim.x * TILE_M) % a.g.P);
         uint32_t aph = 0;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
             const long long q = (long long)tile * TILE_M + quad * 32 + lane;
+            const uint32_t y = __float2uint_rz(((float)r + 0.5f) * inv_wp), x = r - y * Wp;
+            const bool tail = q >= a.g.NP;
+            const bool in = !tail & (y >= 1u) & (y <= (uint32_t)a.g.H) & (x >= 1u) & (x <= (uint32_t)a.g.W);
+            r += dr;
+            if (r >= P) r -= P;
             EpiPrefetch<COUT> pre;
-            epi_prefetch<COUT>(a.ep, a.g, q, pre);          // global loads in flight while the MMAs of this tile run
+            epi_prefetch_known<COUT>(a.ep, q, in, tail, pre);   // global loads in flight while the MMAs of this tile run
             mbar_wait(&tfull[grp], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * ACC_COLS;
@@ -198,7 +217,7 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntil
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[grp]);
-            epi_finish<COUT>(a.ep, a.g, q, v, pre);
+            epi_finish<COUT, true>(a.ep, a.g, q, v, pre, bias_sm);
             aph ^= 1;
         }
     }
@@ -211,6 +230,7 @@ template <int CIN_CHUNKS, int COUT>
 static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
     ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
     CB_CHECK(L.stages >= 2 && L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
+    CB_CHECK(a.g.P < (1 << 20), "conv_umma: image of %d padded pixels (the epilogue's row arithmetic is exact below 2^20)", a.g.P);
     // Opt in to the device maximum once per device: the attribute is per function (contexts on other host threads launch
     // the same instantiation with other window sizes concurrently), and nothing but launches may happen while a
     // CUDA graph is being captured.

@@ -5,7 +5,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_uint8, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcleanba_b200.so")
+# CLEANBA_B200_LIB: another build of the SAME library (developer A/B runs of two builds on one box); default = the in-tree build
+LIB_PATH = os.environ.get("CLEANBA_B200_LIB") or os.path.join(_HERE, "libcleanba_b200.so")
 
 CB_ALGO_PPO, CB_ALGO_IMPALA = 0, 1
 CB_CONV_TCGEN05, CB_CONV_SIMT = 0, 1
