@@ -70,8 +70,10 @@ int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_la
 // memory layout provides for is resident at a time (2 x 320 x 130 > 65,536; the grid of 2 x SMs runs as two waves).  Capping them
 // at 96 (__launch_bounds__(320, 2), 88 bytes of spills) makes both resident and was measured SLOWER at 21x21 (forward 0.160 vs
 // 0.150 ms, dgrad 0.144 vs 0.140 per 3840 frames) and mixed at 11x11: profiles/r02_v9_conv_epilogue_ab.txt.  Not kept.
+// Three CTAs per SM for the 16-channel instantiations (registers capped at 64, 3-4 stage rings, 24 epilogue warps) were measured
+// slower as well (forward 0.925 vs 0.843 ms per four launches): these kernels already move 5.9-6.0 TB/s.
 template <int CIN_CHUNKS, int COUT>
-__global__ void __launch_bounds__(CONV_THREADS) k_conv_umma(ConvArgs a, int ntiles) {
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_umma(ConvArgs a, int ntiles) {
     constexpr int APL = CIN_CHUNKS == 1 ? 1 : 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     griddep_launch();
@@ -871,6 +873,8 @@ __host__ __device__ inline WgSmemLayout wg_smem_layout() {
     // after the last stage where B is smaller than the overrun)
     const int over = (S::MMA_M / 8) * WG_PLANE - ((S::MSTACK ? 2 : 1) * L.a_bytes + L.b_bytes);
     const int pad = over > 0 ? (over + 1023) / 1024 * 1024 : 0;
+    // (three CTAs = three MMA issuers per SM with 2-stage rings: no change, 0.882 vs 0.872 ms per four Cin = 16 launches -- the
+    // tensor pipe's per-instruction time, not the issuing thread, is the limit; profiles/r02_v9_conv_epilogue_ab.txt)
     L.ctas_per_sm = S::DUAL ? 1 : 2;
     const int budget = (S::DUAL ? 226 : 113) * 1024 - 1024 - pad;
     int st = budget / L.stage_bytes;
