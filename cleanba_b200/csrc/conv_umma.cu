@@ -712,6 +712,9 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
             for (int e = 0; e < 8; ++e) { v[e] = 0.f; am[e] = 15; }
             emit(img, ypo, xp, jc, v, am);
         };
+        // pooling item -> (pooled row r of the band, chunk jc, column j).  Every band shape in use has <= 256 items, so a thread's
+        // item is `etid` in every band: decoded once here instead of three integer divisions per item (~90 of ~420 instructions)
+        const int j_0 = etid % Wo, jc_0 = (etid / Wo) % NCH, r_0 = etid / (Wo * NCH);
         for (int bnd = blockIdx.x; bnd < nbands; bnd += gridDim.x) {
             const int img = bnd / a.bands_per_img, b = bnd - img * a.bands_per_img;
             const int kb = band_rows(b), nt = band_tiles(kb);
@@ -741,7 +744,8 @@ __global__ void __launch_bounds__(CONV_THREADS) k_conv_pool_umma(ConvPoolArgs a)
             asm volatile("bar.sync 1, 256;" ::: "memory");       // the band is complete in shared memory
             const int nitems = kb * Wo * NCH;
             for (int it = etid; it < nitems; it += 256) {
-                const int j = it % Wo, jc = (it / Wo) % NCH, r = it / (Wo * NCH);
+                int j = j_0, jc = jc_0, r = r_0;
+                if (it != etid) { j = it % Wo; jc = (it / Wo) % NCH; r = it / (Wo * NCH); }
                 float v[8];
                 int am[8];
 #pragma unroll
