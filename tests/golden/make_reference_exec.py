@@ -11,7 +11,8 @@ path) with them.
 
 What this pins: every line the REFERENCE ITSELF wrote for the path -- GAE recurrence and operand order, bootstrap concat,
 advantage normalisation axes, log-prob / entropy formula, PPO clipping and loss assembly, the epoch shuffle (key split, permutation
-of the flattened batch, minibatch reshape), the scan order of minibatches and epochs, the averaging of the reported scalars, the
+of the flattened batch, minibatch reshape), the scan order of minibatches and epochs, the averaging of the reported scalars, the same update on two
+emulated learner devices (pmean'ed gradients, local advantage normalisation, shared shuffle key), the whole rollout() thread loop, the
 IMPALA slicing ([:-1] / [1:]), discount / mask construction, the T-scaled sums of the rlax losses, the contiguous column split of
 IMPALA minibatches, the RMSProp-pytorch-style update rule, both learning-rate schedules, the Gumbel-max sampling line, the Args
 defaults and the size derivation of `__main__`.
@@ -160,6 +161,12 @@ def scan(f, init, xs, length=None, reverse=False):
 def vmap(f, in_axes=0, out_axes=0):
     def g(*args):
         axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        if tuple(axes) == (None, 0) and out_axes == 0 and args[1].ndim >= 3:
+            # vmap of a batched function over a leading axis IS batching: one call on the flattened [T*B, ...] frames (as XLA
+            # executes it, and with the same CPU conv kernels as a direct batched call -- a per-row loop rounds differently)
+            x = args[1]
+            out = f(args[0], x.reshape((-1,) + tuple(x.shape[2:])))
+            return tree_map(lambda t: t.reshape(tuple(x.shape[:2]) + tuple(t.shape[1:])), out)
         n = next(a.shape[ax] for a, ax in zip(args, axes) if ax is not None)
         outs = [f(*[a if ax is None else a.select(ax, i) for a, ax in zip(args, axes)]) for i in range(n)]
         return _stack_tree(outs, out_axes)
@@ -551,6 +558,58 @@ def digest(prefix, before, after):
             f"{prefix}_step_sum": np.float64(d.sum())}
 
 
+class PMean:
+    """jax.lax.pmean over L emulated devices: every device runs the reference's update function in its own thread and the
+    threads meet here (same call sequence on every device, as under pmap); the mean is taken in device order."""
+
+    def __init__(self, L):
+        import threading
+        self.L, self.slots, self.barrier, self.local = L, [None] * L, threading.Barrier(L), threading.local()
+
+    def __call__(self, x, axis_name=None):
+        self.slots[self.local.dev] = x
+        self.barrier.wait()
+        mean = self.slots[0]
+        for y in self.slots[1:]:
+            mean = mean + y
+        mean = mean / self.L
+        self.barrier.wait()
+        return mean
+
+
+def pmap_threads(ns, fn_name, per_device_args):
+    """The reference's `jax.pmap(single_device_update, axis_name="local_devices")` (cleanba_ppo.py:656-660) on emulated devices."""
+    import threading
+    L = len(per_device_args)
+    pm = PMean(L)
+    saved = ns["jax"]
+    ns["jax"] = NS(**{**jax.__dict__, "lax": NS(**{**jax.lax.__dict__, "pmean": pm})})
+    results, errors = [None] * L, []
+
+    def work(l):
+        pm.local.dev = l
+        torch.set_default_dtype(torch.float32)
+        try:
+            results[l] = ns[fn_name](*per_device_args[l])
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            pm.barrier.abort()
+    threads = [threading.Thread(target=work, args=(l,)) for l in range(L)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ns["jax"] = saved
+    if errors:
+        raise errors[0]
+    return results
+
+
+def cols(t, c):
+    """Env-axis slice of a Transition (what prepare_data / device_put_sharded hand to one learner device)."""
+    return type(t)(*[x[:, c] for x in t])
+
+
 def run_ppo_update(ppo, rng):
     T, Bl, nmb, epochs = 4, 8, 4, 2
     a = ref_args(ppo, num_minibatches=nmb, update_epochs=epochs, num_steps=T, local_num_envs=Bl, num_actor_threads=1)
@@ -584,6 +643,19 @@ def run_ppo_update(ppo, rng):
     out.update(upd_ppo_cfg=np.array([T, Bl, nmb, epochs, 1000], np.int64), upd_ppo_params_seed=np.int64(11), upd_ppo_key=key, upd_ppo_key_after=np.asarray(key2),
                upd_ppo_scalars=np.array([float(loss), float(pg), float(vl), float(el), float(kl)]), **digest("upd_ppo", flat, t2n(state.flat).astype(np.float32)),
                upd_ppo_opt_count=np.int64(state.opt.count))
+    # the same payloads on TWO learner devices (multi_device_update, cleanba_ppo.py:656-660): device l holds env columns
+    # [2l, 2l + 2) of each actor thread's payload, normalises its advantages locally, shuffles with the same key; gradients and
+    # the reported scalars are pmean'ed
+    per_dev = []
+    for l in range(2):
+        c = slice(2 * l, 2 * l + 2)
+        per_dev.append((TrainState(J(flat), optim.Adam(flat.size), a.max_grad_norm, ns["linear_schedule"]), [cols(h, c) for h in halves],
+                        [J(fields[h]["next_obs"][c]) for h in range(2)], [J(fields[h]["next_done"][c]) for h in range(2)], key))
+    res = pmap_threads(ns, "single_device_update", per_dev)
+    (st0, loss, pg, vl, el, kl, key2), st1 = res[0], res[1][0]
+    assert torch.equal(st0.flat, st1.flat), "replicas diverged"
+    out.update(upd_ppo2_scalars=np.array([float(loss), float(pg), float(vl), float(el), float(kl)]), upd_ppo2_key_after=np.asarray(key2),
+               upd_ppo2_opt_count=np.int64(st0.opt.count), **digest("upd_ppo2", flat, t2n(st0.flat).astype(np.float32)))
     return out
 
 
@@ -615,6 +687,17 @@ def run_impala_update(imp, rng):
     out.update(upd_imp_cfg=np.array([T1, Bl, nmb, 1000], np.int64), upd_imp_params_seed=np.int64(12),
                upd_imp_scalars=np.array([float(loss), float(pg), float(vl), float(el)]), **digest("upd_imp", flat, t2n(state.flat).astype(np.float32)),
                upd_imp_opt_count=np.int64(state.opt.count))
+    # two learner devices (cleanba_impala.py:641-645): summed losses per device, pmean'ed gradients
+    per_dev = []
+    for l in range(2):
+        c = slice(2 * l, 2 * l + 2)
+        per_dev.append((TrainState(J(flat), optim.RMSPropPyTorchStyle(flat.size, decay=0.99, eps=0.01), a.max_grad_norm, ns["linear_schedule"]),
+                        [cols(h, c) for h in halves], key))
+    res = pmap_threads(ns, "single_device_update", per_dev)
+    (st0, loss, pg, vl, el, _), st1 = res[0], res[1][0]
+    assert torch.equal(st0.flat, st1.flat), "replicas diverged"
+    out.update(upd_imp2_scalars=np.array([float(loss), float(pg), float(vl), float(el)]), upd_imp2_opt_count=np.int64(st0.opt.count),
+               **digest("upd_imp2", flat, t2n(st0.flat).astype(np.float32)))
     return out
 
 

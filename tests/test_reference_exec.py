@@ -163,6 +163,55 @@ def test_whole_impala_single_device_update():
     assert relerr(learner.params[::53], G["upd_imp_params_after_every53"]) < 1e-5
 
 
+def _two_device_shards(prefix, make):
+    """Device l holds env columns [2l, 2l + 2) of each actor thread's payload (prepare_data's split of the env axis)."""
+    return [make(slice(2 * l, 2 * l + 2)) for l in range(2)]
+
+
+def test_whole_ppo_update_on_two_learner_devices():
+    """multi_device_update (cleanba_ppo.py:656-660) with the reference's update function running on two emulated devices (one thread
+    each, `lax.pmean` = a rendezvous): local advantage normalisation, the same shuffle key on both devices, pmean'ed gradients
+    and scalars -- against the oracle's 2-shard emulation (what the multi-GPU tests compare the CUDA learners with)."""
+    torch.set_num_threads(1)
+    T, Bl, nmb, epochs, num_updates = (int(x) for x in G["upd_ppo_cfg"])
+    obs = [frames(s, (T, Bl // 2, 4, 84, 84)) for s in G["upd_ppo_obs_seeds"]]
+    nobs = [frames(s, (Bl // 2, 4, 84, 84)) for s in G["upd_ppo_next_obs_seeds"]]
+
+    def make(c):
+        cat = lambda k: np.concatenate([G[f"upd_ppo_{k}0"][:, c], G[f"upd_ppo_{k}1"][:, c]], axis=1)
+        return oppo.Shard(obs=np.concatenate([o[:, c] for o in obs], axis=1), dones=cat("dones"), actions=cat("actions"), logprobs=cat("logprobs"),
+                          values=cat("values"), rewards=cat("rewards"), next_obs=np.concatenate([o[c] for o in nobs], axis=0),
+                          next_done=np.concatenate([G["upd_ppo_next_done0"][c], G["upd_ppo_next_done1"][c]]))
+    flat = net.init_params(int(G["upd_ppo_params_seed"]))
+    learner = oppo.PPOLearner(flat, oppo.PPOConfig(num_minibatches=nmb, update_epochs=epochs, num_updates=num_updates))
+    stats, key2 = learner.update(_two_device_shards("upd_ppo", make), G["upd_ppo_key"])
+    assert np.array_equal(key2, G["upd_ppo2_key_after"]) and learner.opt.count == int(G["upd_ppo2_opt_count"])
+    np.testing.assert_allclose(stats, G["upd_ppo2_scalars"], rtol=2e-5)
+    d = learner.params.astype(np.float64) - flat.astype(np.float64)
+    assert abs(np.sqrt((d * d).sum()) - float(G["upd_ppo2_step_l2"])) < 1e-4 * float(G["upd_ppo2_step_l2"])
+    diff = np.abs(learner.params[::53] - G["upd_ppo2_params_after_every53"])
+    assert np.quantile(diff, 0.999) < 0.05 * 2.5e-4 and diff.max() < 8 * 2 * 2.5e-4
+
+
+def test_whole_impala_update_on_two_learner_devices():
+    torch.set_num_threads(1)
+    T1, Bl, nmb, num_updates = (int(x) for x in G["upd_imp_cfg"])
+    obs = [frames(s, (T1, Bl // 2, 4, 84, 84)) for s in G["upd_imp_obs_seeds"]]
+
+    def make(c):
+        cat = lambda k: np.concatenate([G[f"upd_imp_{k}0"][:, c], G[f"upd_imp_{k}1"][:, c]], axis=1)
+        return oimpala.Shard(obs=np.concatenate([o[:, c] for o in obs], axis=1), dones=cat("dones"), actions=cat("actions"), logitss=cat("logitss"),
+                             rewards=cat("rewards"), firststeps=cat("firststeps"))
+    flat = net.init_params(int(G["upd_imp_params_seed"]))
+    learner = oimpala.ImpalaLearner(flat, oimpala.ImpalaConfig(num_minibatches=nmb, num_updates=num_updates))
+    stats = learner.update(_two_device_shards("upd_imp", make))
+    assert learner.opt.count == int(G["upd_imp2_opt_count"])
+    np.testing.assert_allclose(stats, G["upd_imp2_scalars"], rtol=2e-5)
+    d = learner.params.astype(np.float64) - flat.astype(np.float64)
+    assert abs(np.sqrt((d * d).sum()) - float(G["upd_imp2_step_l2"])) < 1e-4 * float(G["upd_imp2_step_l2"])
+    assert relerr(learner.params[::53], G["upd_imp2_params_after_every53"]) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ CUDA path vs reference lines
 @pytest.mark.gpu
 def test_cuda_actor_and_gae_against_reference_lines():
