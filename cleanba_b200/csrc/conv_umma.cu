@@ -45,7 +45,7 @@ long long packed_conv_elems(int cin_chunks, int cout) { return (long long)conv_w
 struct ConvSmemLayout {
     int win, plane_bytes, nplanes, stage_bytes, w_bytes, stages, ctas_per_sm, total;
 };
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int cout, int Wp) {
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int cout, int Wp, int max_ctas = 2) {
     const int apl = 2;
     ConvSmemLayout L;
     // frames path: the zero-weight half of the last K step reads one pixel past the 3x3 window -> load it too
@@ -55,7 +55,7 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int cin_chunks, int c
     L.stage_bytes = L.nplanes * L.plane_bytes;
     L.w_bytes = conv_wbytes(cin_chunks, cout);
     // two CTAs per SM (two MMA-issuing threads) when three stages fit in half an SM, else one CTA with a deeper ring
-    L.ctas_per_sm = 1024 + L.w_bytes + 3 * L.stage_bytes <= 112 * 1024 ? 2 : 1;
+    L.ctas_per_sm = (max_ctas >= 2 && 1024 + L.w_bytes + 3 * L.stage_bytes <= 112 * 1024) ? 2 : 1;
     const int budget = (L.ctas_per_sm == 2 ? 112 : 226) * 1024 - 1024 - L.w_bytes;
     L.stages = budget / L.stage_bytes;
     if (L.stages > CONV_MAXST) L.stages = CONV_MAXST;
@@ -72,12 +72,12 @@ int umma_conv_smem_bytes(int cin_chunks, int cout, int Wp) { return conv_smem_la
 // 0.150 ms, dgrad 0.144 vs 0.140 per 3840 frames) and mixed at 11x11: profiles/r02_v9_conv_epilogue_ab.txt.  Not kept.
 // Three CTAs per SM for the 16-channel instantiations (registers capped at 64, 3-4 stage rings, 24 epilogue warps) were measured
 // slower as well (forward 0.925 vs 0.843 ms per four launches): these kernels already move 5.9-6.0 TB/s.
-template <int CIN_CHUNKS, int COUT>
+template <int CIN_CHUNKS, int COUT, int MAXCTAS = 2>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_umma(ConvArgs a, int ntiles) {
     constexpr int APL = CIN_CHUNKS == 1 ? 1 : 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     griddep_launch();
-    const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
+    const ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, MAXCTAS);
     // [0,1024): barriers + tmem pointer; then the weight image; then the activation stages
     const int NSTAGES = L.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [CONV_MAXST]
@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv_umma(ConvArgs a, int n
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int CIN_CHUNKS, int COUT>
+template <int CIN_CHUNKS, int COUT, int MAXCTAS = 2>
 static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
-    ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp);
+    ConvSmemLayout L = conv_smem_layout(CIN_CHUNKS, COUT, a.g.Wp, MAXCTAS);
     CB_CHECK(L.stages >= 2 && L.total <= 227 * 1024, "conv_umma<%d,%d>: %d bytes of shared memory needed", CIN_CHUNKS, COUT, L.total);
     CB_CHECK(a.g.P < (1 << 20), "conv_umma: image of %d padded pixels (the epilogue's row arithmetic is exact below 2^20)", a.g.P);
     // Opt in to the device maximum once per device: the attribute is per function (contexts on other host threads launch
@@ -240,12 +240,13 @@ static int launch_conv_umma_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     if (!(attr_done.load() & (1u << dev))) {
-        CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CB_CUDA(cudaFuncSetAttribute(k_conv_umma<CIN_CHUNKS, COUT, MAXCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done.fetch_or(1u << dev);
     }
     int ntiles = (int)((a.g.NP + TILE_M - 1) / TILE_M);
     int grid = ntiles < num_sms * L.ctas_per_sm ? ntiles : num_sms * L.ctas_per_sm;
-    launch_pdl(k_conv_umma<CIN_CHUNKS, COUT>, dim3(grid), dim3(CONV_THREADS), (size_t)L.total, st, a, ntiles);
+    // (halving the grid of the 16-channel kernels for small batches was measured too: actor step 0.126 -> 0.136 ms, not kept)
+    launch_pdl(k_conv_umma<CIN_CHUNKS, COUT, MAXCTAS>, dim3(grid), dim3(CONV_THREADS), (size_t)L.total, st, a, ntiles);
     CB_LAUNCH_CHECK();
     return 0;
 }
@@ -257,7 +258,12 @@ int launch_conv_umma(const ConvArgs& a, int num_sms, cudaStream_t st) {
     if (a.cin_chunks == 2 && a.cout == 16) return launch_conv_umma_t<2, 16>(a, num_sms, st);
     if (a.cin_chunks == 2 && a.cout == 32) return launch_conv_umma_t<2, 32>(a, num_sms, st);
     if (a.cin_chunks == 4 && a.cout == 16) return launch_conv_umma_t<4, 16>(a, num_sms, st);
-    if (a.cin_chunks == 4 && a.cout == 32) return launch_conv_umma_t<4, 32>(a, num_sms, st);
+    // Cin = Cout = 32: ~130 registers per thread allow only one resident CTA per SM, so the layout is asked for ONE CTA per SM
+    // with the whole shared memory as an 8-stage ring (grid = SMs) instead of two half-size CTAs that ran as two waves: forward /
+    // dgrad at 21x21 -4..5 %, at 11x11 -8 %, and the n = 60 actor step 0.141 -> 0.123 ms (half as many CTAs load the 37 KB weight
+    // image); CLEANBA_CONV32_CTAS=2 restores the old shape (profiles/r02_v9_conv_epilogue_ab.txt)
+    static const int c32 = [] { const char* e = getenv("CLEANBA_CONV32_CTAS"); return e ? atoi(e) : 1; }();
+    if (a.cin_chunks == 4 && a.cout == 32) return c32 == 1 ? launch_conv_umma_t<4, 32, 1>(a, num_sms, st) : launch_conv_umma_t<4, 32>(a, num_sms, st);
     CB_CHECK(false, "conv_umma: unsupported shape cin_chunks=%d cout=%d", a.cin_chunks, a.cout);
 }
 
