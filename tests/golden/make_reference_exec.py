@@ -281,18 +281,27 @@ class TrainState:
     """flax TrainState + the optax chain of the script, restated by oracle.optim:
     MultiSteps(k=1) o clip_by_global_norm o inject_hyperparams(adam | rmsprop_pytorch_style)(learning_rate=schedule)."""
 
-    def __init__(self, flat, opt, max_grad_norm, schedule):
+    def __init__(self, flat, opt, max_grad_norm, schedule, k=1, mini=0, acc=None):
         self.flat, self.opt, self.max_grad_norm, self.schedule = flat, opt, max_grad_norm, schedule
+        self.k, self.mini, self.acc = k, mini, acc
 
     @property
     def params(self):
         return Params(self.flat)
 
     def apply_gradients(self, grads):
+        if self.k > 1:
+            # optax.MultiSteps(every_k_schedule=k), optax 0.1.4: acc += (g - acc) / (mini_step + 1) from zeros; the inner chain
+            # (and its schedule count) advances on the k-th mini-step only, the other mini-steps emit zero updates
+            g32 = grads.numpy().astype(np.float32)
+            acc = g32.copy() if self.mini == 0 else (self.acc + (g32 - self.acc) / np.float32(self.mini + 1)).astype(np.float32)
+            if self.mini < self.k - 1:
+                return TrainState(self.flat, self.opt, self.max_grad_norm, self.schedule, self.k, self.mini + 1, acc)
+            grads = torch.from_numpy(acc)
         g = optim.clip_by_global_norm(grads.numpy().astype(np.float32), self.max_grad_norm)
         lr = np.float32(self.schedule(self.opt.count))          # the REFERENCE's linear_schedule at the pre-increment count
         new = self.opt.step(self.flat.detach().numpy().astype(np.float32), g, lr)
-        return TrainState(J(new), self.opt, self.max_grad_norm, self.schedule)
+        return TrainState(J(new), self.opt, self.max_grad_norm, self.schedule, self.k)
 
 
 # rlax 0.1.5 (poetry.lock), restated from its published source -- independently of oracle/impala.py
@@ -643,6 +652,14 @@ def run_ppo_update(ppo, rng):
     out.update(upd_ppo_cfg=np.array([T, Bl, nmb, epochs, 1000], np.int64), upd_ppo_params_seed=np.int64(11), upd_ppo_key=key, upd_ppo_key_after=np.asarray(key2),
                upd_ppo_scalars=np.array([float(loss), float(pg), float(vl), float(el), float(kl)]), **digest("upd_ppo", flat, t2n(state.flat).astype(np.float32)),
                upd_ppo_opt_count=np.int64(state.opt.count))
+    # gradient_accumulation_steps = 2 (cleanba_ppo.py:78, 492-500, 607): the shuffled batch is cut into num_minibatches * 2 mini-steps
+    a.gradient_accumulation_steps = 2
+    st_k = TrainState(J(flat), optim.Adam(flat.size), a.max_grad_norm, ns["linear_schedule"], k=2)
+    st_k, loss, pg, vl, el, kl, key_k = ns["single_device_update"](st_k, halves, [J(fields[0]["next_obs"]), J(fields[1]["next_obs"])],
+                                                                    [J(fields[0]["next_done"]), J(fields[1]["next_done"])], key)
+    a.gradient_accumulation_steps = 1
+    out.update(upd_ppok2_scalars=np.array([float(loss), float(pg), float(vl), float(el), float(kl)]), upd_ppok2_key_after=np.asarray(key_k),
+               upd_ppok2_opt_count=np.int64(st_k.opt.count), **digest("upd_ppok2", flat, t2n(st_k.flat).astype(np.float32)))
     # the same payloads on TWO learner devices (multi_device_update, cleanba_ppo.py:656-660): device l holds env columns
     # [2l, 2l + 2) of each actor thread's payload, normalises its advantages locally, shuffles with the same key; gradients and
     # the reported scalars are pmean'ed

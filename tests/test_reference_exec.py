@@ -163,6 +163,24 @@ def test_whole_impala_single_device_update():
     assert relerr(learner.params[::53], G["upd_imp_params_after_every53"]) < 1e-5
 
 
+def test_whole_ppo_update_with_gradient_accumulation():
+    """gradient_accumulation_steps = 2 (cleanba_ppo.py:78, 492-500, 607): the reference's reshape of the shuffled batch into
+    num_minibatches * 2 mini-steps and its scan over them, with optax.MultiSteps restated in the stand-in (running mean of the
+    mini-step gradients, inner chain and schedule count advance on every second mini-step)."""
+    torch.set_num_threads(1)
+    shard, cfg = _ppo_shard()
+    cfg.gradient_accumulation_steps = 2
+    flat = net.init_params(int(G["upd_ppo_params_seed"]))
+    learner = oppo.PPOLearner(flat, cfg)
+    stats, key2 = learner.update([shard], G["upd_ppo_key"])
+    assert np.array_equal(key2, G["upd_ppok2_key_after"]) and learner.opt.count == int(G["upd_ppok2_opt_count"])
+    np.testing.assert_allclose(stats, G["upd_ppok2_scalars"], rtol=2e-5)
+    d = learner.params.astype(np.float64) - flat.astype(np.float64)
+    assert abs(np.sqrt((d * d).sum()) - float(G["upd_ppok2_step_l2"])) < 1e-4 * float(G["upd_ppok2_step_l2"])
+    diff = np.abs(learner.params[::53] - G["upd_ppok2_params_after_every53"])
+    assert np.quantile(diff, 0.999) < 0.05 * 2.5e-4 and diff.max() < 8 * 2 * 2.5e-4
+
+
 def _two_device_shards(prefix, make):
     """Device l holds env columns [2l, 2l + 2) of each actor thread's payload (prepare_data's split of the env axis)."""
     return [make(slice(2 * l, 2 * l + 2)) for l in range(2)]
