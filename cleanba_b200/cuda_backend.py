@@ -392,10 +392,12 @@ class CudaLearner:
         return {k: float(v) for k, v in zip(names, s)}
 
     def current_lr(self):
+        """`charts/learning_rate` (cleanba_ppo.py:737-739): the reference reads the learning rate out of the inject_hyperparams state,
+        i.e. the rate the LAST optimizer step used (the schedule at the count before that step), not the next step's."""
         from .learner import linear_schedule
         lr = self.learners[0]
         spu = self.hyper.num_minibatches * (1 if self.impala else self.hyper.update_epochs)
-        return linear_schedule(lr.opt_count, self.hyper.learning_rate, spu, self.hyper.num_updates, self.hyper.anneal_lr)
+        return linear_schedule(max(lr.opt_count - 1, 0), self.hyper.learning_rate, spu, self.hyper.num_updates, self.hyper.anneal_lr)
 
 
 class CudaBackend:

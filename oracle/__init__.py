@@ -15,7 +15,7 @@ PARITY PINNING STATUS
 * The reference's OWN LINES of the path are PINNED BY EXECUTION: tests/golden/make_reference_exec.py lifts the hot-path
   functions out of cleanba/cleanba_ppo.py and cleanba/cleanba_impala.py with `ast` (get_action_and_value, get_action,
   compute_gae_once / compute_gae, the advantage normalisation block, get_logprob_entropy_value, ppo_loss, impala_loss and its
-  two loss wrappers, scale_by_rms_pytorch_style, both linear_schedules, BOTH whole single_device_update functions (on one and on two emulated learner devices), both whole rollout() thread functions, `class Args`
+  two loss wrappers, scale_by_rms_pytorch_style, both linear_schedules, BOTH whole single_device_update functions (on one and on two emulated learner devices), both whole rollout() thread functions, both whole `__main__` blocks, `class Args`
   and the size derivation of `__main__`) and executes those bodies unchanged over PyTorch-CPU stand-ins for the third-party
   names they call.  tests/test_reference_exec.py holds the oracle to the resulting vectors (GAE bit-exact; fp64 loss values
   1e-12 and gradients 1e-9; whole PPO / IMPALA updates: key, optimizer count, scalars 2e-5, parameters) and, under `-m gpu`,

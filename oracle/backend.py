@@ -118,7 +118,11 @@ class OracleLearner:
         return {k: float(v) for k, v in zip(names, stats)}
 
     def current_lr(self):
-        return 0.0
+        """The rate the last optimizer step used (what the reference logs, cleanba_ppo.py:737-739)."""
+        from . import optim
+        a = self.args
+        spu = a.num_minibatches * (1 if self.impala else a.update_epochs)
+        return float(optim.linear_schedule(max(self.learner.opt.count - 1, 0), a.learning_rate, spu, max(a.num_updates, 1), a.anneal_lr))
 
 
 class OracleBackend:

@@ -185,13 +185,14 @@ def _jnp_array(x, dtype=None):
 
 jnp = NS(
     array=_jnp_array, asarray=_jnp_array, zeros_like=lambda x: torch.zeros_like(x).as_subclass(JT),
-    concatenate=lambda xs, axis=0: torch.cat(list(xs), dim=axis), hstack=lambda xs: torch.hstack(list(xs)),
+    concatenate=lambda xs, axis=0: torch.cat([x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x)) for x in xs], dim=axis).as_subclass(JT),
+    hstack=lambda xs: torch.hstack(list(xs)),
     stack=lambda xs, axis=0: torch.stack([torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x for x in xs], dim=axis).as_subclass(JT),
     split=_split, zeros=lambda n, dtype=None: torch.zeros(n, dtype=dtype).as_subclass(JT),
     exp=torch.exp, log=torch.log, clip=lambda x, a, b: torch.clamp(x, a, b), maximum=torch.maximum, minimum=torch.minimum,
     arange=lambda n: torch.arange(int(n)), finfo=torch.finfo, sum=torch.sum, square=torch.square,
     reshape=lambda x, shape: x.reshape(tuple(shape)), argmax=lambda x, axis=None: torch.argmax(x, dim=axis),
-    full_like=lambda x, v: torch.full_like(x, v).as_subclass(JT), bool_=torch.bool,
+    full_like=lambda x, v: torch.full_like(x, v).as_subclass(JT), bool_=torch.bool, ndarray=torch.Tensor,
 )
 
 
@@ -556,6 +557,8 @@ def build():
     out.update(run_impala_update(imp, rng))
     out.update(run_rollout(ppo, "ppo", rng))
     out.update(run_rollout(imp, "impala", rng))
+    out.update(run_main(ppo, "ppo"))
+    out.update(run_main(imp, "impala"))
     out["meta_json"] = np.array(json.dumps(meta))
     return out
 
@@ -718,6 +721,162 @@ def run_impala_update(imp, rng):
     return out
 
 
+class Sharded(list):
+    """What jax.device_put_sharded / device_put_replicated return here: one entry per (emulated) device."""
+
+
+def _unshard(x, l):
+    if isinstance(x, Sharded):
+        return x[l]
+    if isinstance(x, tuple) and hasattr(x, "_fields"):
+        return type(x)(*[_unshard(e, l) for e in x])
+    if isinstance(x, (list, tuple)):
+        return type(x)(_unshard(e, l) for e in x)
+    return x
+
+
+def pmap_one_device(f, axis_name=None, devices=None):
+    """jax.pmap over ONE learner device: strip the device axis from the arguments, put it back on the results."""
+    def g(*args):
+        out = f(*[_unshard(a, 0) for a in args])
+        return tuple(o.reshape((1,) + tuple(o.shape)) if isinstance(o, torch.Tensor) else (Sharded([o]) if isinstance(o, np.ndarray) else o) for o in out)
+    return g
+
+
+class _LrView:
+    """agent_state.opt_state[2][1].hyperparams["learning_rate"][-1].item() (cleanba_ppo.py:737-739)"""
+
+    def __init__(self, lr):
+        self.hyperparams = {"learning_rate": [torch.tensor(float(lr))]}
+
+    def __getitem__(self, i):
+        return self
+
+
+def run_main(tree, algo):
+    """The reference's whole `if __name__ == "__main__":` block (cleanba_ppo.py:409-801 / cleanba_impala.py:449-...), executed as
+    written: size derivation, seeding, train-state creation, actor threads (the reference's own rollout(), real threads, real
+    size-1 queues), the learner loop with its policy-version accounting and logging, for two updates on tests/golden/tiny_env.py."""
+    import pprint as _pprint
+    import queue
+    import random
+    import threading
+    import time
+    import uuid
+    from collections import deque
+    from types import SimpleNamespace
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import tiny_env
+    N, T, threads_n, seed = 4, 3, 2, 5
+    scalars, started, thread_errors = [], [], []
+    lock = threading.Lock()
+
+    class Writer:
+        def __init__(self, *a, **k):
+            pass
+
+        def add_scalar(self, name, value, step):
+            with lock:
+                scalars.append((name, float(value), int(step), threading.current_thread() is threading.main_thread()))
+
+        def add_text(self, *a, **k):
+            pass
+
+        def close(self):
+            pass
+
+    class Thread(threading.Thread):
+        def __init__(self, target=None, args=()):
+            def guarded(*a):
+                try:
+                    with torch.no_grad():
+                        target(*a)
+                except BaseException as e:  # noqa: BLE001
+                    thread_errors.append(e)
+            super().__init__(target=guarded, args=args, daemon=True)
+            started.append(self)
+
+    flat0 = net.init_params(seed)
+
+    class Net(Network):
+        def init(self, key, x):
+            return Params(J(flat0)).network_params
+
+        def tabulate(self, *a, **k):
+            return ""
+
+    class Act(Actor):
+        init = Net.init
+        tabulate = Net.tabulate
+
+    class Cri(Critic):
+        init = Net.init
+        tabulate = Net.tabulate
+
+    class TS(TrainState):
+        @staticmethod
+        def create(apply_fn=None, params=None, tx=None):
+            _, chain, k = tx
+            (_, max_norm), (_, opt_name, kw) = chain[1]
+            lr = kw["learning_rate"]
+            opt = optim.Adam(flat0.size, eps=kw["eps"]) if opt_name == "adam" else optim.RMSPropPyTorchStyle(flat0.size, decay=kw["decay"], eps=kw["eps"])
+            return TS(J(flat0), opt, max_norm, lr if callable(lr) else (lambda count: lr), k)
+
+        def apply_gradients(self, grads):
+            self_lr = np.float32(self.schedule(self.opt.count))
+            new = TrainState.apply_gradients(self, grads)
+            out = TS(new.flat, new.opt, new.max_grad_norm, new.schedule, new.k, new.mini, new.acc)
+            out.opt_state = _LrView(self_lr)
+            return out
+
+    optax = NS(clip_by_global_norm=lambda c: ("clip", c), adam="adam", chain=lambda *t: ("chain", t),
+               inject_hyperparams=lambda opt: (lambda **kw: ("inner", opt, kw)), MultiSteps=lambda tx, every_k_schedule=1: ("multi", tx, every_k_schedule))
+    flax = NS(core=NS(FrozenDict=dict), jax_utils=NS(replicate=lambda x, devices=None: x, unreplicate=lambda x: x), serialization=NS())
+    jx = NS(**{**jax.__dict__, "process_count": lambda: 1, "process_index": lambda: 0, "local_devices": lambda: [0, 1], "devices": lambda: [0, 1],
+               "device_put_sharded": lambda xs, devices=None: Sharded(xs), "device_put_replicated": lambda x, devices: Sharded([x for _ in devices]),
+               "device_put": lambda x, device=None: x, "pmap": pmap_one_device, "distributed": NS()})
+    ns = base_ns(jax=jx, optax=optax, flax=flax, make_env=tiny_env.make_env, time=time, deque=deque, queue=queue, random=random, uuid=uuid,
+                 threading=NS(Thread=Thread), SimpleNamespace=SimpleNamespace, SummaryWriter=Writer, pprint=lambda *a, **k: None, print=lambda *a, **k: None,
+                 Network=Net, Actor=Act, Critic=Cri, AgentParams=lambda n, a_, c: Params(J(flat0)), TrainState=TS, rmsprop_pytorch_style="rmsprop",
+                 dataclass=dataclasses.dataclass, field=dataclasses.field, os=NS(path=NS(basename=lambda p_: "cleanba"), environ={}), __file__="cleanba.py",
+                 __name__="__main__")
+    run(lift(tree, "Args"), ns)
+    # tame hyper-parameters: this run pins control flow, not optimisation -- with the defaults (16 Adam steps on 6-frame minibatches,
+    # RMSProp's +-10 * lr first step) rounding differences of 1e-7 between two correct implementations grow to 1e-2 within one update
+    over = dict(local_num_envs=N, num_steps=T, num_actor_threads=threads_n, seed=seed, log_frequency=1, total_timesteps=2 * N * T * threads_n,
+                num_minibatches=2)
+    over.update(dict(update_epochs=1) if algo == "ppo" else dict(learning_rate=2e-5))
+
+    def cli(cls):
+        a = cls()
+        for k, v in over.items():
+            setattr(a, k, v)
+        return a
+    ns["tyro"] = NS(cli=cli)
+    run(lift(tree, "Transition"), ns)
+    run(lift(tree, "rollout"), ns)
+    main = next(n for n in tree.body if isinstance(n, ast.If) and "__main__" in ast.unparse(n.test))
+    exec(compile(ast.Module(body=main.body, type_ignores=[]), "<reference __main__>", "exec"), ns)
+    for t in started:
+        t.join(timeout=60)
+    assert not thread_errors, thread_errors
+    assert not any(t.is_alive() for t in started), "an actor thread did not finish"
+    state = ns["agent_state"]
+    learner_scalars = [(n, v, s) for n, v, s, is_main in scalars if is_main]
+    actor_scalars = [(n, v, s) for n, v, s, is_main in scalars if not is_main]
+    keep = ("charts/learning_rate", "losses/value_loss", "losses/policy_loss", "losses/entropy", "losses/approx_kl", "losses/loss")
+    out = {f"main_{algo}_cfg": np.array([N, T, threads_n, seed, int(ns["args"].num_updates)], np.int64),
+           f"main_{algo}_overrides": np.array(json.dumps(over)),
+           f"main_{algo}_learner_scalar_names": np.array(json.dumps([n for n, _, _ in learner_scalars])),
+           f"main_{algo}_learner_scalars": np.array([[v, s] for n, v, s in learner_scalars if n in keep], np.float64),
+           f"main_{algo}_actor_scalar_names": np.array(json.dumps([n for n, _, _ in actor_scalars])),
+           f"main_{algo}_actor_returns": np.array([[v, s] for n, v, s in actor_scalars if n in ("charts/avg_episodic_return", "charts/avg_episodic_length")], np.float64),
+           f"main_{algo}_versions": np.array([int(ns["learner_policy_version"]), int(ns["actor_policy_version"]), int(ns["update"]), int(ns["global_step"])], np.int64),
+           f"main_{algo}_opt_count": np.int64(state.opt.count)}
+    out.update(digest(f"main_{algo}", flat0, t2n(state.flat).astype(np.float32)))
+    return out
+
+
 def run_rollout(tree, algo, rng):
     """The reference's whole rollout() thread function (cleanba_ppo.py:226-406 / cleanba_impala.py:268-447) for three updates on
     tests/golden/tiny_env.py, two learner devices: storage order, done / truncation / first-step flags, the IMPALA carried row,
@@ -732,7 +891,7 @@ def run_rollout(tree, algo, rng):
     a.num_updates, a.world_size = updates - 1, 1          # the loop runs range(1, num_updates + 2)
     scalars = []
     writer = NS(add_scalar=lambda name, value, step: scalars.append((name, float(value), int(step))))
-    jx = NS(**{**jax.__dict__, "process_index": lambda: 0, "device_put_sharded": lambda xs, devices=None: list(xs)})
+    jx = NS(**{**jax.__dict__, "process_index": lambda: 0, "device_put_sharded": lambda xs, devices=None: Sharded(xs)})
     ns = base_ns(args=a, jax=jx, make_env=tiny_env.make_env, time=time, deque=deque, queue=queue, print=lambda *x, **k: None)
     run(lift(tree, "Transition"), ns)
     run(lift(tree, "rollout"), ns)

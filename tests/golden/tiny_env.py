@@ -17,6 +17,7 @@ class TinyEnv:
         self.needs_reset = np.zeros(num_envs, bool)
         self.spec = SimpleNamespace(config=SimpleNamespace(max_episode_steps=self.MAX_STEPS))
         self.single_action_space = SimpleNamespace(n=18)
+        self.single_observation_space = SimpleNamespace(shape=(4, 84, 84), dtype=np.uint8, sample=lambda: np.zeros((4, 84, 84), np.uint8))
         self.pending = None
 
     def _obs(self):

@@ -230,6 +230,57 @@ def test_whole_impala_update_on_two_learner_devices():
     assert relerr(learner.params[::53], G["upd_imp2_params_after_every53"]) < 1e-5
 
 
+@pytest.mark.parametrize("algo", ["ppo", "impala"])
+def test_whole_program_against_the_reference_main_block(algo):
+    """cleanba_b200.sebulba.train (the product's host program: actor threads, size-1 queues, learner loop; here over the CPU oracle
+    backend) against the reference's whole `if __name__ == "__main__":` block executed as written -- its own rollout() in real threads,
+    its own learner loop -- for two updates on the same deterministic env: the order and names of every scalar the learner and the
+    first actor thread log, the loss scalars and the logged learning rate of both updates, learner / actor policy versions (the
+    actor one behind under IMPALA's concurrency), update index, global_step, optimizer count and the final parameters."""
+    import contextlib
+    import io
+    import sys
+    torch.set_num_threads(1)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tiny_env
+    from cleanba_b200 import sebulba
+    from oracle.backend import OracleBackend
+    a = sebulba.Args() if algo == "ppo" else sebulba.impala_defaults(sebulba.Args())
+    for k, v in json.loads(str(G[f"main_{algo}_overrides"])).items():
+        setattr(a, k, v)
+    sebulba.derive_sizes(a)
+    assert a.num_updates == int(G[f"main_{algo}_cfg"][4])
+    learner_sc, actor_sc = [], []
+
+    class W:
+        def add_scalar(self, name, value, step):
+            import threading
+            (learner_sc if threading.current_thread() is threading.main_thread() else actor_sc).append((name, float(value), int(step)))
+
+        def add_text(self, *args, **kw):
+            pass
+
+        def close(self):
+            pass
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = sebulba.train(a, OracleBackend(), tiny_env.make_env, writer=W())
+    assert [n for n, _, _ in learner_sc] == json.loads(str(G[f"main_{algo}_learner_scalar_names"]))
+    assert [n for n, _, _ in actor_sc] == json.loads(str(G[f"main_{algo}_actor_scalar_names"]))
+    keep = ("charts/learning_rate", "losses/value_loss", "losses/policy_loss", "losses/entropy", "losses/approx_kl", "losses/loss")
+    mine = np.array([[v, s] for n, v, s in learner_sc if n in keep])
+    np.testing.assert_allclose(mine, G[f"main_{algo}_learner_scalars"], rtol=1e-4)
+    ret = np.array([[v, s] for n, v, s in actor_sc if n in ("charts/avg_episodic_return", "charts/avg_episodic_length")])
+    np.testing.assert_allclose(ret, G[f"main_{algo}_actor_returns"], rtol=1e-6)
+    lpv, apv, upd, gs = (int(x) for x in G[f"main_{algo}_versions"])
+    assert res.updates == lpv and res.versions[-1] == (apv, upd, lpv) and res.global_step == gs
+    inner = res.learner.learner
+    assert inner.opt.count == int(G[f"main_{algo}_opt_count"])
+    flat0 = net.init_params(int(G[f"main_{algo}_cfg"][3]))
+    d = inner.params.astype(np.float64) - flat0.astype(np.float64)
+    assert abs(np.sqrt((d * d).sum()) - float(G[f"main_{algo}_step_l2"])) < 1e-3 * float(G[f"main_{algo}_step_l2"])
+    assert np.abs(inner.params[::53] - G[f"main_{algo}_params_after_every53"]).max() < 2e-5
+
+
 # ------------------------------------------------------------------------------------------------ CUDA path vs reference lines
 @pytest.mark.gpu
 def test_cuda_actor_and_gae_against_reference_lines():
