@@ -16,6 +16,7 @@ from .prng import first_key
 def evaluate(model_path: str, make_env: Callable, env_id: str, eval_episodes: int, run_name: str = "", Model=None,
              capture_video: bool = False, seed: int = 1, device="cuda:0", max_episode_steps: int = 27000) -> List[float]:
     envs = make_env(env_id, seed, num_envs=1)()
+    envs.reset()                                          # the reference resets once before the episode loop too (:24)
     _, flat = load_cleanrl_model(model_path)
     from .checkpoint import _model_of_size
     ctx = ag.Context(device, max_batch=1, train=False, model=_model_of_size(flat.size, ag.NUM_ACTIONS))
