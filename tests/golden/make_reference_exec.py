@@ -559,6 +559,8 @@ def build():
     out.update(run_rollout(imp, "impala", rng))
     out.update(run_main(ppo, "ppo"))
     out.update(run_main(imp, "impala"))
+    # the PPO script with --concurrency (rollout u+1 beside update u, the `update != 2` rule of cleanba_ppo.py:287-304), three updates
+    out.update(run_main(ppo, "ppo", tag="ppoconc", extra=dict(concurrency=True, total_timesteps=3 * 4 * 3 * 2)))
     out["meta_json"] = np.array(json.dumps(meta))
     return out
 
@@ -753,7 +755,7 @@ class _LrView:
         return self
 
 
-def run_main(tree, algo):
+def run_main(tree, algo, tag=None, extra=None):
     """The reference's whole `if __name__ == "__main__":` block (cleanba_ppo.py:409-801 / cleanba_impala.py:449-...), executed as
     written: size derivation, seeding, train-state creation, actor threads (the reference's own rollout(), real threads, real
     size-1 queues), the learner loop with its policy-version accounting and logging, for two updates on tests/golden/tiny_env.py."""
@@ -846,6 +848,8 @@ def run_main(tree, algo):
     over = dict(local_num_envs=N, num_steps=T, num_actor_threads=threads_n, seed=seed, log_frequency=1, total_timesteps=2 * N * T * threads_n,
                 num_minibatches=2)
     over.update(dict(update_epochs=1) if algo == "ppo" else dict(learning_rate=2e-5))
+    over.update(extra or {})
+    algo = tag or algo
 
     def cli(cls):
         a = cls()

@@ -230,7 +230,7 @@ def test_whole_impala_update_on_two_learner_devices():
     assert relerr(learner.params[::53], G["upd_imp2_params_after_every53"]) < 1e-5
 
 
-@pytest.mark.parametrize("algo", ["ppo", "impala"])
+@pytest.mark.parametrize("algo", ["ppo", "impala", "ppoconc"])      # ppoconc: the PPO script with --concurrency, three updates
 def test_whole_program_against_the_reference_main_block(algo):
     """cleanba_b200.sebulba.train (the product's host program: actor threads, size-1 queues, learner loop; here over the CPU oracle
     backend) against the reference's whole `if __name__ == "__main__":` block executed as written -- its own rollout() in real threads,
@@ -245,7 +245,7 @@ def test_whole_program_against_the_reference_main_block(algo):
     import tiny_env
     from cleanba_b200 import sebulba
     from oracle.backend import OracleBackend
-    a = sebulba.Args() if algo == "ppo" else sebulba.impala_defaults(sebulba.Args())
+    a = sebulba.impala_defaults(sebulba.Args()) if algo == "impala" else sebulba.Args()
     for k, v in json.loads(str(G[f"main_{algo}_overrides"])).items():
         setattr(a, k, v)
     sebulba.derive_sizes(a)
