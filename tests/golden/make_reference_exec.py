@@ -561,6 +561,9 @@ def build():
     out.update(run_main(imp, "impala"))
     # the PPO script with --concurrency (rollout u+1 beside update u, the `update != 2` rule of cleanba_ppo.py:287-304), three updates
     out.update(run_main(ppo, "ppo", tag="ppoconc", extra=dict(concurrency=True, total_timesteps=3 * 4 * 3 * 2)))
+    # two learner devices: flax replicate, device_put_sharded of the env-axis halves, pmap over both, unreplicate for the actors
+    out.update(run_main(ppo, "ppo", tag="ppol2", extra=dict(learner_device_ids=[0, 1])))
+    out.update(run_main(imp, "impala", tag="impalal2", extra=dict(learner_device_ids=[0, 1])))
     out["meta_json"] = np.array(json.dumps(meta))
     return out
 
@@ -591,20 +594,22 @@ class PMean:
         return mean
 
 
-def pmap_threads(ns, fn_name, per_device_args):
-    """The reference's `jax.pmap(single_device_update, axis_name="local_devices")` (cleanba_ppo.py:656-660) on emulated devices."""
+def pmap_threads(ns, fn, per_device_args):
+    """The reference's `jax.pmap(single_device_update, axis_name="local_devices")` (cleanba_ppo.py:656-660) on emulated devices.
+    `fn`: the function object or its name in `ns`."""
     import threading
     L = len(per_device_args)
     pm = PMean(L)
-    saved = ns["jax"]
-    ns["jax"] = NS(**{**jax.__dict__, "lax": NS(**{**jax.lax.__dict__, "pmean": pm})})
+    saved = ns["jax"]       # other threads (actors) keep using the namespace meanwhile: the swapped-in module is a superset
+    ns["jax"] = NS(**{**saved.__dict__, "lax": NS(**{**saved.lax.__dict__, "pmean": pm})})
     results, errors = [None] * L, []
+    f = ns[fn] if isinstance(fn, str) else fn
 
     def work(l):
         pm.local.dev = l
         torch.set_default_dtype(torch.float32)
         try:
-            results[l] = ns[fn_name](*per_device_args[l])
+            results[l] = f(*per_device_args[l])
         except BaseException as e:  # noqa: BLE001
             errors.append(e)
             pm.barrier.abort()
@@ -745,6 +750,39 @@ def pmap_one_device(f, axis_name=None, devices=None):
     return g
 
 
+class Rep:
+    """flax.jax_utils.replicate(agent_state, devices): one train state per (emulated) learner device."""
+
+    def __init__(self, states):
+        self.states = list(states)
+
+    params = property(lambda self: Sharded([st.params for st in self.states]))
+    opt_state = property(lambda self: self.states[0].opt_state)
+    flat = property(lambda self: self.states[0].flat)
+    opt = property(lambda self: self.states[0].opt)
+
+
+def pmap_devices(ns, f, devices):
+    """jax.pmap over several emulated learner devices (threads + pmean rendezvous)."""
+    L = len(devices)
+    if L == 1:
+        return pmap_one_device(f)
+
+    def g(*args):
+        per = [[a.states[l] if isinstance(a, Rep) else _unshard(a, l) for a in args] for l in range(L)]
+        res = pmap_threads(ns, f, per)
+        out = []
+        for parts in zip(*res):
+            if isinstance(parts[0], torch.Tensor):
+                out.append(torch.stack(list(parts)))
+            elif isinstance(parts[0], np.ndarray):
+                out.append(Sharded(list(parts)))
+            else:
+                out.append(Rep(parts))
+        return tuple(out)
+    return g
+
+
 class _LrView:
     """agent_state.opt_state[2][1].hyperparams["learning_rate"][-1].item() (cleanba_ppo.py:737-739)"""
 
@@ -833,10 +871,16 @@ def run_main(tree, algo, tag=None, extra=None):
 
     optax = NS(clip_by_global_norm=lambda c: ("clip", c), adam="adam", chain=lambda *t: ("chain", t),
                inject_hyperparams=lambda opt: (lambda **kw: ("inner", opt, kw)), MultiSteps=lambda tx, every_k_schedule=1: ("multi", tx, every_k_schedule))
-    flax = NS(core=NS(FrozenDict=dict), jax_utils=NS(replicate=lambda x, devices=None: x, unreplicate=lambda x: x), serialization=NS())
+    import copy
+
+    def replicate(x, devices=None):
+        if devices is None or len(devices) == 1:
+            return x
+        return Rep([TS(x.flat.clone(), copy.deepcopy(x.opt), x.max_grad_norm, x.schedule, x.k) for _ in devices])
+    flax = NS(core=NS(FrozenDict=dict), jax_utils=NS(replicate=replicate, unreplicate=lambda x: x[0] if isinstance(x, Sharded) else x), serialization=NS())
     jx = NS(**{**jax.__dict__, "process_count": lambda: 1, "process_index": lambda: 0, "local_devices": lambda: [0, 1], "devices": lambda: [0, 1],
                "device_put_sharded": lambda xs, devices=None: Sharded(xs), "device_put_replicated": lambda x, devices: Sharded([x for _ in devices]),
-               "device_put": lambda x, device=None: x, "pmap": pmap_one_device, "distributed": NS()})
+               "device_put": lambda x, device=None: x, "pmap": lambda f, axis_name=None, devices=None: pmap_devices(ns, f, devices), "distributed": NS()})
     ns = base_ns(jax=jx, optax=optax, flax=flax, make_env=tiny_env.make_env, time=time, deque=deque, queue=queue, random=random, uuid=uuid,
                  threading=NS(Thread=Thread), SimpleNamespace=SimpleNamespace, SummaryWriter=Writer, pprint=lambda *a, **k: None, print=lambda *a, **k: None,
                  Network=Net, Actor=Act, Critic=Cri, AgentParams=lambda n, a_, c: Params(J(flat0)), TrainState=TS, rmsprop_pytorch_style="rmsprop",
@@ -866,6 +910,9 @@ def run_main(tree, algo, tag=None, extra=None):
     assert not thread_errors, thread_errors
     assert not any(t.is_alive() for t in started), "an actor thread did not finish"
     state = ns["agent_state"]
+    if isinstance(state, Rep):
+        assert all(torch.equal(st.flat, state.states[0].flat) for st in state.states), "learner replicas diverged"
+        state = state.states[0]
     learner_scalars = [(n, v, s) for n, v, s, is_main in scalars if is_main]
     actor_scalars = [(n, v, s) for n, v, s, is_main in scalars if not is_main]
     keep = ("charts/learning_rate", "losses/value_loss", "losses/policy_loss", "losses/entropy", "losses/approx_kl", "losses/loss")
