@@ -557,6 +557,7 @@ def build():
     out.update(run_impala_update(imp, rng))
     out.update(run_rollout(ppo, "ppo", rng))
     out.update(run_rollout(imp, "impala", rng))
+    out.update(run_benchmark_tool())
     out.update(run_main(ppo, "ppo"))
     out.update(run_main(imp, "impala"))
     # the PPO script with --concurrency (rollout u+1 beside update u, the `update != 2` rule of cleanba_ppo.py:287-304), three updates
@@ -926,6 +927,53 @@ def run_main(tree, algo, tag=None, extra=None):
            f"main_{algo}_opt_count": np.int64(state.opt.count)}
     out.update(digest(f"main_{algo}", flat0, t2n(state.flat).astype(np.float32)))
     return out
+
+
+def run_benchmark_tool():
+    """cleanrl_utils/benchmark.py is plain Python: run its `__main__` as written (dry run + SLURM rendering of a template of ours with
+    all of its placeholders) and keep what it prints and renders.  `distutils` (gone in Python 3.12) is the only stand-in."""
+    import contextlib
+    import io
+    import runpy
+    import tempfile
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import tiny_env
+    tdir = tempfile.mkdtemp()
+    tpath = os.path.join(tdir, "template.slurm")
+    open(tpath, "w").write(tiny_env.SLURM_TEMPLATE)
+    argv = ["benchmark.py", "--env-ids", "Breakout-v5", "Pong-v5", "--command", "python -m cleanba_b200.cleanba_ppo --local-num-envs 60",
+            "--num-seeds", "3", "--start-seed", "4", "--workers", "0", "--auto-tag", "False",
+            "--slurm-template-path", tpath, "--slurm-gpus-per-task", "4", "--slurm-total-cpus", "50",
+            "--slurm-ntasks", "2", "--slurm-nodes", "2"]
+    du = types.ModuleType("distutils")
+    duu = types.ModuleType("distutils.util")
+    duu.strtobool = lambda v: 1 if str(v).lower() in ("y", "yes", "t", "true", "on", "1") else 0
+    du.util = duu
+    saved_mods = {k: sys.modules.get(k) for k in ("distutils", "distutils.util")}
+    sys.modules["distutils"], sys.modules["distutils.util"] = du, duu
+    saved_argv, cwd = sys.argv, os.getcwd()
+    buf = io.StringIO()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            sys.argv = argv
+            with contextlib.redirect_stdout(buf):
+                runpy.run_path(os.path.join(REF, "cleanrl_utils", "benchmark.py"), run_name="__main__")
+            files = os.listdir("slurm")
+            script = open(os.path.join("slurm", [f for f in files if f.endswith(".slurm")][0])).read()
+        finally:
+            os.chdir(cwd)
+            sys.argv = saved_argv
+            for k, v in saved_mods.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+    lines = buf.getvalue().splitlines()
+    i0 = lines.index("======= commands to run:") + 1
+    commands = [l for l in lines[i0:] if l.startswith("python -m")]
+    argv[argv.index("--slurm-template-path") + 1] = "<tiny_env.SLURM_TEMPLATE>"
+    return {"bench_tool_argv": np.array(json.dumps(argv[1:])), "bench_tool_commands": np.array(json.dumps(commands)), "bench_tool_slurm": np.array(script)}
 
 
 def run_rollout(tree, algo, rng):

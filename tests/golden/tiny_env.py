@@ -67,3 +67,16 @@ class TinyEnv:
 
 def make_env(env_id, seed, num_envs):
     return lambda: TinyEnv(num_envs, seed)
+
+
+# A SLURM template with every placeholder the reference's cleanrl_utils/benchmark.py substitutes (our own text, not the reference's file)
+SLURM_TEMPLATE = """#!/bin/bash
+#SBATCH --gpus-per-task={{gpus_per_task}}
+#SBATCH --cpus-per-gpu={{cpus_per_gpu}}
+#SBATCH --ntasks={{ntasks}}
+#SBATCH --array={{array}}
+{{nodes}}
+envs={{env_ids}}
+seeds={{seeds}}
+srun {{command}} --env-id ${envs[$SLURM_ARRAY_TASK_ID / {{len_seeds}}]} --seed ${seeds[$SLURM_ARRAY_TASK_ID % {{len_seeds}}]}
+"""

@@ -63,6 +63,26 @@ def test_learning_rate_schedules():
             assert abs(float(learner.linear_schedule(int(c), base, per_update, nu, True)) - lr) <= 1e-7 * base
 
 
+def test_benchmark_launcher_against_the_reference_tool(tmp_path, monkeypatch, capsys):
+    """cleanba_b200.benchmark against cleanrl_utils/benchmark.py run as written (plain Python, so no stand-ins but `distutils`): the
+    same argv gives the same command lines in the same order and the same rendered SLURM script."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import tiny_env
+    from cleanba_b200 import benchmark as bm
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.delenv("WANDB_TAGS", raising=False)
+    (tmp_path / "template.slurm").write_text(tiny_env.SLURM_TEMPLATE)
+    argv = [str(tmp_path / "template.slurm") if x == "<tiny_env.SLURM_TEMPLATE>" else x for x in json.loads(str(G["bench_tool_argv"]))]
+    bm.main(argv)
+    out = capsys.readouterr().out.splitlines()
+    commands = [l for l in out[out.index("======= commands to run:") + 1:] if l.startswith("python -m")]
+    assert commands == json.loads(str(G["bench_tool_commands"]))
+    scripts = [f for f in os.listdir(tmp_path / "slurm") if f.endswith(".slurm")]
+    assert len(scripts) == 1 and (tmp_path / "slurm" / scripts[0]).read_text() == str(G["bench_tool_slurm"])
+    assert os.path.isdir(tmp_path / "slurm" / "logs")
+
+
 # ------------------------------------------------------------------------------------------------ oracle vs reference lines
 def test_actor_sampling_lines():
     flat = net.init_params(int(G["act_params_seed"]))
